@@ -1,0 +1,51 @@
+"""Analytic known-answers for the tf.image.psnr / ssim restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import metrics as om
+
+
+def test_gaussian_window():
+    t = om.gaussian_taps()
+    assert abs(t.sum() - 1) < 1e-12
+    assert np.allclose(t[:6], [0.00102838, 0.00759876, 0.03600077, 0.10936069, 0.21300554, 0.26601172], atol=1e-8)
+    assert abs(np.outer(t, t)[5, 5] - 0.07076224) < 1e-8
+
+
+def test_constant_images():
+    a = np.full((2, 16, 20, 3), 0.3, np.float32)
+    b = np.full((2, 16, 20, 3), 0.6, np.float32)
+    assert np.allclose(om.ssim(a, b, dtype=np.float64), 0.80004443, atol=1e-8)
+    # float32 (what tf.image.ssim computes in): E[xy] - mu_x*mu_y cancels against c2 = 9e-4, so
+    # a zero-variance image carries ~1e-4 of rounding noise in any float32 evaluation order.
+    assert np.allclose(om.ssim(a, b), 0.80004443, atol=2e-4)
+    assert np.allclose(om.psnr(a, b), 10.4575749, atol=1e-4)
+    assert np.allclose(om.ssim(a, a), 1.0, atol=1e-6)
+    assert np.all(np.isinf(om.psnr(a, a)))
+
+
+def test_small_images_raise():
+    a = np.zeros((1, 10, 32, 3), np.float32)
+    with pytest.raises(ValueError):
+        om.ssim(a, a)
+
+
+def test_separable_equals_2d_and_fp64(golden_dir):
+    g = np.load(os.path.join(golden_dir, "metrics_oracle.npz"))
+    a, b = g["a"], g["b"]
+    s_sep = om.ssim(a, b)
+    s_2d = om.ssim(a, b, separable=False)
+    assert np.abs(s_sep - s_2d).max() < 2e-6
+    assert np.abs(s_sep - g["ssim64"]).max() < 1e-5
+    assert np.abs(om.psnr(a, b) - g["psnr64"]).max() < 1e-4
+    assert np.array_equal(s_sep, g["ssim32"]) and np.array_equal(om.psnr(a, b), g["psnr32"])
+
+
+def test_evaluate_means_shape():
+    rng = np.random.default_rng(0)
+    a = rng.random((3, 12, 12, 3), dtype=np.float32)
+    b = rng.random((3, 12, 12, 3), dtype=np.float32)
+    loss, p, s = om.evaluate_means(a, b)
+    assert abs(loss - np.mean((a - b) ** 2)) < 1e-7 and -1 < s < 1 and p > 0
