@@ -1,0 +1,125 @@
+/* srb200 - C ABI of the B200-native super-resolution inference path.
+ *
+ * The reference (bgmanuel99/Super-Resolution-Images-for-3D-Printing-Defect-Detection) has no FFI
+ * of its own: its hot path disappears into three third-party engine calls.  Each entry point below
+ * names the reference call it replaces.  All pointers are DEVICE pointers unless the name ends in
+ * `_host`; sizes are element counts; `stream` is a `cudaStream_t` (0 = legacy default stream).
+ * Every function returns 0 on success or a negative `SRB_E_*` code and then `srb_last_error()`
+ * returns a thread-local description.  No entry point owns caller memory; nothing falls back to
+ * the CPU.
+ *
+ *   Keras Conv2D / Add / Lambda / depth_to_space / clip  -> srb_conv2d_nhwc
+ *        SRModels/deep_learning_models/SRCNN_model.py:50-52, EDSR_model.py:55-125,
+ *        ESRGAN_model.py:212-345, model.predict at SRCNN_model.py:210, EDSR_model.py:274
+ *   cv2.resize(..., INTER_CUBIC)                          -> srb_bicubic_f32 / srb_bicubic_u8
+ *        SRModels/classic_super_resolution_algorithms/classic_algorithms.py:11-13,
+ *        SRModels/loading_methods.py:147, SRCNN_model.py:191
+ *   tf.image.psnr / tf.image.ssim (max_val = 1)           -> srb_psnr_ssim_f32
+ *        SRModels/metrics.py:3-7
+ *   add_padding + patch loops + overlap-add               -> srb_pad_extract_f32 / srb_overlap_add_f32
+ *        SRModels/loading_methods.py:6-26, EDSR_model.py:201-256, SRCNN_model.py:127-188
+ */
+#ifndef SRB200_H
+#define SRB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* srb_stream_t;          /* cudaStream_t */
+typedef struct srb_conv_weights srb_conv_weights;   /* opaque, device-resident packed kernel */
+
+enum { SRB_OK = 0, SRB_E_INVALID = -1, SRB_E_UNSUPPORTED = -2, SRB_E_CUDA = -3, SRB_E_NOMEM = -4 };
+enum { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2 };
+enum { SRB_ACT_NONE = 0, SRB_ACT_RELU = 1, SRB_ACT_PRELU = 2, SRB_ACT_LEAKY = 3, SRB_ACT_TANH = 4 };
+/* conv engine selection: AUTO picks tcgen05 when the shape is eligible, else the CUDA-core path */
+enum { SRB_ENGINE_AUTO = 0, SRB_ENGINE_DIRECT = 1, SRB_ENGINE_TCGEN05 = 2 };
+
+const char* srb_last_error(void);
+int srb_version(void);
+/* sm_count / cc of the current device; fails unless the device is sm_100 (B200). */
+int srb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- PSNR + SSIM, fused, one pass over both images (metrics.py:3-7) --------------------------
+ * a, b: [B, H, W, C] float32 NHWC.  psnr, ssim, mse: [B] float32 (each may be NULL); mse is the
+ * per-image mean squared error (the Keras "mean_squared_error" loss of SRCNN_model.py:59).
+ * sums: optional [4] float64 {sum psnr, sum ssim, count, sum mse}, ACCUMULATED (not overwritten) so
+ * that sharded evaluation can all-reduce one 4-vector.  workspace: >= srb_psnr_ssim_workspace(B) bytes.
+ * H and W must be >= 11 (tf.image.ssim raises otherwise) -> SRB_E_INVALID. */
+size_t srb_psnr_ssim_workspace(int batch);
+int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int width, int channels,
+                      float max_val, float* psnr, float* ssim, float* mse, double* sums,
+                      void* workspace, size_t workspace_bytes, srb_stream_t stream);
+
+/* ---- bicubic resampling == cv2.resize(src, (dst_w, dst_h), INTER_CUBIC) ------------------------
+ * NHWC interleaved, any channel count, any ratio.  clip01: clamp to [0,1] (loading_methods.py:148).
+ * u8: fixed_point = 0 -> saturate(rint(float path)) (OpenCV default dispatch);
+ *     fixed_point = 1 -> OpenCV's 11-bit fixed-point path (cv2.setUseOptimized(False)), bit-exact. */
+int srb_bicubic_f32(const float* src, int batch, int src_h, int src_w, int channels,
+                    float* dst, int dst_h, int dst_w, int clip01, srb_stream_t stream);
+int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                   uint8_t* dst, int dst_h, int dst_w, int fixed_point, srb_stream_t stream);
+
+/* ---- tiling (loading_methods.py:6-26; EDSR_model.py:201-256) -----------------------------------
+ * pad_extract: reflect-pad bottom/right by the reference's rule and cut [ny*nx, P, P, C] patches at
+ * stride S.  srb_tiling_geometry returns padded size and patch grid (host-only helper).
+ * overlap_add: average the patches covering each output pixel (patch order = reference loop order),
+ * crop to out_h x out_w, clip to [0,1]. */
+int srb_tiling_geometry(int height, int width, int patch, int stride,
+                        int* padded_h, int* padded_w, int* ny, int* nx);
+int srb_pad_extract_f32(const float* image, int height, int width, int channels, int patch, int stride,
+                        float* patches, srb_stream_t stream);
+int srb_overlap_add_f32(const float* patches, int ny, int nx, int patch_out, int stride_out, int channels,
+                        float* image, int out_h, int out_w, srb_stream_t stream);
+
+/* ---- convolution (Keras Conv2D, padding="same", stride 1) with fused epilogue -------------------
+ * y = clip( alpha * act(conv(x, W) + bias) + beta1 * res1 + beta2 * res2 ), optionally written
+ * through tf.nn.depth_to_space(y, d2s) (DCR).  With d2s = r the output tensor is
+ * [B, H*r, W*r, cout/(r*r)] and PReLU slopes are indexed by the post-shuffle channel. */
+typedef struct srb_conv_args {
+  const void* x;        int x_dtype;   int x_cstride;  int x_coffset;   /* input  NHWC, C-slice allowed */
+  void*       y;        int y_dtype;   int y_cstride;  int y_coffset;   /* output NHWC, C-slice allowed */
+  int batch, height, width;
+  const srb_conv_weights* weights;
+  int act;              float act_slope;               const float* prelu;   /* [cout / d2s^2] */
+  float alpha;
+  const void* res1;     int res1_dtype; int res1_cstride; float beta1;   /* same geometry as y (pre-d2s NOT supported) */
+  const void* res2;     int res2_dtype; int res2_cstride; float beta2;
+  int clip01;
+  int d2s;              /* 1 = none, 2/3/4 = depth_to_space factor */
+  int engine;           /* SRB_ENGINE_* */
+} srb_conv_args;
+
+/* hwio_host: Keras kernel [kh, kw, cin, cout] float32 on the HOST; bias_host: [cout] or NULL.
+ * Packs (and rounds to bf16 for the tcgen05 path) once; the result lives on the current device. */
+int srb_conv_weights_create(const float* hwio_host, const float* bias_host, int kh, int kw, int cin, int cout,
+                            srb_conv_weights** out);
+void srb_conv_weights_destroy(srb_conv_weights* w);
+int srb_conv2d_nhwc(const srb_conv_args* args, srb_stream_t stream);
+/* which engine AUTO would pick for these args: SRB_ENGINE_DIRECT or SRB_ENGINE_TCGEN05 */
+int srb_conv2d_engine(const srb_conv_args* args);
+/* tcgen05 engine A-operand staging variant (process-wide; returns the previous value, or the current
+ * one for variant < 0).  0 = one TMA halo tile per pixel tile, taps addressed by shifted UMMA
+ * descriptors; 1 = as 0 with the descriptor base-offset field set from the shifted address;
+ * 2 = three dx-shifted TMA tiles so that every tap starts on a 1024-byte swizzle boundary. */
+int srb_conv_tc_set_variant(int variant);
+
+/* ---- small layout / elementwise helpers used between layers -------------------------------------- */
+int srb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, float shift,
+             srb_stream_t stream);                                   /* dst = src * scale + shift */
+int srb_maxpool2x2_nhwc(const void* x, int dtype, int batch, int height, int width, int channels, void* y,
+                        srb_stream_t stream);                        /* VGG16_model.py:69 (MaxPooling2D) */
+int srb_gap_dense_softmax(const void* x, int dtype, int batch, int hw, int channels,
+                          const float* w1, const float* b1, int hidden, const float* w2, const float* b2,
+                          int classes, float* probs, srb_stream_t stream);   /* VGG16_model.py:84-97 */
+/* SelfAttention core (ESRGAN_model.py:48-70): o = softmax(g f^T) h per image; f,g: [B,HW,dk], h: [B,HW,dv] */
+int srb_self_attention_f32(const float* f, const float* g, const float* h, int batch, int hw, int dk, int dv,
+                           float* o, srb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRB200_H */

@@ -1,0 +1,172 @@
+// cv2.resize(..., INTER_CUBIC) on the GPU (classic_algorithms.py:11-13, loading_methods.py:147,
+// SRCNN_model.py:191).  Separable 4-tap Keys cubic (A = -0.75), half-pixel centres, tap index clamp.
+//
+// Two kernels: `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only
+// place double precision is used), and `bicubic_kernel` does the separable resampling for a tile of
+// 256 interleaved output elements x TY output rows: the horizontal pass over just the source rows
+// the tile needs goes to shared memory, the vertical pass reads it back column-wise, and both
+// global reads and writes are contiguous across the block.
+//
+// float path  : t from double, FMA-contracted coefficient polynomial, FMA accumulation in tap order
+//               (OpenCV's default dispatch to <= 1e-6; uint8 = saturate(rint(.)) of the same path).
+// fixed path  : OpenCV's 11-bit fixed-point uint8 path (== cv2.setUseOptimized(False)), bit-exact:
+//               float32 f/t, plain float32 polynomial, int32 horizontal pass, float32 vertical pass.
+#include "common.cuh"
+
+namespace srb {
+
+struct AxisTap { int idx[4]; float coef[4]; };   // 32 bytes
+
+__global__ void bicubic_tables(AxisTap* __restrict__ tab, int n_src, int n_dst, int fixed) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_dst) return;
+  const double scale = 1.0 / ((double)n_dst / (double)n_src);
+  const double fd = __dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  const float A = -0.75f;
+  int s;
+  float c0, c1, c2, c3;
+  if (fixed) {
+    const float f = (float)fd;
+    s = (int)floorf(f);
+    const float t = __fsub_rn(f, (float)s);
+    const float x1 = __fadd_rn(t, 1.f);
+    c0 = __fsub_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fsub_rn(__fmul_rn(A, x1), 5.f * A), x1), 8.f * A), x1), 4.f * A);
+    c1 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, t), A + 3.f), t), t), 1.f);
+    const float u = __fsub_rn(1.f, t);
+    c2 = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(__fmul_rn(A + 2.f, u), A + 3.f), u), u), 1.f);
+    c3 = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c0), c1), c2);
+    // INTER_RESIZE_COEF_SCALE = 2048, saturate_cast<short>(rint)
+    c0 = fminf(fmaxf(rintf(__fmul_rn(c0, 2048.f)), -32768.f), 32767.f);
+    c1 = fminf(fmaxf(rintf(__fmul_rn(c1, 2048.f)), -32768.f), 32767.f);
+    c2 = fminf(fmaxf(rintf(__fmul_rn(c2, 2048.f)), -32768.f), 32767.f);
+    c3 = fminf(fmaxf(rintf(__fmul_rn(c3, 2048.f)), -32768.f), 32767.f);
+  } else {
+    const double fl = floor(fd);
+    s = (int)fl;
+    const float t = (float)(fd - fl);
+    const float x1 = __fadd_rn(t, 1.f);
+    c0 = __fmaf_rn(__fmaf_rn(__fmaf_rn(A, x1, -5.f * A), x1, 8.f * A), x1, -4.f * A);
+    c1 = __fmaf_rn(__fmul_rn(__fmaf_rn(A + 2.f, t, -(A + 3.f)), t), t, 1.f);
+    const float u = __fsub_rn(1.f, t);
+    c2 = __fmaf_rn(__fmul_rn(__fmaf_rn(A + 2.f, u, -(A + 3.f)), u), u, 1.f);
+    c3 = __fsub_rn(__fsub_rn(__fsub_rn(1.f, c0), c1), c2);
+  }
+  AxisTap a;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) a.idx[k] = min(max(s - 1 + k, 0), n_src - 1);
+  a.coef[0] = c0; a.coef[1] = c1; a.coef[2] = c2; a.coef[3] = c3;
+  tab[d] = a;
+}
+
+constexpr int kTE = 256;   // interleaved output elements per block (= threads)
+
+template <typename T> __device__ __forceinline__ float px_load(const T* p);
+template <> __device__ __forceinline__ float px_load<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float px_load<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
+
+template <typename T, bool FIXED>
+__global__ void __launch_bounds__(kTE)
+bicubic_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
+               const AxisTap* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w,
+               int tile_rows, int max_src_rows, int clip01) {
+  extern __shared__ float hbuf[];   // [max_src_rows][kTE]  (int32 bit patterns when FIXED)
+  const int t = threadIdx.x;
+  const int DE = dst_w * C;
+  const int e = blockIdx.x * kTE + t;
+  const int y0 = blockIdx.y * tile_rows;
+  const int y1 = min(y0 + tile_rows, dst_h) - 1;
+  const size_t src_img = (size_t)blockIdx.z * src_h * src_w * C;
+  const size_t dst_img = (size_t)blockIdx.z * dst_h * DE;
+  const int r_lo = ytab[y0].idx[0];
+  const int r_hi = ytab[y1].idx[3];
+  const int nr = min(r_hi - r_lo + 1, max_src_rows);
+  const bool valid = e < DE;
+
+  if (valid) {
+    const int x = e / C, c = e - x * C;
+    const AxisTap xt = xtab[x];
+    const int o0 = xt.idx[0] * C + c, o1 = xt.idx[1] * C + c, o2 = xt.idx[2] * C + c, o3 = xt.idx[3] * C + c;
+    const T* row = src + src_img + (size_t)r_lo * src_w * C;
+    for (int r = 0; r < nr; ++r, row += (size_t)src_w * C) {
+      if (FIXED) {
+        const int v = (int)row[o0] * (int)xt.coef[0] + (int)row[o1] * (int)xt.coef[1] +
+                      (int)row[o2] * (int)xt.coef[2] + (int)row[o3] * (int)xt.coef[3];
+        hbuf[r * kTE + t] = __int_as_float(v);
+      } else {
+        float v = __fmul_rn(px_load(row + o0), xt.coef[0]);
+        v = __fmaf_rn(px_load(row + o1), xt.coef[1], v);
+        v = __fmaf_rn(px_load(row + o2), xt.coef[2], v);
+        v = __fmaf_rn(px_load(row + o3), xt.coef[3], v);
+        hbuf[r * kTE + t] = v;
+      }
+    }
+  }
+  // each thread only reads back its own column: no barrier needed
+  if (!valid) return;
+  for (int y = y0; y <= y1; ++y) {
+    const AxisTap yt = ytab[y];
+    float v;
+    if (FIXED) {
+      const float sc = 1.f / (2048.f * 2048.f);
+      v = __fmul_rn((float)__float_as_int(hbuf[(yt.idx[0] - r_lo) * kTE + t]), __fmul_rn(yt.coef[0], sc));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[1] - r_lo) * kTE + t]), __fmul_rn(yt.coef[1], sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[2] - r_lo) * kTE + t]), __fmul_rn(yt.coef[2], sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[3] - r_lo) * kTE + t]), __fmul_rn(yt.coef[3], sc)));
+    } else {
+      v = __fmul_rn(hbuf[(yt.idx[0] - r_lo) * kTE + t], yt.coef[0]);
+      v = __fmaf_rn(hbuf[(yt.idx[1] - r_lo) * kTE + t], yt.coef[1], v);
+      v = __fmaf_rn(hbuf[(yt.idx[2] - r_lo) * kTE + t], yt.coef[2], v);
+      v = __fmaf_rn(hbuf[(yt.idx[3] - r_lo) * kTE + t], yt.coef[3], v);
+    }
+    if (sizeof(T) == 1) {
+      const int q = __float2int_rn(v);                       // round-half-even, then saturate
+      reinterpret_cast<uint8_t*>(dst)[dst_img + (size_t)y * DE + e] = (uint8_t)min(max(q, 0), 255);
+    } else {
+      if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+      reinterpret_cast<float*>(dst)[dst_img + (size_t)y * DE + e] = v;
+    }
+  }
+}
+
+template <typename T, bool FIXED>
+static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, int dh, int dw, int clip01,
+                       cudaStream_t stream) {
+  SRB_REQUIRE(src && dst, "bicubic: null pointer");
+  SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "bicubic: bad geometry");
+  if (batch == 0) return SRB_OK;
+  AxisTap* tabs = nullptr;
+  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh), stream));
+  AxisTap* xtab = tabs;
+  AxisTap* ytab = tabs + dw;
+  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, sw, dw, FIXED ? 1 : 0);
+  bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, sh, dh, FIXED ? 1 : 0);
+  int rc = launch_check("bicubic_tables");
+  if (rc) return rc;
+  int tile_rows = 32;
+  auto src_rows = [&](int tr) { return (int)(((long)tr * sh + dh - 1) / dh) + 5; };
+  while (tile_rows > 1 && (size_t)src_rows(tile_rows) * kTE * sizeof(float) > 96 * 1024) tile_rows >>= 1;
+  const int msr = src_rows(tile_rows);
+  const size_t smem = (size_t)msr * kTE * sizeof(float);
+  SRB_CUDA(cudaFuncSetAttribute(bicubic_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((dw * C + kTE - 1) / kTE, (dh + tile_rows - 1) / tile_rows, batch);
+  bicubic_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, clip01);
+  rc = launch_check("bicubic_kernel");
+  SRB_CUDA(cudaFreeAsync(tabs, stream));
+  return rc;
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" int srb_bicubic_f32(const float* src, int batch, int src_h, int src_w, int channels,
+                               float* dst, int dst_h, int dst_w, int clip01, srb_stream_t stream) {
+  return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream);
+}
+
+extern "C" int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                              uint8_t* dst, int dst_h, int dst_w, int fixed_point, srb_stream_t stream) {
+  if (fixed_point)
+    return run_bicubic<uint8_t, true>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, 0, (cudaStream_t)stream);
+  return run_bicubic<uint8_t, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, 0, (cudaStream_t)stream);
+}

@@ -1,0 +1,74 @@
+// Shared host/device helpers for libsrb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/srb200.h"
+
+namespace srb {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define SRB_CUDA(call)                                            \
+  do {                                                            \
+    cudaError_t _e = (call);                                      \
+    if (_e != cudaSuccess) return ::srb::cuda_fail(_e, #call);    \
+  } while (0)
+
+#define SRB_REQUIRE(cond, ...)                                    \
+  do {                                                            \
+    if (!(cond)) { ::srb::set_error(__VA_ARGS__); return SRB_E_INVALID; } \
+  } while (0)
+
+inline int launch_check(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, what);
+  return SRB_OK;
+}
+
+int sm_count();
+
+template <typename T> __device__ __forceinline__ float load_as_float(const T* p);
+template <> __device__ __forceinline__ float load_as_float<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T> __device__ __forceinline__ void store_from_float(T* p, float v);
+template <> __device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  switch (act) {
+    case SRB_ACT_RELU:  return fmaxf(v, 0.f);
+    case SRB_ACT_PRELU:
+    case SRB_ACT_LEAKY: return v >= 0.f ? v : v * slope;
+    case SRB_ACT_TANH:  return tanhf(v);
+    default:            return v;
+  }
+}
+
+inline size_t dtype_size(int dt) { return dt == SRB_F32 ? 4 : dt == SRB_BF16 ? 2 : 1; }
+
+}  // namespace srb
+
+// Packed conv weights (opaque to C callers).
+struct srb_conv_weights {
+  int kh, kw, cin, cout;
+  float* hwio;            // [kh*kw][cin][cout_pad4] float32 (direct engine), cout padded to a multiple of 4
+  int cout_pad4;
+  float* bias;            // [cout] float32 (zeros when the layer has none)
+  __nv_bfloat16* tc;      // [kh*kw][cout_pad][cin] bf16, K-major rows (tcgen05 engine) or nullptr
+  int tc_cout_pad;        // rows per tap in `tc` (multiple of 16)
+};

@@ -1,0 +1,114 @@
+// srb_conv2d_nhwc: argument validation, weight packing and engine dispatch.
+// Replaces Keras Conv2D(+Add/Lambda/depth_to_space/clip) as used by the reference's networks
+// (SRCNN_model.py:50-52, EDSR_model.py:55-125, ESRGAN_model.py:212-345, VGG16_model.py:69-97).
+#include "common.cuh"
+#include "conv_common.cuh"
+#include <stdlib.h>
+#include <vector>
+
+using namespace srb;
+
+extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int kh, int kw, int cin, int cout,
+                                       srb_conv_weights** out) {
+  SRB_REQUIRE(hwio && out, "conv_weights_create: null pointer");
+  SRB_REQUIRE(kh > 0 && kw > 0 && (kh & 1) && (kw & 1) && cin > 0 && cout > 0,
+              "conv_weights_create: kernel must be odd and channel counts positive (got %dx%d, %d->%d)", kh, kw, cin, cout);
+  srb_conv_weights* w = (srb_conv_weights*)calloc(1, sizeof(srb_conv_weights));
+  if (!w) { set_error("conv_weights_create: out of host memory"); return SRB_E_NOMEM; }
+  w->kh = kh; w->kw = kw; w->cin = cin; w->cout = cout;
+  w->cout_pad4 = (cout + 3) & ~3;
+  const int taps = kh * kw;
+  std::vector<float> packed((size_t)taps * cin * w->cout_pad4, 0.f);
+  for (int t = 0; t < taps; ++t)
+    for (int c = 0; c < cin; ++c)
+      for (int o = 0; o < cout; ++o)
+        packed[((size_t)t * cin + c) * w->cout_pad4 + o] = hwio[((size_t)t * cin + c) * cout + o];
+  std::vector<float> b(cout, 0.f);
+  if (bias) for (int o = 0; o < cout; ++o) b[o] = bias[o];
+  cudaError_t e;
+  if ((e = cudaMalloc(&w->hwio, packed.size() * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemcpy(w->hwio, packed.data(), packed.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+      (e = cudaMalloc(&w->bias, (size_t)cout * sizeof(float))) != cudaSuccess ||
+      (e = cudaMemcpy(w->bias, b.data(), (size_t)cout * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+    srb_conv_weights_destroy(w);
+    return cuda_fail(e, "conv_weights_create");
+  }
+  // tensor-core copy: [tap][cout_pad16][cin] bf16, K(cin)-major rows, for cin a multiple of 64
+  if (cin % 64 == 0 && cout % 16 == 0) {
+    w->tc_cout_pad = cout;
+    std::vector<__nv_bfloat16> tc((size_t)taps * cout * cin);
+    for (int t = 0; t < taps; ++t)
+      for (int o = 0; o < cout; ++o)
+        for (int c = 0; c < cin; ++c)
+          tc[((size_t)t * cout + o) * cin + c] = __float2bfloat16_rn(hwio[((size_t)t * cin + c) * cout + o]);
+    if ((e = cudaMalloc(&w->tc, tc.size() * sizeof(__nv_bfloat16))) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc, tc.data(), tc.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      srb_conv_weights_destroy(w);
+      return cuda_fail(e, "conv_weights_create(tc)");
+    }
+  }
+  *out = w;
+  return SRB_OK;
+}
+
+extern "C" void srb_conv_weights_destroy(srb_conv_weights* w) {
+  if (!w) return;
+  if (w->hwio) cudaFree(w->hwio);
+  if (w->bias) cudaFree(w->bias);
+  if (w->tc) cudaFree(w->tc);
+  free(w);
+}
+
+static int fill_params(const srb_conv_args* a, ConvParams& p) {
+  SRB_REQUIRE(a, "conv2d: null args");
+  SRB_REQUIRE(a->x && a->y && a->weights, "conv2d: null pointer");
+  const srb_conv_weights* w = a->weights;
+  SRB_REQUIRE(a->batch >= 0 && a->height > 0 && a->width > 0, "conv2d: bad geometry %dx%dx%d", a->batch, a->height, a->width);
+  SRB_REQUIRE(a->x_dtype == SRB_F32 || a->x_dtype == SRB_BF16, "conv2d: x dtype must be f32 or bf16");
+  SRB_REQUIRE(a->y_dtype == SRB_F32 || a->y_dtype == SRB_BF16, "conv2d: y dtype must be f32 or bf16");
+  const int d2s = a->d2s <= 0 ? 1 : a->d2s;
+  SRB_REQUIRE(d2s >= 1 && d2s <= 4, "conv2d: depth_to_space factor must be 1..4 (got %d)", a->d2s);
+  SRB_REQUIRE(w->cout % (d2s * d2s) == 0, "conv2d: cout %d is not divisible by d2s^2 = %d", w->cout, d2s * d2s);
+  p.x = a->x; p.x_dtype = a->x_dtype;
+  p.x_cstride = a->x_cstride > 0 ? a->x_cstride : w->cin; p.x_coffset = a->x_coffset;
+  p.c_post = w->cout / (d2s * d2s);
+  p.y = a->y; p.y_dtype = a->y_dtype;
+  p.y_cstride = a->y_cstride > 0 ? a->y_cstride : p.c_post; p.y_coffset = a->y_coffset;
+  SRB_REQUIRE(p.x_coffset >= 0 && p.x_coffset + w->cin <= p.x_cstride, "conv2d: input channel slice out of range");
+  SRB_REQUIRE(p.y_coffset >= 0 && p.y_coffset + p.c_post <= p.y_cstride, "conv2d: output channel slice out of range");
+  p.B = a->batch; p.H = a->height; p.W = a->width;
+  p.kh = w->kh; p.kw = w->kw; p.cin = w->cin; p.cout = w->cout;
+  p.w_hwio = w->hwio; p.w_cout_pad = w->cout_pad4;
+  p.w_tc = w->tc; p.w_tc_rows = w->tc_cout_pad;
+  p.bias = w->bias;
+  p.act = a->act; p.act_slope = a->act_slope; p.prelu = a->prelu;
+  SRB_REQUIRE(a->act >= SRB_ACT_NONE && a->act <= SRB_ACT_TANH, "conv2d: unknown activation %d", a->act);
+  SRB_REQUIRE(a->act != SRB_ACT_PRELU || a->prelu, "conv2d: PReLU needs a slope vector");
+  p.alpha = a->alpha;
+  p.res1 = a->res1; p.res1_dtype = a->res1_dtype; p.res1_cstride = a->res1_cstride > 0 ? a->res1_cstride : p.c_post; p.beta1 = a->beta1;
+  p.res2 = a->res2; p.res2_dtype = a->res2_dtype; p.res2_cstride = a->res2_cstride > 0 ? a->res2_cstride : p.c_post; p.beta2 = a->beta2;
+  p.clip01 = a->clip01;
+  p.d2s = d2s;
+  return SRB_OK;
+}
+
+extern "C" int srb_conv2d_engine(const srb_conv_args* a) {
+  ConvParams p;
+  int rc = fill_params(a, p);
+  if (rc) return rc;
+  return conv_tc_eligible(p) ? SRB_ENGINE_TCGEN05 : SRB_ENGINE_DIRECT;
+}
+
+extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
+  ConvParams p;
+  int rc = fill_params(a, p);
+  if (rc) return rc;
+  if (p.B == 0) return SRB_OK;
+  const bool tc_ok = conv_tc_eligible(p);
+  if (a->engine == SRB_ENGINE_TCGEN05 && !tc_ok) {
+    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16 NHWC input, cin == 64, 3x3, cout %% 16 == 0)");
+    return SRB_E_UNSUPPORTED;
+  }
+  if (a->engine == SRB_ENGINE_TCGEN05 || (a->engine == SRB_ENGINE_AUTO && tc_ok)) return conv_tc_launch(p, (cudaStream_t)stream);
+  return conv_direct_launch(p, (cudaStream_t)stream);
+}

@@ -1,0 +1,73 @@
+// Parameters and the fused epilogue shared by both convolution engines.
+#pragma once
+#include "common.cuh"
+
+namespace srb {
+
+struct ConvParams {
+  const void* x; int x_dtype, x_cstride, x_coffset;
+  void* y;       int y_dtype, y_cstride, y_coffset;
+  int B, H, W;
+  int kh, kw, cin, cout;
+  const float* w_hwio; int w_cout_pad;      // direct engine weights
+  const __nv_bfloat16* w_tc; int w_tc_rows; // tcgen05 engine weights [tap][rows][cin]
+  const float* bias;                        // [cout], never null
+  int act; float act_slope; const float* prelu;
+  float alpha;
+  const void* res1; int res1_dtype, res1_cstride; float beta1;
+  const void* res2; int res2_dtype, res2_cstride; float beta2;
+  int clip01;
+  int d2s;                                  // 1, 2, 3, 4
+  int c_post;                               // cout / (d2s*d2s)
+};
+
+__device__ __forceinline__ float load_elem(const void* base, int dtype, size_t idx) {
+  if (dtype == SRB_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+
+__device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, float v) {
+  if (dtype == SRB_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<float*>(base)[idx] = v;
+}
+
+// value-level epilogue: everything except the store address
+__device__ __forceinline__ float epilogue_value(const ConvParams& p, float acc, int co, int c_out,
+                                                size_t out_pix /* linear output pixel index */) {
+  float v = acc + p.bias[co];
+  const float slope = (p.act == SRB_ACT_PRELU) ? p.prelu[c_out] : p.act_slope;
+  v = apply_act(v, p.act, slope);
+  v *= p.alpha;
+  if (p.res1) v = fmaf(p.beta1, load_elem(p.res1, p.res1_dtype, out_pix * p.res1_cstride + c_out), v);
+  if (p.res2) v = fmaf(p.beta2, load_elem(p.res2, p.res2_dtype, out_pix * p.res2_cstride + c_out), v);
+  if (p.clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+  return v;
+}
+
+// output pixel index and channel for conv-domain (b, y, x, co) under depth_to_space (DCR)
+__device__ __forceinline__ void d2s_map(const ConvParams& p, int b, int y, int x, int co,
+                                        size_t& out_pix, int& c_out) {
+  if (p.d2s == 1) {
+    out_pix = ((size_t)b * p.H + y) * p.W + x;
+    c_out = co;
+  } else {
+    const int r = p.d2s;
+    const int q = co / p.c_post;
+    c_out = co - q * p.c_post;
+    const int i = q / r, j = q - i * r;
+    out_pix = ((size_t)b * p.H * r + (size_t)y * r + i) * ((size_t)p.W * r) + (size_t)x * r + j;
+  }
+}
+
+__device__ __forceinline__ void epilogue_store(const ConvParams& p, int b, int y, int x, int co, float acc) {
+  size_t out_pix; int c_out;
+  d2s_map(p, b, y, x, co, out_pix, c_out);
+  const float v = epilogue_value(p, acc, co, c_out, out_pix);
+  store_elem(p.y, p.y_dtype, out_pix * p.y_cstride + p.y_coffset + c_out, v);
+}
+
+int conv_direct_launch(const ConvParams& p, cudaStream_t stream);
+int conv_tc_launch(const ConvParams& p, cudaStream_t stream);
+bool conv_tc_eligible(const ConvParams& p);
+
+}  // namespace srb

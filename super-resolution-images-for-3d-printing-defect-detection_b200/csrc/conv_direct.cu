@@ -1,0 +1,114 @@
+// CUDA-core convolution engine (Keras Conv2D padding="same", stride 1) - the general path.
+//
+// Covers every shape the tcgen05 engine does not (Cin = 3 head layers, odd channel counts, fp32
+// mode with <= 1e-3 parity) with exact fp32 FMA accumulation.  Register-tiled implicit GEMM:
+// a block owns a 16 x 16 pixel tile x 32 output channels; a thread owns 8 pixels along x times 4
+// output channels.  The input halo is staged per 8-channel slab as [c][y][x] in shared memory, the
+// filter row (kw taps x 8 channels x 32 couts) alongside it.  The epilogue is the same fused
+// bias / activation / scaled-residual / clip / depth_to_space store as the tensor-core engine.
+#include "common.cuh"
+#include "conv_common.cuh"
+
+namespace srb {
+
+constexpr int kDT = 16;      // tile edge (pixels)
+constexpr int kDN = 32;      // output channels per block
+constexpr int kDCK = 8;      // input channels per slab
+
+__global__ void __launch_bounds__(256)
+conv_direct_kernel(const ConvParams p) {
+  extern __shared__ float smem[];
+  const int HH = kDT + p.kh - 1, HW = kDT + p.kw - 1;
+  const int HWp = HW | 1;                               // odd row pitch
+  float* halo = smem;                                   // [kDCK][HH][HWp]
+  float* wsm = smem + kDCK * HH * HWp;                  // [kw][kDCK][kDN]
+
+  const int tid = threadIdx.x;
+  const int cg = tid & 7, pg = tid >> 3;
+  const int py = pg >> 1, x0 = (pg & 1) * 8;
+  const int n_chunks = (p.cout + kDN - 1) / kDN;
+  const int b = blockIdx.z / n_chunks, cc = blockIdx.z % n_chunks;
+  const int ty0 = blockIdx.y * kDT, tx0 = blockIdx.x * kDT;
+  const int ph = p.kh / 2, pw = p.kw / 2;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const size_t x_img = (size_t)b * p.H * p.W;
+  for (int c0 = 0; c0 < p.cin; c0 += kDCK) {
+    __syncthreads();
+    for (int idx = tid; idx < kDCK * HH * HW; idx += 256) {
+      const int c = idx % kDCK;
+      const int hp = idx / kDCK;
+      const int hx = hp % HW, hy = hp / HW;
+      const int gy = ty0 + hy - ph, gx = tx0 + hx - pw;
+      float v = 0.f;
+      if (c0 + c < p.cin && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+        v = load_elem(p.x, p.x_dtype, (x_img + (size_t)gy * p.W + gx) * p.x_cstride + p.x_coffset + c0 + c);
+      halo[(c * HH + hy) * HWp + hx] = v;
+    }
+    for (int dy = 0; dy < p.kh; ++dy) {
+      __syncthreads();
+      for (int idx = tid; idx < p.kw * kDCK * kDN; idx += 256) {
+        const int co = idx % kDN;
+        const int c = (idx / kDN) % kDCK;
+        const int dx = idx / (kDN * kDCK);
+        float v = 0.f;
+        const int gco = cc * kDN + co;
+        if (c0 + c < p.cin && gco < p.w_cout_pad)
+          v = __ldg(p.w_hwio + ((size_t)(dy * p.kw + dx) * p.cin + c0 + c) * p.w_cout_pad + gco);
+        wsm[idx] = v;
+      }
+      __syncthreads();
+      for (int dx = 0; dx < p.kw; ++dx) {
+#pragma unroll
+        for (int c = 0; c < kDCK; ++c) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wsm + (dx * kDCK + c) * kDN + cg * 4);
+          const float* hrow = halo + (c * HH + py + dy) * HWp + x0 + dx;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float a = hrow[i];
+            acc[i][0] = fmaf(a, w4.x, acc[i][0]);
+            acc[i][1] = fmaf(a, w4.y, acc[i][1]);
+            acc[i][2] = fmaf(a, w4.z, acc[i][2]);
+            acc[i][3] = fmaf(a, w4.w, acc[i][3]);
+          }
+        }
+      }
+    }
+  }
+
+  const int oy = ty0 + py;
+  if (oy >= p.H) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int ox = tx0 + x0 + i;
+    if (ox >= p.W) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = cc * kDN + cg * 4 + j;
+      if (co < p.cout) epilogue_store(p, b, oy, ox, co, acc[i][j]);
+    }
+  }
+}
+
+int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
+  const int HH = kDT + p.kh - 1, HW = kDT + p.kw - 1, HWp = HW | 1;
+  const size_t smem = ((size_t)kDCK * HH * HWp + (size_t)p.kw * kDCK * kDN) * sizeof(float);
+  SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SRB_CUDA(cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int n_chunks = (p.cout + kDN - 1) / kDN;
+  dim3 grid((p.W + kDT - 1) / kDT, (p.H + kDT - 1) / kDT, p.B * n_chunks);
+  SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv(direct): grid too large");
+  conv_direct_kernel<<<grid, 256, smem, stream>>>(p);
+  return launch_check("conv_direct_kernel");
+}
+
+}  // namespace srb

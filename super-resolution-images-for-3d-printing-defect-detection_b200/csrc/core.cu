@@ -1,0 +1,253 @@
+// Error channel, device probe and the small elementwise / layout helpers of libsrb200.
+#include "common.cuh"
+#include <string.h>
+
+namespace srb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return SRB_E_CUDA;
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (!cached[dev]) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+// dst = src * scale + shift with dtype conversion; 4 elements per thread when aligned
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n, float scale, float shift) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    store_from_float<D>(dst + i, fmaf(load_as_float<S>(src + i), scale, shift));
+}
+
+template <typename T>
+__global__ void maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C) {
+  const int OH = H / 2, OW = W / 2;
+  const size_t total = (size_t)B * OH * OW * C;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int c = (int)(i % C);
+    size_t r = i / C;
+    const int ox = (int)(r % OW); r /= OW;
+    const int oy = (int)(r % OH);
+    const int b = (int)(r / OH);
+    const T* p = x + (((size_t)b * H + 2 * oy) * W + 2 * ox) * C + c;
+    const float v = fmaxf(fmaxf(load_as_float<T>(p), load_as_float<T>(p + C)),
+                          fmaxf(load_as_float<T>(p + (size_t)W * C), load_as_float<T>(p + (size_t)W * C + C)));
+    store_from_float<T>(y + i, v);
+  }
+}
+
+// GlobalAveragePooling2D -> Dense(hidden, relu) -> Dense(classes, softmax); one block per image.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gap_dense_softmax_kernel(const T* __restrict__ x, int HW, int C, const float* __restrict__ w1,
+                         const float* __restrict__ b1, int hidden, const float* __restrict__ w2,
+                         const float* __restrict__ b2, int classes, float* __restrict__ probs) {
+  extern __shared__ float sm[];
+  float* gap = sm;              // [C]
+  float* hid = sm + C;          // [hidden]
+  float* logit = hid + hidden;  // [classes]
+  const T* xi = x + (size_t)blockIdx.x * HW * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s += load_as_float<T>(xi + (size_t)p * C + c);
+    gap[c] = s / (float)HW;
+  }
+  __syncthreads();
+  for (int h = threadIdx.x; h < hidden; h += blockDim.x) {
+    float s = b1[h];
+    for (int c = 0; c < C; ++c) s = fmaf(gap[c], __ldg(w1 + (size_t)c * hidden + h), s);
+    hid[h] = fmaxf(s, 0.f);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < classes; k += blockDim.x) {
+    float s = b2[k];
+    for (int h = 0; h < hidden; ++h) s = fmaf(hid[h], __ldg(w2 + (size_t)h * classes + k), s);
+    logit[k] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = -INFINITY;
+    for (int k = 0; k < classes; ++k) m = fmaxf(m, logit[k]);
+    float z = 0.f;
+    for (int k = 0; k < classes; ++k) z += expf(logit[k] - m);
+    for (int k = 0; k < classes; ++k) probs[(size_t)blockIdx.x * classes + k] = expf(logit[k] - m) / z;
+  }
+}
+
+// SelfAttention core (ESRGAN_model.py:58-66): o[q] = sum_k softmax_k(g[q] . f[k]) h[k].
+// One warp per query row, online softmax over keys staged through shared memory in tiles of 64.
+template <int DK, int DV>
+__global__ void __launch_bounds__(128)
+self_attention_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ h,
+                      int HW, float* __restrict__ o) {
+  constexpr int KT = 64;
+  __shared__ float sf[KT][DK + 1];
+  __shared__ float sh[KT][DV + 1];
+  const int b = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.x * 4 + warp;
+  const float* fb = f + (size_t)b * HW * DK;
+  const float* hb = h + (size_t)b * HW * DV;
+  float gq[DK];
+#pragma unroll
+  for (int d = 0; d < DK; ++d) gq[d] = q < HW ? __ldg(g + ((size_t)b * HW + q) * DK + d) : 0.f;
+  float m = -INFINITY, z = 0.f;
+  float acc[(DV + 31) / 32];
+#pragma unroll
+  for (int i = 0; i < (DV + 31) / 32; ++i) acc[i] = 0.f;
+  for (int k0 = 0; k0 < HW; k0 += KT) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < KT * DK; i += 128) {
+      const int kk = i / DK, d = i % DK;
+      sf[kk][d] = (k0 + kk < HW) ? __ldg(fb + (size_t)(k0 + kk) * DK + d) : 0.f;
+    }
+    for (int i = threadIdx.x; i < KT * DV; i += 128) {
+      const int kk = i / DV, d = i % DV;
+      sh[kk][d] = (k0 + kk < HW) ? __ldg(hb + (size_t)(k0 + kk) * DV + d) : 0.f;
+    }
+    __syncthreads();
+    // each lane scores keys lane and lane+32 of the tile
+    float s0 = -INFINITY, s1 = -INFINITY;
+    if (k0 + lane < HW) { s0 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) s0 = fmaf(gq[d], sf[lane][d], s0); }
+    if (k0 + lane + 32 < HW) { s1 = 0.f;
+#pragma unroll
+      for (int d = 0; d < DK; ++d) s1 = fmaf(gq[d], sf[lane + 32][d], s1); }
+    float tm = fmaxf(s0, s1);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, off));
+    const float nm = fmaxf(m, tm);
+    const float corr = (m == -INFINITY) ? 0.f : expf(m - nm);
+    const float p0 = (s0 == -INFINITY) ? 0.f : expf(s0 - nm);
+    const float p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - nm);
+    z = z * corr + warp_sum(p0 + p1);
+#pragma unroll
+    for (int i = 0; i < (DV + 31) / 32; ++i) acc[i] *= corr;
+    for (int kk = 0; kk < KT; ++kk) {
+      const float p = __shfl_sync(0xffffffffu, kk < 32 ? p0 : p1, kk & 31);
+#pragma unroll
+      for (int i = 0; i < (DV + 31) / 32; ++i) {
+        const int d = lane + 32 * i;
+        if (d < DV) acc[i] = fmaf(p, sh[kk][d], acc[i]);
+      }
+    }
+    m = nm;
+  }
+  if (q < HW) {
+#pragma unroll
+    for (int i = 0; i < (DV + 31) / 32; ++i) {
+      const int d = lane + 32 * i;
+      if (d < DV) o[((size_t)b * HW + q) * DV + d] = acc[i] / z;
+    }
+  }
+}
+
+static int grid_for(size_t n, int threads) {
+  const size_t want = (n + threads - 1) / threads;
+  const size_t cap = (size_t)sm_count() * 16;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" const char* srb_last_error(void) { return g_err; }
+extern "C" int srb_version(void) { return 100; }
+
+extern "C" int srb_device_info(int* sm, int* cc_major, int* cc_minor) {
+  int dev = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  int n = 0, ma = 0, mi = 0;
+  SRB_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&ma, cudaDevAttrComputeCapabilityMajor, dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&mi, cudaDevAttrComputeCapabilityMinor, dev));
+  if (sm) *sm = n;
+  if (cc_major) *cc_major = ma;
+  if (cc_minor) *cc_minor = mi;
+  if (ma != 10) { set_error("libsrb200 is built for sm_100a only; device is sm_%d%d", ma, mi); return SRB_E_UNSUPPORTED; }
+  return SRB_OK;
+}
+
+extern "C" int srb_cast(const void* src, int sdt, void* dst, int ddt, size_t n, float scale, float shift,
+                        srb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRB_REQUIRE(src && dst, "cast: null pointer");
+  if (n == 0) return SRB_OK;
+  const int g = grid_for(n, 256);
+#define SRB_CAST(S, D) cast_kernel<S, D><<<g, 256, 0, stream>>>((const S*)src, (D*)dst, n, scale, shift)
+  if (sdt == SRB_F32 && ddt == SRB_BF16) SRB_CAST(float, __nv_bfloat16);
+  else if (sdt == SRB_BF16 && ddt == SRB_F32) SRB_CAST(__nv_bfloat16, float);
+  else if (sdt == SRB_F32 && ddt == SRB_F32) SRB_CAST(float, float);
+  else if (sdt == SRB_BF16 && ddt == SRB_BF16) SRB_CAST(__nv_bfloat16, __nv_bfloat16);
+  else { set_error("cast: unsupported dtype pair %d -> %d", sdt, ddt); return SRB_E_UNSUPPORTED; }
+#undef SRB_CAST
+  return launch_check("cast_kernel");
+}
+
+extern "C" int srb_maxpool2x2_nhwc(const void* x, int dtype, int batch, int height, int width, int channels, void* y,
+                                   srb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRB_REQUIRE(x && y, "maxpool: null pointer");
+  SRB_REQUIRE(batch >= 0 && height >= 2 && width >= 2 && channels > 0, "maxpool: bad geometry");
+  const size_t total = (size_t)batch * (height / 2) * (width / 2) * channels;
+  if (total == 0) return SRB_OK;
+  const int g = grid_for(total, 256);
+  if (dtype == SRB_F32) maxpool2x2_kernel<float><<<g, 256, 0, stream>>>((const float*)x, (float*)y, batch, height, width, channels);
+  else if (dtype == SRB_BF16) maxpool2x2_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, height, width, channels);
+  else { set_error("maxpool: unsupported dtype %d", dtype); return SRB_E_UNSUPPORTED; }
+  return launch_check("maxpool2x2_kernel");
+}
+
+extern "C" int srb_gap_dense_softmax(const void* x, int dtype, int batch, int hw, int channels,
+                                     const float* w1, const float* b1, int hidden, const float* w2, const float* b2,
+                                     int classes, float* probs, srb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRB_REQUIRE(x && w1 && b1 && w2 && b2 && probs, "gap_dense_softmax: null pointer");
+  SRB_REQUIRE(batch >= 0 && hw > 0 && channels > 0 && hidden > 0 && classes > 0, "gap_dense_softmax: bad geometry");
+  if (batch == 0) return SRB_OK;
+  const size_t smem = (size_t)(channels + hidden + classes) * sizeof(float);
+  SRB_REQUIRE(smem <= 48 * 1024, "gap_dense_softmax: layer too wide");
+  if (dtype == SRB_F32)
+    gap_dense_softmax_kernel<float><<<batch, 256, smem, stream>>>((const float*)x, hw, channels, w1, b1, hidden, w2, b2, classes, probs);
+  else if (dtype == SRB_BF16)
+    gap_dense_softmax_kernel<__nv_bfloat16><<<batch, 256, smem, stream>>>((const __nv_bfloat16*)x, hw, channels, w1, b1, hidden, w2, b2, classes, probs);
+  else { set_error("gap_dense_softmax: unsupported dtype %d", dtype); return SRB_E_UNSUPPORTED; }
+  return launch_check("gap_dense_softmax_kernel");
+}
+
+extern "C" int srb_self_attention_f32(const float* f, const float* g, const float* h, int batch, int hw, int dk, int dv,
+                                      float* o, srb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRB_REQUIRE(f && g && h && o, "self_attention: null pointer");
+  SRB_REQUIRE(batch >= 0 && hw > 0, "self_attention: bad geometry");
+  if (batch == 0) return SRB_OK;
+  SRB_REQUIRE(batch <= 65535, "self_attention: batch too large for one launch");
+  dim3 grid((hw + 3) / 4, batch);
+  if (dk == 8 && dv == 32) self_attention_kernel<8, 32><<<grid, 128, 0, stream>>>(f, g, h, hw, o);
+  else if (dk == 4 && dv == 16) self_attention_kernel<4, 16><<<grid, 128, 0, stream>>>(f, g, h, hw, o);
+  else if (dk == 16 && dv == 64) self_attention_kernel<16, 64><<<grid, 128, 0, stream>>>(f, g, h, hw, o);
+  else { set_error("self_attention: unsupported head sizes dk=%d dv=%d (channels must be 32, 64 or 128)", dk, dv); return SRB_E_UNSUPPORTED; }
+  return launch_check("self_attention_kernel");
+}

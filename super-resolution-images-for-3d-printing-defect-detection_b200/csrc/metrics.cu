@@ -1,0 +1,183 @@
+// Fused PSNR + SSIM (tf.image.psnr / tf.image.ssim semantics, max_val given; metrics.py:3-7).
+//
+// One pass over both images.  A block owns 128 consecutive interleaved output elements
+// (x*C + c of the (H-10) x (W-10) SSIM map) and a strip of output rows.  Rows are streamed
+// through a double-buffered shared-memory line; each thread evaluates the 11-tap horizontal
+// Gaussian of a, b, a^2+b^2 and a*b for its column and keeps the last 11 results in a register
+// ring (the row loop is unrolled by 11 so ring slots are static), from which the vertical
+// 11-tap pass and the SSIM point function follow.  The squared error for PSNR is accumulated
+// from the same loaded lines over a non-overlapping ownership partition of the image.
+// Per-image double-precision accumulators receive one atomicAdd per block and statistic.
+#include "common.cuh"
+
+namespace srb {
+
+__constant__ float c_gauss[11];
+
+constexpr int kCols = 128;  // output elements (threads) per block
+
+template <int C>
+__global__ void __launch_bounds__(kCols)
+psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
+                 float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
+  constexpr int kLine = kCols + 10 * C;
+  __shared__ float sa[2][kLine];
+  __shared__ float sb[2][kLine];
+  __shared__ float red[2][kCols / 32];
+
+  const int WE = W * C;            // interleaved floats per image row
+  const int OE = (W - 10) * C;     // SSIM-map elements per row
+  const int OH = H - 10;
+  const int t = threadIdx.x;
+  const int e0 = blockIdx.x * kCols;
+  const int y0 = blockIdx.y * rows_per_strip;
+  const int rows_out = min(rows_per_strip, OH - y0);
+  const int nin = rows_out + 10;
+  const bool last_x = (e0 + kCols >= OE);
+  const bool last_y = (y0 + rows_per_strip >= OH);
+  const size_t img_off = (size_t)blockIdx.z * H * WE;
+  const float* pa = a + img_off;
+  const float* pb = b + img_off;
+  const bool col_valid = (e0 + t) < OE;
+
+  float g[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) g[k] = c_gauss[k];
+
+  float ra[11], rb[11], rs[11], rp[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) ra[k] = rb[k] = rs[k] = rp[k] = 0.f;
+
+  float sse = 0.f, ssim_sum = 0.f;
+
+  for (int r = 0; r < nin; r += 11) {
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const int row = r + j;              // block-uniform
+      if (row < nin) {
+        const int y = y0 + row;
+        const int buf = row & 1;
+        const bool row_owned = (row < rows_out) || last_y;
+        const float* la = pa + (size_t)y * WE + e0;
+        const float* lb = pb + (size_t)y * WE + e0;
+        for (int i = t; i < kLine; i += kCols) {
+          float va = 0.f, vb = 0.f;
+          if (e0 + i < WE) { va = __ldg(la + i); vb = __ldg(lb + i); }
+          sa[buf][i] = va;
+          sb[buf][i] = vb;
+          if (row_owned && (i < kCols || last_x)) { const float d = va - vb; sse = fmaf(d, d, sse); }
+        }
+        __syncthreads();
+        float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
+#pragma unroll
+        for (int k = 0; k < 11; ++k) {
+          const float va = sa[buf][t + k * C], vb = sb[buf][t + k * C];
+          ha = fmaf(g[k], va, ha);
+          hb = fmaf(g[k], vb, hb);
+          hs = fmaf(g[k], fmaf(va, va, vb * vb), hs);
+          hp = fmaf(g[k], va * vb, hp);
+        }
+        ra[j] = ha; rb[j] = hb; rs[j] = hs; rp[j] = hp;
+        if (row >= 10 && col_valid) {
+          float ma = 0.f, mb = 0.f, es = 0.f, ep = 0.f;
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const int slot = (j + 1 + k) % 11;   // oldest row first
+            ma = fmaf(g[k], ra[slot], ma);
+            mb = fmaf(g[k], rb[slot], mb);
+            es = fmaf(g[k], rs[slot], es);
+            ep = fmaf(g[k], rp[slot], ep);
+          }
+          const float num0 = 2.f * ma * mb;
+          const float den0 = fmaf(ma, ma, mb * mb);
+          const float num = (num0 + c1) * (2.f * ep - num0 + c2);
+          const float den = (den0 + c1) * (es - den0 + c2);
+          ssim_sum += num / den;
+        }
+      }
+    }
+  }
+
+  sse = warp_sum(sse);
+  ssim_sum = warp_sum(ssim_sum);
+  if ((t & 31) == 0) { red[0][t >> 5] = sse; red[1][t >> 5] = ssim_sum; }
+  __syncthreads();
+  if (t == 0) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < kCols / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+    atomicAdd(&acc[2 * blockIdx.z + 0], s0);
+    atomicAdd(&acc[2 * blockIdx.z + 1], s1);
+  }
+}
+
+__global__ void psnr_ssim_finalize(const double* __restrict__ acc, int B, double n_pix, double n_map,
+                                   float max_val, float* psnr, float* ssim, float* mse_out, double* sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B) return;
+  const double mse = acc[2 * i] / n_pix;
+  // tf.image.psnr: 20*log(max)/log(10) - 10/log(10)*log(mse), evaluated in float32
+  const float p = 20.f * log10f(max_val) - 10.f * log10f((float)mse);
+  const float s = (float)(acc[2 * i + 1] / n_map);
+  if (psnr) psnr[i] = p;
+  if (ssim) ssim[i] = s;
+  if (mse_out) mse_out[i] = (float)mse;
+  if (sums) {
+    atomicAdd(&sums[0], (double)p);
+    atomicAdd(&sums[1], (double)s);
+    atomicAdd(&sums[2], 1.0);
+    atomicAdd(&sums[3], mse);
+  }
+}
+
+static bool g_gauss_ready = false;
+
+static int upload_gauss() {
+  if (g_gauss_ready) return SRB_OK;
+  double g[11], sum = 0.0;
+  for (int i = 0; i < 11; ++i) { const double c = i - 5.0; g[i] = exp(-0.5 * c * c / (1.5 * 1.5)); sum += g[i]; }
+  float gf[11];
+  for (int i = 0; i < 11; ++i) gf[i] = (float)(g[i] / sum);
+  SRB_CUDA(cudaMemcpyToSymbol(c_gauss, gf, sizeof(gf)));
+  g_gauss_ready = true;
+  return SRB_OK;
+}
+
+}  // namespace srb
+
+using namespace srb;
+
+extern "C" size_t srb_psnr_ssim_workspace(int batch) { return (size_t)(batch > 0 ? batch : 0) * 2 * sizeof(double); }
+
+extern "C" int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int width, int channels,
+                                 float max_val, float* psnr, float* ssim, float* mse, double* sums,
+                                 void* workspace, size_t workspace_bytes, srb_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  SRB_REQUIRE(a && b && workspace, "psnr_ssim: null pointer");
+  SRB_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4, "psnr_ssim: channels must be 1..4 (got %d)", channels);
+  SRB_REQUIRE(height >= 11 && width >= 11, "psnr_ssim: image dimensions must be at least 11x11 (got %dx%d)", height, width);
+  SRB_REQUIRE(workspace_bytes >= srb_psnr_ssim_workspace(batch), "psnr_ssim: workspace too small");
+  if (batch == 0) return SRB_OK;
+  int rc = upload_gauss();
+  if (rc) return rc;
+  double* acc = (double*)workspace;
+  SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
+  const int OH = height - 10, OE = (width - 10) * channels;
+  const int gx = (OE + kCols - 1) / kCols;
+  int rows = 64;
+  const long target = 2L * sm_count();
+  while (rows > 16 && (long)gx * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
+  dim3 grid(gx, (OH + rows - 1) / rows, batch);
+  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
+  switch (channels) {
+    case 1: psnr_ssim_kernel<1><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+    case 2: psnr_ssim_kernel<2><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+    case 3: psnr_ssim_kernel<3><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+    default: psnr_ssim_kernel<4><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+  }
+  rc = launch_check("psnr_ssim_kernel");
+  if (rc) return rc;
+  psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(
+      acc, batch, (double)height * width * channels, (double)OH * OE, max_val, psnr, ssim, mse, sums);
+  return launch_check("psnr_ssim_finalize");
+}

@@ -1,0 +1,63 @@
+"""``interpolate_bicubic`` with the reference's signature
+(SRModels/classic_super_resolution_algorithms/classic_algorithms.py:11-13), computed on the GPU.
+
+``target_shape`` is ``(width, height)`` exactly as for ``cv2.resize``; dtype is preserved (uint8 or
+float32); float results are not clipped.  Accepts ``[H, W, C]`` / ``[H, W]`` images or an
+``[B, H, W, C]`` batch; numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+from .. import _capi as capi
+from .. import ops
+
+INTER_LINEAR, INTER_CUBIC, INTER_AREA, INTER_LANCZOS4 = 1, 2, 3, 4   # cv2 codes
+
+
+def resize_cubic(img, target_shape: Tuple[int, int], clip01=False, fixed_point=False):
+    torch = capi.require_cuda()
+    was_numpy = not isinstance(img, torch.Tensor)
+    if was_numpy:
+        arr = np.ascontiguousarray(img)
+        if arr.dtype not in (np.uint8, np.float32):
+            arr = arr.astype(np.float32)
+        t = torch.from_numpy(arr).cuda()
+    else:
+        t = img if img.is_cuda else img.cuda()
+    shape_in = t.dim()
+    if shape_in == 2:
+        t = t[None, :, :, None]
+    elif shape_in == 3:
+        t = t[None]
+    elif shape_in != 4:
+        raise ValueError(f"expected an image or NHWC batch, got shape {tuple(t.shape)}")
+    w, h = int(target_shape[0]), int(target_shape[1])
+    if w <= 0 or h <= 0:
+        raise ValueError("target_shape must be (width, height) with positive entries")
+    out = ops.bicubic(t.contiguous(), h, w, clip01=clip01, fixed_point=fixed_point)
+    if shape_in == 2:
+        out = out[0, :, :, 0]
+    elif shape_in == 3:
+        out = out[0]
+    return out.cpu().numpy() if was_numpy else out
+
+
+def interpolate_bicubic(lr_img, target_shape: Tuple[int, int]):
+    """Bicubic upscaling (== cv2.resize(lr_img, target_shape, interpolation=cv2.INTER_CUBIC))."""
+    return resize_cubic(lr_img, target_shape)
+
+
+def _not_on_path(name):
+    def f(*_a, **_k):
+        raise NotImplementedError(
+            f"{name} is outside the B200 hot path (SURVEY.md section 8f rank 3); only interpolate_bicubic is built")
+    f.__name__ = name
+    return f
+
+
+interpolate_bilinear = _not_on_path("interpolate_bilinear")
+interpolate_area = _not_on_path("interpolate_area")
+interpolate_lanczos = _not_on_path("interpolate_lanczos")

@@ -1,0 +1,290 @@
+"""Network runners: the device-side replacement of Keras ``Model.predict`` for the reference's
+SR networks (SRCNN_model.py:45-53, EDSR_model.py:55-125, ESRGAN_model.py:212-345), the two
+BASELINE-named networks composed from the same layer semantics (ESPCN, SRResNet) and the VGG16
+defect classifier (VGG16_model.py:57-97).
+
+A network is a Keras-layout weight dict (``srb200.weights``) plus a forward function that
+sequences ``ops.conv2d`` launches with fused epilogues on torch's current stream.  Activations
+stay on the device in NHWC; ``precision="bf16"`` keeps them in bfloat16 and routes the 64-channel
+3x3 layers to the tcgen05 engine, ``precision="fp32"`` keeps everything in float32 on the exact
+CUDA-core engine (<= 1e-3 parity mode).
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+
+from . import _capi as capi
+from . import ops
+
+
+def _torch():
+    return capi.require_cuda()
+
+
+class DeviceModel:
+    """Minimal stand-in for the ``keras.Model`` object the reference keeps in ``self.model``."""
+
+    arch = "base"
+
+    def __init__(self, weights: dict, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        torch = _torch()
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == "bf16" else torch.float32
+        self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
+        self.layers = {}
+        for name in self.weights:
+            if name.endswith("/kernel") and self.weights[name].ndim == 4:
+                base = name[:-len("/kernel")]
+                self.layers[base] = ops.ConvWeights(self.weights[name], self.weights.get(base + "/bias"),
+                                                   self.weights.get(base + "/prelu"))
+        self.max_device_batch = None   # images per launch sequence (None = whole input)
+
+    # -- Keras-like surface ---------------------------------------------------------------
+    def count_params(self):
+        return int(sum(v.size for v in self.weights.values()))
+
+    def summary(self):
+        print(f"Model: {self.arch} ({self.precision})")
+        for k, v in self.weights.items():
+            print(f"  {k:40s} {tuple(v.shape)}")
+        print(f"Total params: {self.count_params():,}")
+
+    def get_weights_dict(self):
+        return dict(self.weights)
+
+    def output_scale(self):
+        return 1
+
+    def forward_device(self, x):
+        raise NotImplementedError
+
+    def predict_device(self, x, micro_batch=None):
+        """x: [B,H,W,C] float32 CUDA tensor -> float32 CUDA tensor.  No host synchronisation."""
+        torch = _torch()
+        mb = micro_batch or self.max_device_batch
+        if not mb or x.shape[0] <= mb:
+            return self.forward_device(x)
+        outs = [self.forward_device(x[i:i + mb]) for i in range(0, x.shape[0], mb)]
+        return torch.cat(outs, 0)
+
+    def predict(self, x, batch_size=32, verbose=0):
+        """numpy in, numpy out (``self.model.predict(patches, batch_size=16, verbose=0)``,
+        SRCNN_model.py:210, EDSR_model.py:274).  ``batch_size`` is accepted for signature parity;
+        the device processes the whole array in as few launch sequences as memory allows."""
+        torch = _torch()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 4:
+            raise ValueError(f"expected a 4-D NHWC array, got shape {x.shape}")
+        if x.shape[0] == 0:
+            h, w = x.shape[1] * self.output_scale(), x.shape[2] * self.output_scale()
+            return np.zeros((0, h, w, x.shape[3]), dtype=np.float32)
+        y = self.predict_device(torch.from_numpy(x).cuda(non_blocking=True))
+        return y.cpu().numpy()
+
+    __call__ = predict_device
+
+
+class SRCNNNet(DeviceModel):
+    """conv9x9x96 relu -> conv1x1x32 relu -> conv5x5x3 linear; no clip (SRCNN_model.py:45-53)."""
+    arch = "SRCNN"
+
+    def forward_device(self, x):
+        torch = _torch()
+        L, dt = self.layers, self.act_dtype
+        h = ops.conv2d(x, L["conv1"], act="relu", out_dtype=dt)
+        h = ops.conv2d(h, L["conv2"], act="relu", out_dtype=dt)
+        return ops.conv2d(h, L["conv3"], out_dtype=torch.float32)
+
+
+class EDSRNet(DeviceModel):
+    """EDSR_model.py:96-125.  Residual scaling, skip adds, depth_to_space and the final clip are
+    all conv epilogues; the graph is 2*N+4 (+1 for x4) launches."""
+    arch = "EDSR"
+
+    def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="bf16"):
+        if scale_factor not in (2, 3, 4):
+            raise ValueError(f"Scale factor {scale_factor} not supported. Use 2, 3, or 4.")
+        super().__init__(weights, precision)
+        self.scale_factor, self.num_res_blocks, self.res_scaling = scale_factor, num_res_blocks, float(res_scaling)
+
+    def output_scale(self):
+        return self.scale_factor
+
+    def forward_device(self, x):
+        torch = _torch()
+        L, dt = self.layers, self.act_dtype
+        head = ops.conv2d(x, L["head"], out_dtype=dt)
+        h = head
+        for i in range(self.num_res_blocks):
+            t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
+            h = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, out_dtype=dt)
+        h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
+        if self.scale_factor in (2, 3):
+            h = ops.conv2d(h, L["up0"], d2s=self.scale_factor, out_dtype=dt)
+        else:
+            h = ops.conv2d(h, L["up0"], d2s=2, out_dtype=dt)
+            h = ops.conv2d(h, L["up1"], d2s=2, out_dtype=dt)
+        return ops.conv2d(h, L["tail"], clip01=True, out_dtype=torch.float32)
+
+
+class ESPCNNet(DeviceModel):
+    """ESPCN 5-3-3 + depth_to_space(r) composed from the reference's layer semantics."""
+    arch = "ESPCN"
+
+    def __init__(self, weights, scale_factor=4, activation="relu", precision="bf16"):
+        super().__init__(weights, precision)
+        self.scale_factor, self.activation = scale_factor, activation
+
+    def output_scale(self):
+        return self.scale_factor
+
+    def forward_device(self, x):
+        torch = _torch()
+        L, dt = self.layers, self.act_dtype
+        h = ops.conv2d(x, L["conv1"], act=self.activation, out_dtype=dt)
+        h = ops.conv2d(h, L["conv2"], act=self.activation, out_dtype=dt)
+        return ops.conv2d(h, L["conv3"], d2s=self.scale_factor, out_dtype=torch.float32)
+
+
+class SRResNetNet(DeviceModel):
+    """SRResNet / SRGAN generator with BatchNorm folded."""
+    arch = "SRResNet"
+
+    def __init__(self, weights, scale_factor=4, num_res_blocks=16, precision="bf16"):
+        if scale_factor not in (2, 4):
+            raise ValueError("SRResNet scale factor must be 2 or 4")
+        super().__init__(weights, precision)
+        self.scale_factor, self.num_res_blocks = scale_factor, num_res_blocks
+
+    def output_scale(self):
+        return self.scale_factor
+
+    def forward_device(self, x):
+        torch = _torch()
+        L, dt = self.layers, self.act_dtype
+        head = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt)
+        h = head
+        for i in range(self.num_res_blocks):
+            t = ops.conv2d(h, L[f"rb{i}_c1"], act="prelu", out_dtype=dt)
+            h = ops.conv2d(t, L[f"rb{i}_c2"], res1=h, out_dtype=dt)
+        h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
+        for i in range(2 if self.scale_factor == 4 else 1):
+            h = ops.conv2d(h, L[f"up{i}"], act="prelu", d2s=2, out_dtype=dt)   # PReLU after the shuffle == before it
+        return ops.conv2d(h, L["tail"], out_dtype=torch.float32)
+
+
+class ESRGANGeneratorNet(DeviceModel):
+    """RRDBNet + two SelfAttention layers (ESRGAN_model.py:30-79, 212-345).  Input/output in [-1, 1].
+
+    Dense blocks are concat-free: each growth conv writes its slice of one NHWC buffer and the
+    next conv reads the widened prefix."""
+    arch = "ESRGAN-generator"
+
+    def __init__(self, weights, scale_factor=2, growth_channels=32, num_rrdb_blocks=23, precision="fp32"):
+        super().__init__(weights, precision)
+        self.scale_factor, self.growth, self.num_rrdb = scale_factor, growth_channels, num_rrdb_blocks
+
+    def output_scale(self):
+        return self.scale_factor
+
+    def _dense(self, x, name, outer=None):
+        """x + 0.2 * conv5(...) (ESRGAN_model.py:249-252).  With ``outer`` (the RRDB input) the block's
+        own ``outer + 0.2 * (.)`` (ESRGAN_model.py:277-280) is folded into the same epilogue."""
+        torch = _torch()
+        L, g = self.layers, self.growth
+        B, H, W, Cc = x.shape
+        buf = torch.empty((B, H, W, 64 + 4 * g), dtype=x.dtype, device=x.device)
+        buf[..., :64].copy_(x)
+        for j in range(4):
+            # reads channels [0, 64 + j*g) of the wide buffer via cstride; writes slice j
+            ops.conv2d(buf, L[f"{name}_conv{j + 1}"], act="relu", out=buf, out_coffset=64 + j * g)
+        if outer is None:
+            return ops.conv2d(buf, L[f"{name}_conv5"], alpha=0.2, res1=x, out_dtype=x.dtype)
+        return ops.conv2d(buf, L[f"{name}_conv5"], alpha=0.04, res1=x, beta1=0.2, res2=outer, beta2=1.0,
+                          out_dtype=x.dtype)
+
+    def _attention(self, x, name):
+        torch = _torch()
+        L = self.layers
+        B, H, W, Cc = x.shape
+        f = ops.conv2d(x, L[name + "_f"], out_dtype=torch.float32)
+        g = ops.conv2d(x, L[name + "_g"], out_dtype=torch.float32)
+        h = ops.conv2d(x, L[name + "_h"], out_dtype=torch.float32)
+        o = ops.self_attention_core(f.view(B, H * W, -1), g.view(B, H * W, -1), h.view(B, H * W, -1))
+        return ops.conv2d(o.view(B, H, W, -1), L[name + "_v"], res1=x, out_dtype=x.dtype)
+
+    def forward_device(self, x):
+        torch = _torch()
+        L, dt = self.layers, self.act_dtype
+        h = ops.conv2d(x, L["initial_conv"], out_dtype=dt)
+        trunk = h
+        for i in range(self.num_rrdb):
+            inp = h
+            for d in (1, 2, 3):
+                h = self._dense(h, f"rrdb_{i}_dense{d}", outer=inp if d == 3 else None)
+        h = ops.conv2d(h, L["trunk_conv"], res1=trunk, out_dtype=dt)
+        h = self._attention(h, "self_attention_trunk")
+        for i in range(int(math.log2(self.scale_factor))):
+            h = ops.conv2d(h, L[f"upsample_{i}_conv"], act="leaky_relu", act_slope=0.2, d2s=2, out_dtype=dt)
+            if i == 0:
+                h = self._attention(h, "self_attention_upsample_0")
+        h = ops.conv2d(h, L["final_conv1"], act="relu", out_dtype=dt)
+        return ops.conv2d(h, L["final_conv2"], act="tanh", out_dtype=torch.float32)
+
+
+class VGG16ClassifierNet(DeviceModel):
+    """VGG16 conv base + GAP + Dense(256, relu) + Dense(C, softmax) (VGG16_model.py:57-97)."""
+    arch = "VGG16-classifier"
+    CFG = [(1, 2), (2, 2), (3, 3), (4, 3), (5, 3)]
+
+    def __init__(self, weights, precision="fp32"):
+        super().__init__(weights, precision)
+        torch = _torch()
+        self.dense = {k: torch.from_numpy(self.weights[k]).cuda() for k in
+                      ("dense/kernel", "dense/bias", "predictions/kernel", "predictions/bias")}
+
+    def forward_device(self, x):
+        L, dt = self.layers, self.act_dtype
+        h = x
+        for blk, n in self.CFG:
+            for j in range(1, n + 1):
+                h = ops.conv2d(h, L[f"block{blk}_conv{j}"], act="relu", out_dtype=dt)
+            h = ops.maxpool2x2(h)
+        d = self.dense
+        return ops.gap_dense_softmax(h, d["dense/kernel"], d["dense/bias"], d["predictions/kernel"],
+                                     d["predictions/bias"])
+
+    def predict(self, x, batch_size=32, verbose=0):
+        torch = _torch()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        return self.predict_device(torch.from_numpy(x).cuda(non_blocking=True)).cpu().numpy()
+
+
+def gpu_memory_info():
+    """``tf.config.experimental.get_memory_info("GPU:0")`` analogue -> {"current", "peak"} bytes."""
+    torch = _torch()
+    return {"current": int(torch.cuda.memory_allocated()), "peak": int(torch.cuda.max_memory_allocated())}
+
+
+def timed_predict(model: DeviceModel, patches_device):
+    """Run ``predict_device`` bracketed the way the reference brackets ``model.predict``
+    (perf_counter + memory info, SRCNN_model.py:200-242) -> (output, inference_metrics)."""
+    torch = _torch()
+    begin = gpu_memory_info()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = model.predict_device(patches_device)
+    torch.cuda.synchronize()
+    elapsed = time.perf_counter() - t0
+    end = gpu_memory_info()
+    mb = 1024.0 * 1024.0
+    return out, {
+        "time_sec": float(elapsed),
+        "gpu_mean_current_mb": (begin["current"] + end["current"]) / 2.0 / mb,
+        "gpu_peak_mb": max(begin["peak"], end["peak"]) / mb,
+    }

@@ -1,0 +1,84 @@
+"""GPU: the reference-facing wrappers (SRCNNModel / EDSR / ESRGAN / FineTunedVGG16) end to end
+against the oracle pipeline (bicubic -> tiling -> network -> overlap-add; evaluate means)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bicubic as ob, convnets as oc, metrics as om, tiling as ot
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_tiled(forward, img, patch, stride, scale):
+    padded = ot.add_padding(img, patch, stride)
+    patches, pos = ot.extract_patches(padded, patch, stride)
+    preds = forward(patches)
+    return ot.reconstruct(preds, pos, padded.shape, (img.shape[0] * scale, img.shape[1] * scale), scale)
+
+
+def test_srcnn_super_resolve_image_config1_flow():
+    from srb200 import synth, weights
+    from srb200.deep_learning_models.SRCNN_model import SRCNNModel
+    hr = synth.hr_image(96, 80, 0)
+    lr = synth.area_downsample(hr, 2)
+    w = weights.srcnn_weights(bias_scale=0.05)
+    m = SRCNNModel()
+    m.setup_model(input_shape=(33, 33, 3))
+    with pytest.raises(RuntimeError):
+        m.super_resolve_image(lr, 96, 80)
+    m.load_weights(w)
+    sr, info = m.super_resolve_image(lr, 96, 80, patch_size=33, stride=14)
+    up = ob.cv2_resize(lr, (80, 96))
+    want = _oracle_tiled(lambda p: oc.srcnn_forward(w, p), up, 33, 14, 1)
+    assert sr.shape == (96, 80, 3) and sr.dtype == np.float32
+    assert np.abs(sr - want).max() <= 1e-3
+    assert set(info) == {"time_sec", "gpu_mean_current_mb", "gpu_peak_mb"}
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_edsr_super_resolve_and_evaluate(precision, tol):
+    from srb200 import synth, weights
+    from srb200.deep_learning_models.EDSR_model import EDSR
+    w = weights.edsr_weights(2, num_res_blocks=3, bias_scale=0.05)
+    m = EDSR()
+    m.setup_model(scale_factor=2, num_res_blocks=3, precision=precision)
+    m.load_weights(w)
+    hr = synth.hr_batch(6, 48, 48)
+    lr = synth.area_downsample(hr, 2)
+    fwd = lambda p: oc.edsr_forward(w, p, 2, 3)
+    sr, _ = m.super_resolve_image(lr[0], patch_size_lr=24, stride=12)
+    want = _oracle_tiled(fwd, lr[0], 24, 12, 2)
+    assert sr.shape == (48, 48, 3) and np.abs(sr - want).max() <= tol
+    loss, psnr, ssim = m.evaluate(lr, hr)
+    ref = om.evaluate_means(hr, fwd(lr))
+    assert abs(loss - ref[0]) <= 1e-4 and abs(psnr - ref[1]) <= (0.01 if precision == "fp32" else 0.3)
+    assert abs(ssim - ref[2]) <= (1e-4 if precision == "fp32" else 5e-3)
+
+
+def test_esrgan_super_resolve_image():
+    from srb200 import synth, weights
+    from srb200.deep_learning_models.ESRGAN_model import ESRGAN
+    w = weights.esrgan_generator_weights(2, 8, 1, bias_scale=0.05)
+    m = ESRGAN()
+    m.setup_model(scale_factor=2, growth_channels=8, num_rrdb_blocks=1)
+    m.load_weights(w)
+    lr = synth.area_downsample(synth.hr_image(48, 48, 3), 2)
+    sr, _ = m.super_resolve_image(lr, patch_size_lr=24, stride=12)
+    fwd = lambda p: (oc.esrgan_generator_forward(w, p * 2 - 1, 2, 1) + 1) / 2
+    want = _oracle_tiled(fwd, lr, 24, 12, 2)
+    assert np.abs(sr - want).max() <= 1e-3
+
+
+def test_vgg16_classify_defects_method():
+    from srb200 import synth, weights
+    from srb200.defect_detection_models.VGG16_model import FineTunedVGG16, vote
+    w = weights.vgg16_classifier_weights(2, bias_scale=0.05)
+    m = FineTunedVGG16()
+    m.setup_model(input_shape=(32, 32, 3))
+    m.load_weights(w)
+    img = synth.hr_image(70, 50, 1)
+    cls, conf = m.classify_defects_method(img)
+    padded = ot.add_padding(img, 32, 16)
+    patches, _ = ot.extract_patches(padded, 32, 16)
+    want = vote(oc.vgg16_classifier_forward(w, patches))
+    assert cls == want[0] and abs(conf - want[1]) <= 2e-3

@@ -1,0 +1,77 @@
+"""GPU parity: bicubic kernel vs cv2.resize(INTER_CUBIC) golden outputs and the numpy restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import bicubic as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bicubic_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw = (int(v) for v in g[f"c{n}_shape"])
+        yield n, g, (dw, dh)
+
+
+def test_float32_vs_cv2_golden(golden_dir):
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_bicubic
+    for n, g, dsize in _cases(golden_dir):
+        out = interpolate_bicubic(g[f"c{n}_f32_in"], dsize)
+        assert out.dtype == np.float32 and out.shape == g[f"c{n}_f32_default"].shape
+        assert np.abs(out - g[f"c{n}_f32_default"]).max() <= 2e-6, n      # OpenCV default dispatch
+        assert np.abs(out - g[f"c{n}_f32_scalar"]).max() <= 2e-6, n
+
+
+def test_uint8_vs_cv2_golden(golden_dir):
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_bicubic, resize_cubic
+    for n, g, dsize in _cases(golden_dir):
+        src = g[f"c{n}_u8_in"]
+        fixed = resize_cubic(src, dsize, fixed_point=True)
+        assert fixed.dtype == np.uint8
+        assert np.array_equal(fixed, g[f"c{n}_u8_scalar"]), n                # bit-exact fixed-point path
+        dflt = interpolate_bicubic(src, dsize)
+        diff = np.abs(dflt.astype(np.int32) - g[f"c{n}_u8_default"].astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.01, n              # <= 1 LSB on < 1 % of pixels
+
+
+@pytest.mark.parametrize("shape,dsize", [((64, 64, 3), (128, 128)), ((239, 239, 3), (478, 478)),
+                                         ((100, 75, 3), (225, 300)), ((341, 341, 3), (1024, 1024)),
+                                         ((50, 60, 1), (240, 200)), ((30, 20, 4), (35, 41))])
+def test_against_restatement(shape, dsize):
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_bicubic, resize_cubic
+    rng = np.random.default_rng(shape[0])
+    f = rng.random(shape, dtype=np.float32)
+    assert np.abs(interpolate_bicubic(f, dsize) - ob.resize_cubic_f32(f, dsize, "default")).max() <= 1e-6
+    u = rng.integers(0, 256, shape, dtype=np.uint8)
+    assert np.array_equal(resize_cubic(u, dsize, fixed_point=True), ob.resize_cubic_u8(u, dsize, "scalar"))
+
+
+def test_clip_batch_and_identity():
+    import torch
+    from srb200 import ops
+    rng = np.random.default_rng(0)
+    x = torch.from_numpy(rng.random((3, 20, 24, 3), dtype=np.float32)).cuda()
+    y = ops.bicubic(x, 40, 48)
+    yc = ops.bicubic(x, 40, 48, clip01=True)
+    assert y.min() < 0 or y.max() > 1                       # cubic overshoot exists and is kept
+    assert torch.equal(yc, y.clamp(0, 1))
+    for i in range(3):
+        assert torch.equal(ops.bicubic(x[i:i + 1], 40, 48)[0], y[i])
+    assert torch.allclose(ops.bicubic(x, 20, 24), x, atol=1e-6)   # same size = identity
+
+
+def test_full_size_linearity():
+    """BASELINE config 5 size: resampling is linear, so B(a*x + b*y) == a*B(x) + b*B(y)."""
+    import torch
+    from srb200 import ops
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand((1, 1080, 1920, 3), device="cuda", generator=g)
+    y = torch.rand((1, 1080, 1920, 3), device="cuda", generator=g)
+    lhs = ops.bicubic(0.25 * x + 0.75 * y, 2160, 3840)
+    rhs = 0.25 * ops.bicubic(x, 2160, 3840) + 0.75 * ops.bicubic(y, 2160, 3840)
+    assert (lhs - rhs).abs().max() <= 1e-5
+    ones = torch.full((1, 1080, 1920, 3), 0.5, device="cuda")
+    assert (ops.bicubic(ones, 2160, 3840) - 0.5).abs().max() <= 1e-6     # taps sum to one

@@ -1,0 +1,165 @@
+"""GPU parity: srb_conv2d_nhwc (both engines) and the network runners vs the Keras-semantics oracle.
+
+Tolerances (BASELINE.json north_star): SR output max-abs <= 1e-3 in fp32 mode, <= 2e-2 in bf16 mode,
+on [0,1] pixels.  Single layers in fp32 mode are held to 1e-4 relative to the layer's output scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import convnets as oc
+
+pytestmark = pytest.mark.gpu
+FP32_TOL, BF16_TOL = 1e-3, 2e-2
+
+
+def _ref_layer(x, k, b, act=None, slope=0.0, prelu=None, alpha=1.0, res1=None, beta1=1.0, res2=None, beta2=1.0,
+               clip=False, d2s=1):
+    y = oc.conv2d_same_numpy(x, k, b)
+    if act == "relu":
+        y = np.maximum(y, 0)
+    elif act == "leaky_relu":
+        y = np.where(y >= 0, y, slope * y)
+    elif act == "tanh":
+        y = np.tanh(y)
+    if d2s > 1:
+        y = oc.depth_to_space_numpy(y, d2s)
+    if act == "prelu":
+        y = np.where(y >= 0, y, prelu * y)
+    y = alpha * y
+    if res1 is not None:
+        y = y + beta1 * res1
+    if res2 is not None:
+        y = y + beta2 * res2
+    return np.clip(y, 0, 1) if clip else y
+
+
+def _rand(shape, seed, lo=-1.0, hi=1.0):
+    return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
+
+
+LAYER_CASES = [
+    # (B, H, W, kh, cin, cout, kwargs)
+    (2, 20, 24, 9, 3, 96, dict(act="relu")),                       # SRCNN conv1
+    (2, 20, 24, 1, 96, 32, dict(act="relu")),                      # SRCNN conv2
+    (2, 20, 24, 5, 32, 3, dict()),                                 # SRCNN conv3
+    (1, 17, 33, 3, 3, 64, dict()),                                 # EDSR head, ragged tile edges
+    (2, 16, 16, 3, 64, 64, dict(act="relu")),                      # EDSR rb conv1
+    (1, 19, 21, 3, 64, 64, dict(alpha=0.1, res1=True)),            # EDSR rb conv2 + scaled residual
+    (1, 12, 10, 3, 64, 256, dict(d2s=2)),                          # EDSR up conv + depth_to_space(2)
+    (1, 9, 11, 3, 64, 576, dict(d2s=3)),                           # EDSR x3 up conv
+    (1, 24, 24, 3, 64, 3, dict(clip=True)),                        # EDSR tail + clip
+    (1, 10, 12, 3, 32, 48, dict(d2s=4)),                           # ESPCN conv3 + d2s(4)
+    (1, 12, 12, 3, 64, 256, dict(act="prelu", d2s=2)),             # SRResNet up + PReLU
+    (1, 14, 9, 3, 72, 8, dict(act="relu")),                        # ESRGAN growth conv (odd cin)
+    (1, 14, 9, 3, 64, 64, dict(alpha=0.04, res1=True, beta1=0.2, res2=True)),   # RRDB tail, two residuals
+    (1, 8, 8, 3, 64, 3, dict(act="tanh")),                         # ESRGAN final conv
+    (1, 16, 16, 3, 64, 256, dict(act="leaky_relu", slope=0.2, d2s=2)),
+]
+
+
+@pytest.mark.parametrize("case", LAYER_CASES, ids=lambda c: f"{c[3]}x{c[3]}_{c[4]}to{c[5]}_{'_'.join(c[6]) or 'plain'}")
+def test_layer_fp32_direct(case):
+    from srb200 import ops, _capi
+    B, H, W, k, cin, cout, kw = case
+    kw = dict(kw)
+    x = _rand((B, H, W, cin), 1)
+    kern = _rand((k, k, cin, cout), 2, -0.2, 0.2)
+    bias = _rand((cout,), 3, -0.1, 0.1)
+    r = kw.get("d2s", 1)
+    c_post = cout // (r * r)
+    prelu = _rand((c_post,), 4, 0.1, 0.4) if kw.get("act") == "prelu" else None
+    res1 = _rand((B, H * r, W * r, c_post), 5) if kw.pop("res1", False) else None
+    res2 = _rand((B, H * r, W * r, c_post), 6) if kw.pop("res2", False) else None
+    want = _ref_layer(x, kern, bias, prelu=prelu, res1=res1, res2=res2, **kw)
+    w = ops.ConvWeights(kern, bias, prelu)
+    t = lambda a: None if a is None else torch.from_numpy(a).cuda()
+    got = ops.conv2d(t(x), w, act=kw.get("act"), act_slope=kw.get("slope", 0.0), alpha=kw.get("alpha", 1.0),
+                     res1=t(res1), beta1=kw.get("beta1", 1.0), res2=t(res2), beta2=kw.get("beta2", 1.0),
+                     clip01=kw.get("clip", False), d2s=r, engine=_capi.ENGINE_DIRECT).cpu().numpy()
+    assert got.shape == want.shape
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= 1e-4 * scale
+
+
+def test_channel_slices_concat_free():
+    """Dense-block pattern: read a channel prefix of a wide buffer, write a slice of it."""
+    from srb200 import ops, _capi
+    x = _rand((1, 10, 10, 80), 7)
+    kern = _rand((3, 3, 72, 8), 8, -0.2, 0.2)
+    w = ops.ConvWeights(kern, None)
+    buf = torch.from_numpy(x).cuda()
+    ops.conv2d(buf, w, act="relu", out=buf, out_coffset=72, engine=_capi.ENGINE_DIRECT)
+    want = np.maximum(oc.conv2d_same_numpy(x[..., :72], kern), 0)
+    got = buf.cpu().numpy()
+    assert np.abs(got[..., 72:] - want).max() <= 1e-4
+    assert np.array_equal(got[..., :72], x[..., :72])
+
+
+def test_bad_arguments():
+    from srb200 import ops, _capi
+    w = ops.ConvWeights(_rand((3, 3, 64, 256), 1), None)
+    x = torch.zeros((1, 8, 8, 64), device="cuda")
+    with pytest.raises(ValueError):
+        ops.conv2d(x, w, d2s=3)                                    # 256 not divisible by 9
+    with pytest.raises(ValueError):
+        ops.ConvWeights(_rand((2, 2, 3, 3), 1))                    # even kernel has no "same" centre
+    with pytest.raises(NotImplementedError):
+        ops.conv2d(x, w, engine=_capi.ENGINE_TCGEN05)              # fp32 input is not tcgen05-eligible
+    assert ops.conv2d(torch.zeros((0, 8, 8, 64), device="cuda"), w).shape == (0, 8, 8, 256)   # empty batch
+
+
+def _golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "convnets_oracle.npz"))
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_networks_vs_golden(golden_dir, precision, tol):
+    from srb200 import engine, weights
+    g = _golden(golden_dir)
+    lr = g["lr"]
+    nets = {
+        "srcnn": engine.SRCNNNet(weights.srcnn_weights(bias_scale=0.1), precision=precision),
+        "edsr_x4_2blocks": engine.EDSRNet(weights.edsr_weights(4, num_res_blocks=2, bias_scale=0.1), 4, 2,
+                                          precision=precision),
+        "edsr_x3_1block": engine.EDSRNet(weights.edsr_weights(3, num_res_blocks=1, bias_scale=0.1), 3, 1,
+                                         precision=precision),
+        "espcn_x4": engine.ESPCNNet(weights.espcn_weights(bias_scale=0.1), 4, precision=precision),
+        "srresnet_x4_2blocks": engine.SRResNetNet(weights.srresnet_weights(num_res_blocks=2, bias_scale=0.1), 4, 2,
+                                                  precision=precision),
+    }
+    for name, net in nets.items():
+        out = net.predict(lr)
+        err = np.abs(out - g[name]).max()
+        assert out.shape == g[name].shape and err <= tol, (name, err)
+
+
+def test_esrgan_generator_vs_golden(golden_dir):
+    from srb200 import engine, weights
+    g = _golden(golden_dir)
+    net = engine.ESRGANGeneratorNet(weights.esrgan_generator_weights(2, 8, 1, bias_scale=0.1), 2, 8, 1,
+                                    precision="fp32")
+    out = net.predict(g["lr"] * 2 - 1)
+    assert np.abs(out - g["esrgan_x2_1rrdb_g8"]).max() <= FP32_TOL
+
+
+def test_vgg16_classifier_vs_oracle():
+    from srb200 import engine, weights
+    w = weights.vgg16_classifier_weights(2, bias_scale=0.05)
+    x = np.random.default_rng(0).random((3, 32, 32, 3), dtype=np.float32)
+    want = oc.vgg16_classifier_forward(w, x)
+    got = engine.VGG16ClassifierNet(w, precision="fp32").predict(x)
+    assert np.abs(got - want).max() <= 2e-3 and np.array_equal(got.argmax(1), want.argmax(1))
+
+
+def test_edsr_full_depth_vs_oracle():
+    """The benchmark network (16 blocks, x4) on a small tile, both precisions, oracle computed live."""
+    from srb200 import engine, weights, synth
+    w = weights.edsr_weights(4, bias_scale=0.0)
+    lr = synth.area_downsample(synth.hr_batch(2, 96, 96), 4)
+    want = oc.edsr_forward(w, lr, 4, 16, dtype=torch.float64)
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_TOL)):
+        got = engine.EDSRNet(w, 4, 16, precision=precision).predict(lr)
+        err = np.abs(got - want).max()
+        assert err <= tol, (precision, err)

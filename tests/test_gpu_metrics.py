@@ -1,0 +1,88 @@
+"""GPU parity: fused PSNR+SSIM kernel vs the tf.image restatement (oracle/metrics.py).
+Tolerances are BASELINE.json's: PSNR within 0.01 dB, SSIM within 1e-4."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import metrics as om
+
+pytestmark = pytest.mark.gpu
+PSNR_TOL, SSIM_TOL = 0.01, 1e-4
+
+
+def _pair(shape, seed, noise=0.05):
+    from srb200 import synth
+    n, h, w, c = shape
+    hr = synth.hr_batch(n, h, w, channels=c, first_index=seed)
+    rng = np.random.default_rng(seed)
+    pred = np.clip(hr + noise * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    return hr, pred
+
+
+def test_golden_vectors(golden_dir):
+    from srb200 import metrics
+    g = np.load(os.path.join(golden_dir, "metrics_oracle.npz"))
+    p, s = metrics.psnr(g["a"], g["b"]), metrics.ssim(g["a"], g["b"])
+    assert p.dtype == np.float32 and p.shape == (4,)
+    assert np.abs(p - g["psnr64"]).max() <= PSNR_TOL
+    assert np.abs(s - g["ssim64"]).max() <= SSIM_TOL
+
+
+@pytest.mark.parametrize("shape", [(3, 11, 11, 3), (2, 24, 24, 3), (2, 37, 150, 3), (1, 130, 47, 1), (2, 64, 300, 4),
+                                   (1, 478, 478, 3)])
+def test_against_oracle(shape):
+    from srb200 import metrics
+    a, b = _pair(shape, seed=shape[1])
+    p, s = metrics.psnr_ssim(a, b)
+    assert np.abs(p - om.psnr(a, b, dtype=np.float64)).max() <= PSNR_TOL
+    assert np.abs(s - om.ssim(a, b, dtype=np.float64)).max() <= SSIM_TOL
+
+
+def test_known_answers():
+    from srb200 import metrics
+    a = np.full((2, 16, 20, 3), 0.3, np.float32)
+    b = np.full((2, 16, 20, 3), 0.6, np.float32)
+    assert np.allclose(metrics.ssim(a, b), 0.80004443, atol=2e-4)
+    assert np.allclose(metrics.psnr(a, b), 10.4575749, atol=1e-3)
+    assert np.allclose(metrics.ssim(a, a), 1.0, atol=1e-6)
+    assert np.all(np.isinf(metrics.psnr(a, a)))
+
+
+def test_small_images_raise_and_single_image():
+    from srb200 import metrics
+    with pytest.raises(ValueError):
+        metrics.ssim(np.zeros((1, 10, 32, 3), np.float32), np.zeros((1, 10, 32, 3), np.float32))
+    a, b = _pair((1, 32, 32, 3), 5)
+    assert np.ndim(metrics.psnr(a[0], b[0])) == 0
+
+
+def test_device_tensors_and_sums():
+    import torch
+    from srb200 import ops
+    a, b = _pair((5, 40, 40, 3), 9)
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    sums = torch.zeros(4, dtype=torch.float64, device="cuda")
+    p, s, m = ops.psnr_ssim(ta, tb, sums=sums, want_mse=True)
+    ops.psnr_ssim(ta, tb, sums=sums)            # accumulates
+    sums = sums.cpu().numpy()
+    assert sums[2] == 10
+    assert np.isclose(sums[0], 2 * p.double().sum().item()) and np.isclose(sums[1], 2 * s.double().sum().item())
+    assert np.allclose(m.cpu().numpy(), ((a - b) ** 2).mean(axis=(1, 2, 3)), rtol=1e-5)
+
+
+def test_full_size_properties():
+    """BASELINE config 5 size (4K frame): symmetry and noise monotonicity, no oracle needed."""
+    import torch
+    from srb200 import ops
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.rand((2, 2160, 3840, 3), device="cuda", generator=g)
+    n1 = (a + 0.02 * torch.randn(a.shape, device="cuda", generator=g)).clamp_(0, 1)
+    n2 = (a + 0.08 * torch.randn(a.shape, device="cuda", generator=g)).clamp_(0, 1)
+    p1, s1 = ops.psnr_ssim(a, n1)
+    p1r, s1r = ops.psnr_ssim(n1, a)
+    p2, s2 = ops.psnr_ssim(a, n2)
+    assert torch.allclose(p1, p1r, atol=1e-4) and torch.allclose(s1, s1r, atol=1e-6)
+    assert (p1 > p2).all() and (s1 > s2).all()
+    mse = ((a - n1) ** 2).mean(dim=(1, 2, 3))
+    assert torch.allclose(p1, -10 * torch.log10(mse), atol=PSNR_TOL)

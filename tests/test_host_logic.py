@@ -1,0 +1,82 @@
+"""CPU: host-side logic - voting, sharding, metric aggregation, world_size-2 gloo all-reduce."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, PKG
+
+
+def test_vote_majority_and_tiebreak():
+    from srb200.defect_detection_models.VGG16_model import vote
+    probs = np.array([[0.9, 0.1], [0.4, 0.6], [0.3, 0.7]])
+    assert vote(probs) == (1, pytest.approx((0.1 + 0.6 + 0.7) / 3))
+    tie = np.array([[0.9, 0.1], [0.4, 0.6]])          # 1 vote each -> higher mean prob wins (class 0)
+    assert vote(tie)[0] == 0
+
+
+def test_shard_bounds_cover_everything():
+    from srb200.distributed import shard_bounds
+    for n in (0, 1, 7, 512, 513):
+        for world in (1, 2, 4, 8):
+            spans = [shard_bounds(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_means_from_sums():
+    from srb200.distributed import means_from_sums
+    assert means_from_sums([60.0, 1.8, 2.0, 0.004]) == [0.002, 30.0, 0.9]
+
+
+def test_error_conventions_of_the_wrappers():
+    from srb200.deep_learning_models.SRCNN_model import SRCNNModel
+    from srb200.deep_learning_models.EDSR_model import EDSR
+    m = SRCNNModel()
+    with pytest.raises(RuntimeError, match="Model has not been trained"):
+        m.evaluate(None, None)
+    with pytest.raises(RuntimeError, match="Model has not been trained"):
+        m.super_resolve_image(np.zeros((8, 8, 3), np.float32), 16, 16)
+    with pytest.raises(FileNotFoundError):
+        m.setup_model(from_pretrained=True, pretrained_path="/nonexistent.npz")
+    e = EDSR()
+    with pytest.raises(RuntimeError, match="Model has not been trained"):
+        e.super_resolve_image(np.zeros((8, 8, 3), np.float32))
+    with pytest.raises(FileNotFoundError):
+        e.setup_model(from_pretrained=True, pretrained_path=None)
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {pkg!r})
+import torch, torch.distributed as dist
+from srb200 import distributed as D
+rank, world, _ = D.init_from_env(backend="gloo")
+lo, hi = D.shard_bounds(10)
+# each rank owns images [lo, hi) with psnr = 20 + index, ssim = index / 10, mse = 0.001 * index
+idx = torch.arange(lo, hi, dtype=torch.float64)
+sums = torch.stack([(20 + idx).sum(), (idx / 10).sum(), torch.tensor(float(hi - lo), dtype=torch.float64), (0.001 * idx).sum()])
+total = D.allreduce_sums(sums)
+vec = D.allgather_vector(torch.full((5,), float(rank)))
+if rank == 0:
+    print("RESULT", (D.means_from_sums(total.tolist()), vec.tolist()))
+dist.destroy_process_group()
+"""
+
+
+def test_gloo_world2_allreduce(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(pkg=PKG))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29531", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    line = [l for l in outs[0][0].splitlines() if l.startswith("RESULT")][0]
+    means, vec = eval(line[len("RESULT"):])
+    assert means == pytest.approx([0.0045, 24.5, 0.45])
+    assert vec == [0.0] * 5 + [1.0] * 5
