@@ -33,7 +33,7 @@ typedef void* srb_stream_t;          /* cudaStream_t */
 typedef struct srb_conv_weights srb_conv_weights;   /* opaque, device-resident packed kernel */
 
 enum { SRB_OK = 0, SRB_E_INVALID = -1, SRB_E_UNSUPPORTED = -2, SRB_E_CUDA = -3, SRB_E_NOMEM = -4 };
-enum { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2 };
+enum { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2, SRB_F16 = 3 };
 enum { SRB_ACT_NONE = 0, SRB_ACT_RELU = 1, SRB_ACT_PRELU = 2, SRB_ACT_LEAKY = 3, SRB_ACT_TANH = 4 };
 /* conv engine selection: AUTO picks tcgen05 when the shape is eligible, else the CUDA-core path */
 enum { SRB_ENGINE_AUTO = 0, SRB_ENGINE_DIRECT = 1, SRB_ENGINE_TCGEN05 = 2 };
@@ -82,6 +82,9 @@ int srb_overlap_add_f32(const float* patches, int ny, int nx, int patch_out, int
 typedef struct srb_conv_args {
   const void* x;        int x_dtype;   int x_cstride;  int x_coffset;   /* input  NHWC, C-slice allowed */
   void*       y;        int y_dtype;   int y_cstride;  int y_coffset;   /* output NHWC, C-slice allowed */
+  void*       y2;       int y2_dtype;  int y2_cstride;                  /* optional second copy of the output in
+                                                                           another dtype (fp32 residual trunk next
+                                                                           to the 16-bit operand of the next layer) */
   int batch, height, width;
   const srb_conv_weights* weights;
   int act;              float act_slope;               const float* prelu;   /* [cout / d2s^2] */
@@ -94,7 +97,7 @@ typedef struct srb_conv_args {
 } srb_conv_args;
 
 /* hwio_host: Keras kernel [kh, kw, cin, cout] float32 on the HOST; bias_host: [cout] or NULL.
- * Packs (and rounds to bf16 for the tcgen05 path) once; the result lives on the current device. */
+ * Packs (and rounds to bf16 and fp16 for the tcgen05 path) once; the result lives on the current device. */
 int srb_conv_weights_create(const float* hwio_host, const float* bias_host, int kh, int kw, int cin, int cout,
                             srb_conv_weights** out);
 void srb_conv_weights_destroy(srb_conv_weights* w);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -37,7 +38,9 @@ template <> __device__ __forceinline__ float load_as_float<float>(const float* p
 template <> __device__ __forceinline__ float load_as_float<__nv_bfloat16>(const __nv_bfloat16* p) {
   return __bfloat162float(*p);
 }
+template <> __device__ __forceinline__ float load_as_float<__half>(const __half* p) { return __half2float(*p); }
 template <typename T> __device__ __forceinline__ void store_from_float(T* p, float v);
+template <> __device__ __forceinline__ void store_from_float<__half>(__half* p, float v) { *p = __float2half_rn(v); }
 template <> __device__ __forceinline__ void store_from_float<float>(float* p, float v) { *p = v; }
 template <> __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16_rn(v);
@@ -59,7 +62,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
-inline size_t dtype_size(int dt) { return dt == SRB_F32 ? 4 : dt == SRB_BF16 ? 2 : 1; }
+inline size_t dtype_size(int dt) { return dt == SRB_F32 ? 4 : (dt == SRB_BF16 || dt == SRB_F16) ? 2 : 1; }
 
 }  // namespace srb
 
@@ -70,5 +73,6 @@ struct srb_conv_weights {
   int cout_pad4;
   float* bias;            // [cout] float32 (zeros when the layer has none)
   __nv_bfloat16* tc;      // [kh*kw][cout_pad][cin] bf16, K-major rows (tcgen05 engine) or nullptr
+  __half* tc_f16;         // same, IEEE half
   int tc_cout_pad;        // rows per tap in `tc` (multiple of 16)
 };

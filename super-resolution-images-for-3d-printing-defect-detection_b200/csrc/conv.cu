@@ -33,16 +33,23 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
     srb_conv_weights_destroy(w);
     return cuda_fail(e, "conv_weights_create");
   }
-  // tensor-core copy: [tap][cout_pad16][cin] bf16, K(cin)-major rows, for cin a multiple of 64
-  if (cin % 64 == 0 && cout % 16 == 0) {
-    w->tc_cout_pad = cout;
-    std::vector<__nv_bfloat16> tc((size_t)taps * cout * cin);
+  // tensor-core copies: [tap][cout_pad16][cin] K(cin)-major rows in bf16 and fp16, for cin == 64
+  if (cin == 64) {
+    const int rows = (cout + 15) & ~15;
+    w->tc_cout_pad = rows;
+    std::vector<__nv_bfloat16> tb((size_t)taps * rows * cin, __float2bfloat16_rn(0.f));
+    std::vector<__half> th((size_t)taps * rows * cin, __float2half_rn(0.f));
     for (int t = 0; t < taps; ++t)
       for (int o = 0; o < cout; ++o)
-        for (int c = 0; c < cin; ++c)
-          tc[((size_t)t * cout + o) * cin + c] = __float2bfloat16_rn(hwio[((size_t)t * cin + c) * cout + o]);
-    if ((e = cudaMalloc(&w->tc, tc.size() * sizeof(__nv_bfloat16))) != cudaSuccess ||
-        (e = cudaMemcpy(w->tc, tc.data(), tc.size() * sizeof(__nv_bfloat16), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        for (int c = 0; c < cin; ++c) {
+          const float v = hwio[((size_t)t * cin + c) * cout + o];
+          tb[((size_t)t * rows + o) * cin + c] = __float2bfloat16_rn(v);
+          th[((size_t)t * rows + o) * cin + c] = __float2half_rn(v);
+        }
+    if ((e = cudaMalloc(&w->tc, tb.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&w->tc_f16, th.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc_f16, th.data(), th.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
       srb_conv_weights_destroy(w);
       return cuda_fail(e, "conv_weights_create(tc)");
     }
@@ -56,6 +63,7 @@ extern "C" void srb_conv_weights_destroy(srb_conv_weights* w) {
   if (w->hwio) cudaFree(w->hwio);
   if (w->bias) cudaFree(w->bias);
   if (w->tc) cudaFree(w->tc);
+  if (w->tc_f16) cudaFree(w->tc_f16);
   free(w);
 }
 
@@ -64,8 +72,12 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   SRB_REQUIRE(a->x && a->y && a->weights, "conv2d: null pointer");
   const srb_conv_weights* w = a->weights;
   SRB_REQUIRE(a->batch >= 0 && a->height > 0 && a->width > 0, "conv2d: bad geometry %dx%dx%d", a->batch, a->height, a->width);
-  SRB_REQUIRE(a->x_dtype == SRB_F32 || a->x_dtype == SRB_BF16, "conv2d: x dtype must be f32 or bf16");
-  SRB_REQUIRE(a->y_dtype == SRB_F32 || a->y_dtype == SRB_BF16, "conv2d: y dtype must be f32 or bf16");
+  auto float_dt = [](int d) { return d == SRB_F32 || d == SRB_BF16 || d == SRB_F16; };
+  SRB_REQUIRE(float_dt(a->x_dtype), "conv2d: x dtype must be f32, bf16 or f16");
+  SRB_REQUIRE(float_dt(a->y_dtype), "conv2d: y dtype must be f32, bf16 or f16");
+  SRB_REQUIRE(!a->y2 || float_dt(a->y2_dtype), "conv2d: y2 dtype must be f32, bf16 or f16");
+  SRB_REQUIRE(!a->res1 || float_dt(a->res1_dtype), "conv2d: res1 dtype must be f32, bf16 or f16");
+  SRB_REQUIRE(!a->res2 || float_dt(a->res2_dtype), "conv2d: res2 dtype must be f32, bf16 or f16");
   const int d2s = a->d2s <= 0 ? 1 : a->d2s;
   SRB_REQUIRE(d2s >= 1 && d2s <= 4, "conv2d: depth_to_space factor must be 1..4 (got %d)", a->d2s);
   SRB_REQUIRE(w->cout % (d2s * d2s) == 0, "conv2d: cout %d is not divisible by d2s^2 = %d", w->cout, d2s * d2s);
@@ -74,12 +86,13 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.c_post = w->cout / (d2s * d2s);
   p.y = a->y; p.y_dtype = a->y_dtype;
   p.y_cstride = a->y_cstride > 0 ? a->y_cstride : p.c_post; p.y_coffset = a->y_coffset;
+  p.y2 = a->y2; p.y2_dtype = a->y2_dtype; p.y2_cstride = a->y2_cstride > 0 ? a->y2_cstride : p.c_post;
   SRB_REQUIRE(p.x_coffset >= 0 && p.x_coffset + w->cin <= p.x_cstride, "conv2d: input channel slice out of range");
   SRB_REQUIRE(p.y_coffset >= 0 && p.y_coffset + p.c_post <= p.y_cstride, "conv2d: output channel slice out of range");
   p.B = a->batch; p.H = a->height; p.W = a->width;
   p.kh = w->kh; p.kw = w->kw; p.cin = w->cin; p.cout = w->cout;
   p.w_hwio = w->hwio; p.w_cout_pad = w->cout_pad4;
-  p.w_tc = w->tc; p.w_tc_rows = w->tc_cout_pad;
+  p.w_tc = a->x_dtype == SRB_F16 ? (const void*)w->tc_f16 : (const void*)w->tc; p.w_tc_rows = w->tc_cout_pad;
   p.bias = w->bias;
   p.act = a->act; p.act_slope = a->act_slope; p.prelu = a->prelu;
   SRB_REQUIRE(a->act >= SRB_ACT_NONE && a->act <= SRB_ACT_TANH, "conv2d: unknown activation %d", a->act);
@@ -100,13 +113,14 @@ extern "C" int srb_conv2d_engine(const srb_conv_args* a) {
 }
 
 extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
+  if (a && a->batch == 0 && a->weights) return SRB_OK;   // empty batch: nothing to do, pointers may be null
   ConvParams p;
   int rc = fill_params(a, p);
   if (rc) return rc;
   if (p.B == 0) return SRB_OK;
   const bool tc_ok = conv_tc_eligible(p);
   if (a->engine == SRB_ENGINE_TCGEN05 && !tc_ok) {
-    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16 NHWC input, cin == 64, 3x3, cout %% 16 == 0)");
+    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, cin == 64, 3x3)");
     return SRB_E_UNSUPPORTED;
   }
   if (a->engine == SRB_ENGINE_TCGEN05 || (a->engine == SRB_ENGINE_AUTO && tc_ok)) return conv_tc_launch(p, (cudaStream_t)stream);

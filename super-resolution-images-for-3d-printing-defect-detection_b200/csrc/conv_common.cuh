@@ -7,10 +7,11 @@ namespace srb {
 struct ConvParams {
   const void* x; int x_dtype, x_cstride, x_coffset;
   void* y;       int y_dtype, y_cstride, y_coffset;
+  void* y2;      int y2_dtype, y2_cstride;
   int B, H, W;
   int kh, kw, cin, cout;
   const float* w_hwio; int w_cout_pad;      // direct engine weights
-  const __nv_bfloat16* w_tc; int w_tc_rows; // tcgen05 engine weights [tap][rows][cin]
+  const void* w_tc; int w_tc_rows;          // tcgen05 engine weights [tap][rows][cin] in the dtype of x
   const float* bias;                        // [cout], never null
   int act; float act_slope; const float* prelu;
   float alpha;
@@ -23,11 +24,13 @@ struct ConvParams {
 
 __device__ __forceinline__ float load_elem(const void* base, int dtype, size_t idx) {
   if (dtype == SRB_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+  if (dtype == SRB_F16) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
   return __ldg(reinterpret_cast<const float*>(base) + idx);
 }
 
 __device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, float v) {
   if (dtype == SRB_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else if (dtype == SRB_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
   else reinterpret_cast<float*>(base)[idx] = v;
 }
 
@@ -64,6 +67,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int b, int y
   d2s_map(p, b, y, x, co, out_pix, c_out);
   const float v = epilogue_value(p, acc, co, c_out, out_pix);
   store_elem(p.y, p.y_dtype, out_pix * p.y_cstride + p.y_coffset + c_out, v);
+  if (p.y2) store_elem(p.y2, p.y2_dtype, out_pix * p.y2_cstride + c_out, v);
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream);

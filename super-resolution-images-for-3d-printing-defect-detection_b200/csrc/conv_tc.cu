@@ -1,8 +1,475 @@
-// placeholder until the tcgen05 engine lands
+// tcgen05 / TMEM implicit-GEMM engine for 3x3, Cin = 64 convolutions on NHWC bf16 / fp16 activations
+// (the EDSR / SRResNet / ESRGAN body, up-sampling and tail layers: EDSR_model.py:61,65,80-89,112,121).
+//
+// GEMM view per CTA tile:  D[128 pixels x N] += sum over 9 taps  A_tap[128 x 64] * W_tap[64 x N]
+//   * a tile is 16 rows x 8 columns of output pixels of one image; pixel (ty, tx) is GEMM row ty*8+tx, so
+//     every 8-row swizzle group of the A operand is one image row of the tile;
+//   * the input halo (18 x 10 pixels x 64 channels = 128 B per pixel) is brought in by ONE 4-D TMA load
+//     per tile with 128-byte swizzle; `same` zero padding is the TMA out-of-bounds fill;
+//   * the nine taps are nine UMMA shared-memory descriptors into that one halo tile, shifted by
+//     (dy * pitch + dx) pixels; K = 64 channels is four k16 steps inside the 128-byte swizzle row;
+//   * the layer's weights [9][N][64] stay resident in shared memory for the whole persistent CTA;
+//   * accumulators live in TMEM, double buffered, so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   * the epilogue (4 warps, one pixel per thread) fuses bias, activation, alpha, two scaled residuals,
+//     clip, the depth_to_space address permutation and an optional second-dtype copy of the output.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
 #include "common.cuh"
 #include "conv_common.cuh"
+#include <cuda.h>
+
 namespace srb {
-bool conv_tc_eligible(const ConvParams&) { return false; }
-int conv_tc_launch(const ConvParams&, cudaStream_t) { set_error("tcgen05 engine not built"); return SRB_E_UNSUPPORTED; }
+
+constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM rows
+constexpr int kHaloH = kTileH + 2;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 6;
+
+struct TcParams {
+  int n_tile;            // output channels per CTA (multiple of 16, <= 128)
+  int n_chunks;          // ceil(cout_pad / n_tile); CTA c owns chunk c % n_chunks
+  int w_rows;            // rows per tap in the packed weight matrix
+  int tiles_x, tiles_y, total_tiles;
+  int stages;
+  uint32_t stage_bytes;  // multiple of 1024
+  int pitch;             // halo row pitch in pixels (= TMA box width)
+  int n_loads;           // 1 (one halo tile) or 3 (one tile per dx)
+  uint32_t load_bytes;   // bytes per TMA load
+  int base_off_mode;     // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
+  uint32_t tmem_cols;
+  uint32_t idesc;
+  int vec_ok;            // epilogue may use 16-byte vector accesses
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-extern "C" int srb_conv_tc_set_variant(int) { return 0; }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle row of K),
+//   [32,46) stride byte offset >> 4 (distance between 8-row groups), [46,48) version = 1,
+//   [49,52) base offset, [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, int base_off_mode) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  if (base_off_mode) d |= (uint64_t)((addr >> 7) & 7u) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// epilogue helpers: 8 consecutive channels at a time
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load8(const void* base, int dtype, size_t idx, float (&v)[8]) {
+  if (dtype == SRB_F32) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + idx));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == SRB_BF16) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        v[2 * i] = f.x; v[2 * i + 1] = f.y;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(void* base, int dtype, size_t idx, const float (&v)[8]) {
+  if (dtype == SRB_F32) {
+    float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx);
+    d[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (dtype == SRB_BF16) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      } else {
+        const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + idx) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const TcParams q, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is what the 128-byte swizzle pattern of TMA and UMMA is anchored to
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+
+  const uint32_t w_bytes = 9u * (uint32_t)q.n_tile * 128u;         // multiple of 1024 (n_tile % 16 == 0 -> 18432 | ...)
+  const uint32_t w_smem = base;
+  const uint32_t a_smem = base + ((w_bytes + 1023u) & ~1023u);
+  uint8_t* tail = smem + ((w_bytes + 1023u) & ~1023u) + (size_t)q.stages * q.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);               // full[S], empty[S], w_full, tfull[2], tempty[2]
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(kMaxStages + s); };
+  const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxStages);
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 3 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = (int)(blockIdx.x % (unsigned)q.n_chunks);
+  const int first_tile = (int)(blockIdx.x / (unsigned)q.n_chunks);
+  const int tile_step = (int)(gridDim.x / (unsigned)q.n_chunks);
+  const int co_base = chunk * q.n_tile;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(wfull_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), q.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = q.tiles_x * q.tiles_y;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_expect_tx(wfull_bar, w_bytes);
+      for (int t = 0; t < 9; ++t)
+        tma_load_2d(w_smem + (uint32_t)t * (uint32_t)q.n_tile * 128u, &tmap_w, wfull_bar, 0, t * q.w_rows + co_base);
+      int s = 0; uint32_t ph = 0;
+      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
+        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+        const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * kTileW;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), q.load_bytes * (uint32_t)q.n_loads);
+        const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
+        for (int l = 0; l < q.n_loads; ++l)
+          tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
+        if (++s == q.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      mbar_wait(wfull_bar, 0);
+      int s = 0; uint32_t ph = 0; int it = 0;
+      const uint32_t sbo = (uint32_t)q.pitch * 128u;
+      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t a_tap = (q.n_loads == 1)
+                                     ? a_stage + (uint32_t)(dy * q.pitch + dx) * 128u
+                                     : a_stage + (uint32_t)dx * q.load_bytes + (uint32_t)(dy * q.pitch) * 128u;
+          const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = make_desc(a_tap + (uint32_t)k * 32u, sbo, q.base_off_mode);
+            const uint64_t bd = make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0);
+            umma_f16(d_tmem, ad, bd, q.idesc, (uint32_t)((tap | k) != 0));
+          }
+        }
+        umma_commit(empty_bar(s));       // smem stage reusable once these MMAs have read it
+        umma_commit(tfull_bar(acc));     // accumulator complete
+        if (++s == q.stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;                     // GEMM row = pixel within the tile
+    const int ty = m >> 3, tx = m & 7;
+    int it = 0;
+    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int oy = (r / q.tiles_x) * kTileH + ty, ox = (r % q.tiles_x) * kTileW + tx;
+      const bool valid = oy < p.H && ox < p.W;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile);
+      for (int c0 = 0; c0 < q.n_tile; c0 += 16) {
+        uint32_t rr[16];
+        __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld16(t_row + (uint32_t)c0, rr);
+        tmem_ld_wait();
+        if (c0 + 16 >= q.n_tile) {                      // last read of this accumulator: hand it back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(tempty_bar(acc));
+        }
+        if (valid && q.vec_ok) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int co = co_base + c0 + g * 8;
+            if (co >= p.cout) break;
+            size_t out_pix; int c_out;
+            d2s_map(p, b, oy, ox, co, out_pix, c_out);
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float a = __uint_as_float(rr[g * 8 + e]) + bias_s[c0 + g * 8 + e];
+              const float slope = (p.act == SRB_ACT_PRELU) ? __ldg(p.prelu + c_out + e) : p.act_slope;
+              v[e] = apply_act(a, p.act, slope) * p.alpha;
+            }
+            if (p.res1) {
+              float rv[8];
+              load8(p.res1, p.res1_dtype, out_pix * p.res1_cstride + c_out, rv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta1, rv[e], v[e]);
+            }
+            if (p.res2) {
+              float rv[8];
+              load8(p.res2, p.res2_dtype, out_pix * p.res2_cstride + c_out, rv);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta2, rv[e], v[e]);
+            }
+            if (p.clip01) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
+            }
+            store8(p.y, p.y_dtype, out_pix * p.y_cstride + p.y_coffset + c_out, v);
+            if (p.y2) store8(p.y2, p.y2_dtype, out_pix * p.y2_cstride + c_out, v);
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const int co = co_base + c0 + e;
+            if (co < p.cout) epilogue_store(p, b, oy, ox, co, __uint_as_float(rr[e]));   // adds p.bias[co] itself
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, q.tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+static int g_variant = 0;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+bool conv_tc_eligible(const ConvParams& p) {
+  if (p.kh != 3 || p.kw != 3 || p.cin != 64 || !p.w_tc) return false;
+  if (p.x_dtype != SRB_BF16 && p.x_dtype != SRB_F16) return false;
+  if ((p.x_cstride % 8) || (p.x_coffset % 8) || !aligned16(p.x)) return false;
+  if (p.W < 1 || p.H < 1) return false;
+  return true;
+}
+
+// 8 consecutive channels per access: one 16-byte vector for 16-bit types, two for fp32
+static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
+  const int per16 = dtype == SRB_F32 ? 4 : 8;
+  return aligned16(ptr) && (cstride % per16 == 0) && (coffset % per16 == 0);
+}
+
+int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
+  EncodeTiledFn encode = encode_fn();
+  if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
+
+  TcParams q{};
+  const int rows = p.w_tc_rows;                       // cout padded to 16
+  q.n_tile = (rows % 64 == 0) ? 64 : (rows < 64 ? rows : 16);
+  if (rows % q.n_tile) q.n_tile = 16;
+  q.n_chunks = rows / q.n_tile;
+  q.w_rows = rows;
+  q.tiles_x = (p.W + kTileW - 1) / kTileW;
+  q.tiles_y = (p.H + kTileH - 1) / kTileH;
+  const long total = (long)p.B * q.tiles_x * q.tiles_y;
+  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
+  q.total_tiles = (int)total;
+  const int variant = g_variant;
+  if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
+  else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
+  else { q.pitch = kTileW + 2; q.n_loads = 1; }
+  q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
+  q.load_bytes = (uint32_t)(kHaloH * q.pitch * 128);
+  q.stage_bytes = ((q.load_bytes * (uint32_t)q.n_loads) + 1023u) & ~1023u;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < (uint32_t)(2 * q.n_tile)) q.tmem_cols <<= 1;
+  const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
+  q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  const bool d2s_vec = (p.d2s == 1) || (p.c_post % 8 == 0);
+  q.vec_ok = d2s_vec && (p.cout % 8 == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
+             (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
+             (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
+             (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
+
+  const size_t w_bytes = ((size_t)9 * q.n_tile * 128 + 1023) & ~(size_t)1023;
+  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)q.n_tile * sizeof(float);
+  int dev = 0, max_smem = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  q.stages = kMaxStages;
+  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + tail_bytes; };
+  while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
+  if (q.stages > 4) q.stages = 4;
+  const size_t smem = smem_need(q.stages);
+  SRB_REQUIRE(smem <= (size_t)max_smem, "conv(tcgen05): tile does not fit shared memory");
+
+  // ---- tensor maps ----
+  const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmx, tmw;
+  {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2,
+                                   (cuuint64_t)p.H * p.W * p.x_cstride * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)q.pitch, (cuuint32_t)kHaloH, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    void* gptr = (void*)((const uint16_t*)p.x + p.x_coffset);
+    CUresult r = encode(&tmx, tdt, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
+  }
+  {
+    const cuuint64_t dims[2] = {64, (cuuint64_t)9 * rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)q.n_tile};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tmw, tdt, 2, (void*)p.w_tc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
+  }
+
+  static size_t configured = 0;
+  if (smem > configured) {
+    SRB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int grid = sm_count();
+  grid -= grid % q.n_chunks;
+  if (grid < q.n_chunks) grid = q.n_chunks;
+  const long work = (long)q.total_tiles * q.n_chunks;
+  if ((long)grid > work) grid = (int)(work - work % q.n_chunks);
+  conv3x3_tc_kernel<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
+  return launch_check("conv3x3_tc_kernel");
+}
+
+}  // namespace srb
+
+extern "C" int srb_conv_tc_set_variant(int variant) {
+  const int prev = srb::g_variant;
+  if (variant >= 0 && variant <= 3) srb::g_variant = variant;
+  return prev;
+}

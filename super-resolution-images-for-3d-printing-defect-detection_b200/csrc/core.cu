@@ -197,11 +197,16 @@ extern "C" int srb_cast(const void* src, int sdt, void* dst, int ddt, size_t n, 
   if (n == 0) return SRB_OK;
   const int g = grid_for(n, 256);
 #define SRB_CAST(S, D) cast_kernel<S, D><<<g, 256, 0, stream>>>((const S*)src, (D*)dst, n, scale, shift)
-  if (sdt == SRB_F32 && ddt == SRB_BF16) SRB_CAST(float, __nv_bfloat16);
-  else if (sdt == SRB_BF16 && ddt == SRB_F32) SRB_CAST(__nv_bfloat16, float);
-  else if (sdt == SRB_F32 && ddt == SRB_F32) SRB_CAST(float, float);
-  else if (sdt == SRB_BF16 && ddt == SRB_BF16) SRB_CAST(__nv_bfloat16, __nv_bfloat16);
-  else { set_error("cast: unsupported dtype pair %d -> %d", sdt, ddt); return SRB_E_UNSUPPORTED; }
+#define SRB_CAST_FROM(S)                                                                       \
+  if (ddt == SRB_F32) SRB_CAST(S, float);                                                      \
+  else if (ddt == SRB_BF16) SRB_CAST(S, __nv_bfloat16);                                        \
+  else if (ddt == SRB_F16) SRB_CAST(S, __half);                                                \
+  else { set_error("cast: unsupported destination dtype %d", ddt); return SRB_E_UNSUPPORTED; }
+  if (sdt == SRB_F32) { SRB_CAST_FROM(float) }
+  else if (sdt == SRB_BF16) { SRB_CAST_FROM(__nv_bfloat16) }
+  else if (sdt == SRB_F16) { SRB_CAST_FROM(__half) }
+  else { set_error("cast: unsupported source dtype %d", sdt); return SRB_E_UNSUPPORTED; }
+#undef SRB_CAST_FROM
 #undef SRB_CAST
   return launch_check("cast_kernel");
 }
@@ -216,6 +221,7 @@ extern "C" int srb_maxpool2x2_nhwc(const void* x, int dtype, int batch, int heig
   const int g = grid_for(total, 256);
   if (dtype == SRB_F32) maxpool2x2_kernel<float><<<g, 256, 0, stream>>>((const float*)x, (float*)y, batch, height, width, channels);
   else if (dtype == SRB_BF16) maxpool2x2_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, height, width, channels);
+  else if (dtype == SRB_F16) maxpool2x2_kernel<__half><<<g, 256, 0, stream>>>((const __half*)x, (__half*)y, batch, height, width, channels);
   else { set_error("maxpool: unsupported dtype %d", dtype); return SRB_E_UNSUPPORTED; }
   return launch_check("maxpool2x2_kernel");
 }
@@ -233,6 +239,8 @@ extern "C" int srb_gap_dense_softmax(const void* x, int dtype, int batch, int hw
     gap_dense_softmax_kernel<float><<<batch, 256, smem, stream>>>((const float*)x, hw, channels, w1, b1, hidden, w2, b2, classes, probs);
   else if (dtype == SRB_BF16)
     gap_dense_softmax_kernel<__nv_bfloat16><<<batch, 256, smem, stream>>>((const __nv_bfloat16*)x, hw, channels, w1, b1, hidden, w2, b2, classes, probs);
+  else if (dtype == SRB_F16)
+    gap_dense_softmax_kernel<__half><<<batch, 256, smem, stream>>>((const __half*)x, hw, channels, w1, b1, hidden, w2, b2, classes, probs);
   else { set_error("gap_dense_softmax: unsupported dtype %d", dtype); return SRB_E_UNSUPPORTED; }
   return launch_check("gap_dense_softmax_kernel");
 }

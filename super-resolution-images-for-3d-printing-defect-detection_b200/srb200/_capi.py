@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 
 SRB_OK, SRB_E_INVALID, SRB_E_UNSUPPORTED, SRB_E_CUDA, SRB_E_NOMEM = 0, -1, -2, -3, -4
-F32, BF16, U8 = 0, 1, 2
+F32, BF16, U8, F16 = 0, 1, 2, 3
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 ACTIVATIONS = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "prelu": ACT_PRELU,
@@ -26,6 +26,7 @@ class ConvArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_dtype", C.c_int), ("x_cstride", C.c_int), ("x_coffset", C.c_int),
         ("y", C.c_void_p), ("y_dtype", C.c_int), ("y_cstride", C.c_int), ("y_coffset", C.c_int),
+        ("y2", C.c_void_p), ("y2_dtype", C.c_int), ("y2_cstride", C.c_int),
         ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
         ("weights", C.c_void_p),
         ("act", C.c_int), ("act_slope", C.c_float), ("prelu", C.c_void_p),
@@ -133,6 +134,8 @@ def dtype_code(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     if t.dtype == torch.uint8:
         return U8
     raise TypeError(f"unsupported tensor dtype {t.dtype}")

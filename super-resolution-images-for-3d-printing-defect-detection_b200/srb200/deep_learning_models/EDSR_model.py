@@ -22,7 +22,7 @@ class EDSR:
 
     def setup_model(self, scale_factor=2, channels=3, num_res_blocks=16, num_filters=64, res_scaling=0.1,
                     learning_rate=1e-4, loss="mean_absolute_error", from_pretrained=False, pretrained_path=None,
-                    precision="bf16", seed=1234):
+                    precision="fp16", seed=1234):
         """Set up the EDSR model, either by loading pretrained weights (.npz) or building a new one."""
         self.scale_factor = scale_factor
         self._arch = dict(scale_factor=scale_factor, num_res_blocks=num_res_blocks, res_scaling=res_scaling)

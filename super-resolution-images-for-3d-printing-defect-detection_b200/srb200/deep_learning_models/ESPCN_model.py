@@ -14,7 +14,7 @@ class ESPCN:
         self.trained = False
 
     def setup_model(self, scale_factor=4, channels=3, activation="relu", from_pretrained=False, pretrained_path=None,
-                    precision="bf16", seed=1234):
+                    precision="fp16", seed=1234):
         self.scale_factor = scale_factor
         if from_pretrained:
             w = common.load_weight_file(pretrained_path)

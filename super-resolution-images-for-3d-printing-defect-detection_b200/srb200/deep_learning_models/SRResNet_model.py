@@ -14,7 +14,7 @@ class SRResNet:
         self._blocks = 16
 
     def setup_model(self, scale_factor=4, channels=3, num_res_blocks=16, num_filters=64, from_pretrained=False,
-                    pretrained_path=None, precision="bf16", seed=1234):
+                    pretrained_path=None, precision="fp16", seed=1234):
         self.scale_factor, self._blocks = scale_factor, num_res_blocks
         if from_pretrained:
             w = common.load_weight_file(pretrained_path)

@@ -146,11 +146,14 @@ class ConvWeights:
 
 
 def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, beta1=1.0, res2=None, beta2=1.0,
-           clip01=False, d2s=1, out_dtype=None, out=None, out_coffset=0, x_coffset=0, engine=capi.ENGINE_AUTO):
+           clip01=False, d2s=1, out_dtype=None, out=None, out_coffset=0, x_coffset=0, engine=capi.ENGINE_AUTO,
+           out2_dtype=None):
     """y = clip(alpha * act(conv(x, W) + b) + beta1 * res1 + beta2 * res2), optionally depth_to_space'd.
 
     ``x`` may be a wider NHWC buffer of which channels [x_coffset, x_coffset + cin) are read, and
-    ``out`` a wider buffer written at ``out_coffset`` (concat-free dense blocks)."""
+    ``out`` a wider buffer written at ``out_coffset`` (concat-free dense blocks).  With ``out2_dtype`` the
+    result is also written in a second dtype and ``(out, out2)`` is returned (fp32 residual trunk next to
+    the 16-bit operand of the following layer)."""
     torch = _torch()
     _check_nhwc(x, "x")
     B, H, W, Cx = x.shape
@@ -163,6 +166,10 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     a = capi.ConvArgs()
     a.x, a.x_dtype, a.x_cstride, a.x_coffset = x.data_ptr(), capi.dtype_code(x), Cx, int(x_coffset)
     a.y, a.y_dtype, a.y_cstride, a.y_coffset = out.data_ptr(), capi.dtype_code(out), out.shape[3], int(out_coffset)
+    out2 = None
+    if out2_dtype is not None:
+        out2 = torch.empty((B, H * r, W * r, c_post), dtype=out2_dtype, device=x.device)
+        a.y2, a.y2_dtype, a.y2_cstride = out2.data_ptr(), capi.dtype_code(out2), c_post
     a.batch, a.height, a.width = B, H, W
     a.weights = w.handle
     a.act = capi.ACTIVATIONS[act] if not isinstance(act, int) else act
@@ -181,7 +188,7 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     a.clip01, a.d2s, a.engine = int(bool(clip01)), r, int(engine)
     with torch.cuda.device(x.device):
         capi.check(capi.lib().srb_conv2d_nhwc(C.byref(a), capi.stream_ptr()))
-    return out
+    return out if out2 is None else (out, out2)
 
 
 def conv2d_engine(x, w: ConvWeights, d2s=1):

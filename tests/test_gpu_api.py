@@ -35,7 +35,7 @@ def test_srcnn_super_resolve_image_config1_flow():
     assert set(info) == {"time_sec", "gpu_mean_current_mb", "gpu_peak_mb"}
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("fp16", 2e-2)])
 def test_edsr_super_resolve_and_evaluate(precision, tol):
     from srb200 import synth, weights
     from srb200.deep_learning_models.EDSR_model import EDSR
@@ -51,8 +51,8 @@ def test_edsr_super_resolve_and_evaluate(precision, tol):
     assert sr.shape == (48, 48, 3) and np.abs(sr - want).max() <= tol
     loss, psnr, ssim = m.evaluate(lr, hr)
     ref = om.evaluate_means(hr, fwd(lr))
-    assert abs(loss - ref[0]) <= 1e-4 and abs(psnr - ref[1]) <= (0.01 if precision == "fp32" else 0.3)
-    assert abs(ssim - ref[2]) <= (1e-4 if precision == "fp32" else 5e-3)
+    assert abs(loss - ref[0]) <= 1e-4 and abs(psnr - ref[1]) <= (0.01 if precision == "fp32" else 0.05)
+    assert abs(ssim - ref[2]) <= (1e-4 if precision == "fp32" else 1e-3)
 
 
 def test_esrgan_super_resolve_image():

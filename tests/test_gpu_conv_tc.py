@@ -1,0 +1,124 @@
+"""GPU parity: the tcgen05 / TMEM implicit-GEMM engine against the float64 im2col oracle.
+
+Inputs and weights are pre-rounded to the 16-bit operand format, so the only difference to the
+oracle is fp32 accumulation order plus the final output rounding: tolerances are tight (a few ULP of
+the output format), which is what exposes any swizzle / descriptor / tap-addressing mistake."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import convnets as oc
+
+pytestmark = pytest.mark.gpu
+
+DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _round(a, kind):
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    return (t.bfloat16() if kind == "bf16" else t.half()).float().numpy()
+
+
+def _rand(shape, seed, lo=-1.0, hi=1.0):
+    return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
+
+
+def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, **kw):
+    from srb200 import ops, _capi
+    x = _round(_rand((B, H, W, 64), 1), kind)
+    kern = _round(_rand((3, 3, 64, cout), 2, -0.1, 0.1), kind)
+    bias = _rand((cout,), 3, -0.1, 0.1)
+    r = kw.get("d2s", 1)
+    c_post = cout // (r * r)
+    res1 = _rand((B, H * r, W * r, c_post), 5) if kw.pop("res1", False) else None
+    want = oc.conv2d_same_numpy(x, kern, bias)
+    if kw.get("act") == "relu":
+        want = np.maximum(want, 0)
+    if r > 1:
+        want = oc.depth_to_space_numpy(want, r)
+    want = want * kw.get("alpha", 1.0)
+    if res1 is not None:
+        want = want + res1
+    if kw.get("clip01"):
+        want = np.clip(want, 0, 1)
+    w = ops.ConvWeights(kern, bias)
+    xd = torch.from_numpy(x).cuda().to(DT[kind])
+    prev = _capi.lib().srb_conv_tc_set_variant(-1 if variant is None else variant)
+    try:
+        assert ops.conv2d_engine(xd, w, r) == _capi.ENGINE_TCGEN05
+        got = ops.conv2d(xd, w, act=kw.get("act"), alpha=kw.get("alpha", 1.0), clip01=kw.get("clip01", False),
+                         res1=None if res1 is None else torch.from_numpy(res1).cuda(), d2s=r,
+                         out_dtype=out_dtype, engine=_capi.ENGINE_TCGEN05)
+        torch.cuda.synchronize()
+    finally:
+        _capi.lib().srb_conv_tc_set_variant(prev)
+    return got.float().cpu().numpy(), want
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+def test_operand_staging_variants(variant):
+    """Which A-operand staging schemes produce the right answer on this silicon (diagnostic: the
+    default variant must pass; the result table is recorded in DESIGN.md)."""
+    from srb200 import _capi
+    got, want = _run("fp16", 1, 32, 24, 64, variant=variant)
+    err = np.abs(got - want).max()
+    print(f"variant {variant}: max-abs {err:.3e}")
+    if variant == _capi.lib().srb_conv_tc_set_variant(-1):
+        assert err <= 2e-3
+    elif err > 2e-3:
+        pytest.xfail(f"variant {variant} is not a valid operand layout on this GPU (max-abs {err:.3e})")
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 16, 8, 64), (1, 48, 48, 64), (3, 21, 13, 64), (1, 5, 3, 64), (1, 192, 192, 64),
+                                   (1, 24, 24, 256), (1, 17, 9, 576), (2, 24, 24, 3), (1, 20, 12, 32), (1, 16, 16, 48)])
+def test_plain_conv(kind, shape):
+    B, H, W, cout = shape
+    got, want = _run(kind, B, H, W, cout)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 2e-3
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+def test_fused_epilogues(kind):
+    tol16 = 2e-2 if kind == "bf16" else 4e-3                 # output rounding of values up to ~3
+    got, want = _run(kind, 2, 20, 20, 64, act="relu", out_dtype=DT[kind])
+    assert np.abs(got - want).max() <= tol16
+    got, want = _run(kind, 1, 19, 21, 64, alpha=0.1, res1=True)
+    assert np.abs(got - want).max() <= 2e-3
+    got, want = _run(kind, 1, 12, 10, 256, d2s=2, out_dtype=DT[kind])
+    assert got.shape == (1, 24, 20, 64) and np.abs(got - want).max() <= tol16
+    got, want = _run(kind, 1, 9, 11, 576, d2s=3)
+    assert got.shape == (1, 27, 33, 64) and np.abs(got - want).max() <= 2e-3
+    got, want = _run(kind, 1, 24, 24, 3, clip01=True)
+    assert np.abs(got - want).max() <= 2e-3
+
+
+def test_second_output_copy_and_channel_slice():
+    from srb200 import ops, _capi
+    x = _round(_rand((1, 16, 16, 64), 1), "fp16")
+    kern = _round(_rand((3, 3, 64, 64), 2, -0.1, 0.1), "fp16")
+    w = ops.ConvWeights(kern, None)
+    xd = torch.from_numpy(x).cuda().half()
+    y32, y16 = ops.conv2d(xd, w, out_dtype=torch.float32, out2_dtype=torch.float16, engine=_capi.ENGINE_TCGEN05)
+    want = oc.conv2d_same_numpy(x, kern)
+    assert np.abs(y32.cpu().numpy() - want).max() <= 2e-3
+    assert torch.equal(y16, y32.half())
+    # input is a 64-channel slice (offset 8) of a wider buffer
+    wide = torch.zeros((1, 16, 16, 80), dtype=torch.float16, device="cuda")
+    wide[..., 8:72] = xd
+    got = ops.conv2d(wide, w, x_coffset=8, out_dtype=torch.float32, engine=_capi.ENGINE_TCGEN05)
+    assert np.abs(got.cpu().numpy() - want).max() <= 2e-3
+
+
+def test_engines_agree_at_benchmark_tile_size():
+    """192 x 192 x 64 (BASELINE config 3 tile): tcgen05 vs the exact CUDA-core engine on the same
+    16-bit inputs - a full-size check that needs no CPU oracle."""
+    from srb200 import ops, _capi
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = (torch.rand((4, 192, 192, 64), device="cuda", generator=g) * 2 - 1).half()
+    kern = _round(_rand((3, 3, 64, 64), 2, -0.1, 0.1), "fp16")
+    w = ops.ConvWeights(kern, _rand((64,), 3, -0.1, 0.1))
+    a = ops.conv2d(x, w, act="relu", out_dtype=torch.float32, engine=_capi.ENGINE_TCGEN05)
+    b = ops.conv2d(x, w, act="relu", out_dtype=torch.float32, engine=_capi.ENGINE_DIRECT)
+    assert (a - b).abs().max().item() <= 2e-3
