@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py - SR output megapixels/s of the B200 hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload edsr|espcn|bicubic|metrics]
+
+Default workload (BASELINE configs[2]): EDSR-baseline x4 (16 res-blocks, 64 channels), 16-bit operands /
+fp32 accumulation, batch 512 LR tiles of 192x192x3 -> 768x768x3, sharded contiguously over N GPUs (one
+process per GPU, no data-path collective).  A step is one pass of the network over the whole batch.
+Prints ONE JSON line on rank 0.
+
+* ``value``: whole-job throughput with the LR batch already resident in HBM (CUDA events, max over ranks).
+* ``e2e``: the same metric through the reference-facing call ``EDSR.model.predict(host array)`` with pinned
+  host buffers: H2D of the LR batch and D2H of the SR batch are inside the timed region (pipelined against
+  compute on copy streams).
+* ``roofline``: the tcgen05 conv kernel (every layer but the 3-channel head): algorithmic FLOPs / CUDA-event
+  time of the spans that contain only that kernel, against the measured sustained bf16 peak.
+* ``cpu_baseline`` / ``--impl reference``: the reference's engine (TensorFlow) cannot be installed here, so the
+  CPU arm is the fp32 oracle port (torch CPU, all host threads) on a bounded sample of the same tiles.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "super-resolution-images-for-3d-printing-defect-detection_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+EDSR_FLOP_PER_LR_PX = 2 * 1_983_168          # SURVEY.md section 8 row A5 (x4, 16 blocks, 64 ch)
+EDSR_HEAD_FLOP_PER_LR_PX = 2 * 27 * 64       # the one layer that is not on the tcgen05 kernel
+ESPCN_FLOP_PER_LR_PX = 2 * 37_056
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc = index, None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return
+        self.proc.terminate()
+        try:
+            out = self.proc.communicate(timeout=5)[0]
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, watts = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); watts.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                           "samples": len(sm), "power_w_max": max(watts)}
+
+
+def lr_tiles(lo, hi, size):
+    from srb200 import synth
+    return np.stack([synth.hr_image(size, size, i) for i in range(lo, hi)]) if hi > lo else \
+        np.zeros((0, size, size, 3), np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on host cores (reference engine = TensorFlow 2.10, not installable here)
+# ------------------------------------------------------------------------------------------------
+def cpu_edsr_mp_per_s(n_tiles, tile, repeats=1):
+    import torch
+    from oracle import convnets as oc
+    from srb200 import weights
+    w = weights.edsr_weights(4)
+    x = lr_tiles(0, n_tiles, tile)
+    oc.edsr_forward(w, x[:1], 4, 16)                      # warm-up (thread pool, allocator)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        for i in range(n_tiles):
+            oc.edsr_forward(w, x[i:i + 1], 4, 16)
+        best = min(best, time.perf_counter() - t0)
+    return n_tiles * (tile * 4) ** 2 / 1e6 / best, torch.get_num_threads(), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    tile, per_step = args.tile, 4
+    import torch
+    from oracle import convnets as oc
+    from srb200 import weights
+    w = weights.edsr_weights(4)
+    x = lr_tiles(0, per_step, tile)
+    for _ in range(max(args.warmup, 1)):
+        oc.edsr_forward(w, x[:1], 4, 16)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for i in range(per_step):
+            oc.edsr_forward(w, x[i:i + 1], 4, 16)
+    dt = time.perf_counter() - t0
+    mp = args.steps * per_step * (tile * 4) ** 2 / 1e6
+    val = mp / dt
+    cores = torch.get_num_threads()
+    sample = f"{per_step} of the {args.batch} LR tiles ({tile}x{tile}) per step, fp32 oracle port (torch CPU conv2d), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": "sr_output_megapixels_per_sec", "value": val, "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 0),
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference engine (TensorFlow/Keras 2.10) is not installable offline; CPU arm = oracle restatement",
+    }))
+
+
+def workload_config(args, micro_batch):
+    return {"workload": f"EDSR-baseline x4 (16 res-blocks, 64 ch) inference, {args.batch} LR tiles {args.tile}x{args.tile}x3 "
+                        f"-> {args.tile * 4}x{args.tile * 4}x3 (BASELINE configs[2])",
+            "global_batch": args.batch, "tile": args.tile, "scale": 4, "micro_batch": micro_batch,
+            "parallelism": f"dp{args.gpus} (batch-sharded, no data-path collective)",
+            "operands": f"{args.dtype} operands, fp32 accumulate, fp32 residual trunk",
+            "l2": "inputs larger than L2 (LR batch + activations stream through HBM every step); no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    from srb200 import distributed as D
+    from srb200 import engine, ops, weights
+
+    rank, world, local = D.init_from_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    lo, hi = D.shard_bounds(args.batch, rank, world)
+    n_local = hi - lo
+    tile, out_px = args.tile, (args.tile * 4) ** 2
+    mb = min(args.micro_batch, max(n_local, 1))
+
+    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype)
+    net.max_device_batch = mb
+    x_host = torch.from_numpy(lr_tiles(lo, hi, tile)).pin_memory()
+    x_dev = x_host.to(dev)
+    out_host = torch.empty((n_local, tile * 4, tile * 4, 3), dtype=torch.float32).pin_memory()
+
+    # spans that contain only tcgen05 conv launches: [after head conv, after tail conv] of every micro-batch
+    spans = []
+
+    def hook(tag):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        spans.append((tag, ev))
+    net.event_hook = hook
+
+    def device_step():
+        outs = []
+        for i in range(0, n_local, mb):
+            outs.append(net.forward_device(x_dev[i:i + mb]))
+        return outs
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    spans.clear()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            device_step()
+        e1.record()
+        barrier()
+    launches = ops.launch_count()
+    ms = e0.elapsed_time(e1)
+    tc_ms = sum(a[1].elapsed_time(b[1]) for a, b in zip(spans[0::2], spans[1::2]))
+    n_tc_launches = args.steps * ((n_local + mb - 1) // mb) * 36 if n_local else 0
+    net.event_hook = None
+
+    # end to end through the reference-facing API with host buffers
+    e2e_ms = None
+    if n_local:
+        net.predict(x_host.numpy(), out=out_host.numpy())          # warm-up (pinned staging, streams)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        if n_local:
+            net.predict(x_host.numpy(), out=out_host.numpy())
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+
+    t = torch.tensor([ms, e2e_ms, tc_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms, tc_ms_max = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peaks = measured_peaks()
+        total_mp = args.batch * out_px / 1e6
+        value = total_mp * args.steps / (ms / 1e3)
+        e2e = total_mp * args.steps / (e2e_ms / 1e3)
+        tc_flops = (EDSR_FLOP_PER_LR_PX - EDSR_HEAD_FLOP_PER_LR_PX) * tile * tile * n_local * args.steps
+        achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
+        line = {
+            "metric": "sr_output_megapixels_per_sec", "value": value, "unit": "MP/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": workload_config(args, mb),
+            "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": args.batch * tile * tile * 3 * 4,
+                    "d2h_bytes_per_step": args.batch * out_px * 3 * 4, "ms_per_step": e2e_ms / args.steps,
+                    "api": "EDSRNet.predict(host NHWC float32, out=pinned host)"},
+            "gpu_launches": launches * world,
+            "clocks": clk.result,
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel", "achieved": achieved, "peak": peaks["tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+                         "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
+                         "flop_per_launch": tc_flops / max(n_tc_launches, 1),
+                         "avg_launch_ms": tc_ms / max(n_tc_launches, 1), "launches": n_tc_launches,
+                         "whole_net_tflops": EDSR_FLOP_PER_LR_PX * tile * tile * args.batch * args.steps / (ms / 1e3) / 1e12},
+        }
+        if args.gpus == 1 and not args.no_cpu:
+            n_cpu = 24
+            mp_s, cores, secs = cpu_edsr_mp_per_s(n_cpu, tile)
+            line["cpu_baseline"] = {"value": mp_s, "unit": "MP/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {n_cpu} of the {args.batch} LR tiles, fp32 oracle port (torch CPU), {secs:.1f} s"}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--tile", type=int, default=192)
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,7 +38,11 @@ struct TcParams {
   int base_off_mode;     // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
   uint32_t tmem_cols;
   uint32_t idesc;
-  int vec_ok;            // epilogue may use 16-byte vector accesses
+  int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses)
+  int f_bufs;            // per-warp fp32 staging buffers (0, 1, or 2 when the residual is prefetched)
+  int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
+  int res_prefetch;      // res1 is fp32 and is prefetched into the F buffers with cp.async
+  uint32_t epi_warp_bytes;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -174,6 +178,32 @@ __device__ __forceinline__ void store8(void* base, int dtype, size_t idx, const 
 // ---------------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
+  if (dtype == SRB_BF16) { const __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<const uint32_t*>(&h); }
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __noinline__ float act_generic(float v, int act, float slope) { return apply_act(v, act, slope); }
+
+// generic per-element epilogue, kept out of line so that the staged path stays small in the instruction cache
+__device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, int y, int x, int co, float acc) {
+  epilogue_store(p, b, y, x, co, acc);
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const TcParams q, const ConvParams p) {
@@ -183,10 +213,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
 
-  const uint32_t w_bytes = 9u * (uint32_t)q.n_tile * 128u;         // multiple of 1024 (n_tile % 16 == 0 -> 18432 | ...)
+  const uint32_t w_bytes = 9u * (uint32_t)q.n_tile * 128u;
+  const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base;
-  const uint32_t a_smem = base + ((w_bytes + 1023u) & ~1023u);
-  uint8_t* tail = smem + ((w_bytes + 1023u) & ~1023u) + (size_t)q.stages * q.stage_bytes;
+  const uint32_t a_smem = base + w_span;
+  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * q.stage_bytes;
+  uint8_t* tail = smem + w_span + (size_t)q.stages * q.stage_bytes + 4u * q.epi_warp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);               // full[S], empty[S], w_full, tfull[2], tempty[2]
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -195,7 +227,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 1 + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 3 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile]
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunk = (int)(blockIdx.x % (unsigned)q.n_chunks);
@@ -243,6 +275,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_wait(wfull_bar, 0);
       int s = 0; uint32_t ph = 0; int it = 0;
       const uint32_t sbo = (uint32_t)q.pitch * 128u;
+      const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
+      const uint32_t b_tap_step = ((uint32_t)q.n_tile * 128u) >> 4;      // descriptor address units (16 B)
       for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
@@ -251,18 +285,27 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_after();
         const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t a_tap = (q.n_loads == 1)
-                                     ? a_stage + (uint32_t)(dy * q.pitch + dx) * 128u
-                                     : a_stage + (uint32_t)dx * q.load_bytes + (uint32_t)(dy * q.pitch) * 128u;
-          const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
+        if (q.base_off_mode == 0) {
+          // start-address field arithmetic: the tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
+          const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = make_desc(a_tap + (uint32_t)k * 32u, sbo, q.base_off_mode);
-            const uint64_t bd = make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0);
-            umma_f16(d_tmem, ad, bd, q.idesc, (uint32_t)((tap | k) != 0));
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_off = (q.n_loads == 1) ? (uint32_t)(dy * q.pitch + dx) * 8u
+                                                    : ((uint32_t)dx * q.load_bytes >> 4) + (uint32_t)(dy * q.pitch) * 8u;
+            const uint64_t ad = a_desc0 + a_off, bd = b_desc0 + (uint64_t)tap * b_tap_step;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((tap | k) != 0));
+          }
+        } else {
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap) {
+            const int dy = tap / 3, dx = tap - dy * 3;
+            const uint32_t a_tap = a_stage + (uint32_t)(dy * q.pitch + dx) * 128u;
+            const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
+            for (int k = 0; k < 4; ++k)
+              umma_f16(d_tmem, make_desc(a_tap + (uint32_t)k * 32u, sbo, 1), make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0),
+                       q.idesc, (uint32_t)((tap | k) != 0));
           }
         }
         umma_commit(empty_bar(s));       // smem stage reusable once these MMAs have read it
@@ -271,20 +314,85 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
     const int m = quad * 32 + lane;                     // GEMM row = pixel within the tile
     const int ty = m >> 3, tx = m & 7;
+    // depth_to_space constants of this CTA's channel chunk (vector path: the chunk maps to one (i, j) sub-pixel)
+    const int r = p.d2s;
+    int qi = 0, qj = 0, c_out0 = co_base;
+    if (r > 1) { const int qq = co_base / p.c_post; c_out0 = co_base - qq * p.c_post; qi = qq / r; qj = qq - qi * r; }
+    const size_t OW = (size_t)p.W * r, OH = (size_t)p.H * r;
+    auto out_pixel = [&](int b, int oy, int ox) -> size_t {
+      return ((size_t)b * OH + (size_t)oy * r + qi) * OW + (size_t)ox * r + qj;
+    };
+    // per-warp staging: F = fp32 rows (residual prefetch / fp32 output), H = 16-bit output rows; XOR-swizzled 16-B chunks
+    const uint32_t f_rb = (uint32_t)q.n_tile * 4u, h_rb = (uint32_t)q.n_tile * 2u;
+    const uint32_t f_cpr = f_rb >> 4, h_cpr = h_rb >> 4;
+    const uint32_t f_swz = f_cpr > 8 ? 7u : f_cpr - 1u, h_swz = h_cpr > 8 ? 7u : h_cpr - 1u;
+    const uint32_t my_epi = epi_smem + (uint32_t)quad * q.epi_warp_bytes;
+    const uint32_t h_buf = my_epi + (uint32_t)q.f_bufs * 32u * f_rb;
+    const int f_dtype_dst = q.f_dst, h_dst = q.h_dst;
+    const int h_dtype = h_dst == 1 ? p.y_dtype : p.y2_dtype;
+
+    auto prefetch_res = [&](int tile, int fb) {
+      const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
+      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
+      const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
+      const uint32_t rows_per_it = 32u / f_cpr;
+      const uint32_t ch = (uint32_t)lane % f_cpr, rsub = (uint32_t)lane / f_cpr;
+      for (uint32_t i = 0; i < f_cpr; ++i) {
+        const uint32_t row = i * rows_per_it + rsub;
+        const int mm = quad * 32 + (int)row;
+        const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+        if (oy < p.H && ox < p.W) {
+          const float* src = reinterpret_cast<const float*>(p.res1) + out_pixel(b, oy, ox) * p.res1_cstride + c_out0 + ch * 4u;
+          cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src);
+        }
+      }
+    };
+    auto copy_out = [&](uint32_t buf, uint32_t rb, uint32_t cpr, uint32_t swz, void* dst, int cstride, int coffset,
+                        int esize, int b, int y0, int x0) {
+      const uint32_t rows_per_it = 32u / cpr;
+      const uint32_t ch = (uint32_t)lane % cpr, rsub = (uint32_t)lane / cpr;
+      for (uint32_t i = 0; i < cpr; ++i) {
+        const uint32_t row = i * rows_per_it + rsub;
+        const int mm = quad * 32 + (int)row;
+        const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
+        if (oy < p.H && ox < p.W) {
+          const uint4 v = lds128(buf + row * rb + ((ch ^ (row & swz)) << 4));
+          uint8_t* g = reinterpret_cast<uint8_t*>(dst) +
+                       (out_pixel(b, oy, ox) * (size_t)cstride + (size_t)(coffset + c_out0)) * (size_t)esize + ch * 16u;
+          *reinterpret_cast<uint4*>(g) = v;
+        }
+      }
+    };
+
     int it = 0;
+    if (q.epi_mode == 1 && q.res_prefetch) {
+      if (first_tile < q.total_tiles) prefetch_res(first_tile, 0);
+      cp_async_commit();
+    }
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
-      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-      const int oy = (r / q.tiles_x) * kTileH + ty, ox = (r % q.tiles_x) * kTileW + tx;
+      const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
+      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
+      const int oy = y0 + ty, ox = x0 + tx;
       const bool valid = oy < p.H && ox < p.W;
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      uint32_t f_buf = my_epi;
+      if (q.epi_mode == 1 && q.res_prefetch) {
+        if (tile + tile_step < q.total_tiles) prefetch_res(tile + tile_step, (it + 1) & 1);
+        cp_async_commit();
+        cp_async_wait1();                               // this tile's residual rows have landed
+        __syncwarp();
+        f_buf = my_epi + (uint32_t)(it & 1) * 32u * f_rb;
+      }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile);
+      const size_t my_pix = valid ? out_pixel(b, oy, ox) : 0;
+#pragma unroll 1
       for (int c0 = 0; c0 < q.n_tile; c0 += 16) {
         uint32_t rr[16];
         __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
@@ -294,29 +402,49 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        if (valid && q.vec_ok) {
+        if (q.epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            const int co = co_base + c0 + g * 8;
-            if (co >= p.cout) break;
-            size_t out_pix; int c_out;
-            d2s_map(p, b, oy, ox, co, out_pix, c_out);
+            const int cc = c0 + g * 8;                  // channel offset inside this CTA's chunk
             float v[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc), b1 = *reinterpret_cast<const float4*>(bias_s + cc + 4);
+            v[0] = __uint_as_float(rr[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[g * 8 + 1]) + b0.y;
+            v[2] = __uint_as_float(rr[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[g * 8 + 3]) + b0.w;
+            v[4] = __uint_as_float(rr[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[g * 8 + 5]) + b1.y;
+            v[6] = __uint_as_float(rr[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[g * 8 + 7]) + b1.w;
+            if (p.act == SRB_ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float a = __uint_as_float(rr[g * 8 + e]) + bias_s[c0 + g * 8 + e];
-              const float slope = (p.act == SRB_ACT_PRELU) ? __ldg(p.prelu + c_out + e) : p.act_slope;
-              v[e] = apply_act(a, p.act, slope) * p.alpha;
+              for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            } else if (p.act != SRB_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float slope = (p.act == SRB_ACT_PRELU) ? __ldg(p.prelu + c_out0 + cc + e) : p.act_slope;
+                v[e] = act_generic(v[e], p.act, slope);
+              }
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+            const uint32_t fc = (uint32_t)cc >> 2;      // first of the two fp32 chunks of these 8 channels
+            const uint32_t f_a0 = f_buf + (uint32_t)lane * f_rb + (((fc) ^ ((uint32_t)lane & f_swz)) << 4);
+            const uint32_t f_a1 = f_buf + (uint32_t)lane * f_rb + (((fc + 1u) ^ ((uint32_t)lane & f_swz)) << 4);
             if (p.res1) {
               float rv[8];
-              load8(p.res1, p.res1_dtype, out_pix * p.res1_cstride + c_out, rv);
+              if (q.res_prefetch) {
+                const uint4 u0 = lds128(f_a0), u1 = lds128(f_a1);
+                rv[0] = __uint_as_float(u0.x); rv[1] = __uint_as_float(u0.y); rv[2] = __uint_as_float(u0.z); rv[3] = __uint_as_float(u0.w);
+                rv[4] = __uint_as_float(u1.x); rv[5] = __uint_as_float(u1.y); rv[6] = __uint_as_float(u1.z); rv[7] = __uint_as_float(u1.w);
+              } else if (valid) {
+                load8(p.res1, p.res1_dtype, my_pix * p.res1_cstride + c_out0 + cc, rv);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) rv[e] = 0.f;
+              }
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta1, rv[e], v[e]);
             }
-            if (p.res2) {
+            if (p.res2 && valid) {
               float rv[8];
-              load8(p.res2, p.res2_dtype, out_pix * p.res2_cstride + c_out, rv);
+              load8(p.res2, p.res2_dtype, my_pix * p.res2_cstride + c_out0 + cc, rv);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta2, rv[e], v[e]);
             }
@@ -324,16 +452,34 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
             }
-            store8(p.y, p.y_dtype, out_pix * p.y_cstride + p.y_coffset + c_out, v);
-            if (p.y2) store8(p.y2, p.y2_dtype, out_pix * p.y2_cstride + c_out, v);
+            if (f_dtype_dst) {
+              sts128(f_a0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+              sts128(f_a1, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
+            }
+            if (h_dst) {
+              const uint32_t hc = (uint32_t)cc >> 3;
+              sts128(h_buf + (uint32_t)lane * h_rb + ((hc ^ ((uint32_t)lane & h_swz)) << 4),
+                     make_uint4(pack2(v[0], v[1], h_dtype), pack2(v[2], v[3], h_dtype), pack2(v[4], v[5], h_dtype),
+                                pack2(v[6], v[7], h_dtype)));
+            }
           }
         } else if (valid) {
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const int co = co_base + c0 + e;
-            if (co < p.cout) epilogue_store(p, b, oy, ox, co, __uint_as_float(rr[e]));   // adds p.bias[co] itself
+            if (co < p.cout) epilogue_store_generic(p, b, oy, ox, co, __uint_as_float(rr[e]));   // adds p.bias[co] itself
           }
         }
+      }
+      if (q.epi_mode == 1) {
+        __syncwarp();                                   // rows written by their owner lanes -> read by all lanes
+        if (f_dtype_dst)
+          copy_out(f_buf, f_rb, f_cpr, f_swz, f_dtype_dst == 1 ? p.y : p.y2, f_dtype_dst == 1 ? p.y_cstride : p.y2_cstride,
+                   f_dtype_dst == 1 ? p.y_coffset : 0, 4, b, y0, x0);
+        if (h_dst)
+          copy_out(h_buf, h_rb, h_cpr, h_swz, h_dst == 1 ? p.y : p.y2, h_dst == 1 ? p.y_cstride : p.y2_cstride,
+                   h_dst == 1 ? p.y_coffset : 0, 2, b, y0, x0);
+        __syncwarp();                                   // staging rows are free for the next tile
       }
     }
   }
@@ -410,21 +556,34 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   while (q.tmem_cols < (uint32_t)(2 * q.n_tile)) q.tmem_cols <<= 1;
   const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  const bool d2s_vec = (p.d2s == 1) || (p.c_post % 8 == 0);
-  q.vec_ok = d2s_vec && (p.cout % 8 == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
+  // staged vector epilogue: one fp32 and/or one 16-bit destination, the chunk maps to one depth_to_space sub-pixel
+  const bool is16 = true;
+  (void)is16;
+  auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
+  const bool two_outputs = p.y2 != nullptr;
+  bool vec = (q.n_tile == 16 || q.n_tile == 32 || q.n_tile == 64) && (p.cout % q.n_tile == 0) &&
+             (p.d2s == 1 || p.c_post % q.n_tile == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
              (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
              (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
              (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
+  if (two_outputs && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
+  q.epi_mode = vec ? 1 : 0;
+  if (vec) {
+    q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
+    q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
+    q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
+    q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
+    q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * q.n_tile * 4 + (q.h_dst ? 32 * q.n_tile * 2 : 0));
+  }
 
   const size_t w_bytes = ((size_t)9 * q.n_tile * 128 + 1023) & ~(size_t)1023;
   const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)q.n_tile * sizeof(float);
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  q.stages = kMaxStages;
-  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + tail_bytes; };
+  q.stages = 4;
+  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + 4 * (size_t)q.epi_warp_bytes + tail_bytes; };
   while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
-  if (q.stages > 4) q.stages = 4;
   const size_t smem = smem_need(q.stages);
   SRB_REQUIRE(smem <= (size_t)max_smem, "conv(tcgen05): tile does not fit shared memory");
 

@@ -47,6 +47,7 @@ class DeviceModel:
                 self.layers[base] = ops.ConvWeights(self.weights[name], self.weights.get(base + "/bias"),
                                                    self.weights.get(base + "/prelu"))
         self.max_device_batch = None   # images per launch sequence (None = whole input)
+        self.event_hook = None         # bench.py: called with a tag at kernel-span boundaries
 
     # -- Keras-like surface ---------------------------------------------------------------
     def count_params(self):
@@ -76,19 +77,50 @@ class DeviceModel:
         outs = [self.forward_device(x[i:i + mb]) for i in range(0, x.shape[0], mb)]
         return torch.cat(outs, 0)
 
-    def predict(self, x, batch_size=32, verbose=0):
+    def predict(self, x, batch_size=32, verbose=0, out=None):
         """numpy in, numpy out (``self.model.predict(patches, batch_size=16, verbose=0)``,
-        SRCNN_model.py:210, EDSR_model.py:274).  ``batch_size`` is accepted for signature parity;
-        the device processes the whole array in as few launch sequences as memory allows."""
+        SRCNN_model.py:210, EDSR_model.py:274).  ``batch_size`` is accepted for signature parity; the
+        device works in micro-batches of ``max_device_batch`` images, with the host->device copy of
+        micro-batch i+1 and the device->host copy of micro-batch i-1 overlapping the kernels of
+        micro-batch i on separate copy streams.  ``out`` may be a preallocated (ideally pinned) host array."""
         torch = _torch()
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 4:
             raise ValueError(f"expected a 4-D NHWC array, got shape {x.shape}")
-        if x.shape[0] == 0:
-            h, w = x.shape[1] * self.output_scale(), x.shape[2] * self.output_scale()
-            return np.zeros((0, h, w, x.shape[3]), dtype=np.float32)
-        y = self.predict_device(torch.from_numpy(x).cuda(non_blocking=True))
-        return y.cpu().numpy()
+        n, s = x.shape[0], self.output_scale()
+        out_shape = self.output_shape(x.shape)
+        if out is None:
+            out = np.empty(out_shape, dtype=np.float32)
+        elif tuple(out.shape) != tuple(out_shape) or out.dtype != np.float32:
+            raise ValueError(f"out must be float32 of shape {out_shape}")
+        if n == 0:
+            return out
+        xt, ot = torch.from_numpy(x), torch.from_numpy(out)
+        mb = self.max_device_batch or 64
+        comp = torch.cuda.current_stream()
+        cin, cout = self._copy_streams()
+        for i in range(0, n, mb):
+            with torch.cuda.stream(cin):
+                xd = xt[i:i + mb].to("cuda", non_blocking=True)
+            comp.wait_stream(cin)
+            xd.record_stream(comp)
+            y = self.forward_device(xd)
+            cout.wait_stream(comp)
+            with torch.cuda.stream(cout):
+                ot[i:i + mb].copy_(y, non_blocking=True)
+            y.record_stream(cout)
+        cout.synchronize()
+        return out
+
+    def output_shape(self, in_shape):
+        s = self.output_scale()
+        return (in_shape[0], in_shape[1] * s, in_shape[2] * s, in_shape[3])
+
+    def _copy_streams(self):
+        torch = _torch()
+        if getattr(self, "_streams", None) is None:
+            self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+        return self._streams
 
     __call__ = predict_device
 
@@ -125,6 +157,8 @@ class EDSRNet(DeviceModel):
         if self.fp32_trunk:
             # trunk in fp32 (y), 16-bit copy (y2) as the next conv's tensor-core operand
             head, h = ops.conv2d(x, L["head"], out_dtype=torch.float32, out2_dtype=dt)
+            if self.event_hook:
+                self.event_hook("tc_begin")
             trunk = head
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
@@ -142,7 +176,10 @@ class EDSRNet(DeviceModel):
         else:
             h = ops.conv2d(h, L["up0"], d2s=2, out_dtype=dt)
             h = ops.conv2d(h, L["up1"], d2s=2, out_dtype=dt)
-        return ops.conv2d(h, L["tail"], clip01=True, out_dtype=torch.float32)
+        y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=torch.float32)
+        if self.event_hook and self.fp32_trunk:
+            self.event_hook("tc_end")
+        return y
 
 
 class ESPCNNet(DeviceModel):
@@ -279,7 +316,7 @@ class VGG16ClassifierNet(DeviceModel):
         return ops.gap_dense_softmax(h, d["dense/kernel"], d["dense/bias"], d["predictions/kernel"],
                                      d["predictions/bias"])
 
-    def predict(self, x, batch_size=32, verbose=0):
+    def predict(self, x, batch_size=32, verbose=0, out=None):
         torch = _torch()
         x = np.ascontiguousarray(x, dtype=np.float32)
         return self.predict_device(torch.from_numpy(x).cuda(non_blocking=True)).cpu().numpy()

@@ -16,6 +16,18 @@ def _torch():
     return capi.require_cuda()
 
 
+# kernels launched by this process through the C ABI (bench.py reports it as gpu_launches)
+_LAUNCHES = [0]
+
+
+def reset_launch_count():
+    _LAUNCHES[0] = 0
+
+
+def launch_count():
+    return _LAUNCHES[0]
+
+
 def _check_nhwc(t, name):
     if t.dim() != 4:
         raise ValueError(f"{name} must be a 4-D NHWC tensor, got shape {tuple(t.shape)}")
@@ -49,6 +61,7 @@ def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False):
         capi.check(capi.lib().srb_psnr_ssim_f32(capi.ptr(a), capi.ptr(b), B, H, W, Cc, float(max_val),
                                                 capi.ptr(psnr), capi.ptr(ssim), capi.ptr(mse), capi.ptr(sums),
                                                 capi.ptr(ws), ws_bytes, capi.stream_ptr()))
+    _LAUNCHES[0] += 2
     return (psnr, ssim, mse) if want_mse else (psnr, ssim)
 
 
@@ -70,6 +83,7 @@ def bicubic(src, dst_h, dst_w, clip01=False, fixed_point=False):
                                                  int(bool(fixed_point)), capi.stream_ptr()))
         else:
             raise TypeError(f"bicubic supports float32 and uint8, got {src.dtype}")
+    _LAUNCHES[0] += 3
     return dst
 
 
@@ -88,6 +102,7 @@ def pad_extract(image, patch, stride):
     with torch.cuda.device(image.device):
         capi.check(capi.lib().srb_pad_extract_f32(capi.ptr(image), H, W, Cc, int(patch), int(stride),
                                                   capi.ptr(patches), capi.stream_ptr()))
+    _LAUNCHES[0] += 1
     return patches, (ph, pw, ny, nx)
 
 
@@ -104,6 +119,7 @@ def overlap_add(patches, ny, nx, stride_out, out_h, out_w):
     with torch.cuda.device(patches.device):
         capi.check(capi.lib().srb_overlap_add_f32(capi.ptr(patches), int(ny), int(nx), P, int(stride_out), Cc,
                                                   capi.ptr(out), int(out_h), int(out_w), capi.stream_ptr()))
+    _LAUNCHES[0] += 1
     return out
 
 
@@ -188,6 +204,7 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     a.clip01, a.d2s, a.engine = int(bool(clip01)), r, int(engine)
     with torch.cuda.device(x.device):
         capi.check(capi.lib().srb_conv2d_nhwc(C.byref(a), capi.stream_ptr()))
+    _LAUNCHES[0] += 1
     return out if out2 is None else (out, out2)
 
 
