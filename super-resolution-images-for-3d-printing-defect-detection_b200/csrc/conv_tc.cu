@@ -13,7 +13,8 @@
 //   * the epilogue (4 warps, one pixel per thread) fuses bias, activation, alpha, two scaled residuals,
 //     clip, the depth_to_space address permutation and an optional second-dtype copy of the output.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (two warps per TMEM lane quadrant, each taking half of the accumulator columns).
 #include "common.cuh"
 #include "conv_common.cuh"
 #include <cuda.h>
@@ -22,7 +23,8 @@ namespace srb {
 
 constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM rows
 constexpr int kHaloH = kTileH + 2;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 6;
 
 struct TcParams {
@@ -38,7 +40,8 @@ struct TcParams {
   int base_off_mode;     // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
   uint32_t tmem_cols;
   uint32_t idesc;
-  int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses)
+  int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses);
+                         // 2: few-channel epilogue (cout <= 4, e.g. the RGB tail)
   int f_bufs;            // per-warp fp32 staging buffers (0, 1, or 2 when the residual is prefetched)
   int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
   int res_prefetch;      // res1 is fp32 and is prefetched into the F buffers with cp.async
@@ -69,6 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n"
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .b32 rx;\n"
+      ".reg .pred px;\n"
+      "elect.sync rx|px, 0xffffffff;\n"
+      "selp.b32 %0, 1, 0, px;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -218,7 +232,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t w_smem = base;
   const uint32_t a_smem = base + w_span;
   const uint32_t epi_smem = a_smem + (uint32_t)q.stages * q.stage_bytes;
-  uint8_t* tail = smem + w_span + (size_t)q.stages * q.stage_bytes + 4u * q.epi_warp_bytes;
+  uint8_t* tail = smem + w_span + (size_t)q.stages * q.stage_bytes + (uint32_t)kEpiWarps * q.epi_warp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);               // full[S], empty[S], w_full, tfull[2], tempty[2]
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -238,7 +252,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * kEpiWarps); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
@@ -253,135 +267,155 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // the whole warp runs the (warp-uniform) loop so that addresses live in uniform registers; one elected
+    // lane issues the asynchronous copies
+    if (elect_one()) {
       mbar_expect_tx(wfull_bar, w_bytes);
       for (int t = 0; t < 9; ++t)
         tma_load_2d(w_smem + (uint32_t)t * (uint32_t)q.n_tile * 128u, &tmap_w, wfull_bar, 0, t * q.w_rows + co_base);
-      int s = 0; uint32_t ph = 0;
-      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
-        const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-        const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * kTileW;
-        mbar_wait(empty_bar(s), ph ^ 1u);
+    }
+    __syncwarp();
+    int s = 0; uint32_t ph = 0;
+    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * kTileW;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
+      if (elect_one()) {
         mbar_expect_tx(full_bar(s), q.load_bytes * (uint32_t)q.n_loads);
-        const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
         for (int l = 0; l < q.n_loads; ++l)
           tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
-        if (++s == q.stages) { s = 0; ph ^= 1u; }
       }
+      __syncwarp();
+      if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      mbar_wait(wfull_bar, 0);
-      int s = 0; uint32_t ph = 0; int it = 0;
-      const uint32_t sbo = (uint32_t)q.pitch * 128u;
-      const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
-      const uint32_t b_tap_step = ((uint32_t)q.n_tile * 128u) >> 4;      // descriptor address units (16 B)
-      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
-        if (q.base_off_mode == 0) {
-          // start-address field arithmetic: the tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
-          const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
+    // warp-uniform loop (descriptors in uniform registers); one elected lane issues the 36 MMAs of a tile
+    mbar_wait(wfull_bar, 0);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    const uint32_t sbo = (uint32_t)q.pitch * 128u;
+    const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
+    const uint32_t b_tap_step = ((uint32_t)q.n_tile * 128u) >> 4;      // descriptor address units (16 B)
+    const uint32_t a_dy = (uint32_t)q.pitch * 8u;                       // one halo row, in 16-B units
+    const uint32_t a_dx = (q.n_loads == 1) ? 8u : (q.load_bytes >> 4);  // one pixel / one dx sub-tile
+    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
+      if (q.base_off_mode == 0) {
+        // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
+        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
+        if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_off = (q.n_loads == 1) ? (uint32_t)(dy * q.pitch + dx) * 8u
-                                                    : ((uint32_t)dx * q.load_bytes >> 4) + (uint32_t)(dy * q.pitch) * 8u;
-            const uint64_t ad = a_desc0 + a_off, bd = b_desc0 + (uint64_t)tap * b_tap_step;
+            const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
+            const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((tap | k) != 0));
           }
-        } else {
-#pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap) {
-            const int dy = tap / 3, dx = tap - dy * 3;
-            const uint32_t a_tap = a_stage + (uint32_t)(dy * q.pitch + dx) * 128u;
-            const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
-            for (int k = 0; k < 4; ++k)
-              umma_f16(d_tmem, make_desc(a_tap + (uint32_t)k * 32u, sbo, 1), make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0),
-                       q.idesc, (uint32_t)((tap | k) != 0));
-          }
+          umma_commit(empty_bar(s));       // smem stage reusable once these MMAs have read it
+          umma_commit(tfull_bar(acc));     // accumulator complete
         }
-        umma_commit(empty_bar(s));       // smem stage reusable once these MMAs have read it
-        umma_commit(tfull_bar(acc));     // accumulator complete
-        if (++s == q.stages) { s = 0; ph ^= 1u; }
+      } else if (elect_one()) {            // diagnostic variants 1 / 3 (descriptor base-offset field set)
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const int dy = tap / 3, dx = tap - dy * 3;
+          const uint32_t a_tap = a_stage + (uint32_t)(dy * q.pitch + dx) * 128u;
+          const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
+          for (int k = 0; k < 4; ++k)
+            umma_f16(d_tmem, make_desc(a_tap + (uint32_t)k * 32u, sbo, 1), make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0),
+                     q.idesc, (uint32_t)((tap | k) != 0));
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
       }
+      __syncwarp();
+      if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
-    const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+    // 8 warps: warp w may only touch TMEM lanes [32 * (w % 4), +32); the two warps of a lane quadrant split the
+    // accumulator columns (output channels) in halves when the chunk has >= 32 channels.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const int split = q.n_tile >= 32 ? 2 : 1;
+    const int half = ew >> 2;
+    const bool active = half < split;
+    const int ncols = q.n_tile / split;                 // channels this warp handles per pixel
+    const int col0 = half * ncols * (split - 1);        // first accumulator column of this warp
     const int m = quad * 32 + lane;                     // GEMM row = pixel within the tile
-    const int ty = m >> 3, tx = m & 7;
     // depth_to_space constants of this CTA's channel chunk (vector path: the chunk maps to one (i, j) sub-pixel)
     const int r = p.d2s;
     int qi = 0, qj = 0, c_out0 = co_base;
     if (r > 1) { const int qq = co_base / p.c_post; c_out0 = co_base - qq * p.c_post; qi = qq / r; qj = qq - qi * r; }
+    c_out0 += col0;
     const size_t OW = (size_t)p.W * r, OH = (size_t)p.H * r;
-    auto out_pixel = [&](int b, int oy, int ox) -> size_t {
-      return ((size_t)b * OH + (size_t)oy * r + qi) * OW + (size_t)ox * r + qj;
+    const uint32_t pitch_y = (uint32_t)(r * OW);        // output pixels between consecutive tile rows
+    auto tile_pixel = [&](int b, int y0, int x0) -> size_t {
+      return ((size_t)b * OH + (size_t)y0 * r + qi) * OW + (size_t)x0 * r + qj;
     };
+    auto pix_off = [&](int mm) -> uint32_t { return (uint32_t)(mm >> 3) * pitch_y + (uint32_t)(mm & 7) * (uint32_t)r; };
     // per-warp staging: F = fp32 rows (residual prefetch / fp32 output), H = 16-bit output rows; XOR-swizzled 16-B chunks
-    const uint32_t f_rb = (uint32_t)q.n_tile * 4u, h_rb = (uint32_t)q.n_tile * 2u;
+    const uint32_t f_rb = (uint32_t)ncols * 4u, h_rb = (uint32_t)ncols * 2u;
     const uint32_t f_cpr = f_rb >> 4, h_cpr = h_rb >> 4;
     const uint32_t f_swz = f_cpr > 8 ? 7u : f_cpr - 1u, h_swz = h_cpr > 8 ? 7u : h_cpr - 1u;
-    const uint32_t my_epi = epi_smem + (uint32_t)quad * q.epi_warp_bytes;
+    const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
     const uint32_t h_buf = my_epi + (uint32_t)q.f_bufs * 32u * f_rb;
-    const int f_dtype_dst = q.f_dst, h_dst = q.h_dst;
+    const int f_dst = q.f_dst, h_dst = q.h_dst;
     const int h_dtype = h_dst == 1 ? p.y_dtype : p.y2_dtype;
+    const uint32_t my_row_sw = (uint32_t)lane;          // this lane's staging row
 
+    // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
       const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
+      const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
+      const float* src0 = reinterpret_cast<const float*>(p.res1) + tile_pixel(b, y0, x0) * (size_t)p.res1_cstride + c_out0;
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
       const uint32_t rows_per_it = 32u / f_cpr;
       const uint32_t ch = (uint32_t)lane % f_cpr, rsub = (uint32_t)lane / f_cpr;
-      for (uint32_t i = 0; i < f_cpr; ++i) {
-        const uint32_t row = i * rows_per_it + rsub;
+      for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
         const int mm = quad * 32 + (int)row;
-        const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
-        if (oy < p.H && ox < p.W) {
-          const float* src = reinterpret_cast<const float*>(p.res1) + out_pixel(b, oy, ox) * p.res1_cstride + c_out0 + ch * 4u;
-          cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src);
-        }
+        if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
+          cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src0 + (size_t)pix_off(mm) * (size_t)p.res1_cstride + ch * 4u);
       }
     };
     auto copy_out = [&](uint32_t buf, uint32_t rb, uint32_t cpr, uint32_t swz, void* dst, int cstride, int coffset,
-                        int esize, int b, int y0, int x0) {
+                        uint32_t esize, size_t tpix, bool full, int y0, int x0) {
+      uint8_t* dst0 = reinterpret_cast<uint8_t*>(dst) + (tpix * (size_t)cstride + (size_t)(coffset + c_out0)) * esize;
+      const uint32_t pix_bytes = (uint32_t)cstride * esize;
       const uint32_t rows_per_it = 32u / cpr;
       const uint32_t ch = (uint32_t)lane % cpr, rsub = (uint32_t)lane / cpr;
-      for (uint32_t i = 0; i < cpr; ++i) {
-        const uint32_t row = i * rows_per_it + rsub;
+      for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
         const int mm = quad * 32 + (int)row;
-        const int oy = y0 + (mm >> 3), ox = x0 + (mm & 7);
-        if (oy < p.H && ox < p.W) {
+        if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W)) {
           const uint4 v = lds128(buf + row * rb + ((ch ^ (row & swz)) << 4));
-          uint8_t* g = reinterpret_cast<uint8_t*>(dst) +
-                       (out_pixel(b, oy, ox) * (size_t)cstride + (size_t)(coffset + c_out0)) * (size_t)esize + ch * 16u;
-          *reinterpret_cast<uint4*>(g) = v;
+          *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes + ch * 16u) = v;
         }
       }
     };
 
     int it = 0;
-    if (q.epi_mode == 1 && q.res_prefetch) {
+    const bool staged = q.epi_mode == 1 && active;
+    const bool prefetch = staged && q.res_prefetch;
+    if (prefetch) {
       if (first_tile < q.total_tiles) prefetch_res(first_tile, 0);
       cp_async_commit();
     }
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
       const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
-      const int oy = y0 + ty, ox = x0 + tx;
-      const bool valid = oy < p.H && ox < p.W;
+      const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
+      const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       uint32_t f_buf = my_epi;
-      if (q.epi_mode == 1 && q.res_prefetch) {
+      if (prefetch) {
         if (tile + tile_step < q.total_tiles) prefetch_res(tile + tile_step, (it + 1) & 1);
         cp_async_commit();
         cp_async_wait1();                               // this tile's residual rows have landed
@@ -390,24 +424,31 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile);
-      const size_t my_pix = valid ? out_pixel(b, oy, ox) : 0;
+      if (!active) {                                    // chunk too narrow to split: this warp only keeps the protocol
+        tc_fence_before();
+        mbar_arrive(tempty_bar(acc));
+        continue;
+      }
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
+      const size_t tpix = tile_pixel(b, y0, x0);
+      const size_t my_pix = tpix + pix_off(m);
 #pragma unroll 1
-      for (int c0 = 0; c0 < q.n_tile; c0 += 16) {
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t rr[16];
         __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld16(t_row + (uint32_t)c0, rr);
         tmem_ld_wait();
-        if (c0 + 16 >= q.n_tile) {                      // last read of this accumulator: hand it back to the MMA warp
+        if (c0 + 16 >= ncols) {                         // last read of this accumulator: hand it back to the MMA warp
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
         if (q.epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
-            const int cc = c0 + g * 8;                  // channel offset inside this CTA's chunk
+            const int cc = c0 + g * 8;                  // channel offset inside this warp's column range
             float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + cc), b1 = *reinterpret_cast<const float4*>(bias_s + cc + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col0 + cc);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col0 + cc + 4);
             v[0] = __uint_as_float(rr[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[g * 8 + 1]) + b0.y;
             v[2] = __uint_as_float(rr[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[g * 8 + 3]) + b0.w;
             v[4] = __uint_as_float(rr[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[g * 8 + 5]) + b1.y;
@@ -422,11 +463,13 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 v[e] = act_generic(v[e], p.act, slope);
               }
             }
+            if (p.alpha != 1.f) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+              for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
+            }
             const uint32_t fc = (uint32_t)cc >> 2;      // first of the two fp32 chunks of these 8 channels
-            const uint32_t f_a0 = f_buf + (uint32_t)lane * f_rb + (((fc) ^ ((uint32_t)lane & f_swz)) << 4);
-            const uint32_t f_a1 = f_buf + (uint32_t)lane * f_rb + (((fc + 1u) ^ ((uint32_t)lane & f_swz)) << 4);
+            const uint32_t f_a0 = f_buf + my_row_sw * f_rb + (((fc) ^ (my_row_sw & f_swz)) << 4);
+            const uint32_t f_a1 = f_buf + my_row_sw * f_rb + (((fc + 1u) ^ (my_row_sw & f_swz)) << 4);
             if (p.res1) {
               float rv[8];
               if (q.res_prefetch) {
@@ -452,33 +495,52 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
             }
-            if (f_dtype_dst) {
+            if (f_dst) {
               sts128(f_a0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
               sts128(f_a1, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
             }
             if (h_dst) {
               const uint32_t hc = (uint32_t)cc >> 3;
-              sts128(h_buf + (uint32_t)lane * h_rb + ((hc ^ ((uint32_t)lane & h_swz)) << 4),
+              sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4),
                      make_uint4(pack2(v[0], v[1], h_dtype), pack2(v[2], v[3], h_dtype), pack2(v[4], v[5], h_dtype),
                                 pack2(v[6], v[7], h_dtype)));
             }
           }
+        } else if (q.epi_mode == 2) {
+          // few output channels (the RGB tail layers): <= 4 channels per pixel, no residual, no shuffle
+          if (valid && c0 == 0) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[e] = __uint_as_float(rr[e]) + bias_s[e];
+              if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+              else if (p.act != SRB_ACT_NONE)
+                v[e] = act_generic(v[e], p.act, (p.act == SRB_ACT_PRELU && e < p.cout) ? __ldg(p.prelu + e) : p.act_slope);
+              v[e] *= p.alpha;
+              if (p.clip01) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
+            }
+            const size_t o = my_pix * p.y_cstride + p.y_coffset;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < p.cout) store_elem(p.y, p.y_dtype, o + e, v[e]);
+          }
         } else if (valid) {
+          const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int co = co_base + c0 + e;
+            const int co = co_base + col0 + c0 + e;
             if (co < p.cout) epilogue_store_generic(p, b, oy, ox, co, __uint_as_float(rr[e]));   // adds p.bias[co] itself
           }
         }
       }
       if (q.epi_mode == 1) {
         __syncwarp();                                   // rows written by their owner lanes -> read by all lanes
-        if (f_dtype_dst)
-          copy_out(f_buf, f_rb, f_cpr, f_swz, f_dtype_dst == 1 ? p.y : p.y2, f_dtype_dst == 1 ? p.y_cstride : p.y2_cstride,
-                   f_dtype_dst == 1 ? p.y_coffset : 0, 4, b, y0, x0);
+        if (f_dst)
+          copy_out(f_buf, f_rb, f_cpr, f_swz, f_dst == 1 ? p.y : p.y2, f_dst == 1 ? p.y_cstride : p.y2_cstride,
+                   f_dst == 1 ? p.y_coffset : 0, 4u, tpix, full, y0, x0);
         if (h_dst)
           copy_out(h_buf, h_rb, h_cpr, h_swz, h_dst == 1 ? p.y : p.y2, h_dst == 1 ? p.y_cstride : p.y2_cstride,
-                   h_dst == 1 ? p.y_coffset : 0, 2, b, y0, x0);
+                   h_dst == 1 ? p.y_coffset : 0, 2u, tpix, full, y0, x0);
         __syncwarp();                                   // staging rows are free for the next tile
       }
     }
@@ -568,12 +630,14 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
              (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
   if (two_outputs && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
   q.epi_mode = vec ? 1 : 0;
+  if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
   if (vec) {
     q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
     q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
     q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
     q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
-    q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * q.n_tile * 4 + (q.h_dst ? 32 * q.n_tile * 2 : 0));
+    const int ncols = q.n_tile >= 32 ? q.n_tile / 2 : q.n_tile;
+    q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * ncols * 4 + (q.h_dst ? 32 * ncols * 2 : 0));
   }
 
   const size_t w_bytes = ((size_t)9 * q.n_tile * 128 + 1023) & ~(size_t)1023;
@@ -582,7 +646,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   q.stages = 4;
-  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + 4 * (size_t)q.epi_warp_bytes + tail_bytes; };
+  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
   while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
   const size_t smem = smem_need(q.stages);
   SRB_REQUIRE(smem <= (size_t)max_smem, "conv(tcgen05): tile does not fit shared memory");
