@@ -71,6 +71,8 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int b, int y
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream);
+int conv_head_launch(const ConvParams& p, cudaStream_t stream);
+bool conv_head_eligible(const ConvParams& p);
 int conv_tc_launch(const ConvParams& p, cudaStream_t stream);
 bool conv_tc_eligible(const ConvParams& p);
 

@@ -96,6 +96,7 @@ conv_direct_kernel(const ConvParams p) {
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
+  if (conv_head_eligible(p)) return conv_head_launch(p, stream);   // RGB 3x3 head layers: coalesced-store kernel
   const int HH = kDT + p.kh - 1, HW = kDT + p.kw - 1, HWp = HW | 1;
   const size_t smem = ((size_t)kDCK * HH * HWp + (size_t)p.kw * kDCK * kDN) * sizeof(float);
   SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);

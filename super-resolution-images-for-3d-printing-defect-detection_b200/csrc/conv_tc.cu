@@ -218,6 +218,11 @@ __device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, 
   epilogue_store(p, b, y, x, co, acc);
 }
 
+// kSpec selects a compile-time specialisation of the staged epilogue (the runtime-flag version costs ~14
+// instructions per channel, the specialised ones ~4):
+//   0 generic (all flags read at run time)      1 act none, 16-bit y            2 ReLU, 16-bit y
+//   3 fp32 residual, fp32 y + 16-bit y2         4 fp32 residual, 16-bit y
+template <int kSpec>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const TcParams q, const ConvParams p) {
@@ -400,9 +405,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     };
 
+    constexpr bool G = kSpec == 0;
+    const bool act_relu = G ? p.act == SRB_ACT_RELU : kSpec == 2;
+    const bool act_other = G && p.act != SRB_ACT_NONE && p.act != SRB_ACT_RELU;
+    const bool use_alpha = G ? p.alpha != 1.f : kSpec >= 3;
+    const bool has_res1 = G ? p.res1 != nullptr : kSpec >= 3;
+    const bool res_pref = G ? q.res_prefetch != 0 : kSpec >= 3;
+    const bool has_res2 = G && p.res2 != nullptr;
+    const bool do_clip = G && p.clip01;
+    const bool f_on = G ? f_dst != 0 : kSpec == 3;
+    const bool h_on = G ? h_dst != 0 : true;
+    const int epi_mode = G ? q.epi_mode : 1;
     int it = 0;
-    const bool staged = q.epi_mode == 1 && active;
-    const bool prefetch = staged && q.res_prefetch;
+    const bool staged = epi_mode == 1 && active;
+    const bool prefetch = staged && res_pref;
     if (prefetch) {
       if (first_tile < q.total_tiles) prefetch_res(first_tile, 0);
       cp_async_commit();
@@ -442,7 +458,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           tc_fence_before();
           mbar_arrive(tempty_bar(acc));
         }
-        if (q.epi_mode == 1) {
+        if (epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cc = c0 + g * 8;                  // channel offset inside this warp's column range
@@ -453,26 +469,26 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             v[2] = __uint_as_float(rr[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[g * 8 + 3]) + b0.w;
             v[4] = __uint_as_float(rr[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[g * 8 + 5]) + b1.y;
             v[6] = __uint_as_float(rr[g * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[g * 8 + 7]) + b1.w;
-            if (p.act == SRB_ACT_RELU) {
+            if (act_relu) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-            } else if (p.act != SRB_ACT_NONE) {
+            } else if (act_other) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float slope = (p.act == SRB_ACT_PRELU) ? __ldg(p.prelu + c_out0 + cc + e) : p.act_slope;
                 v[e] = act_generic(v[e], p.act, slope);
               }
             }
-            if (p.alpha != 1.f) {
+            if (use_alpha) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] *= p.alpha;
             }
             const uint32_t fc = (uint32_t)cc >> 2;      // first of the two fp32 chunks of these 8 channels
             const uint32_t f_a0 = f_buf + my_row_sw * f_rb + (((fc) ^ (my_row_sw & f_swz)) << 4);
             const uint32_t f_a1 = f_buf + my_row_sw * f_rb + (((fc + 1u) ^ (my_row_sw & f_swz)) << 4);
-            if (p.res1) {
+            if (has_res1) {
               float rv[8];
-              if (q.res_prefetch) {
+              if (res_pref) {
                 const uint4 u0 = lds128(f_a0), u1 = lds128(f_a1);
                 rv[0] = __uint_as_float(u0.x); rv[1] = __uint_as_float(u0.y); rv[2] = __uint_as_float(u0.z); rv[3] = __uint_as_float(u0.w);
                 rv[4] = __uint_as_float(u1.x); rv[5] = __uint_as_float(u1.y); rv[6] = __uint_as_float(u1.z); rv[7] = __uint_as_float(u1.w);
@@ -485,28 +501,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta1, rv[e], v[e]);
             }
-            if (p.res2 && valid) {
+            if (has_res2 && valid) {
               float rv[8];
               load8(p.res2, p.res2_dtype, my_pix * p.res2_cstride + c_out0 + cc, rv);
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fmaf(p.beta2, rv[e], v[e]);
             }
-            if (p.clip01) {
+            if (do_clip) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
             }
-            if (f_dst) {
+            if (f_on) {
               sts128(f_a0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
               sts128(f_a1, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
             }
-            if (h_dst) {
+            if (h_on) {
               const uint32_t hc = (uint32_t)cc >> 3;
-              sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4),
-                     make_uint4(pack2(v[0], v[1], h_dtype), pack2(v[2], v[3], h_dtype), pack2(v[4], v[5], h_dtype),
-                                pack2(v[6], v[7], h_dtype)));
+              uint4 pk;
+              if (h_dtype == SRB_BF16)
+                pk = make_uint4(pack2(v[0], v[1], SRB_BF16), pack2(v[2], v[3], SRB_BF16), pack2(v[4], v[5], SRB_BF16),
+                                pack2(v[6], v[7], SRB_BF16));
+              else
+                pk = make_uint4(pack2(v[0], v[1], SRB_F16), pack2(v[2], v[3], SRB_F16), pack2(v[4], v[5], SRB_F16),
+                                pack2(v[6], v[7], SRB_F16));
+              sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4), pk);
             }
           }
-        } else if (q.epi_mode == 2) {
+        } else if (epi_mode == 2) {
           // few output channels (the RGB tail layers): <= 4 channels per pixel, no residual, no shuffle
           if (valid && c0 == 0) {
             float v[4];
@@ -533,12 +554,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (q.epi_mode == 1) {
+      if (epi_mode == 1) {
         __syncwarp();                                   // rows written by their owner lanes -> read by all lanes
-        if (f_dst)
+        if (f_on)
           copy_out(f_buf, f_rb, f_cpr, f_swz, f_dst == 1 ? p.y : p.y2, f_dst == 1 ? p.y_cstride : p.y2_cstride,
                    f_dst == 1 ? p.y_coffset : 0, 4u, tpix, full, y0, x0);
-        if (h_dst)
+        if (h_on)
           copy_out(h_buf, h_rb, h_cpr, h_swz, h_dst == 1 ? p.y : p.y2, h_dst == 1 ? p.y_cstride : p.y2_cstride,
                    h_dst == 1 ? p.y_coffset : 0, 2u, tpix, full, y0, x0);
         __syncwarp();                                   // staging rows are free for the next tile
@@ -675,17 +696,30 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
   }
 
-  static size_t configured = 0;
-  if (smem > configured) {
-    SRB_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  int spec = 0;
+  if (q.epi_mode == 1 && !p.res2 && !p.clip01) {
+    if (!p.res1 && p.alpha == 1.f && q.f_dst == 0 && q.h_dst == 1 && !p.y2) {
+      if (p.act == SRB_ACT_NONE) spec = 1;
+      else if (p.act == SRB_ACT_RELU) spec = 2;
+    } else if (q.res_prefetch && p.act == SRB_ACT_NONE) {
+      if (q.f_dst == 1 && q.h_dst == 2) spec = 3;
+      else if (q.f_dst == 0 && q.h_dst == 1 && !p.y2) spec = 4;
+    }
+  }
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const ConvParams);
+  static const KernelFn kernels[5] = {conv3x3_tc_kernel<0>, conv3x3_tc_kernel<1>, conv3x3_tc_kernel<2>,
+                                      conv3x3_tc_kernel<3>, conv3x3_tc_kernel<4>};
+  static size_t configured[5] = {0, 0, 0, 0, 0};
+  if (smem > configured[spec]) {
+    SRB_CUDA(cudaFuncSetAttribute(kernels[spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[spec] = smem;
   }
   int grid = sm_count();
   grid -= grid % q.n_chunks;
   if (grid < q.n_chunks) grid = q.n_chunks;
   const long work = (long)q.total_tiles * q.n_chunks;
   if ((long)grid > work) grid = (int)(work - work % q.n_chunks);
-  conv3x3_tc_kernel<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
+  kernels[spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
   return launch_check("conv3x3_tc_kernel");
 }
 
