@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "conv_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace srb {
 
@@ -355,10 +356,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int col0 = half * ncols * (split - 1);        // first accumulator column of this warp
     const int m = quad * 32 + lane;                     // GEMM row = pixel within the tile
     // depth_to_space constants of this CTA's channel chunk (vector path: the chunk maps to one (i, j) sub-pixel)
+    // (per warp: with 128-channel chunks the two column halves belong to different sub-pixels)
     const int r = p.d2s;
-    int qi = 0, qj = 0, c_out0 = co_base;
-    if (r > 1) { const int qq = co_base / p.c_post; c_out0 = co_base - qq * p.c_post; qi = qq / r; qj = qq - qi * r; }
-    c_out0 += col0;
+    const int c_first = co_base + col0;                 // first conv-domain channel of this warp
+    int qi = 0, qj = 0, c_out0 = c_first;
+    if (r > 1) { const int qq = c_first / p.c_post; c_out0 = c_first - qq * p.c_post; qi = qq / r; qj = qq - qi * r; }
     const size_t OW = (size_t)p.W * r, OH = (size_t)p.H * r;
     const uint32_t pitch_y = (uint32_t)(r * OW);        // output pixels between consecutive tile rows
     auto tile_pixel = [&](int b, int y0, int x0) -> size_t {
@@ -369,6 +371,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t f_rb = (uint32_t)ncols * 4u, h_rb = (uint32_t)ncols * 2u;
     const uint32_t f_cpr = f_rb >> 4, h_cpr = h_rb >> 4;
     const uint32_t f_swz = f_cpr > 8 ? 7u : f_cpr - 1u, h_swz = h_cpr > 8 ? 7u : h_cpr - 1u;
+    const uint32_t f_lg = 31u - (uint32_t)__clz((int)f_cpr), h_lg = 31u - (uint32_t)__clz((int)h_cpr);   // chunks per row are powers of 2
     const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
     const uint32_t h_buf = my_epi + (uint32_t)q.f_bufs * 32u * f_rb;
     const int f_dst = q.f_dst, h_dst = q.h_dst;
@@ -382,20 +385,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const float* src0 = reinterpret_cast<const float*>(p.res1) + tile_pixel(b, y0, x0) * (size_t)p.res1_cstride + c_out0;
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
-      const uint32_t rows_per_it = 32u / f_cpr;
-      const uint32_t ch = (uint32_t)lane % f_cpr, rsub = (uint32_t)lane / f_cpr;
+      const uint32_t rows_per_it = 32u >> f_lg;
+      const uint32_t ch = (uint32_t)lane & (f_cpr - 1u), rsub = (uint32_t)lane >> f_lg;
+#pragma unroll 4
       for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
         const int mm = quad * 32 + (int)row;
         if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
           cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src0 + (size_t)pix_off(mm) * (size_t)p.res1_cstride + ch * 4u);
       }
     };
-    auto copy_out = [&](uint32_t buf, uint32_t rb, uint32_t cpr, uint32_t swz, void* dst, int cstride, int coffset,
+    auto copy_out = [&](uint32_t buf, uint32_t rb, uint32_t cpr, uint32_t lg, uint32_t swz, void* dst, int cstride, int coffset,
                         uint32_t esize, size_t tpix, bool full, int y0, int x0) {
       uint8_t* dst0 = reinterpret_cast<uint8_t*>(dst) + (tpix * (size_t)cstride + (size_t)(coffset + c_out0)) * esize;
       const uint32_t pix_bytes = (uint32_t)cstride * esize;
-      const uint32_t rows_per_it = 32u / cpr;
-      const uint32_t ch = (uint32_t)lane % cpr, rsub = (uint32_t)lane / cpr;
+      const uint32_t rows_per_it = 32u >> lg;
+      const uint32_t ch = (uint32_t)lane & (cpr - 1u), rsub = (uint32_t)lane >> lg;
+#pragma unroll 4
       for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
         const int mm = quad * 32 + (int)row;
         if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W)) {
@@ -451,6 +456,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll 1
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t rr[16];
+        float4 bv[4];                                   // bias of these 16 channels, fetched ahead of the TMEM read
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_s + col0 + c0 + 4 * j);
         __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld16(t_row + (uint32_t)c0, rr);
         tmem_ld_wait();
@@ -463,8 +471,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int g = 0; g < 2; ++g) {
             const int cc = c0 + g * 8;                  // channel offset inside this warp's column range
             float v[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_s + col0 + cc);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_s + col0 + cc + 4);
+            const float4 b0 = bv[2 * g], b1 = bv[2 * g + 1];
             v[0] = __uint_as_float(rr[g * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[g * 8 + 1]) + b0.y;
             v[2] = __uint_as_float(rr[g * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[g * 8 + 3]) + b0.w;
             v[4] = __uint_as_float(rr[g * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[g * 8 + 5]) + b1.y;
@@ -557,10 +564,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (epi_mode == 1) {
         __syncwarp();                                   // rows written by their owner lanes -> read by all lanes
         if (f_on)
-          copy_out(f_buf, f_rb, f_cpr, f_swz, f_dst == 1 ? p.y : p.y2, f_dst == 1 ? p.y_cstride : p.y2_cstride,
+          copy_out(f_buf, f_rb, f_cpr, f_lg, f_swz, f_dst == 1 ? p.y : p.y2, f_dst == 1 ? p.y_cstride : p.y2_cstride,
                    f_dst == 1 ? p.y_coffset : 0, 4u, tpix, full, y0, x0);
         if (h_on)
-          copy_out(h_buf, h_rb, h_cpr, h_swz, h_dst == 1 ? p.y : p.y2, h_dst == 1 ? p.y_cstride : p.y2_cstride,
+          copy_out(h_buf, h_rb, h_cpr, h_lg, h_swz, h_dst == 1 ? p.y : p.y2, h_dst == 1 ? p.y_cstride : p.y2_cstride,
                    h_dst == 1 ? p.y_coffset : 0, 2u, tpix, full, y0, x0);
         __syncwarp();                                   // staging rows are free for the next tile
       }
@@ -617,60 +624,69 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   EncodeTiledFn encode = encode_fn();
   if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
 
-  TcParams q{};
   const int rows = p.w_tc_rows;                       // cout padded to 16
-  q.n_tile = (rows % 64 == 0) ? 64 : (rows < 64 ? rows : 16);
-  if (rows % q.n_tile) q.n_tile = 16;
-  q.n_chunks = rows / q.n_tile;
-  q.w_rows = rows;
-  q.tiles_x = (p.W + kTileW - 1) / kTileW;
-  q.tiles_y = (p.H + kTileH - 1) / kTileH;
-  const long total = (long)p.B * q.tiles_x * q.tiles_y;
-  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
-  q.total_tiles = (int)total;
-  const int variant = g_variant;
-  if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
-  else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
-  else { q.pitch = kTileW + 2; q.n_loads = 1; }
-  q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
-  q.load_bytes = (uint32_t)(kHaloH * q.pitch * 128);
-  q.stage_bytes = ((q.load_bytes * (uint32_t)q.n_loads) + 1023u) & ~1023u;
-  q.tmem_cols = 32;
-  while (q.tmem_cols < (uint32_t)(2 * q.n_tile)) q.tmem_cols <<= 1;
-  const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
-  q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  // staged vector epilogue: one fp32 and/or one 16-bit destination, the chunk maps to one depth_to_space sub-pixel
-  const bool is16 = true;
-  (void)is16;
-  auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
-  const bool two_outputs = p.y2 != nullptr;
-  bool vec = (q.n_tile == 16 || q.n_tile == 32 || q.n_tile == 64) && (p.cout % q.n_tile == 0) &&
-             (p.d2s == 1 || p.c_post % q.n_tile == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
-             (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
-             (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
-             (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
-  if (two_outputs && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
-  q.epi_mode = vec ? 1 : 0;
-  if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
-  if (vec) {
-    q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
-    q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
-    q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
-    q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
-    const int ncols = q.n_tile >= 32 ? q.n_tile / 2 : q.n_tile;
-    q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * ncols * 4 + (q.h_dst ? 32 * ncols * 2 : 0));
-  }
-
-  const size_t w_bytes = ((size_t)9 * q.n_tile * 128 + 1023) & ~(size_t)1023;
-  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)q.n_tile * sizeof(float);
+  static int ntile_max = 0;
+  if (!ntile_max) { const char* e = getenv("SRB_TC_NTILE"); ntile_max = e ? atoi(e) : 128; if (ntile_max < 16) ntile_max = 128; }
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  q.stages = 4;
-  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
-  while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
-  const size_t smem = smem_need(q.stages);
-  SRB_REQUIRE(smem <= (size_t)max_smem, "conv(tcgen05): tile does not fit shared memory");
+  const long total = (long)p.B * ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
+  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
+  const int variant = g_variant;
+  auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
+
+  // channel-chunk width per CTA: the widest of {128, 64, rows, 16} that divides the padded cout and whose weights,
+  // >= 2 A stages and epilogue staging fit shared memory (N = 128 halves the A-operand smem traffic per FLOP)
+  TcParams q{};
+  size_t smem = 0;
+  const int cand[4] = {128, 64, rows < 64 ? rows : 16, 16};
+  bool found = false;
+  for (int ci = 0; ci < 4 && !found; ++ci) {
+    const int nt = cand[ci];
+    if (nt > ntile_max || rows % nt) continue;
+    q = TcParams{};
+    q.n_tile = nt;
+    q.n_chunks = rows / nt;
+    q.w_rows = rows;
+    q.tiles_x = (p.W + kTileW - 1) / kTileW;
+    q.tiles_y = (p.H + kTileH - 1) / kTileH;
+    q.total_tiles = (int)total;
+    if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
+    else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
+    else { q.pitch = kTileW + 2; q.n_loads = 1; }
+    q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
+    q.load_bytes = (uint32_t)(kHaloH * q.pitch * 128);
+    q.stage_bytes = ((q.load_bytes * (uint32_t)q.n_loads) + 1023u) & ~1023u;
+    q.tmem_cols = 32;
+    while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
+    const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
+    q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    // staged vector epilogue: one fp32 and/or one 16-bit destination; a warp's columns map to one d2s sub-pixel
+    const int warp_cols = nt >= 32 ? nt / 2 : nt;
+    bool vec = (nt == 16 || nt == 32 || nt == 64 || nt == 128) && (p.cout % nt == 0) &&
+               (p.d2s == 1 || p.c_post % warp_cols == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
+               (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
+               (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
+               (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
+    if (p.y2 && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
+    q.epi_mode = vec ? 1 : 0;
+    if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
+    if (vec) {
+      q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
+      q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
+      q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
+      q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
+      q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
+    }
+    const size_t w_bytes = ((size_t)9 * nt * 128 + 1023) & ~(size_t)1023;
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float);
+    auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
+    q.stages = 4;
+    while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
+    smem = smem_need(q.stages);
+    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16);
+  }
+  SRB_REQUIRE(found, "conv(tcgen05): tile does not fit shared memory");
 
   // ---- tensor maps ----
   const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
