@@ -1,11 +1,13 @@
 // cv2.resize(..., INTER_CUBIC) on the GPU (classic_algorithms.py:11-13, loading_methods.py:147,
 // SRCNN_model.py:191).  Separable 4-tap Keys cubic (A = -0.75), half-pixel centres, tap index clamp.
 //
-// Two kernels: `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only
-// place double precision is used), and `bicubic_kernel` does the separable resampling for a tile of
-// 256 interleaved output elements x TY output rows: the horizontal pass over just the source rows
-// the tile needs goes to shared memory, the vertical pass reads it back column-wise, and both
-// global reads and writes are contiguous across the block.
+// `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only place double
+// precision is used).  `bicubic_tile_kernel` does the separable resampling for a tile of 256 interleaved
+// output elements x TY output rows in three shared-memory stages: (1) the source rows/columns the tile
+// needs are streamed in with coalesced cp.async, (2) the horizontal 4-tap pass runs smem -> smem, (3) the
+// vertical 4-tap pass reads the thread's own column back and writes contiguous output rows.  The older
+// `bicubic_kernel` (horizontal taps gathered straight from global memory) remains as the fallback for
+// strong down-scaling, where the source footprint of a tile does not fit shared memory.
 //
 // float path  : t from double, FMA-contracted coefficient polynomial, FMA accumulation in tap order
 //               (OpenCV's default dispatch to <= 1e-6; uint8 = saturate(rint(.)) of the same path).
@@ -128,6 +130,107 @@ bicubic_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __
   }
 }
 
+
+struct __align__(16) RowTap { int off[4]; float coef[4]; };   // vertical taps of one output row, offsets into the H buffer
+
+template <typename T, bool FIXED>
+__global__ void __launch_bounds__(kTE)
+bicubic_tile_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
+                    const AxisTap* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w,
+                    int tile_rows, int max_src_rows, int max_src_cols, int clip01) {
+  extern __shared__ float tsm[];
+  float* S = tsm;                                            // [max_src_rows][max_src_cols] source tile (as float)
+  float* Hb = S + (size_t)max_src_rows * max_src_cols;       // [max_src_rows][kTE] horizontal-pass results
+  RowTap* rt = reinterpret_cast<RowTap*>(Hb + (size_t)max_src_rows * kTE);   // [tile_rows]
+  const int t = threadIdx.x;
+  const int DE = dst_w * C, SE = src_w * C;
+  const int e0 = blockIdx.x * kTE;
+  const int e = e0 + t;
+  const int y0 = blockIdx.y * tile_rows;
+  const int y1 = min(y0 + tile_rows, dst_h) - 1;
+  const size_t src_img = (size_t)blockIdx.z * src_h * SE;
+  const size_t dst_img = (size_t)blockIdx.z * dst_h * DE;
+  const int r_lo = ytab[y0].idx[0];
+  const int nr = min(ytab[y1].idx[3] - r_lo + 1, max_src_rows);
+  const int x_first = e0 / C, x_last = (min(e0 + kTE, DE) - 1) / C;
+  const int c_lo = xtab[x_first].idx[0] * C;
+  const int nc = min(xtab[x_last].idx[3] * C + C - c_lo, max_src_cols);
+  const bool valid = e < DE;
+
+  // stage 1: source footprint -> shared memory (coalesced along the row)
+  for (int r = 0; r < nr; ++r) {
+    const T* row = src + src_img + (size_t)(r_lo + r) * SE + c_lo;
+    for (int i = t; i < nc; i += kTE) {
+      if (sizeof(T) == 4) {
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(S + r * max_src_cols + i);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(row + i) : "memory");
+      } else {
+        S[r * max_src_cols + i] = px_load(row + i);
+      }
+    }
+  }
+  for (int i = t; i <= y1 - y0; i += kTE) {
+    const AxisTap a = ytab[y0 + i];
+    RowTap q;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { q.off[k] = (a.idx[k] - r_lo) * kTE; q.coef[k] = a.coef[k]; }
+    rt[i] = q;
+  }
+  if (sizeof(T) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+
+  if (!valid) return;
+  // stage 2: horizontal pass, one output column per thread, all source rows of the tile
+  {
+    const int x = e / C, c = e - x * C;
+    const AxisTap xt = xtab[x];
+    const int o0 = xt.idx[0] * C + c - c_lo, o1 = xt.idx[1] * C + c - c_lo, o2 = xt.idx[2] * C + c - c_lo,
+              o3 = xt.idx[3] * C + c - c_lo;
+    const float* srow = S;
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r, srow += max_src_cols) {
+      if (FIXED) {
+        const int v = (int)srow[o0] * (int)xt.coef[0] + (int)srow[o1] * (int)xt.coef[1] +
+                      (int)srow[o2] * (int)xt.coef[2] + (int)srow[o3] * (int)xt.coef[3];
+        Hb[r * kTE + t] = __int_as_float(v);
+      } else {
+        float v = __fmul_rn(srow[o0], xt.coef[0]);
+        v = __fmaf_rn(srow[o1], xt.coef[1], v);
+        v = __fmaf_rn(srow[o2], xt.coef[2], v);
+        v = __fmaf_rn(srow[o3], xt.coef[3], v);
+        Hb[r * kTE + t] = v;
+      }
+    }
+  }
+  // stage 3: vertical pass; each thread only reads back its own column of Hb (no barrier needed)
+  const float* hcol = Hb + t;
+  T* out = dst + dst_img + (size_t)y0 * DE + e;
+#pragma unroll 4
+  for (int i = 0; i <= y1 - y0; ++i, out += DE) {
+    const RowTap q = rt[i];
+    float v;
+    if (FIXED) {
+      const float sc = 1.f / (2048.f * 2048.f);
+      v = __fmul_rn((float)__float_as_int(hcol[q.off[0]]), __fmul_rn(q.coef[0], sc));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hcol[q.off[1]]), __fmul_rn(q.coef[1], sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hcol[q.off[2]]), __fmul_rn(q.coef[2], sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hcol[q.off[3]]), __fmul_rn(q.coef[3], sc)));
+    } else {
+      v = __fmul_rn(hcol[q.off[0]], q.coef[0]);
+      v = __fmaf_rn(hcol[q.off[1]], q.coef[1], v);
+      v = __fmaf_rn(hcol[q.off[2]], q.coef[2], v);
+      v = __fmaf_rn(hcol[q.off[3]], q.coef[3], v);
+    }
+    if (sizeof(T) == 1) {
+      const int qv = __float2int_rn(v);                      // round-half-even, then saturate
+      *reinterpret_cast<uint8_t*>(out) = (uint8_t)min(max(qv, 0), 255);
+    } else {
+      if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+      *reinterpret_cast<float*>(out) = v;
+    }
+  }
+}
+
 template <typename T, bool FIXED>
 static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, int dh, int dw, int clip01,
                        cudaStream_t stream) {
@@ -144,12 +247,30 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
   if (rc) return rc;
   int tile_rows = 32;
   auto src_rows = [&](int tr) { return (int)(((long)tr * sh + dh - 1) / dh) + 5; };
-  while (tile_rows > 1 && (size_t)src_rows(tile_rows) * kTE * sizeof(float) > 96 * 1024) tile_rows >>= 1;
-  const int msr = src_rows(tile_rows);
-  const size_t smem = (size_t)msr * kTE * sizeof(float);
-  SRB_CUDA(cudaFuncSetAttribute(bicubic_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((dw * C + kTE - 1) / kTE, (dh + tile_rows - 1) / tile_rows, batch);
-  bicubic_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, clip01);
+  // source columns one 256-element block can touch: its output pixels scaled back, plus the 4-tap support
+  const double ratio = (double)sw / (double)dw;
+  const int src_px = (int)((kTE / C + 2) * (ratio > 1.0 ? ratio : 1.0)) + 6;
+  const int msc = ((src_px * C) + 3) & ~3;
+  auto tile_smem = [&](int tr) {
+    return ((size_t)src_rows(tr) * (msc + kTE)) * sizeof(float) + (size_t)tr * sizeof(RowTap);
+  };
+  while (tile_rows > 4 && tile_smem(tile_rows) > 64 * 1024) tile_rows >>= 1;
+  if (tile_smem(tile_rows) <= 96 * 1024) {
+    const int msr = src_rows(tile_rows);
+    const size_t smem = tile_smem(tile_rows);
+    SRB_CUDA(cudaFuncSetAttribute(bicubic_tile_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((dw * C + kTE - 1) / kTE, (dh + tile_rows - 1) / tile_rows, batch);
+    SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
+    bicubic_tile_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, msc, clip01);
+  } else {
+    tile_rows = 32;
+    while (tile_rows > 1 && (size_t)src_rows(tile_rows) * kTE * sizeof(float) > 96 * 1024) tile_rows >>= 1;
+    const int msr = src_rows(tile_rows);
+    const size_t smem = (size_t)msr * kTE * sizeof(float);
+    SRB_CUDA(cudaFuncSetAttribute(bicubic_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((dw * C + kTE - 1) / kTE, (dh + tile_rows - 1) / tile_rows, batch);
+    bicubic_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, clip01);
+  }
   rc = launch_check("bicubic_kernel");
   SRB_CUDA(cudaFreeAsync(tabs, stream));
   return rc;

@@ -2,7 +2,8 @@
 //
 // One pass over both images.  A block owns 128 consecutive interleaved output elements
 // (x*C + c of the (H-10) x (W-10) SSIM map) and a strip of output rows.  Rows are streamed
-// through a double-buffered shared-memory line; each thread evaluates the 11-tap horizontal
+// through a ring of shared-memory lines filled by cp.async four rows ahead of the arithmetic
+// (no register staging, one barrier per row); each thread evaluates the 11-tap horizontal
 // Gaussian of a, b, a^2+b^2 and a*b for its column and keeps the last 11 results in a register
 // ring (the row loop is unrolled by 11 so ring slots are static), from which the vertical
 // 11-tap pass and the SSIM point function follow.  The squared error for PSNR is accumulated
@@ -21,8 +22,9 @@ __global__ void __launch_bounds__(kCols)
 psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
                  float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
   constexpr int kLine = kCols + 10 * C;
-  __shared__ float sa[2][kLine];
-  __shared__ float sb[2][kLine];
+  constexpr int kAhead = 4, kRing = kAhead + 1;      // rows in flight / line buffers
+  __shared__ float sa[kRing][kLine];
+  __shared__ float sb[kRing][kLine];
   __shared__ float red[2][kCols / 32];
 
   const int WE = W * C;            // interleaved floats per image row
@@ -50,24 +52,43 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
 
   float sse = 0.f, ssim_sum = 0.f;
 
+  // asynchronous fill of one line pair (row is block-uniform); columns past the image are zero
+  auto fetch = [&](int row) {
+    if (row < nin) {
+      const int buf = row % kRing;
+      const float* la = pa + (size_t)(y0 + row) * WE + e0;
+      const float* lb = pb + (size_t)(y0 + row) * WE + e0;
+      for (int i = t; i < kLine; i += kCols) {
+        if (e0 + i < WE) {
+          const uint32_t da = (uint32_t)__cvta_generic_to_shared(&sa[buf][i]);
+          const uint32_t db = (uint32_t)__cvta_generic_to_shared(&sb[buf][i]);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(da), "l"(la + i) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(db), "l"(lb + i) : "memory");
+        } else {
+          sa[buf][i] = 0.f;
+          sb[buf][i] = 0.f;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");   // one group per row, empty past the end
+  };
+#pragma unroll
+  for (int r = 0; r < kAhead; ++r) fetch(r);
+
   for (int r = 0; r < nin; r += 11) {
 #pragma unroll
     for (int j = 0; j < 11; ++j) {
       const int row = r + j;              // block-uniform
       if (row < nin) {
-        const int y = y0 + row;
-        const int buf = row & 1;
+        const int buf = row % kRing;
         const bool row_owned = (row < rows_out) || last_y;
-        const float* la = pa + (size_t)y * WE + e0;
-        const float* lb = pb + (size_t)y * WE + e0;
-        for (int i = t; i < kLine; i += kCols) {
-          float va = 0.f, vb = 0.f;
-          if (e0 + i < WE) { va = __ldg(la + i); vb = __ldg(lb + i); }
-          sa[buf][i] = va;
-          sb[buf][i] = vb;
-          if (row_owned && (i < kCols || last_x)) { const float d = va - vb; sse = fmaf(d, d, sse); }
+        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");   // this row's line has landed
+        __syncthreads();                  // ... for every thread, and line (row-1) % kRing is no longer read
+        fetch(row + kAhead);
+        if (row_owned) {                  // squared error: every element of the row exactly once
+          { const float d = sa[buf][t] - sb[buf][t]; sse = fmaf(d, d, sse); }
+          if (last_x && t < 10 * C) { const float d = sa[buf][kCols + t] - sb[buf][kCols + t]; sse = fmaf(d, d, sse); }
         }
-        __syncthreads();
         float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
