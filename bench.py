@@ -145,7 +145,7 @@ def run_reference(args):
         "impl": "reference", "metric": "sr_output_megapixels_per_sec", "value": val, "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 0),
+        "config": dict(workload_config(args, 0), operands="fp32 (oracle port, torch CPU conv2d)", micro_batch=per_step),
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference engine (TensorFlow/Keras 2.10) is not installable offline; CPU arm = oracle restatement",
