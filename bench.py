@@ -106,6 +106,7 @@ def lr_tiles(lo, hi, size):
 # ------------------------------------------------------------------------------------------------
 def cpu_edsr_mp_per_s(n_tiles, tile, repeats=1):
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)
     from oracle import convnets as oc
     from srb200 import weights
     w = weights.edsr_weights(4)
@@ -126,6 +127,7 @@ def run_reference(args):
         return
     tile, per_step = args.tile, 4
     import torch
+    torch.set_num_threads(os.cpu_count() or 1)            # torchrun exports OMP_NUM_THREADS=1; use every host core
     from oracle import convnets as oc
     from srb200 import weights
     w = weights.edsr_weights(4)
