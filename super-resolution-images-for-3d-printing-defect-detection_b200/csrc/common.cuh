@@ -75,4 +75,6 @@ struct srb_conv_weights {
   __nv_bfloat16* tc;      // [kh*kw][cout_pad][cin] bf16, K-major rows (tcgen05 engine) or nullptr
   __half* tc_f16;         // same, IEEE half
   int tc_cout_pad;        // rows per tap in `tc` (multiple of 16)
+  __nv_bfloat16* tc_fold; // cout <= 4 only: [dy][16 rows = dx*5+co][cin] (horizontal taps folded into N) or nullptr
+  __half* tc_fold_f16;
 };

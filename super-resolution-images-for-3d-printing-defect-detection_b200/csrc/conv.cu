@@ -53,6 +53,26 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
       srb_conv_weights_destroy(w);
       return cuda_fail(e, "conv_weights_create(tc)");
     }
+    if (kh == 3 && kw == 3 && cout <= 5) {
+      // few-channel layers (RGB tails): fold the horizontal taps into N so that a tile needs 12 instead of 36 MMAs
+      std::vector<__nv_bfloat16> fb((size_t)3 * 16 * cin, __float2bfloat16_rn(0.f));
+      std::vector<__half> fh((size_t)3 * 16 * cin, __float2half_rn(0.f));
+      for (int dy = 0; dy < 3; ++dy)
+        for (int dx = 0; dx < 3; ++dx)
+          for (int o = 0; o < cout; ++o)
+            for (int c = 0; c < cin; ++c) {
+              const float v = hwio[((size_t)(dy * 3 + dx) * cin + c) * cout + o];
+              fb[((size_t)dy * 16 + dx * 5 + o) * cin + c] = __float2bfloat16_rn(v);
+              fh[((size_t)dy * 16 + dx * 5 + o) * cin + c] = __float2half_rn(v);
+            }
+      if ((e = cudaMalloc(&w->tc_fold, fb.size() * 2)) != cudaSuccess ||
+          (e = cudaMemcpy(w->tc_fold, fb.data(), fb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+          (e = cudaMalloc(&w->tc_fold_f16, fh.size() * 2)) != cudaSuccess ||
+          (e = cudaMemcpy(w->tc_fold_f16, fh.data(), fh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        srb_conv_weights_destroy(w);
+        return cuda_fail(e, "conv_weights_create(tc fold)");
+      }
+    }
   }
   *out = w;
   return SRB_OK;
@@ -64,6 +84,8 @@ extern "C" void srb_conv_weights_destroy(srb_conv_weights* w) {
   if (w->bias) cudaFree(w->bias);
   if (w->tc) cudaFree(w->tc);
   if (w->tc_f16) cudaFree(w->tc_f16);
+  if (w->tc_fold) cudaFree(w->tc_fold);
+  if (w->tc_fold_f16) cudaFree(w->tc_fold_f16);
   free(w);
 }
 
@@ -93,6 +115,7 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.kh = w->kh; p.kw = w->kw; p.cin = w->cin; p.cout = w->cout;
   p.w_hwio = w->hwio; p.w_cout_pad = w->cout_pad4;
   p.w_tc = a->x_dtype == SRB_F16 ? (const void*)w->tc_f16 : (const void*)w->tc; p.w_tc_rows = w->tc_cout_pad;
+  p.w_tc_fold = a->x_dtype == SRB_F16 ? (const void*)w->tc_fold_f16 : (const void*)w->tc_fold;
   p.bias = w->bias;
   p.act = a->act; p.act_slope = a->act_slope; p.prelu = a->prelu;
   SRB_REQUIRE(a->act >= SRB_ACT_NONE && a->act <= SRB_ACT_TANH, "conv2d: unknown activation %d", a->act);

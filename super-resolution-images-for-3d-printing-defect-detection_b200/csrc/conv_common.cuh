@@ -12,6 +12,7 @@ struct ConvParams {
   int kh, kw, cin, cout;
   const float* w_hwio; int w_cout_pad;      // direct engine weights
   const void* w_tc; int w_tc_rows;          // tcgen05 engine weights [tap][rows][cin] in the dtype of x
+  const void* w_tc_fold;                    // [dy][16][cin] dx-folded weights for cout <= 4, or nullptr
   const float* bias;                        // [cout], never null
   int act; float act_slope; const float* prelu;
   float alpha;

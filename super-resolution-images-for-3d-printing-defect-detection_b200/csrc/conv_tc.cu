@@ -26,7 +26,7 @@ constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM r
 constexpr int kHaloH = kTileH + 2;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
-constexpr int kMaxStages = 6;
+constexpr int kMaxStages = 8;
 
 struct TcParams {
   int n_tile;            // output channels per CTA (multiple of 16, <= 128)
@@ -47,6 +47,8 @@ struct TcParams {
   int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
   int res_prefetch;      // res1 is fp32 and is prefetched into the F buffers with cp.async
   uint32_t epi_warp_bytes;
+  int fold;              // horizontal taps folded into N (cout <= 4): 3 MMA taps (dy), 8 input columns -> 6 output columns
+  int tile_cols_out;     // 8, or 6 when folded
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -233,7 +235,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
 
-  const uint32_t w_bytes = 9u * (uint32_t)q.n_tile * 128u;
+  const int n_taps = q.fold ? 3 : 9;
+  const uint32_t w_bytes = (uint32_t)n_taps * (uint32_t)q.n_tile * 128u;
   const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base;
   const uint32_t a_smem = base + w_span;
@@ -258,7 +261,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 32 * kEpiWarps); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (q.n_tile < 32 && q.epi_mode != 1) ? 16 * kEpiWarps : 32 * kEpiWarps); }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
@@ -277,14 +280,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // lane issues the asynchronous copies
     if (elect_one()) {
       mbar_expect_tx(wfull_bar, w_bytes);
-      for (int t = 0; t < 9; ++t)
+      for (int t = 0; t < n_taps; ++t)
         tma_load_2d(w_smem + (uint32_t)t * (uint32_t)q.n_tile * 128u, &tmap_w, wfull_bar, 0, t * q.w_rows + co_base);
     }
     __syncwarp();
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
       const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
-      const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * kTileW;
+      const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * q.tile_cols_out;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
       if (elect_one()) {
@@ -313,7 +316,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tc_fence_after();
       const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
-      if (q.base_off_mode == 0) {
+      if (q.fold) {
+        // dx folded into N: D[input pixel, (dx, co)] += sum over dy of A shifted by dy halo rows (1,024-B aligned)
+        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
+        if (elect_one()) {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t ad = a_desc0 + (uint64_t)(dy * a_dy), bd = b_desc0 + (uint64_t)dy * b_tap_step;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
+          }
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(acc));
+        }
+      } else if (q.base_off_mode == 0) {
         // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
         const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
         if (elect_one()) {
@@ -349,11 +365,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // accumulator columns (output channels) in halves when the chunk has >= 32 channels.
     const int ew = warp - 2;
     const int quad = warp & 3;
+    // narrow chunks (n_tile = 16) are not split: the two warp sets take alternate tiles instead (set h owns TMEM
+    // accumulator h), which doubles the per-tile latency budget of the epilogue
     const int split = q.n_tile >= 32 ? 2 : 1;
     const int half = ew >> 2;
-    const bool active = half < split;
+    const bool alt = q.n_tile < 32 && q.epi_mode != 1;  // (the staged epilogue keeps its per-warp tile sequence)
+    const bool active = alt || half < split;
     const int ncols = q.n_tile / split;                 // channels this warp handles per pixel
-    const int col0 = half * ncols * (split - 1);        // first accumulator column of this warp
+    const int col0 = half * ncols * (split - 1);        // first accumulator column of this warp (0 when not split)
     const int m = quad * 32 + lane;                     // GEMM row = pixel within the tile
     // depth_to_space constants of this CTA's channel chunk (vector path: the chunk maps to one (i, j) sub-pixel)
     // (per warp: with 128-channel chunks the two column halves belong to different sub-pixels)
@@ -372,7 +391,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t f_cpr = f_rb >> 4, h_cpr = h_rb >> 4;
     const uint32_t f_swz = f_cpr > 8 ? 7u : f_cpr - 1u, h_swz = h_cpr > 8 ? 7u : h_cpr - 1u;
     const uint32_t f_lg = 31u - (uint32_t)__clz((int)f_cpr), h_lg = 31u - (uint32_t)__clz((int)h_cpr);   // chunks per row are powers of 2
-    const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
+    const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;   // (n_tile = 16 staged layers: one buffer per warp, both sets)
     const uint32_t h_buf = my_epi + (uint32_t)q.f_bufs * 32u * f_rb;
     const int f_dst = q.f_dst, h_dst = q.h_dst;
     const int h_dtype = h_dst == 1 ? p.y_dtype : p.y2_dtype;
@@ -381,7 +400,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
-      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
+      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const float* src0 = reinterpret_cast<const float*>(p.res1) + tile_pixel(b, y0, x0) * (size_t)p.res1_cstride + c_out0;
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
@@ -430,11 +449,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     }
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
-      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * kTileW;
+      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      if (alt && acc != half) continue;                 // the other warp set owns this tile
       uint32_t f_buf = my_epi;
       if (prefetch) {
         if (tile + tile_step < q.total_tiles) prefetch_res(tile + tile_step, (it + 1) & 1);
@@ -534,6 +554,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4), pk);
             }
           }
+        } else if (epi_mode == 3) {
+          // dx-folded few-channel layer: lane m holds D[input pixel (ty, xx), (dx, co)], xx = 0..7 <-> image column x0-1+xx.
+          // Output column xx (1..6) = D[xx-1][dx=0] + D[xx][dx=1] + D[xx+1][dx=2]: neighbours are adjacent lanes.
+          const int xx = m & 7;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(rr[0 * 5 + e]), 1);
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[2 * 5 + e]), 1);
+            v[e] = bias_s[e] + left + __uint_as_float(rr[1 * 5 + e]) + right;
+          }
+          const int oy = y0 + (m >> 3), ox = x0 + xx - 1;
+          if (xx >= 1 && xx <= 6 && oy < p.H && ox < p.W) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+              else if (p.act != SRB_ACT_NONE)
+                v[e] = act_generic(v[e], p.act, (p.act == SRB_ACT_PRELU && e < p.cout) ? __ldg(p.prelu + e) : p.act_slope);
+              v[e] *= p.alpha;
+              if (p.clip01) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
+            }
+            const size_t o = (my_pix - 1) * p.y_cstride + p.y_coffset;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (e < p.cout) store_elem(p.y, p.y_dtype, o + e, v[e]);
+          }
         } else if (epi_mode == 2) {
           // few output channels (the RGB tail layers): <= 4 channels per pixel, no residual, no shuffle
           if (valid && c0 == 0) {
@@ -630,9 +676,12 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const long total = (long)p.B * ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
-  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
   const int variant = g_variant;
+  static const bool fold_enabled = getenv("SRB_TC_NOFOLD") == nullptr;
+  const bool fold = fold_enabled && variant == 0 && p.w_tc_fold && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2;
+  const int cols_out = fold ? kTileW - 2 : kTileW;
+  const long total = (long)p.B * ((p.W + cols_out - 1) / cols_out) * ((p.H + kTileH - 1) / kTileH);
+  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
 
   // channel-chunk width per CTA: the widest of {128, 64, rows, 16} that divides the padded cout and whose weights,
@@ -642,16 +691,19 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   const int cand[4] = {128, 64, rows < 64 ? rows : 16, 16};
   bool found = false;
   for (int ci = 0; ci < 4 && !found; ++ci) {
-    const int nt = cand[ci];
-    if (nt > ntile_max || rows % nt) continue;
+    const int nt = fold ? 16 : cand[ci];
+    if (!fold && (nt > ntile_max || rows % nt)) continue;
     q = TcParams{};
+    q.fold = fold ? 1 : 0;
+    q.tile_cols_out = cols_out;
     q.n_tile = nt;
-    q.n_chunks = rows / nt;
-    q.w_rows = rows;
-    q.tiles_x = (p.W + kTileW - 1) / kTileW;
+    q.n_chunks = fold ? 1 : rows / nt;
+    q.w_rows = fold ? 16 : rows;
+    q.tiles_x = (p.W + cols_out - 1) / cols_out;
     q.tiles_y = (p.H + kTileH - 1) / kTileH;
     q.total_tiles = (int)total;
-    if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
+    if (fold) { q.pitch = kTileW; q.n_loads = 1; }       // 8 input columns: every dy shift is 1,024-B aligned
+    else if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
     else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
     else { q.pitch = kTileW + 2; q.n_loads = 1; }
     q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
@@ -671,6 +723,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (p.y2 && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
+    if (fold) { vec = false; q.epi_mode = 3; }
     if (vec) {
       q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
       q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
@@ -678,10 +731,12 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
     }
-    const size_t w_bytes = ((size_t)9 * nt * 128 + 1023) & ~(size_t)1023;
+    const size_t w_bytes = ((size_t)(fold ? 3 : 9) * nt * 128 + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float);
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
-    q.stages = 4;
+    static int stage_cap = 0;
+    if (!stage_cap) { const char* e = getenv("SRB_TC_STAGES"); stage_cap = e ? atoi(e) : kMaxStages; if (stage_cap < 1 || stage_cap > kMaxStages) stage_cap = kMaxStages; }
+    q.stages = stage_cap;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);
     found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16);
@@ -703,11 +758,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)9 * rows};
+    const cuuint64_t dims[2] = {64, q.fold ? (cuuint64_t)48 : (cuuint64_t)9 * rows};
     const cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {64, (cuuint32_t)q.n_tile};
     const cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tmw, tdt, 2, (void*)p.w_tc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&tmw, tdt, 2, (void*)(q.fold ? p.w_tc_fold : p.w_tc), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
   }

@@ -71,7 +71,8 @@ def test_operand_staging_variants(variant):
 
 @pytest.mark.parametrize("kind", ["fp16", "bf16"])
 @pytest.mark.parametrize("shape", [(2, 16, 8, 64), (1, 48, 48, 64), (3, 21, 13, 64), (1, 5, 3, 64), (1, 192, 192, 64),
-                                   (1, 24, 24, 256), (1, 17, 9, 576), (2, 24, 24, 3), (1, 20, 12, 32), (1, 16, 16, 48)])
+                                   (1, 24, 24, 256), (1, 17, 9, 576), (2, 24, 24, 3), (1, 20, 12, 32), (1, 16, 16, 48),
+                                   (1, 17, 9, 3), (2, 29, 13, 3), (1, 14, 8, 3), (1, 15, 8, 5), (1, 64, 64, 3)])
 def test_plain_conv(kind, shape):
     B, H, W, cout = shape
     got, want = _run(kind, B, H, W, cout)
