@@ -159,7 +159,7 @@ def workload_config(args, micro_batch):
                         f"-> {args.tile * 4}x{args.tile * 4}x3 (BASELINE configs[2])",
             "global_batch": args.batch, "tile": args.tile, "scale": 4, "micro_batch": micro_batch,
             "parallelism": f"dp{args.gpus} (batch-sharded, no data-path collective)",
-            "operands": f"{args.dtype} operands, fp32 accumulate, fp32 residual trunk",
+            "operands": f"{args.dtype} operands, fp32 accumulate, residual trunk = {args.trunk}",
             "l2": "inputs larger than L2 (LR batch + activations stream through HBM every step); no flush needed"}
 
 
@@ -181,7 +181,7 @@ def run_gpu(args):
     tile, out_px = args.tile, (args.tile * 4) ** 2
     mb = min(args.micro_batch, max(n_local, 1))
 
-    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype)
+    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype, trunk=args.trunk)
     net.max_device_batch = mb
     x_host = torch.from_numpy(lr_tiles(lo, hi, tile)).pin_memory()
     x_dev = x_host.to(dev)
@@ -288,6 +288,8 @@ def main():
     ap.add_argument("--tile", type=int, default=192)
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--trunk", default="fp32", choices=["fp32", "pair", "half"],
+                    help="residual trunk storage: fp32 (default), compensated 16-bit pair, or plain 16-bit")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

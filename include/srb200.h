@@ -82,9 +82,12 @@ int srb_overlap_add_f32(const float* patches, int ny, int nx, int patch_out, int
 typedef struct srb_conv_args {
   const void* x;        int x_dtype;   int x_cstride;  int x_coffset;   /* input  NHWC, C-slice allowed */
   void*       y;        int y_dtype;   int y_cstride;  int y_coffset;   /* output NHWC, C-slice allowed */
-  void*       y2;       int y2_dtype;  int y2_cstride;                  /* optional second copy of the output in
-                                                                           another dtype (fp32 residual trunk next
-                                                                           to the 16-bit operand of the next layer) */
+  void*       y2;       int y2_dtype;  int y2_cstride;  int y2_mode;    /* optional second output, same geometry:
+                                                                           mode 0 = the same values in another dtype
+                                                                           (fp32 trunk next to the 16-bit operand);
+                                                                           mode 1 = v - round_to_y_dtype(v), the
+                                                                           rounding error of y, so that y + y2 carries
+                                                                           ~22 bits in two 16-bit tensors */
   int batch, height, width;
   const srb_conv_weights* weights;
   int act;              float act_slope;               const float* prelu;   /* [cout / d2s^2] */

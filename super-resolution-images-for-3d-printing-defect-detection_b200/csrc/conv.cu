@@ -109,6 +109,8 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.y = a->y; p.y_dtype = a->y_dtype;
   p.y_cstride = a->y_cstride > 0 ? a->y_cstride : p.c_post; p.y_coffset = a->y_coffset;
   p.y2 = a->y2; p.y2_dtype = a->y2_dtype; p.y2_cstride = a->y2_cstride > 0 ? a->y2_cstride : p.c_post;
+  p.y2_mode = a->y2 ? a->y2_mode : 0;
+  SRB_REQUIRE(p.y2_mode == 0 || p.y2_mode == 1, "conv2d: y2_mode must be 0 (copy) or 1 (rounding error of y)");
   SRB_REQUIRE(p.x_coffset >= 0 && p.x_coffset + w->cin <= p.x_cstride, "conv2d: input channel slice out of range");
   SRB_REQUIRE(p.y_coffset >= 0 && p.y_coffset + p.c_post <= p.y_cstride, "conv2d: output channel slice out of range");
   p.B = a->batch; p.H = a->height; p.W = a->width;

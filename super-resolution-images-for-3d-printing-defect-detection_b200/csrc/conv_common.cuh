@@ -7,7 +7,7 @@ namespace srb {
 struct ConvParams {
   const void* x; int x_dtype, x_cstride, x_coffset;
   void* y;       int y_dtype, y_cstride, y_coffset;
-  void* y2;      int y2_dtype, y2_cstride;
+  void* y2;      int y2_dtype, y2_cstride, y2_mode;
   int B, H, W;
   int kh, kw, cin, cout;
   const float* w_hwio; int w_cout_pad;      // direct engine weights
@@ -33,6 +33,13 @@ __device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, fl
   if (dtype == SRB_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
   else if (dtype == SRB_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
   else reinterpret_cast<float*>(base)[idx] = v;
+}
+
+// v as it reads back from a tensor of the given dtype
+__device__ __forceinline__ float round_to(int dtype, float v) {
+  if (dtype == SRB_BF16) return __bfloat162float(__float2bfloat16_rn(v));
+  if (dtype == SRB_F16) return __half2float(__float2half_rn(v));
+  return v;
 }
 
 // value-level epilogue: everything except the store address
@@ -68,7 +75,7 @@ __device__ __forceinline__ void epilogue_store(const ConvParams& p, int b, int y
   d2s_map(p, b, y, x, co, out_pix, c_out);
   const float v = epilogue_value(p, acc, co, c_out, out_pix);
   store_elem(p.y, p.y_dtype, out_pix * p.y_cstride + p.y_coffset + c_out, v);
-  if (p.y2) store_elem(p.y2, p.y2_dtype, out_pix * p.y2_cstride + c_out, v);
+  if (p.y2) store_elem(p.y2, p.y2_dtype, out_pix * p.y2_cstride + c_out, p.y2_mode == 1 ? v - round_to(p.y_dtype, v) : v);
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream);

@@ -106,7 +106,13 @@ conv_head_kernel(const ConvParams p, int tiles_x, int tiles_y) {
             }
             const size_t pix = ((size_t)b * p.H + oy) * p.W + ox;
             head_store4(p.y, p.y_dtype, pix * p.y_cstride + p.y_coffset + cq * 4, v);
-            if (p.y2) head_store4(p.y2, p.y2_dtype, pix * p.y2_cstride + cq * 4, v);
+            if (p.y2) {
+              if (p.y2_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] -= round_to(p.y_dtype, v[j]);
+              }
+              head_store4(p.y2, p.y2_dtype, pix * p.y2_cstride + cq * 4, v);
+            }
           }
         }
       }

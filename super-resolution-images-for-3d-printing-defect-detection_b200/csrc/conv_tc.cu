@@ -225,6 +225,7 @@ __device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, 
 // instructions per channel, the specialised ones ~4):
 //   0 generic (all flags read at run time)      1 act none, 16-bit y            2 ReLU, 16-bit y
 //   3 fp32 residual, fp32 y + 16-bit y2         4 fp32 residual, 16-bit y
+//   5 16-bit (hi, lo) residual pair -> 16-bit y + its rounding error y2 (compensated trunk, all in the F rows)
 template <int kSpec>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -397,20 +398,47 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int h_dtype = h_dst == 1 ? p.y_dtype : p.y2_dtype;
     const uint32_t my_row_sw = (uint32_t)lane;          // this lane's staging row
 
+    constexpr bool G = kSpec == 0;
+    const bool act_relu = G ? p.act == SRB_ACT_RELU : kSpec == 2;
+    const bool act_other = G && p.act != SRB_ACT_NONE && p.act != SRB_ACT_RELU;
+    const bool pair = G ? q.res_prefetch == 2 : kSpec == 5;     // F rows = [16-bit hi half | 16-bit lo half]
+    const bool use_alpha = G ? p.alpha != 1.f : kSpec >= 3;
+    const bool has_res1 = G ? p.res1 != nullptr : kSpec >= 3;
+    const bool res_pref = G ? q.res_prefetch != 0 : kSpec >= 3;
+    const bool has_res2 = G && p.res2 != nullptr && !pair;
+    const bool do_clip = G && p.clip01;
+    const bool f_on = G ? f_dst != 0 : kSpec == 3;
+    const bool h_on = G ? h_dst != 0 : kSpec != 5;
+    const int epi_mode = G ? q.epi_mode : 1;
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
       const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
-      const float* src0 = reinterpret_cast<const float*>(p.res1) + tile_pixel(b, y0, x0) * (size_t)p.res1_cstride + c_out0;
+      const size_t tp = tile_pixel(b, y0, x0);
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
       const uint32_t rows_per_it = 32u >> f_lg;
       const uint32_t ch = (uint32_t)lane & (f_cpr - 1u), rsub = (uint32_t)lane >> f_lg;
+      // fp32 residual: one tensor fills the row; (hi, lo) pair: res1 fills the first half of the chunks, res2 the second
+      const uint32_t hc = f_cpr >> 1;
+      const bool second = pair && ch >= hc;
+      const uint8_t* src0;
+      uint32_t pix_bytes;
+      if (!pair) {
+        src0 = reinterpret_cast<const uint8_t*>(p.res1) + (tp * (size_t)p.res1_cstride + c_out0) * 4u + ch * 16u;
+        pix_bytes = (uint32_t)p.res1_cstride * 4u;
+      } else if (!second) {
+        src0 = reinterpret_cast<const uint8_t*>(p.res1) + (tp * (size_t)p.res1_cstride + c_out0) * 2u + ch * 16u;
+        pix_bytes = (uint32_t)p.res1_cstride * 2u;
+      } else {
+        src0 = reinterpret_cast<const uint8_t*>(p.res2) + (tp * (size_t)p.res2_cstride + c_out0) * 2u + (ch - hc) * 16u;
+        pix_bytes = (uint32_t)p.res2_cstride * 2u;
+      }
 #pragma unroll 4
       for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
         const int mm = quad * 32 + (int)row;
         if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
-          cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src0 + (size_t)pix_off(mm) * (size_t)p.res1_cstride + ch * 4u);
+          cp_async16(buf + row * f_rb + ((ch ^ (row & f_swz)) << 4), src0 + (size_t)pix_off(mm) * pix_bytes);
       }
     };
     auto copy_out = [&](uint32_t buf, uint32_t rb, uint32_t cpr, uint32_t lg, uint32_t swz, void* dst, int cstride, int coffset,
@@ -429,17 +457,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     };
 
-    constexpr bool G = kSpec == 0;
-    const bool act_relu = G ? p.act == SRB_ACT_RELU : kSpec == 2;
-    const bool act_other = G && p.act != SRB_ACT_NONE && p.act != SRB_ACT_RELU;
-    const bool use_alpha = G ? p.alpha != 1.f : kSpec >= 3;
-    const bool has_res1 = G ? p.res1 != nullptr : kSpec >= 3;
-    const bool res_pref = G ? q.res_prefetch != 0 : kSpec >= 3;
-    const bool has_res2 = G && p.res2 != nullptr;
-    const bool do_clip = G && p.clip01;
-    const bool f_on = G ? f_dst != 0 : kSpec == 3;
-    const bool h_on = G ? h_dst != 0 : true;
-    const int epi_mode = G ? q.epi_mode : 1;
     int it = 0;
     const bool staged = epi_mode == 1 && active;
     const bool prefetch = staged && res_pref;
@@ -513,7 +530,36 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint32_t fc = (uint32_t)cc >> 2;      // first of the two fp32 chunks of these 8 channels
             const uint32_t f_a0 = f_buf + my_row_sw * f_rb + (((fc) ^ (my_row_sw & f_swz)) << 4);
             const uint32_t f_a1 = f_buf + my_row_sw * f_rb + (((fc + 1u) ^ (my_row_sw & f_swz)) << 4);
-            if (has_res1) {
+            if (pair) {
+              // compensated 16-bit trunk: residual = hi + lo (two halves of the staged row); outputs y = round16(v)
+              // and y2 = v - y go back into the same two chunks
+              const uint32_t hcn = f_cpr >> 1, gc = (uint32_t)cc >> 3;
+              const uint32_t a_hi = f_buf + my_row_sw * f_rb + (((gc) ^ (my_row_sw & f_swz)) << 4);
+              const uint32_t a_lo = f_buf + my_row_sw * f_rb + (((gc + hcn) ^ (my_row_sw & f_swz)) << 4);
+              const uint4 uh = lds128(a_hi), ul = lds128(a_lo);
+              const uint32_t wh[4] = {uh.x, uh.y, uh.z, uh.w}, wl[4] = {ul.x, ul.y, ul.z, ul.w};
+              uint32_t oh[4], ol[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                float2 fh, fl;
+                if (p.y_dtype == SRB_BF16) {
+                  fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[i]));
+                  fl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wl[i]));
+                } else {
+                  fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[i]));
+                  fl = __half22float2(*reinterpret_cast<const __half2*>(&wl[i]));
+                }
+                const float v0 = v[2 * i] + fmaf(p.beta2, fl.x, p.beta1 * fh.x);
+                const float v1 = v[2 * i + 1] + fmaf(p.beta2, fl.y, p.beta1 * fh.y);
+                oh[i] = pack2(v0, v1, p.y_dtype);
+                float2 back;
+                if (p.y_dtype == SRB_BF16) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&oh[i]));
+                else back = __half22float2(*reinterpret_cast<const __half2*>(&oh[i]));
+                ol[i] = pack2(v0 - back.x, v1 - back.y, p.y_dtype);
+              }
+              sts128(a_hi, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+              if (p.y2) sts128(a_lo, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+            } else if (has_res1) {
               float rv[8];
               if (res_pref) {
                 const uint4 u0 = lds128(f_a0), u1 = lds128(f_a1);
@@ -538,11 +584,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
             }
-            if (f_on) {
+            if (f_on && !pair) {
               sts128(f_a0, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
               sts128(f_a1, make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
             }
-            if (h_on) {
+            if (h_on && !pair) {
               const uint32_t hc = (uint32_t)cc >> 3;
               uint4 pk;
               if (h_dtype == SRB_BF16)
@@ -607,7 +653,25 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (epi_mode == 1) {
+      if (epi_mode == 1 && pair) {
+        __syncwarp();
+        // chunks [0, cpr/2) of every staged row -> y, chunks [cpr/2, cpr) -> y2 (both 16-bit)
+        const uint32_t hcn = f_cpr >> 1;
+        const uint32_t rows_per_it = 32u >> f_lg;
+        const uint32_t ch = (uint32_t)lane & (f_cpr - 1u), rsub = (uint32_t)lane >> f_lg;
+        const bool second = ch >= hcn;
+        uint8_t* dst0 = second
+            ? reinterpret_cast<uint8_t*>(p.y2) + (tpix * (size_t)p.y2_cstride + (size_t)c_out0) * 2u + (ch - hcn) * 16u
+            : reinterpret_cast<uint8_t*>(p.y) + (tpix * (size_t)p.y_cstride + (size_t)(p.y_coffset + c_out0)) * 2u + ch * 16u;
+        const uint32_t pix_bytes = (uint32_t)(second ? p.y2_cstride : p.y_cstride) * 2u;
+#pragma unroll 4
+        for (uint32_t row = rsub; row < 32u; row += rows_per_it) {
+          const int mm = quad * 32 + (int)row;
+          if ((!second || p.y2) && (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W)))
+            *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes) = lds128(f_buf + row * f_rb + ((ch ^ (row & f_swz)) << 4));
+        }
+        __syncwarp();
+      } else if (epi_mode == 1) {
         __syncwarp();                                   // rows written by their owner lanes -> read by all lanes
         if (f_on)
           copy_out(f_buf, f_rb, f_cpr, f_lg, f_swz, f_dst == 1 ? p.y : p.y2, f_dst == 1 ? p.y_cstride : p.y2_cstride,
@@ -720,7 +784,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
                (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
                (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
                (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
-    if (p.y2 && ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32))) vec = false;   // need one of each kind
+    // compensated 16-bit trunk: (hi, lo) residual pair in, y + rounding error out, all the same 16-bit dtype
+    // (y2 may be absent: the layer that leaves the trunk only needs the rounded sum)
+    const bool pair = dt16(p.y_dtype) && (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == p.y_dtype)) && p.res1 && p.res2 &&
+                      p.res1_dtype == p.y_dtype && p.res2_dtype == p.y_dtype && p.act == SRB_ACT_NONE && !p.clip01;
+    if (p.y2 && !pair && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
     if (fold) { vec = false; q.epi_mode = 3; }
@@ -728,6 +796,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
       q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
       q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
+      if (pair) { q.res_prefetch = 2; q.f_dst = 0; q.h_dst = 0; }
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
     }
@@ -768,7 +837,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   }
 
   int spec = 0;
-  if (q.epi_mode == 1 && !p.res2 && !p.clip01) {
+  if (q.epi_mode == 1 && q.res_prefetch == 2) {
+    spec = 5;
+  } else if (q.epi_mode == 1 && !p.res2 && !p.clip01) {
     if (!p.res1 && p.alpha == 1.f && q.f_dst == 0 && q.h_dst == 1 && !p.y2) {
       if (p.act == SRB_ACT_NONE) spec = 1;
       else if (p.act == SRB_ACT_RELU) spec = 2;
@@ -778,9 +849,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     }
   }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const ConvParams);
-  static const KernelFn kernels[5] = {conv3x3_tc_kernel<0>, conv3x3_tc_kernel<1>, conv3x3_tc_kernel<2>,
-                                      conv3x3_tc_kernel<3>, conv3x3_tc_kernel<4>};
-  static size_t configured[5] = {0, 0, 0, 0, 0};
+  static const KernelFn kernels[6] = {conv3x3_tc_kernel<0>, conv3x3_tc_kernel<1>, conv3x3_tc_kernel<2>,
+                                      conv3x3_tc_kernel<3>, conv3x3_tc_kernel<4>, conv3x3_tc_kernel<5>};
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
   if (smem > configured[spec]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[spec] = smem;

@@ -26,7 +26,7 @@ class ConvArgs(C.Structure):
     _fields_ = [
         ("x", C.c_void_p), ("x_dtype", C.c_int), ("x_cstride", C.c_int), ("x_coffset", C.c_int),
         ("y", C.c_void_p), ("y_dtype", C.c_int), ("y_cstride", C.c_int), ("y_coffset", C.c_int),
-        ("y2", C.c_void_p), ("y2_dtype", C.c_int), ("y2_cstride", C.c_int),
+        ("y2", C.c_void_p), ("y2_dtype", C.c_int), ("y2_cstride", C.c_int), ("y2_mode", C.c_int),
         ("batch", C.c_int), ("height", C.c_int), ("width", C.c_int),
         ("weights", C.c_void_p),
         ("act", C.c_int), ("act_slope", C.c_float), ("prelu", C.c_void_p),

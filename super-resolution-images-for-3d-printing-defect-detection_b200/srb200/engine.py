@@ -38,7 +38,12 @@ class DeviceModel:
         torch = _torch()
         self.precision = precision
         self.act_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
-        self.fp32_trunk = precision != "fp32"
+        # how the residual trunk is carried in the 16-bit modes:
+        #   "fp32" - fp32 trunk next to a 16-bit operand copy (default);  "half" - plain 16-bit trunk
+        #   "pair" - compensated: h = round16(x) plus e = round16(x - h), two 16-bit tensors (~22 bits, 17 % fewer
+        #            HBM bytes per res-block, same speed on B200 because conv2 is shared-memory-pipe bound)
+        self.trunk = "fp32" if precision != "fp32" else "none"
+        self.fp32_trunk = False
         self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         self.layers = {}
         for name in self.weights:
@@ -142,10 +147,14 @@ class EDSRNet(DeviceModel):
     all conv epilogues; the graph is 2*N+4 (+1 for x4) launches."""
     arch = "EDSR"
 
-    def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16"):
+    def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16", trunk=None):
         if scale_factor not in (2, 3, 4):
             raise ValueError(f"Scale factor {scale_factor} not supported. Use 2, 3, or 4.")
         super().__init__(weights, precision)
+        if trunk is not None and precision != "fp32":
+            if trunk not in ("pair", "fp32", "half"):
+                raise ValueError("trunk must be 'pair', 'fp32' or 'half'")
+            self.trunk = trunk
         self.scale_factor, self.num_res_blocks, self.res_scaling = scale_factor, num_res_blocks, float(res_scaling)
 
     def output_scale(self):
@@ -154,7 +163,18 @@ class EDSRNet(DeviceModel):
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        if self.fp32_trunk:
+        if self.trunk == "pair":
+            # compensated 16-bit trunk: (h, e) with h the tensor-core operand of the next conv and h + e the trunk value
+            head, head_e = ops.conv2d(x, L["head"], out_dtype=dt, out2_dtype=dt, out2_error=True)
+            if self.event_hook:
+                self.event_hook("tc_begin")
+            h, e = head, head_e
+            for i in range(self.num_res_blocks):
+                t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
+                h, e = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, res2=e, out_dtype=dt,
+                                  out2_dtype=dt, out2_error=True)
+            h = ops.conv2d(h, L["body"], res1=head, res2=head_e, out_dtype=dt)
+        elif self.trunk == "fp32":
             # trunk in fp32 (y), 16-bit copy (y2) as the next conv's tensor-core operand
             head, h = ops.conv2d(x, L["head"], out_dtype=torch.float32, out2_dtype=dt)
             if self.event_hook:
@@ -164,20 +184,23 @@ class EDSRNet(DeviceModel):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
                 trunk, h = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=trunk,
                                       out_dtype=torch.float32, out2_dtype=dt)
+            h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
         else:
             head = ops.conv2d(x, L["head"], out_dtype=dt)
+            if self.event_hook:
+                self.event_hook("tc_begin")
             h = head
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
                 h = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, out_dtype=dt)
-        h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
+            h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
         if self.scale_factor in (2, 3):
             h = ops.conv2d(h, L["up0"], d2s=self.scale_factor, out_dtype=dt)
         else:
             h = ops.conv2d(h, L["up0"], d2s=2, out_dtype=dt)
             h = ops.conv2d(h, L["up1"], d2s=2, out_dtype=dt)
         y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=torch.float32)
-        if self.event_hook and self.fp32_trunk:
+        if self.event_hook:
             self.event_hook("tc_end")
         return y
 
@@ -217,19 +240,20 @@ class SRResNetNet(DeviceModel):
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        if self.fp32_trunk:
-            head, h = ops.conv2d(x, L["head"], act="prelu", out_dtype=torch.float32, out2_dtype=dt)
-            trunk = head
+        if self.trunk == "pair":
+            head, head_e = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt, out2_dtype=dt, out2_error=True)
+            h, e = head, head_e
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="prelu", out_dtype=dt)
-                trunk, h = ops.conv2d(t, L[f"rb{i}_c2"], res1=trunk, out_dtype=torch.float32, out2_dtype=dt)
+                h, e = ops.conv2d(t, L[f"rb{i}_c2"], res1=h, res2=e, out_dtype=dt, out2_dtype=dt, out2_error=True)
+            h = ops.conv2d(h, L["body"], res1=head, res2=head_e, out_dtype=dt)
         else:
             head = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt)
             h = head
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="prelu", out_dtype=dt)
                 h = ops.conv2d(t, L[f"rb{i}_c2"], res1=h, out_dtype=dt)
-        h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
+            h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
         for i in range(2 if self.scale_factor == 4 else 1):
             h = ops.conv2d(h, L[f"up{i}"], act="prelu", d2s=2, out_dtype=dt)   # PReLU after the shuffle == before it
         return ops.conv2d(h, L["tail"], out_dtype=torch.float32)

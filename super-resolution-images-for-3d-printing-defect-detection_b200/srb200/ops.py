@@ -163,13 +163,14 @@ class ConvWeights:
 
 def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, beta1=1.0, res2=None, beta2=1.0,
            clip01=False, d2s=1, out_dtype=None, out=None, out_coffset=0, x_coffset=0, engine=capi.ENGINE_AUTO,
-           out2_dtype=None):
+           out2_dtype=None, out2_error=False):
     """y = clip(alpha * act(conv(x, W) + b) + beta1 * res1 + beta2 * res2), optionally depth_to_space'd.
 
     ``x`` may be a wider NHWC buffer of which channels [x_coffset, x_coffset + cin) are read, and
     ``out`` a wider buffer written at ``out_coffset`` (concat-free dense blocks).  With ``out2_dtype`` the
     result is also written in a second dtype and ``(out, out2)`` is returned (fp32 residual trunk next to
-    the 16-bit operand of the following layer)."""
+    the 16-bit operand of the following layer); with ``out2_error`` the second output is the rounding error
+    ``v - round(out)`` instead, so that ``out + out2`` carries the value to ~22 bits in two 16-bit tensors."""
     torch = _torch()
     _check_nhwc(x, "x")
     B, H, W, Cx = x.shape
@@ -186,6 +187,7 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     if out2_dtype is not None:
         out2 = torch.empty((B, H * r, W * r, c_post), dtype=out2_dtype, device=x.device)
         a.y2, a.y2_dtype, a.y2_cstride = out2.data_ptr(), capi.dtype_code(out2), c_post
+        a.y2_mode = 1 if out2_error else 0
     a.batch, a.height, a.width = B, H, W
     a.weights = w.handle
     a.act = capi.ACTIVATIONS[act] if not isinstance(act, int) else act

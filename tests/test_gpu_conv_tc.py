@@ -123,3 +123,31 @@ def test_engines_agree_at_benchmark_tile_size():
     a = ops.conv2d(x, w, act="relu", out_dtype=torch.float32, engine=_capi.ENGINE_TCGEN05)
     b = ops.conv2d(x, w, act="relu", out_dtype=torch.float32, engine=_capi.ENGINE_DIRECT)
     assert (a - b).abs().max().item() <= 2e-3
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 32, 24), (1, 19, 21)])
+def test_compensated_trunk_pair(kind, shape):
+    """y2_mode = 1: residual given as a 16-bit (hi, lo) pair, output as y = round16(v) and y2 = v - y.
+    hi + lo must reproduce the fp64 oracle to ~2^-20 relative, far beyond a single 16-bit tensor."""
+    from srb200 import ops, _capi
+    B, H, W = shape
+    dt = DT[kind]
+    x = _round(_rand((B, H, W, 64), 1), kind)
+    kern = _round(_rand((3, 3, 64, 64), 2, -0.1, 0.1), kind)
+    bias = _rand((64,), 3, -0.1, 0.1)
+    trunk = _rand((B, H, W, 64), 5, -2.0, 2.0)
+    hi = _round(trunk, kind)
+    lo = _round(trunk - hi, kind)
+    want = 0.1 * oc.conv2d_same_numpy(x, kern, bias) + (hi.astype(np.float64) + lo)
+    w = ops.ConvWeights(kern, bias)
+    t = lambda a: torch.from_numpy(a).cuda().to(dt)
+    tol = 2e-4 if kind == "fp16" else 2e-3
+    for engine in (_capi.ENGINE_TCGEN05, _capi.ENGINE_DIRECT):
+        y, y2 = ops.conv2d(t(x), w, alpha=0.1, res1=t(hi), res2=t(lo), out_dtype=dt, out2_dtype=dt, out2_error=True,
+                           engine=engine)
+        got = y.double().cpu().numpy() + y2.double().cpu().numpy()
+        assert np.abs(got - want).max() <= tol, engine
+        assert np.abs(y.double().cpu().numpy() - want).max() > 2 * tol          # one 16-bit tensor alone is far coarser
+        y_only = ops.conv2d(t(x), w, alpha=0.1, res1=t(hi), res2=t(lo), out_dtype=dt, engine=engine)
+        assert torch.equal(y_only, y)                                           # trunk exit: same rounded sum, no y2

@@ -22,8 +22,9 @@ def main():
     ap.add_argument("--tile", type=int, default=192)
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--trunk", default="fp32")
     a = ap.parse_args()
-    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=a.dtype)
+    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=a.dtype, trunk=a.trunk)
     x = torch.rand((a.batch, a.tile, a.tile, 3), device="cuda")
     records = []
     orig = ops.conv2d
@@ -57,8 +58,9 @@ def main():
         out_b = npx * w.cout * (2 if kw.get("out_dtype") != torch.float32 else 4)
         if kw.get("out2_dtype") is not None:
             out_b += npx * w.cout * 2
-        if kw.get("res1") is not None:
-            in_b += npx * w.cout * kw["res1"].element_size()
+        for rk in ("res1", "res2"):
+            if kw.get(rk) is not None:
+                in_b += npx * w.cout * kw[rk].element_size()
         print(f"{i:3d} {w.kh}x{w.kw} {w.cin:3d}->{w.cout:3d} {npx:10d} {ms:8.3f} {flop / ms / 1e9:9.1f} {(in_b + out_b) / ms / 1e6:10.1f}")
     print(f"total {total:.3f} ms for {a.batch} tiles -> {a.batch * (a.tile * 4) ** 2 / 1e6 / (total / 1e3):.1f} MP/s")
 
