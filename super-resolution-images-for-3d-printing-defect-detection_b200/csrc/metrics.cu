@@ -22,9 +22,8 @@ __global__ void __launch_bounds__(kCols)
 psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
                  float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
   constexpr int kLine = kCols + 10 * C;
-  constexpr int kAhead = 4, kRing = kAhead + 1;      // rows in flight / line buffers
-  __shared__ float sa[kRing][kLine];
-  __shared__ float sb[kRing][kLine];
+  constexpr int kAhead = 4, kRing = 8;               // rows in flight / line buffers (power of two >= kAhead + 1)
+  __shared__ float2 sab[kRing][kLine];               // (a, b) interleaved: one 8-byte shared load per tap
   __shared__ float red[2][kCols / 32];
 
   const int WE = W * C;            // interleaved floats per image row
@@ -42,33 +41,42 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
   const float* pb = b + img_off;
   const bool col_valid = (e0 + t) < OE;
 
-  float g[11];
+  // packed fp32x2 arithmetic (FFMA2 / FMUL2, sm_100): the maps are carried as (mu_a, mu_b), (E[a^2], E[b^2]) pairs
+  // plus E[ab]; tf.image.ssim's E[a^2 + b^2] is the sum of the second pair
+  float2 g2[11];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) g[k] = c_gauss[k];
+  for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_gauss[k], c_gauss[k]);
 
-  float ra[11], rb[11], rs[11], rp[11];
+  float2 rab[11], rqq[11];
+  float rp[11];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) ra[k] = rb[k] = rs[k] = rp[k] = 0.f;
+  for (int k = 0; k < 11; ++k) { rab[k] = rqq[k] = make_float2(0.f, 0.f); rp[k] = 0.f; }
 
   float sse = 0.f, ssim_sum = 0.f;
 
-  // asynchronous fill of one line pair (row is block-uniform); columns past the image are zero
+  // asynchronous fill of one line pair (row is block-uniform).  A thread always fetches the same (at most two)
+  // line positions, so the range checks and addresses are hoisted; columns past the image stay zero
+  static_assert(kLine <= 2 * kCols, "two fetch slots per thread");
+  const bool ok0 = (e0 + t) < WE;
+  const bool ok1 = (t + kCols) < kLine && (e0 + t + kCols) < WE;
+  for (int i = t; i < kRing * kLine; i += kCols) (&sab[0][0])[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  const uint32_t s0 = (uint32_t)__cvta_generic_to_shared(&sab[0][t]);
+  const float* fa = pa + (size_t)y0 * WE + e0 + t;
+  const float* fb = pb + (size_t)y0 * WE + e0 + t;
   auto fetch = [&](int row) {
     if (row < nin) {
-      const int buf = row % kRing;
-      const float* la = pa + (size_t)(y0 + row) * WE + e0;
-      const float* lb = pb + (size_t)(y0 + row) * WE + e0;
-      for (int i = t; i < kLine; i += kCols) {
-        if (e0 + i < WE) {
-          const uint32_t da = (uint32_t)__cvta_generic_to_shared(&sa[buf][i]);
-          const uint32_t db = (uint32_t)__cvta_generic_to_shared(&sb[buf][i]);
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(da), "l"(la + i) : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(db), "l"(lb + i) : "memory");
-        } else {
-          sa[buf][i] = 0.f;
-          sb[buf][i] = 0.f;
-        }
+      const uint32_t d = s0 + (uint32_t)(row & (kRing - 1)) * (uint32_t)(kLine * sizeof(float2));
+      if (ok0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(fa) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u), "l"(fb) : "memory");
       }
+      if (ok1) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + (uint32_t)(kCols * sizeof(float2))), "l"(fa + kCols) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + (uint32_t)(kCols * sizeof(float2)) + 4u), "l"(fb + kCols) : "memory");
+      }
+      fa += WE;
+      fb += WE;
     }
     asm volatile("cp.async.commit_group;" ::: "memory");   // one group per row, empty past the end
   };
@@ -80,35 +88,36 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
     for (int j = 0; j < 11; ++j) {
       const int row = r + j;              // block-uniform
       if (row < nin) {
-        const int buf = row % kRing;
+        const int buf = row & (kRing - 1);
         const bool row_owned = (row < rows_out) || last_y;
         asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");   // this row's line has landed
         __syncthreads();                  // ... for every thread, and line (row-1) % kRing is no longer read
         fetch(row + kAhead);
         if (row_owned) {                  // squared error: every element of the row exactly once
-          { const float d = sa[buf][t] - sb[buf][t]; sse = fmaf(d, d, sse); }
-          if (last_x && t < 10 * C) { const float d = sa[buf][kCols + t] - sb[buf][kCols + t]; sse = fmaf(d, d, sse); }
+          { const float2 v = sab[buf][t]; const float d = v.x - v.y; sse = fmaf(d, d, sse); }
+          if (last_x && t < 10 * C) { const float2 v = sab[buf][kCols + t]; const float d = v.x - v.y; sse = fmaf(d, d, sse); }
         }
-        float ha = 0.f, hb = 0.f, hs = 0.f, hp = 0.f;
+        float2 hab = make_float2(0.f, 0.f), hqq = make_float2(0.f, 0.f);
+        float hp = 0.f;
 #pragma unroll
         for (int k = 0; k < 11; ++k) {
-          const float va = sa[buf][t + k * C], vb = sb[buf][t + k * C];
-          ha = fmaf(g[k], va, ha);
-          hb = fmaf(g[k], vb, hb);
-          hs = fmaf(g[k], fmaf(va, va, vb * vb), hs);
-          hp = fmaf(g[k], va * vb, hp);
+          const float2 v = sab[buf][t + k * C];
+          hab = __ffma2_rn(g2[k], v, hab);
+          hqq = __ffma2_rn(g2[k], __fmul2_rn(v, v), hqq);
+          hp = fmaf(g2[k].x, v.x * v.y, hp);
         }
-        ra[j] = ha; rb[j] = hb; rs[j] = hs; rp[j] = hp;
+        rab[j] = hab; rqq[j] = hqq; rp[j] = hp;
         if (row >= 10 && col_valid) {
-          float ma = 0.f, mb = 0.f, es = 0.f, ep = 0.f;
+          float2 mab = make_float2(0.f, 0.f), eqq = make_float2(0.f, 0.f);
+          float ep = 0.f;
 #pragma unroll
           for (int k = 0; k < 11; ++k) {
             const int slot = (j + 1 + k) % 11;   // oldest row first
-            ma = fmaf(g[k], ra[slot], ma);
-            mb = fmaf(g[k], rb[slot], mb);
-            es = fmaf(g[k], rs[slot], es);
-            ep = fmaf(g[k], rp[slot], ep);
+            mab = __ffma2_rn(g2[k], rab[slot], mab);
+            eqq = __ffma2_rn(g2[k], rqq[slot], eqq);
+            ep = fmaf(g2[k].x, rp[slot], ep);
           }
+          const float ma = mab.x, mb = mab.y, es = eqq.x + eqq.y;
           const float num0 = 2.f * ma * mb;
           const float den0 = fmaf(ma, ma, mb * mb);
           const float num = (num0 + c1) * (2.f * ep - num0 + c2);
