@@ -31,11 +31,10 @@ conv_direct_kernel(const ConvParams p) {
   const int ty0 = blockIdx.y * kDT, tx0 = blockIdx.x * kDT;
   const int ph = p.kh / 2, pw = p.kw / 2;
 
-  float acc[8][4];
+  // packed fp32x2 accumulators (FFMA2, sm_100): output-channel pairs (0,1) and (2,3) of each of the 8 pixels
+  float2 acc01[8], acc23[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int i = 0; i < 8; ++i) acc01[i] = acc23[i] = make_float2(0.f, 0.f);
 
   const size_t x_img = (size_t)b * p.H * p.W;
   for (int c0 = 0; c0 < p.cin; c0 += kDCK) {
@@ -67,14 +66,14 @@ conv_direct_kernel(const ConvParams p) {
 #pragma unroll
         for (int c = 0; c < kDCK; ++c) {
           const float4 w4 = *reinterpret_cast<const float4*>(wsm + (dx * kDCK + c) * kDN + cg * 4);
+          const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
           const float* hrow = halo + (c * HH + py + dy) * HWp + x0 + dx;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float a = hrow[i];
-            acc[i][0] = fmaf(a, w4.x, acc[i][0]);
-            acc[i][1] = fmaf(a, w4.y, acc[i][1]);
-            acc[i][2] = fmaf(a, w4.z, acc[i][2]);
-            acc[i][3] = fmaf(a, w4.w, acc[i][3]);
+            const float2 aa = make_float2(a, a);
+            acc01[i] = __ffma2_rn(aa, w01, acc01[i]);
+            acc23[i] = __ffma2_rn(aa, w23, acc23[i]);
           }
         }
       }
@@ -90,7 +89,7 @@ conv_direct_kernel(const ConvParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = cc * kDN + cg * 4 + j;
-      if (co < p.cout) epilogue_store(p, b, oy, ox, co, acc[i][j]);
+      if (co < p.cout) epilogue_store(p, b, oy, ox, co, j == 0 ? acc01[i].x : j == 1 ? acc01[i].y : j == 2 ? acc23[i].x : acc23[i].y);
     }
   }
 }

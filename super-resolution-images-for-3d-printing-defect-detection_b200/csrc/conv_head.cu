@@ -29,11 +29,12 @@ __device__ __forceinline__ void head_store4(void* base, int dtype, size_t idx, c
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 conv_head_kernel(const ConvParams p, int tiles_x, int tiles_y) {
   extern __shared__ float hsm[];
-  float* halo = hsm;                                   // [kHaloH][kHaloW][3]
-  float* wsm = hsm + kHaloH * kHaloW * 3;              // [27][cout]; 540 floats of halo keep it 16-B aligned
+  constexpr int kHaloN = kHaloH * kHaloW * 3;          // 540 floats (keeps everything after it 16-B aligned)
+  float* halo2 = hsm;                                  // [2][kHaloH][kHaloW][3], double buffered
+  float* wsm = hsm + 2 * kHaloN;                       // [27][cout]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int lpp = p.cout >> 2;                         // lanes per pixel
   const int ppw = 32 / lpp;                            // pixels per warp instruction
@@ -47,33 +48,59 @@ conv_head_kernel(const ConvParams p, int tiles_x, int tiles_y) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) bias[j] = __ldg(p.bias + cq * 4 + j);
 
+  // the (at most three) halo elements this thread fetches for every tile: position inside the halo is tile-invariant
+  int h_off[3], h_dy[3], h_dx[3], h_c[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int i = tid + k * 256;
+    const int hp = i / 3;
+    h_off[k] = i < kHaloN ? i : -1;
+    h_c[k] = i - hp * 3;
+    h_dx[k] = hp % kHaloW - 1;
+    h_dy[k] = hp / kHaloW - 1;
+  }
   const int tiles_per_img = tiles_x * tiles_y;
   const int total = p.B * tiles_per_img;
   const float* xin = reinterpret_cast<const float*>(p.x);
-  for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  auto fetch = [&](int tile, int buf) {                // asynchronous halo fill; out-of-image pixels are zero (same padding)
+    if (tile < total) {
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+      const int y0 = (r / tiles_x) * kHT_H, x0 = (r % tiles_x) * kHT_W;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (h_off[k] >= 0) {
+          float* d = halo2 + buf * kHaloN + h_off[k];
+          const int gy = y0 + h_dy[k], gx = x0 + h_dx[k];
+          if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+            const float* src = xin + (((size_t)b * p.H + gy) * p.W + gx) * p.x_cstride + p.x_coffset + h_c[k];
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(d)), "l"(src) : "memory");
+          } else {
+            *d = 0.f;
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  fetch(blockIdx.x, 0);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
     const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
     const int y0 = (r / tiles_x) * kHT_H, x0 = (r % tiles_x) * kHT_W;
-    __syncthreads();                                   // previous tile's halo fully consumed; filter visible
-    for (int i = tid; i < kHaloH * kHaloW * 3; i += 256) {
-      const int c = i % 3, hp = i / 3;
-      const int hx = hp % kHaloW, hy = hp / kHaloW;
-      const int gy = y0 + hy - 1, gx = x0 + hx - 1;
-      float v = 0.f;
-      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-        v = __ldg(xin + (((size_t)b * p.H + gy) * p.W + gx) * p.x_cstride + p.x_coffset + c);
-      halo[i] = v;
-    }
-    __syncthreads();
+    const float* halo = halo2 + (it & 1) * kHaloN;
+    __syncthreads();                                   // everyone is done with the buffer the next fetch overwrites
+    fetch(tile + gridDim.x, (it + 1) & 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();                                   // this tile's halo (and, first time, the filter) is visible
     // columns of the tile are dealt to (warp, psub) pairs; each thread does 4 vertically adjacent pixels
     for (int col = warp * ppw + psub; col < kHT_W; col += 8 * ppw) {
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         const int row0 = half * 4;
-        float acc[4][4];
+        // packed fp32x2 FMAs (FFMA2): channel pairs (0,1) and (2,3) of each of the 4 pixels
+        float2 acc01[4], acc23[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[q][j] = bias[j];
+        for (int q = 0; q < 4; ++q) { acc01[q] = make_float2(bias[0], bias[1]); acc23[q] = make_float2(bias[2], bias[3]); }
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
           float4 w[9];
@@ -85,13 +112,15 @@ conv_head_kernel(const ConvParams p, int tiles_x, int tiles_y) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               const float a = hrow[t];
-              acc[q][0] = fmaf(a, w[t].x, acc[q][0]);
-              acc[q][1] = fmaf(a, w[t].y, acc[q][1]);
-              acc[q][2] = fmaf(a, w[t].z, acc[q][2]);
-              acc[q][3] = fmaf(a, w[t].w, acc[q][3]);
+              const float2 aa = make_float2(a, a);
+              acc01[q] = __ffma2_rn(aa, make_float2(w[t].x, w[t].y), acc01[q]);
+              acc23[q] = __ffma2_rn(aa, make_float2(w[t].z, w[t].w), acc23[q]);
             }
           }
         }
+        float acc[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { acc[q][0] = acc01[q].x; acc[q][1] = acc01[q].y; acc[q][2] = acc23[q].x; acc[q][3] = acc23[q].y; }
         const int ox = x0 + col;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -137,7 +166,7 @@ bool conv_head_eligible(const ConvParams& p) {
 int conv_head_launch(const ConvParams& p, cudaStream_t stream) {
   const int tiles_x = (p.W + kHT_W - 1) / kHT_W, tiles_y = (p.H + kHT_H - 1) / kHT_H;
   const long total = (long)p.B * tiles_x * tiles_y;
-  const size_t smem = ((size_t)kHaloH * kHaloW * 3 + 27 * (size_t)p.cout) * sizeof(float);
+  const size_t smem = ((size_t)2 * kHaloH * kHaloW * 3 + 27 * (size_t)p.cout) * sizeof(float);
   const long cap = (long)sm_count() * 8;
   const int grid = (int)(total < cap ? total : cap);
   conv_head_kernel<<<grid, 256, smem, stream>>>(p, tiles_x, tiles_y);
