@@ -1,13 +1,10 @@
 // cv2.resize(..., INTER_CUBIC) on the GPU (classic_algorithms.py:11-13, loading_methods.py:147,
 // SRCNN_model.py:191).  Separable 4-tap Keys cubic (A = -0.75), half-pixel centres, tap index clamp.
 //
-// `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only place double
-// precision is used).  `bicubic_tile_kernel` does the separable resampling for a tile of 256 interleaved
-// output elements x TY output rows in three shared-memory stages: (1) the source rows/columns the tile
-// needs are streamed in with coalesced cp.async, (2) the horizontal 4-tap pass runs smem -> smem, (3) the
-// vertical 4-tap pass reads the thread's own column back and writes contiguous output rows.  The older
-// `bicubic_kernel` (horizontal taps gathered straight from global memory) remains as the fallback for
-// strong down-scaling, where the source footprint of a tile does not fit shared memory.
+// `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only place double precision is
+// used).  `bicubic_swin_kernel` (default) stages the source footprint of a 256-element x 32-row output tile in shared
+// memory with coalesced cp.async and lets every thread slide a 4-row register window of horizontal-pass results down
+// its output column; `bicubic_stream_kernel` is the same loop reading global memory, for strong down-scaling.
 //
 // float path  : t from double, FMA-contracted coefficient polynomial, FMA accumulation in tap order
 //               (OpenCV's default dispatch to <= 1e-6; uint8 = saturate(rint(.)) of the same path).
@@ -20,7 +17,7 @@ namespace srb {
 
 struct AxisTap { int idx[4]; float coef[4]; };   // 32 bytes
 
-__global__ void bicubic_tables(AxisTap* __restrict__ tab, int n_src, int n_dst, int fixed) {
+__global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base_out, int n_src, int n_dst, int fixed) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_dst) return;
   const double scale = 1.0 / ((double)n_dst / (double)n_src);
@@ -59,6 +56,7 @@ __global__ void bicubic_tables(AxisTap* __restrict__ tab, int n_src, int n_dst, 
   for (int k = 0; k < 4; ++k) a.idx[k] = min(max(s - 1 + k, 0), n_src - 1);
   a.coef[0] = c0; a.coef[1] = c1; a.coef[2] = c2; a.coef[3] = c3;
   tab[d] = a;
+  if (base_out) base_out[d] = s - 1;   // first tap row before clamping
 }
 
 constexpr int kTE = 256;   // interleaved output elements per block (= threads)
@@ -67,104 +65,103 @@ template <typename T> __device__ __forceinline__ float px_load(const T* p);
 template <> __device__ __forceinline__ float px_load<float>(const float* p) { return __ldg(p); }
 template <> __device__ __forceinline__ float px_load<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
+// Streaming variant (fallback for strong down-scaling, where a tile's source footprint does not fit shared memory):
+// a thread owns one interleaved output column (x*C + c) over a strip of output
+// rows and keeps the horizontal-pass results of the four source rows under the vertical taps in registers.  When the
+// tap window moves down by a source row, one new horizontal result is computed (4 L1-cached, block-coalesced loads +
+// 4 FMAs) - so an up-scale by s costs (4 loads + 4 FMA)/s + 4 FMA + 1 coalesced store per output element, with no
+// shared memory and no barriers.  Index clamping is applied when a row is fetched, which keeps the window a run of four
+// consecutive (unclamped) rows at the image borders.  Same arithmetic order as OpenCV, so uint8 stays bit-exact.
 template <typename T, bool FIXED>
 __global__ void __launch_bounds__(kTE)
-bicubic_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
-               const AxisTap* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w,
-               int tile_rows, int max_src_rows, int clip01) {
-  extern __shared__ float hbuf[];   // [max_src_rows][kTE]  (int32 bit patterns when FIXED)
-  const int t = threadIdx.x;
-  const int DE = dst_w * C;
-  const int e = blockIdx.x * kTE + t;
-  const int y0 = blockIdx.y * tile_rows;
-  const int y1 = min(y0 + tile_rows, dst_h) - 1;
-  const size_t src_img = (size_t)blockIdx.z * src_h * src_w * C;
-  const size_t dst_img = (size_t)blockIdx.z * dst_h * DE;
-  const int r_lo = ytab[y0].idx[0];
-  const int r_hi = ytab[y1].idx[3];
-  const int nr = min(r_hi - r_lo + 1, max_src_rows);
-  const bool valid = e < DE;
+bicubic_stream_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
+                      const AxisTap* __restrict__ ytab, const int* __restrict__ ybase, int src_h, int src_w, int C,
+                      int dst_h, int dst_w, int rows_per_block, int clip01) {
+  const int DE = dst_w * C, SE = src_w * C;
+  const int e = blockIdx.x * kTE + threadIdx.x;
+  if (e >= DE) return;
+  const int x = e / C, c = e - x * C;
+  const AxisTap xt = xtab[x];
+  const int o0 = xt.idx[0] * C + c, o1 = xt.idx[1] * C + c, o2 = xt.idx[2] * C + c, o3 = xt.idx[3] * C + c;
+  const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, dst_h);
+  const T* simg = src + (size_t)blockIdx.z * src_h * SE;
+  T* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
 
-  if (valid) {
-    const int x = e / C, c = e - x * C;
-    const AxisTap xt = xtab[x];
-    const int o0 = xt.idx[0] * C + c, o1 = xt.idx[1] * C + c, o2 = xt.idx[2] * C + c, o3 = xt.idx[3] * C + c;
-    const T* row = src + src_img + (size_t)r_lo * src_w * C;
-    for (int r = 0; r < nr; ++r, row += (size_t)src_w * C) {
-      if (FIXED) {
-        const int v = (int)row[o0] * (int)xt.coef[0] + (int)row[o1] * (int)xt.coef[1] +
-                      (int)row[o2] * (int)xt.coef[2] + (int)row[o3] * (int)xt.coef[3];
-        hbuf[r * kTE + t] = __int_as_float(v);
-      } else {
-        float v = __fmul_rn(px_load(row + o0), xt.coef[0]);
-        v = __fmaf_rn(px_load(row + o1), xt.coef[1], v);
-        v = __fmaf_rn(px_load(row + o2), xt.coef[2], v);
-        v = __fmaf_rn(px_load(row + o3), xt.coef[3], v);
-        hbuf[r * kTE + t] = v;
-      }
+  auto hrow = [&](int r) -> float {                 // horizontal pass of (clamped) source row r for this column
+    r = min(max(r, 0), src_h - 1);
+    const T* row = simg + (size_t)r * SE;
+    if (FIXED) {
+      const int v = (int)row[o0] * (int)xt.coef[0] + (int)row[o1] * (int)xt.coef[1] +
+                    (int)row[o2] * (int)xt.coef[2] + (int)row[o3] * (int)xt.coef[3];
+      return __int_as_float(v);
     }
-  }
-  // each thread only reads back its own column: no barrier needed
-  if (!valid) return;
-  for (int y = y0; y <= y1; ++y) {
-    const AxisTap yt = ytab[y];
+    float v = __fmul_rn(px_load(row + o0), xt.coef[0]);
+    v = __fmaf_rn(px_load(row + o1), xt.coef[1], v);
+    v = __fmaf_rn(px_load(row + o2), xt.coef[2], v);
+    v = __fmaf_rn(px_load(row + o3), xt.coef[3], v);
+    return v;
+  };
+
+  int u = __ldg(ybase + y0);
+  float w0 = hrow(u), w1 = hrow(u + 1), w2 = hrow(u + 2), w3 = hrow(u + 3);
+  for (int y = y0; y < y1; ++y, out += DE) {
+    const int ub = __ldg(ybase + y);                // block-uniform
+    while (u < ub) { w0 = w1; w1 = w2; w2 = w3; ++u; w3 = hrow(u + 3); }
+    const float4 cy = __ldg(reinterpret_cast<const float4*>(ytab[y].coef));
     float v;
     if (FIXED) {
       const float sc = 1.f / (2048.f * 2048.f);
-      v = __fmul_rn((float)__float_as_int(hbuf[(yt.idx[0] - r_lo) * kTE + t]), __fmul_rn(yt.coef[0], sc));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[1] - r_lo) * kTE + t]), __fmul_rn(yt.coef[1], sc)));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[2] - r_lo) * kTE + t]), __fmul_rn(yt.coef[2], sc)));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(hbuf[(yt.idx[3] - r_lo) * kTE + t]), __fmul_rn(yt.coef[3], sc)));
+      v = __fmul_rn((float)__float_as_int(w0), __fmul_rn(cy.x, sc));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w1), __fmul_rn(cy.y, sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w2), __fmul_rn(cy.z, sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w3), __fmul_rn(cy.w, sc)));
     } else {
-      v = __fmul_rn(hbuf[(yt.idx[0] - r_lo) * kTE + t], yt.coef[0]);
-      v = __fmaf_rn(hbuf[(yt.idx[1] - r_lo) * kTE + t], yt.coef[1], v);
-      v = __fmaf_rn(hbuf[(yt.idx[2] - r_lo) * kTE + t], yt.coef[2], v);
-      v = __fmaf_rn(hbuf[(yt.idx[3] - r_lo) * kTE + t], yt.coef[3], v);
+      v = __fmul_rn(w0, cy.x);
+      v = __fmaf_rn(w1, cy.y, v);
+      v = __fmaf_rn(w2, cy.z, v);
+      v = __fmaf_rn(w3, cy.w, v);
     }
     if (sizeof(T) == 1) {
-      const int q = __float2int_rn(v);                       // round-half-even, then saturate
-      reinterpret_cast<uint8_t*>(dst)[dst_img + (size_t)y * DE + e] = (uint8_t)min(max(q, 0), 255);
+      const int qv = __float2int_rn(v);                      // round-half-even, then saturate
+      *reinterpret_cast<uint8_t*>(out) = (uint8_t)min(max(qv, 0), 255);
     } else {
       if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-      reinterpret_cast<float*>(dst)[dst_img + (size_t)y * DE + e] = v;
+      *reinterpret_cast<float*>(out) = v;
     }
   }
 }
 
-
-struct __align__(16) RowTap { int off[4]; float coef[4]; };   // vertical taps of one output row, offsets into the H buffer
-
-// V consecutive output elements per thread (V = 4: 16-byte shared / global accesses, needs dst_w * C % 4 == 0),
-// NT threads per block; a block covers NT * V interleaved output elements x tile_rows output rows.
-template <typename T, bool FIXED, int V, int NT>
-__global__ void __launch_bounds__(NT)
-bicubic_tile_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
-                    const AxisTap* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w,
-                    int tile_rows, int max_src_rows, int max_src_cols, int clip01) {
-  constexpr int kBE = NT * V;                                // output elements per block row
-  extern __shared__ __align__(16) float tsm[];
-  float* S = tsm;                                            // [max_src_rows][max_src_cols] source tile (as float)
-  float* Hb = S + (size_t)max_src_rows * max_src_cols;       // [max_src_rows][kBE] horizontal-pass results
-  RowTap* rt = reinterpret_cast<RowTap*>(Hb + (size_t)max_src_rows * kBE);   // [tile_rows]
+// Shared-memory sliding-window variant (the default): stage 1 of the tiled kernel (coalesced cp.async of the source
+// footprint) feeds the register window of the streaming kernel, so the horizontal pass reads shared memory instead of
+// global memory and there is no horizontal-result buffer: per output element an up-scale by s costs 4/s shared gathers
+// + 2 uniform shared loads (row coefficients, row base) + 1 coalesced store, and ~20 KB of shared memory per block.
+template <typename T, bool FIXED>
+__global__ void __launch_bounds__(kTE)
+bicubic_swin_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
+                    const AxisTap* __restrict__ ytab, const int* __restrict__ ybase, int src_h, int src_w, int C,
+                    int dst_h, int dst_w, int tile_rows, int max_src_rows, int max_src_cols, int clip01) {
+  extern __shared__ __align__(16) float wsm_[];
+  float* S = wsm_;                                               // [max_src_rows][max_src_cols]
+  float4* cy = reinterpret_cast<float4*>(S + (size_t)max_src_rows * max_src_cols);   // [tile_rows] vertical coefficients
+  int* ub = reinterpret_cast<int*>(cy + tile_rows);              // [tile_rows] first (unclamped) tap row, tile-relative
   const int t = threadIdx.x;
   const int DE = dst_w * C, SE = src_w * C;
-  const int e0 = blockIdx.x * kBE;
-  const int e = e0 + t * V;                                  // first element of this thread
+  const int e0 = blockIdx.x * kTE;
+  const int e = e0 + t;
   const int y0 = blockIdx.y * tile_rows;
-  const int y1 = min(y0 + tile_rows, dst_h) - 1;
+  const int y1 = min(y0 + tile_rows, dst_h);
   const size_t src_img = (size_t)blockIdx.z * src_h * SE;
-  const size_t dst_img = (size_t)blockIdx.z * dst_h * DE;
-  const int r_lo = ytab[y0].idx[0];
-  const int nr = min(ytab[y1].idx[3] - r_lo + 1, max_src_rows);
-  const int x_first = e0 / C, x_last = (min(e0 + kBE, DE) - 1) / C;
+  const int u0 = __ldg(ybase + y0);                              // unclamped first source row of the tile
+  const int nr = min(__ldg(ybase + y1 - 1) + 4 - u0, max_src_rows);
+  const int x_first = e0 / C, x_last = (min(e0 + kTE, DE) - 1) / C;
   const int c_lo = xtab[x_first].idx[0] * C;
   const int nc = min(xtab[x_last].idx[3] * C + C - c_lo, max_src_cols);
-  const bool valid = e < DE;                                 // DE % V == 0, so all V elements are in range together
 
-  // stage 1: source footprint -> shared memory (coalesced along the row)
+  // stage 1: rows u0 .. u0+nr-1 (clamped to the image) x columns c_lo .. c_lo+nc-1 -> shared memory
   for (int r = 0; r < nr; ++r) {
-    const T* row = src + src_img + (size_t)(r_lo + r) * SE + c_lo;
-    for (int i = t; i < nc; i += NT) {
+    const int gr = min(max(u0 + r, 0), src_h - 1);
+    const T* row = src + src_img + (size_t)gr * SE + c_lo;
+    for (int i = t; i < nc; i += kTE) {
       if (sizeof(T) == 4) {
         const uint32_t d = (uint32_t)__cvta_generic_to_shared(S + r * max_src_cols + i);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(row + i) : "memory");
@@ -173,100 +170,57 @@ bicubic_tile_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
       }
     }
   }
-  for (int i = t; i <= y1 - y0; i += NT) {
-    const AxisTap a = ytab[y0 + i];
-    RowTap q;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { q.off[k] = (a.idx[k] - r_lo) * kBE; q.coef[k] = a.coef[k]; }
-    rt[i] = q;
+  for (int i = t; i < y1 - y0; i += kTE) {
+    cy[i] = __ldg(reinterpret_cast<const float4*>(ytab[y0 + i].coef));
+    ub[i] = __ldg(ybase + y0 + i) - u0;
   }
   if (sizeof(T) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
+  if (e >= DE) return;
 
-  if (!valid) return;
-  // stage 2: horizontal pass, V output columns per thread, all source rows of the tile
-  {
-    int o[V][4];
-    float cf[V][4];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const int x = (e + v) / C, c = (e + v) - x * C;
-      const AxisTap xt = xtab[x];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) { o[v][k] = xt.idx[k] * C + c - c_lo; cf[v][k] = xt.coef[k]; }
+  const int x = e / C, c = e - x * C;
+  const AxisTap xt = xtab[x];
+  const int o0 = xt.idx[0] * C + c - c_lo, o1 = xt.idx[1] * C + c - c_lo, o2 = xt.idx[2] * C + c - c_lo,
+            o3 = xt.idx[3] * C + c - c_lo;
+  auto hrow = [&](int r) -> float {                    // horizontal pass of tile row r for this column
+    const float* row = S + min(r, nr - 1) * max_src_cols;
+    if (FIXED) {
+      const int v = (int)row[o0] * (int)xt.coef[0] + (int)row[o1] * (int)xt.coef[1] +
+                    (int)row[o2] * (int)xt.coef[2] + (int)row[o3] * (int)xt.coef[3];
+      return __int_as_float(v);
     }
-    const float* srow = S;
-#pragma unroll 2
-    for (int r = 0; r < nr; ++r, srow += max_src_cols) {
-      float h[V];
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        if (FIXED) {
-          const int iv = (int)srow[o[v][0]] * (int)cf[v][0] + (int)srow[o[v][1]] * (int)cf[v][1] +
-                         (int)srow[o[v][2]] * (int)cf[v][2] + (int)srow[o[v][3]] * (int)cf[v][3];
-          h[v] = __int_as_float(iv);
-        } else {
-          float a = __fmul_rn(srow[o[v][0]], cf[v][0]);
-          a = __fmaf_rn(srow[o[v][1]], cf[v][1], a);
-          a = __fmaf_rn(srow[o[v][2]], cf[v][2], a);
-          a = __fmaf_rn(srow[o[v][3]], cf[v][3], a);
-          h[v] = a;
-        }
-      }
-      if (V == 4) *reinterpret_cast<float4*>(Hb + r * kBE + t * 4) = make_float4(h[0], h[1], h[2], h[3]);
-      else Hb[r * kBE + t] = h[0];
-    }
-  }
-  // stage 3: vertical pass; each thread only reads back its own columns of Hb (no barrier needed)
-  const float* hcol = Hb + t * V;
-  T* out = dst + dst_img + (size_t)y0 * DE + e;
-#pragma unroll 2
-  for (int i = 0; i <= y1 - y0; ++i, out += DE) {
-    const RowTap q = rt[i];
-    float hv[4][V];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (V == 4) {
-        const float4 f = *reinterpret_cast<const float4*>(hcol + q.off[k]);
-        hv[k][0] = f.x; hv[k][1 % V] = f.y; hv[k][2 % V] = f.z; hv[k][3 % V] = f.w;
-      } else {
-        hv[k][0] = hcol[q.off[k]];
-      }
-    }
-    float res[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float a;
-      if (FIXED) {
-        const float sc = 1.f / (2048.f * 2048.f);
-        a = __fmul_rn((float)__float_as_int(hv[0][v]), __fmul_rn(q.coef[0], sc));
-        a = __fadd_rn(a, __fmul_rn((float)__float_as_int(hv[1][v]), __fmul_rn(q.coef[1], sc)));
-        a = __fadd_rn(a, __fmul_rn((float)__float_as_int(hv[2][v]), __fmul_rn(q.coef[2], sc)));
-        a = __fadd_rn(a, __fmul_rn((float)__float_as_int(hv[3][v]), __fmul_rn(q.coef[3], sc)));
-      } else {
-        a = __fmul_rn(hv[0][v], q.coef[0]);
-        a = __fmaf_rn(hv[1][v], q.coef[1], a);
-        a = __fmaf_rn(hv[2][v], q.coef[2], a);
-        a = __fmaf_rn(hv[3][v], q.coef[3], a);
-      }
-      res[v] = a;
+    float v = __fmul_rn(row[o0], xt.coef[0]);
+    v = __fmaf_rn(row[o1], xt.coef[1], v);
+    v = __fmaf_rn(row[o2], xt.coef[2], v);
+    v = __fmaf_rn(row[o3], xt.coef[3], v);
+    return v;
+  };
+  int u = 0;
+  float w0 = hrow(0), w1 = hrow(1), w2 = hrow(2), w3 = hrow(3);
+  T* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
+  for (int i = 0; i < y1 - y0; ++i, out += DE) {
+    const int un = ub[i];                              // block-uniform
+    while (u < un) { w0 = w1; w1 = w2; w2 = w3; ++u; w3 = hrow(u + 3); }
+    const float4 k = cy[i];
+    float v;
+    if (FIXED) {
+      const float sc = 1.f / (2048.f * 2048.f);
+      v = __fmul_rn((float)__float_as_int(w0), __fmul_rn(k.x, sc));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w1), __fmul_rn(k.y, sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w2), __fmul_rn(k.z, sc)));
+      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w3), __fmul_rn(k.w, sc)));
+    } else {
+      v = __fmul_rn(w0, k.x);
+      v = __fmaf_rn(w1, k.y, v);
+      v = __fmaf_rn(w2, k.z, v);
+      v = __fmaf_rn(w3, k.w, v);
     }
     if (sizeof(T) == 1) {
-      uint32_t pk = 0;
-#pragma unroll
-      for (int v = 0; v < V; ++v) {
-        const int qv = min(max(__float2int_rn(res[v]), 0), 255);     // round-half-even, then saturate
-        pk |= (uint32_t)qv << (8 * v);
-      }
-      if (V == 4) *reinterpret_cast<uint32_t*>(out) = pk;
-      else *reinterpret_cast<uint8_t*>(out) = (uint8_t)pk;
+      const int qv = __float2int_rn(v);                      // round-half-even, then saturate
+      *reinterpret_cast<uint8_t*>(out) = (uint8_t)min(max(qv, 0), 255);
     } else {
-      if (clip01) {
-#pragma unroll
-        for (int v = 0; v < V; ++v) res[v] = fminf(fmaxf(res[v], 0.f), 1.f);
-      }
-      if (V == 4) *reinterpret_cast<float4*>(out) = make_float4(res[0], res[1 % V], res[2 % V], res[3 % V]);
-      else *reinterpret_cast<float*>(out) = res[0];
+      if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+      *reinterpret_cast<float*>(out) = v;
     }
   }
 }
@@ -278,52 +232,42 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
   SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "bicubic: bad geometry");
   if (batch == 0) return SRB_OK;
   AxisTap* tabs = nullptr;
-  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh), stream));
+  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh) + sizeof(int) * (size_t)dh, stream));
+  int* ybase = reinterpret_cast<int*>(tabs + (size_t)dw + dh);
   AxisTap* xtab = tabs;
   AxisTap* ytab = tabs + dw;
-  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, sw, dw, FIXED ? 1 : 0);
-  bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, sh, dh, FIXED ? 1 : 0);
+  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, nullptr, sw, dw, FIXED ? 1 : 0);
+  bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, ybase, sh, dh, FIXED ? 1 : 0);
   int rc = launch_check("bicubic_tables");
   if (rc) return rc;
-  int tile_rows = 32;
-  auto src_rows = [&](int tr) { return (int)(((long)tr * sh + dh - 1) / dh) + 5; };
-  // vector path: 4 consecutive elements per thread when rows of the output keep 16-byte (uint8: 4-byte) alignment
-  // (opt-in: measured slower than the scalar mapping on B200 - 22 % vs 35 % of HBM at x2 - because 128-thread blocks
-  //  with 40 KB of staging leave too few warps to cover the stage-1 load latency; kept for the double-buffered rewrite)
-  static const bool vec4_enabled = getenv("SRB_BICUBIC_VEC4") != nullptr;
-  const bool vec4 = vec4_enabled && ((dw * C) % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) % (4 * sizeof(T))) == 0);
-  const int NT = vec4 ? 128 : kTE, V = vec4 ? 4 : 1, BE = NT * V;
-  // source columns one block can touch: its output pixels scaled back, plus the 4-tap support
-  const double ratio = (double)sw / (double)dw;
-  const int src_px = (int)((BE / C + 2) * (ratio > 1.0 ? ratio : 1.0)) + 6;
-  const int msc = ((src_px * C) + 3) & ~3;
-  auto tile_smem = [&](int tr) {
-    return ((size_t)src_rows(tr) * (msc + BE)) * sizeof(float) + (size_t)tr * sizeof(RowTap);
-  };
-  if (vec4) tile_rows = 16;
-  while (tile_rows > 4 && tile_smem(tile_rows) > 48 * 1024) tile_rows >>= 1;
-  if (tile_smem(tile_rows) <= 96 * 1024) {
-    const int msr = src_rows(tile_rows);
-    const size_t smem = tile_smem(tile_rows);
-    dim3 grid((dw * C + BE - 1) / BE, (dh + tile_rows - 1) / tile_rows, batch);
-    SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
-    if (vec4) {
-      SRB_CUDA(cudaFuncSetAttribute(bicubic_tile_kernel<T, FIXED, 4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bicubic_tile_kernel<T, FIXED, 4, 128><<<grid, 128, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, msc, clip01);
+  {
+    // default: shared-memory sliding window
+    const double ratio = (double)sw / (double)dw;
+    const int src_px = (int)((kTE / C + 2) * (ratio > 1.0 ? ratio : 1.0)) + 6;
+    const int msc = ((src_px * C) + 3) & ~3;
+    int tr = 32;
+    auto rows_needed = [&](int n) { return (int)(((long)n * sh + dh - 1) / dh) + 6; };
+    auto need = [&](int n) { return (size_t)rows_needed(n) * msc * sizeof(float) + (size_t)n * (sizeof(float4) + sizeof(int)); };
+    while (tr > 4 && need(tr) > 40 * 1024) tr >>= 1;
+    if (need(tr) <= 96 * 1024) {
+      const size_t smem = need(tr);
+      SRB_CUDA(cudaFuncSetAttribute(bicubic_swin_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dim3 grid((dw * C + kTE - 1) / kTE, (dh + tr - 1) / tr, batch);
+      SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
+      bicubic_swin_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, ybase, sh, sw, C, dh, dw, tr,
+                                                                 rows_needed(tr), msc, clip01);
+      rc = launch_check("bicubic_swin_kernel");
     } else {
-      SRB_CUDA(cudaFuncSetAttribute(bicubic_tile_kernel<T, FIXED, 1, kTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      bicubic_tile_kernel<T, FIXED, 1, kTE><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, msc, clip01);
+      // strong down-scaling: stream straight from global memory
+      int rows = 64;
+      const long target = 4L * sm_count();
+      while (rows > 8 && (long)((dw * C + kTE - 1) / kTE) * ((dh + rows - 1) / rows) * batch < target) rows >>= 1;
+      dim3 grid((dw * C + kTE - 1) / kTE, (dh + rows - 1) / rows, batch);
+      SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
+      bicubic_stream_kernel<T, FIXED><<<grid, kTE, 0, stream>>>(src, dst, xtab, ytab, ybase, sh, sw, C, dh, dw, rows, clip01);
+      rc = launch_check("bicubic_stream_kernel");
     }
-  } else {
-    tile_rows = 32;
-    while (tile_rows > 1 && (size_t)src_rows(tile_rows) * kTE * sizeof(float) > 96 * 1024) tile_rows >>= 1;
-    const int msr = src_rows(tile_rows);
-    const size_t smem = (size_t)msr * kTE * sizeof(float);
-    SRB_CUDA(cudaFuncSetAttribute(bicubic_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((dw * C + kTE - 1) / kTE, (dh + tile_rows - 1) / tile_rows, batch);
-    bicubic_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, sh, sw, C, dh, dw, tile_rows, msr, clip01);
   }
-  rc = launch_check("bicubic_kernel");
   SRB_CUDA(cudaFreeAsync(tabs, stream));
   return rc;
 }

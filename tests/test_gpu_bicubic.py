@@ -75,3 +75,14 @@ def test_full_size_linearity():
     assert (lhs - rhs).abs().max() <= 1e-5
     ones = torch.full((1, 1080, 1920, 3), 0.5, device="cuda")
     assert (ops.bicubic(ones, 2160, 3840) - 0.5).abs().max() <= 1e-6     # taps sum to one
+
+
+def test_downscale_uses_streaming_fallback():
+    """Strong down-scaling: the source footprint of a tile exceeds shared memory -> global-memory streaming kernel."""
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_bicubic, resize_cubic
+    rng = np.random.default_rng(5)
+    f = rng.random((400, 500, 3), dtype=np.float32)
+    assert np.abs(interpolate_bicubic(f, (31, 20)) - ob.resize_cubic_f32(f, (31, 20), "default")).max() <= 1e-6
+    u = rng.integers(0, 256, (300, 300, 3), dtype=np.uint8)
+    assert np.array_equal(resize_cubic(u, (23, 17), fixed_point=True), ob.resize_cubic_u8(u, (23, 17), "scalar"))
+    assert np.abs(interpolate_bicubic(f, (250, 200)) - ob.cv2_resize(f, (250, 200))).max() <= 2e-6   # mild x0.5 (smem path)
