@@ -112,6 +112,11 @@ int srb_conv2d_engine(const srb_conv_args* args);
  * descriptors; 1 = as 0 with the descriptor base-offset field set from the shifted address;
  * 2 = three dx-shifted TMA tiles so that every tap starts on a 1024-byte swizzle boundary. */
 int srb_conv_tc_set_variant(int variant);
+/* tcgen05 engine: launch eligible layers (>= 32-channel chunks) as CTA pairs - clusters of two CTAs issuing
+ * cta_group::2 MMAs (M = 256) from the leader, each CTA keeping half of the weight rows.  Returns the previous
+ * setting (on < 0 only queries).  Default off (environment SRB_TC_2CTA=1 turns it on): measured equal to the
+ * single-CTA kernel on B200 for these N <= 128 tiles. */
+int srb_conv_tc_set_cta_pairs(int on);
 
 /* ---- small layout / elementwise helpers used between layers -------------------------------------- */
 int srb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, float shift,

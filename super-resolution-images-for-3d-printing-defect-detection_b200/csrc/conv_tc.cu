@@ -49,6 +49,7 @@ struct TcParams {
   uint32_t epi_warp_bytes;
   int fold;              // horizontal taps folded into N (cout <= 4): 3 MMA taps (dy), 8 input columns -> 6 output columns
   int tile_cols_out;     // 8, or 6 when folded
+  int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -123,6 +124,51 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- cta_group::2 (CTA pair) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> the pair's leader
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {     // arrives on the barrier at this offset in BOTH CTAs
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // arrive on the leader CTA's copy of the barrier
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar) : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -226,7 +272,10 @@ __device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, 
 //   0 generic (all flags read at run time)      1 act none, 16-bit y            2 ReLU, 16-bit y
 //   3 fp32 residual, fp32 y + 16-bit y2         4 fp32 residual, 16-bit y
 //   5 16-bit (hi, lo) residual pair -> 16-bit y + its rounding error y2 (compensated trunk, all in the F rows)
-template <int kSpec>
+// k2: cta_group::2 - a cluster of two CTAs issues M = 256 MMAs (128 pixels per CTA) from the leader; each CTA keeps
+// only half of the weight rows (the tensor cores fetch the other half from the peer), which cuts the per-CTA
+// B-operand shared-memory traffic and the resident weight footprint in half.
+template <int kSpec, bool k2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const TcParams q, const ConvParams p) {
@@ -237,7 +286,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint8_t* smem = smem_raw + (base - raw);
 
   const int n_taps = q.fold ? 3 : 9;
-  const uint32_t w_bytes = (uint32_t)n_taps * (uint32_t)q.n_tile * 128u;
+  const uint32_t rank = k2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
+  const uint32_t n_local = k2 ? (uint32_t)q.n_tile / 2u : (uint32_t)q.n_tile;   // weight rows held by this CTA
+  const uint32_t w_bytes = (uint32_t)n_taps * n_local * 128u;
   const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base;
   const uint32_t a_smem = base + w_span;
@@ -254,22 +305,30 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile], 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int chunk = (int)(blockIdx.x % (unsigned)q.n_chunks);
-  const int first_tile = (int)(blockIdx.x / (unsigned)q.n_chunks);
-  const int tile_step = (int)(gridDim.x / (unsigned)q.n_chunks);
+  // work units: a CTA (or a CTA pair) owns channel chunk `unit % n_chunks` and every (units / n_chunks)-th tile (pair)
+  const unsigned unit = k2 ? blockIdx.x >> 1 : blockIdx.x, units = k2 ? gridDim.x >> 1 : gridDim.x;
+  const int chunk = (int)(unit % (unsigned)q.n_chunks);
+  const int first_tile = (int)(unit / (unsigned)q.n_chunks) * (k2 ? 2 : 1) + (int)rank;
+  const int tile_step = (int)(units / (unsigned)q.n_chunks) * (k2 ? 2 : 1);
+  // both CTAs of a pair run the same number of iterations; the odd one may get a dummy tile past the end
+  const int tile_end = q.total_tiles + (int)rank;
   const int co_base = chunk * q.n_tile;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     mbar_init(wfull_bar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), (q.n_tile < 32 && q.epi_mode != 1) ? 16 * kEpiWarps : 32 * kEpiWarps); }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      // one arrival per participating epilogue warp (an elected lane, after the warp's TMEM reads have completed)
+      mbar_init(tempty_bar(a), ((q.n_tile < 32 && q.epi_mode != 1) ? kEpiWarps / 2 : kEpiWarps) * (k2 ? 2 : 1));
+    }
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), q.tmem_cols);
+  if (warp == 1) { if (k2) tmem_alloc_2sm(smem_u32(tmem_slot), q.tmem_cols); else tmem_alloc(smem_u32(tmem_slot), q.tmem_cols); }
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();   // barrier inits must be visible to the peer before it signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -280,36 +339,51 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // the whole warp runs the (warp-uniform) loop so that addresses live in uniform registers; one elected
     // lane issues the asynchronous copies
     if (elect_one()) {
-      mbar_expect_tx(wfull_bar, w_bytes);
-      for (int t = 0; t < n_taps; ++t)
-        tma_load_2d(w_smem + (uint32_t)t * (uint32_t)q.n_tile * 128u, &tmap_w, wfull_bar, 0, t * q.w_rows + co_base);
+      // k2: both CTAs' weight halves and A tiles report to the LEADER's barriers (it issues the MMAs for the pair)
+      if (!k2) mbar_expect_tx(wfull_bar, w_bytes);
+      else if (rank == 0) mbar_expect_tx(wfull_bar, 2u * w_bytes);
+      for (int t = 0; t < n_taps; ++t) {
+        const uint32_t dstw = w_smem + (uint32_t)t * n_local * 128u;
+        const int row = t * q.w_rows + co_base + (int)(rank * n_local);
+        if (k2) tma_load_2d_2sm(dstw, &tmap_w, wfull_bar, 0, row); else tma_load_2d(dstw, &tmap_w, wfull_bar, 0, row);
+      }
     }
     __syncwarp();
     int s = 0; uint32_t ph = 0;
-    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
-      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;
+    for (int tile = first_tile; tile < tile_end; tile += tile_step) {
+      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
       const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * q.tile_cols_out;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
       if (elect_one()) {
-        mbar_expect_tx(full_bar(s), q.load_bytes * (uint32_t)q.n_loads);
-        for (int l = 0; l < q.n_loads; ++l)
-          tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
+        const uint32_t bytes = q.load_bytes * (uint32_t)q.n_loads;
+        if (!k2) mbar_expect_tx(full_bar(s), bytes);
+        else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes);
+        for (int l = 0; l < q.n_loads; ++l) {
+          if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
+          else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
+        }
       }
       __syncwarp();
       if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // warp-uniform loop (descriptors in uniform registers); one elected lane issues the 36 MMAs of a tile
+    // warp-uniform loop (descriptors in uniform registers); one elected lane issues the 36 MMAs of a tile.
+    // k2: only the leader CTA issues (cta_group::2 instructions act on both CTAs' shared and tensor memory)
+    auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc_flag) {
+      if (k2) umma_f16_2sm(d, ad, bd, q.idesc, acc_flag); else umma_f16(d, ad, bd, q.idesc, acc_flag);
+    };
+    auto commit = [&](uint32_t bar) { if (k2) umma_commit_2sm(bar); else umma_commit(bar); };
+    if (!k2 || rank == 0) {
     mbar_wait(wfull_bar, 0);
     int s = 0; uint32_t ph = 0; int it = 0;
     const uint32_t sbo = (uint32_t)q.pitch * 128u;
     const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
-    const uint32_t b_tap_step = ((uint32_t)q.n_tile * 128u) >> 4;      // descriptor address units (16 B)
+    const uint32_t b_tap_step = (n_local * 128u) >> 4;                  // descriptor address units (16 B)
     const uint32_t a_dy = (uint32_t)q.pitch * 8u;                       // one halo row, in 16-B units
     const uint32_t a_dx = (q.n_loads == 1) ? 8u : (q.load_bytes >> 4);  // one pixel / one dx sub-tile
-    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
@@ -325,10 +399,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int dy = 0; dy < 3; ++dy) {
             const uint64_t ad = a_desc0 + (uint64_t)(dy * a_dy), bd = b_desc0 + (uint64_t)dy * b_tap_step;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
+            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((dy | k) != 0));
           }
-          umma_commit(empty_bar(s));
-          umma_commit(tfull_bar(acc));
+          commit(empty_bar(s));
+          commit(tfull_bar(acc));
         }
       } else if (q.base_off_mode == 0) {
         // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
@@ -339,10 +413,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
             const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((tap | k) != 0));
+            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
           }
-          umma_commit(empty_bar(s));       // smem stage reusable once these MMAs have read it
-          umma_commit(tfull_bar(acc));     // accumulator complete
+          commit(empty_bar(s));            // smem stage reusable once these MMAs have read it (both CTAs in k2)
+          commit(tfull_bar(acc));          // accumulator complete
         }
       } else if (elect_one()) {            // diagnostic variants 1 / 3 (descriptor base-offset field set)
 #pragma unroll 1
@@ -359,6 +433,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       __syncwarp();
       if (++s == q.stages) { s = 0; ph ^= 1u; }
+    }
     }
   } else {
     // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
@@ -464,9 +539,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (first_tile < q.total_tiles) prefetch_res(first_tile, 0);
       cp_async_commit();
     }
-    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+    auto release_tmem = [&](int acc) {                  // accumulator drained -> the (leader's) MMA warp may overwrite it
+      tc_fence_before();
+      __syncwarp();                                     // every lane's tcgen05.wait::ld has retired
+      if (lane == 0) { if (k2 && rank != 0) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
+    };
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
+      const bool live = tile < q.total_tiles;           // (k2: the pair's odd CTA may hold a dummy tile)
       const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
-      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
+      const int y0 = live ? (rr_ / q.tiles_x) * kTileH : p.H, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
       const int acc = it & 1;
@@ -483,8 +564,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       if (!active) {                                    // chunk too narrow to split: this warp only keeps the protocol
-        tc_fence_before();
-        mbar_arrive(tempty_bar(acc));
+        release_tmem(acc);
         continue;
       }
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
@@ -499,10 +579,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         __syncwarp();                                   // tcgen05.ld is warp-collective (.sync.aligned)
         tmem_ld16(t_row + (uint32_t)c0, rr);
         tmem_ld_wait();
-        if (c0 + 16 >= ncols) {                         // last read of this accumulator: hand it back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(tempty_bar(acc));
-        }
+        if (c0 + 16 >= ncols) release_tmem(acc);        // last read of this accumulator: hand it back to the MMA warp
         if (epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
@@ -685,11 +762,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (k2) cluster_sync_all(); else __syncthreads();    // (k2: the peer may still be reading this CTA's smem / signalling its barriers)
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, q.tmem_cols);
+    if (k2) tmem_dealloc_2sm(tmem_base, q.tmem_cols); else tmem_dealloc(tmem_base, q.tmem_cols);
   }
 }
 
@@ -697,6 +774,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int g_variant = 0;
+static int g_two_cta = -1;      // -1: read SRB_TC_2CTA on first use
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -748,6 +826,10 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
 
+  // cta_group::2 (CTA pairs): 0 = off, 1 = on for every eligible layer
+  if (g_two_cta < 0) { const char* e = getenv("SRB_TC_2CTA"); g_two_cta = e ? atoi(e) : 0; }
+  const int two_cta = g_two_cta;
+
   // channel-chunk width per CTA: the widest of {128, 64, rows, 16} that divides the padded cout and whose weights,
   // >= 2 A stages and epilogue staging fit shared memory (N = 128 halves the A-operand smem traffic per FLOP)
   TcParams q{};
@@ -776,7 +858,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.tmem_cols = 32;
     while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
     const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
-    q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const bool k2c = two_cta && !fold && variant == 0 && nt >= 32;
+    q.two_cta = k2c ? 1 : 0;
+    q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)((k2c ? 2 * kTileM : kTileM) >> 4) << 24);
     // staged vector epilogue: one fp32 and/or one 16-bit destination; a warp's columns map to one d2s sub-pixel
     const int warp_cols = nt >= 32 ? nt / 2 : nt;
     bool vec = (nt == 16 || nt == 32 || nt == 64 || nt == 128) && (p.cout % nt == 0) &&
@@ -800,7 +884,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
     }
-    const size_t w_bytes = ((size_t)(fold ? 3 : 9) * nt * 128 + 1023) & ~(size_t)1023;
+    const size_t w_bytes = ((size_t)(fold ? 3 : 9) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float);
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
@@ -829,7 +913,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   {
     const cuuint64_t dims[2] = {64, q.fold ? (cuuint64_t)48 : (cuuint64_t)9 * rows};
     const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, (cuuint32_t)q.n_tile};
+    const cuuint32_t box[2] = {64, (cuuint32_t)(q.two_cta ? q.n_tile / 2 : q.n_tile)};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&tmw, tdt, 2, (void*)(q.fold ? p.w_tc_fold : p.w_tc), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -849,23 +933,47 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     }
   }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const ConvParams);
-  static const KernelFn kernels[6] = {conv3x3_tc_kernel<0>, conv3x3_tc_kernel<1>, conv3x3_tc_kernel<2>,
-                                      conv3x3_tc_kernel<3>, conv3x3_tc_kernel<4>, conv3x3_tc_kernel<5>};
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  if (smem > configured[spec]) {
-    SRB_CUDA(cudaFuncSetAttribute(kernels[spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[spec] = smem;
+  static const KernelFn kernels[2][6] = {
+      {conv3x3_tc_kernel<0, false>, conv3x3_tc_kernel<1, false>, conv3x3_tc_kernel<2, false>,
+       conv3x3_tc_kernel<3, false>, conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>},
+      {conv3x3_tc_kernel<0, true>, conv3x3_tc_kernel<1, true>, conv3x3_tc_kernel<2, true>,
+       conv3x3_tc_kernel<3, true>, conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>}};
+  static size_t configured[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+  const int k2 = q.two_cta;
+  if (smem > configured[k2][spec]) {
+    SRB_CUDA(cudaFuncSetAttribute(kernels[k2][spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[k2][spec] = smem;
   }
+  const int unit = q.n_chunks * (k2 ? 2 : 1);          // CTAs per (chunk-complete) scheduling unit
   int grid = sm_count();
-  grid -= grid % q.n_chunks;
-  if (grid < q.n_chunks) grid = q.n_chunks;
-  const long work = (long)q.total_tiles * q.n_chunks;
-  if ((long)grid > work) grid = (int)(work - work % q.n_chunks);
-  kernels[spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
+  grid -= grid % unit;
+  if (grid < unit) grid = unit;
+  const long work = ((long)(k2 ? (q.total_tiles + 1) / 2 : q.total_tiles)) * unit;
+  if ((long)grid > work) grid = (int)work;
+  if (k2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SRB_CUDA(cudaLaunchKernelEx(&cfg, kernels[1][spec], tmx, tmw, q, p));
+  } else {
+    kernels[0][spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
+  }
   return launch_check("conv3x3_tc_kernel");
 }
 
 }  // namespace srb
+
+extern "C" int srb_conv_tc_set_cta_pairs(int on) {
+  const int prev = srb::g_two_cta > 0 ? 1 : 0;
+  if (on >= 0) srb::g_two_cta = on ? 1 : 0;
+  return prev;
+}
 
 extern "C" int srb_conv_tc_set_variant(int variant) {
   const int prev = srb::g_variant;

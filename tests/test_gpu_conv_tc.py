@@ -151,3 +151,27 @@ def test_compensated_trunk_pair(kind, shape):
         assert np.abs(y.double().cpu().numpy() - want).max() > 2 * tol          # one 16-bit tensor alone is far coarser
         y_only = ops.conv2d(t(x), w, alpha=0.1, res1=t(hi), res2=t(lo), out_dtype=dt, engine=engine)
         assert torch.equal(y_only, y)                                           # trunk exit: same rounded sum, no y2
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 24, 64), (1, 21, 13, 64), (1, 24, 24, 256), (3, 16, 8, 64)])
+def test_cta_pairs_match_single_cta(shape):
+    """cta_group::2 launch (cluster of two CTAs, M = 256 MMAs, weights split across the pair, odd tile counts give
+    the second CTA a dummy tile) must give bit-identical results to the single-CTA kernel."""
+    from srb200 import ops, _capi
+    B, H, W, cout = shape
+    x = torch.from_numpy(_round(_rand((B, H, W, 64), 1), "fp16")).cuda().half()
+    w = ops.ConvWeights(_round(_rand((3, 3, 64, cout), 2, -0.1, 0.1), "fp16"), _rand((cout,), 3, -0.1, 0.1))
+    res = torch.from_numpy(_rand((B, H, W, cout), 5)).cuda()
+    outs = []
+    for pairs in (0, 1):
+        prev = _capi.lib().srb_conv_tc_set_cta_pairs(pairs)
+        try:
+            a = ops.conv2d(x, w, act="relu", out_dtype=torch.float16, engine=_capi.ENGINE_TCGEN05)
+            b32, b16 = ops.conv2d(x, w, alpha=0.1, res1=res, out_dtype=torch.float32, out2_dtype=torch.float16,
+                                  engine=_capi.ENGINE_TCGEN05)
+            torch.cuda.synchronize()
+        finally:
+            _capi.lib().srb_conv_tc_set_cta_pairs(prev)
+        outs.append((a, b32, b16))
+    for u, v in zip(*outs):
+        assert torch.equal(u, v)
