@@ -145,9 +145,13 @@ extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
   if (p.B == 0) return SRB_OK;
   const bool tc_ok = conv_tc_eligible(p);
   if (a->engine == SRB_ENGINE_TCGEN05 && !tc_ok) {
-    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, cin == 64, 3x3)");
+    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, cin == 64, odd filter up to 9x9)");
     return SRB_E_UNSUPPORTED;
   }
-  if (a->engine == SRB_ENGINE_TCGEN05 || (a->engine == SRB_ENGINE_AUTO && tc_ok)) return conv_tc_launch(p, (cudaStream_t)stream);
+  if (a->engine == SRB_ENGINE_TCGEN05) return conv_tc_launch(p, (cudaStream_t)stream);
+  if (a->engine == SRB_ENGINE_AUTO && tc_ok) {
+    rc = conv_tc_launch(p, (cudaStream_t)stream);
+    if (rc != SRB_E_UNSUPPORTED) return rc;          // (a shape whose staging does not fit shared memory falls through)
+  }
   return conv_direct_launch(p, (cudaStream_t)stream);
 }

@@ -23,7 +23,6 @@
 namespace srb {
 
 constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM rows
-constexpr int kHaloH = kTileH + 2;
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kMaxStages = 8;
@@ -42,7 +41,8 @@ struct TcParams {
   uint32_t tmem_cols;
   uint32_t idesc;
   int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses);
-                         // 2: few-channel epilogue (cout <= 4, e.g. the RGB tail)
+                         // 2: few-channel epilogue (cout <= 4, e.g. the RGB tail); 3: dx-folded few-channel epilogue;
+                         // 4: depth_to_space to few channels (ESPCN): r*c_post contiguous floats per output row
   int f_bufs;            // per-warp fp32 staging buffers (0, 1, or 2 when the residual is prefetched)
   int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
   int res_prefetch;      // res1 is fp32 and is prefetched into the F buffers with cp.async
@@ -50,6 +50,8 @@ struct TcParams {
   int fold;              // horizontal taps folded into N (cout <= 4): 3 MMA taps (dy), 8 input columns -> 6 output columns
   int tile_cols_out;     // 8, or 6 when folded
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
+  int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
+  int halo_rows;         // kTileH + kh - 1
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -285,7 +287,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
 
-  const int n_taps = q.fold ? 3 : 9;
+  const int n_taps = q.fold ? 3 : q.kh * q.kw;
   const uint32_t rank = k2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   const uint32_t n_local = k2 ? (uint32_t)q.n_tile / 2u : (uint32_t)q.n_tile;   // weight rows held by this CTA
   const uint32_t w_bytes = (uint32_t)n_taps * n_local * 128u;
@@ -360,8 +362,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         if (!k2) mbar_expect_tx(full_bar(s), bytes);
         else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes);
         for (int l = 0; l < q.n_loads; ++l) {
-          if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
-          else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - 1 + l, y0 - 1, b);
+          if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
+          else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
         }
       }
       __syncwarp();
@@ -401,6 +403,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
             for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((dy | k) != 0));
           }
+          commit(empty_bar(s));
+          commit(tfull_bar(acc));
+        }
+      } else if (q.kh != 3 || q.kw != 3) {
+        // general odd filter (5x5, 9x9 ...): same shifted-descriptor scheme, rolled tap loops
+        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
+        if (elect_one()) {
+          int tap = 0;
+          for (int ty_ = 0; ty_ < q.kh; ++ty_)
+            for (int tx_ = 0; tx_ < q.kw; ++tx_, ++tap) {
+              const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ty_ * a_dy + (uint32_t)tx_ * 8u);
+              const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
+            }
           commit(empty_bar(s));
           commit(tfull_bar(acc));
         }
@@ -570,6 +587,42 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
       const size_t tpix = tile_pixel(b, y0, x0);
       const size_t my_pix = tpix + pix_off(m);
+      if (epi_mode == 4) {
+        // depth_to_space straight to a few-channel image (ESPCN: 48 -> 4x4 x RGB): the r*c_post channels of one
+        // sub-row i are r*c_post contiguous floats of output row oy*r + i, and neighbouring lanes continue the run
+        uint32_t ra[16], rb[16];
+        __syncwarp();
+        tmem_ld16(t_row, ra);
+        tmem_ld16(t_row + 16u, rb);                     // (ncols <= 32; columns past ncols belong to the peer warp, unused)
+        tmem_ld_wait();
+        release_tmem(acc);
+        if (valid) {
+          const int rg = r * p.c_post;                  // floats per output sub-row (a multiple of 4)
+          const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
+          float* drow = reinterpret_cast<float*>(p.y) + (((size_t)b * OH + (size_t)oy * r) * OW + (size_t)ox * r) * p.c_post;
+          const size_t sub_row = OW * (size_t)p.c_post;  // floats between output rows
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) {              // static register indices: groups of 4 columns
+            if (4 * c4 < ncols) {
+              float v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int cidx = 4 * c4 + u;
+                float t = __uint_as_float(cidx < 16 ? ra[cidx & 15] : rb[cidx & 15]) + bias_s[col0 + cidx];
+                if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
+                else if (p.act != SRB_ACT_NONE) t = act_generic(t, p.act, p.act_slope);
+                t *= p.alpha;
+                if (p.clip01) t = fminf(fmaxf(t, 0.f), 1.f);
+                v[u] = t;
+              }
+              const int cb = c_first + 4 * c4;          // conv-domain channel of v[0]
+              const int i = cb / rg, off = cb - i * rg;
+              *reinterpret_cast<float4*>(drow + (size_t)i * sub_row + off) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll 1
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t rr[16];
@@ -795,7 +848,10 @@ static EncodeTiledFn encode_fn() {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 bool conv_tc_eligible(const ConvParams& p) {
-  if (p.kh != 3 || p.kw != 3 || p.cin != 64 || !p.w_tc) return false;
+  if (p.cin != 64 || !p.w_tc || p.kh > 9 || p.kw > 9) return false;
+  if ((p.kh != 3 || p.kw != 3) && g_variant != 0) return false;   // the staging experiments are 3x3 only
+  // 16-row weight chunk for every tap + one halo stage must fit next to barriers and staging (9x9: 166 KB + 48 KB)
+  if ((size_t)p.kh * p.kw * 16 * 128 + (size_t)(kTileH + p.kh - 1) * (kTileW + p.kw - 1) * 128 > 216 * 1024) return false;
   if (p.x_dtype != SRB_BF16 && p.x_dtype != SRB_F16) return false;
   if ((p.x_cstride % 8) || (p.x_coffset % 8) || !aligned16(p.x)) return false;
   if (p.W < 1 || p.H < 1) return false;
@@ -820,7 +876,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int variant = g_variant;
   static const bool fold_enabled = getenv("SRB_TC_NOFOLD") == nullptr;
-  const bool fold = fold_enabled && variant == 0 && p.w_tc_fold && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2;
+  const bool fold = fold_enabled && variant == 0 && p.kh == 3 && p.kw == 3 && p.w_tc_fold && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2;
   const int cols_out = fold ? kTileW - 2 : kTileW;
   const long total = (long)p.B * ((p.W + cols_out - 1) / cols_out) * ((p.H + kTileH - 1) / kTileH);
   SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
@@ -841,6 +897,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (!fold && (nt > ntile_max || rows % nt)) continue;
     q = TcParams{};
     q.fold = fold ? 1 : 0;
+    q.kh = p.kh; q.kw = p.kw;
+    q.halo_rows = kTileH + p.kh - 1;
     q.tile_cols_out = cols_out;
     q.n_tile = nt;
     q.n_chunks = fold ? 1 : rows / nt;
@@ -851,9 +909,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (fold) { q.pitch = kTileW; q.n_loads = 1; }       // 8 input columns: every dy shift is 1,024-B aligned
     else if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
     else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
-    else { q.pitch = kTileW + 2; q.n_loads = 1; }
+    else { q.pitch = kTileW + p.kw - 1; q.n_loads = 1; }
     q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
-    q.load_bytes = (uint32_t)(kHaloH * q.pitch * 128);
+    q.load_bytes = (uint32_t)(q.halo_rows * q.pitch * 128);
     q.stage_bytes = ((q.load_bytes * (uint32_t)q.n_loads) + 1023u) & ~1023u;
     q.tmem_cols = 32;
     while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
@@ -876,6 +934,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
     if (fold) { vec = false; q.epi_mode = 3; }
+    // depth_to_space onto a few-channel fp32 image: every warp's column range is whole sub-rows of r*c_post floats
+    if (!vec && !fold && p.d2s > 1 && p.y_dtype == SRB_F32 && !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU &&
+        p.y_cstride == p.c_post && p.y_coffset == 0 && (p.d2s * p.c_post) % 4 == 0 && aligned16(p.y) &&
+        nt <= 64 && p.cout == nt && warp_cols % (p.d2s * p.c_post) == 0)
+      q.epi_mode = 4;
     if (vec) {
       q.f_dst = p.y_dtype == SRB_F32 ? 1 : (p.y2 && p.y2_dtype == SRB_F32 ? 2 : 0);
       q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
@@ -884,7 +947,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
     }
-    const size_t w_bytes = ((size_t)(fold ? 3 : 9) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
+    const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float);
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
@@ -892,9 +955,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.stages = stage_cap;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);
-    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16);
+    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16 || ci == 3);
   }
-  SRB_REQUIRE(found, "conv(tcgen05): tile does not fit shared memory");
+  if (!found) { set_error("conv(tcgen05): weights + one pipeline stage + epilogue staging do not fit shared memory"); return SRB_E_UNSUPPORTED; }
 
   // ---- tensor maps ----
   const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -903,7 +966,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2,
                                    (cuuint64_t)p.H * p.W * p.x_cstride * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)q.pitch, (cuuint32_t)kHaloH, 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)q.pitch, (cuuint32_t)q.halo_rows, 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     void* gptr = (void*)((const uint16_t*)p.x + p.x_coffset);
     CUresult r = encode(&tmx, tdt, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -911,7 +974,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, q.fold ? (cuuint64_t)48 : (cuuint64_t)9 * rows};
+    const cuuint64_t dims[2] = {64, q.fold ? (cuuint64_t)48 : (cuuint64_t)(p.kh * p.kw) * rows};
     const cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {64, (cuuint32_t)(q.two_cta ? q.n_tile / 2 : q.n_tile)};
     const cuuint32_t es[2] = {1, 1};

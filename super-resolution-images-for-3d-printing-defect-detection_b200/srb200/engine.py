@@ -212,6 +212,15 @@ class ESPCNNet(DeviceModel):
     def __init__(self, weights, scale_factor=4, activation="relu", precision="fp16"):
         super().__init__(weights, precision)
         self.scale_factor, self.activation = scale_factor, activation
+        # 16-bit modes: the tensor-core engine needs Cin = 64, so conv3's 32 input channels are zero-padded to 64
+        # (conv2 writes channels [0, 32) of a 64-wide buffer whose upper half stays zero; conv3's kernel gets zero
+        # rows for the padded channels) - twice the MMA work of an exact K = 288 GEMM, still far ahead of CUDA cores
+        k3 = self.weights["conv3/kernel"]
+        self._pad3 = None
+        if precision != "fp32" and k3.shape[2] == 32:
+            k3p = np.zeros((k3.shape[0], k3.shape[1], 64, k3.shape[3]), np.float32)
+            k3p[:, :, :32, :] = k3
+            self._pad3 = ops.ConvWeights(k3p, self.weights.get("conv3/bias"))
 
     def output_scale(self):
         return self.scale_factor
@@ -220,6 +229,11 @@ class ESPCNNet(DeviceModel):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
         h = ops.conv2d(x, L["conv1"], act=self.activation, out_dtype=dt)
+        if self._pad3 is not None:
+            B, H, W, _ = h.shape
+            wide = torch.zeros((B, H, W, 64), dtype=dt, device=h.device)
+            ops.conv2d(h, L["conv2"], act=self.activation, out=wide, out_coffset=0)
+            return ops.conv2d(wide, self._pad3, d2s=self.scale_factor, out_dtype=torch.float32)
         h = ops.conv2d(h, L["conv2"], act=self.activation, out_dtype=dt)
         return ops.conv2d(h, L["conv3"], d2s=self.scale_factor, out_dtype=torch.float32)
 

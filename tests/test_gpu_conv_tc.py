@@ -23,10 +23,10 @@ def _rand(shape, seed, lo=-1.0, hi=1.0):
     return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
 
 
-def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, **kw):
+def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, **kw):
     from srb200 import ops, _capi
     x = _round(_rand((B, H, W, 64), 1), kind)
-    kern = _round(_rand((3, 3, 64, cout), 2, -0.1, 0.1), kind)
+    kern = _round(_rand((ksize, ksize, 64, cout), 2, -0.1, 0.1), kind)
     bias = _rand((cout,), 3, -0.1, 0.1)
     r = kw.get("d2s", 1)
     c_post = cout // (r * r)
@@ -175,3 +175,24 @@ def test_cta_pairs_match_single_cta(shape):
         outs.append((a, b32, b16))
     for u, v in zip(*outs):
         assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("ksize,shape", [(5, (1, 20, 13, 64)), (9, (1, 33, 17, 3)), (9, (2, 16, 8, 64)), (7, (1, 9, 30, 32)),
+                                         (1, (1, 18, 10, 64))])
+def test_larger_filters(ksize, shape):
+    """Odd K x K filters with Cin = 64 (SRResNet's 9x9 tail, 5x5 / 7x7 / 1x1): same shifted-descriptor scheme, K*K taps."""
+    B, H, W, cout = shape
+    big = ksize == 9 and cout == 64                        # 166 KB of weights: only the 16-bit staging fits next to them
+    got, want = _run("fp16", B, H, W, cout, ksize=ksize, out_dtype=torch.float16 if big else torch.float32)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= (2e-2 if big else 2e-3 * max(1.0, ksize * ksize / 9.0))
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16), (1, 21, 13)])
+def test_depth_to_space_to_rgb(shape):
+    """ESPCN tail: 64 (zero-padded from 32) -> 48 channels + depth_to_space(4) -> RGB, written as 48-byte runs."""
+    B, H, W = shape
+    got, want = _run("fp16", B, H, W, 48, d2s=4)
+    assert got.shape == (B, 4 * H, 4 * W, 3) and np.abs(got - want).max() <= 2e-3
+    got, want = _run("fp16", B, H, W, 12, d2s=2, act="relu")
+    assert got.shape == (B, 2 * H, 2 * W, 3) and np.abs(got - want).max() <= 2e-3
