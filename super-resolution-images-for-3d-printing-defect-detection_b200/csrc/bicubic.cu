@@ -2,9 +2,10 @@
 // SRCNN_model.py:191).  Separable 4-tap Keys cubic (A = -0.75), half-pixel centres, tap index clamp.
 //
 // `bicubic_tables` evaluates the per-axis tap indices and coefficients once (the only place double precision is
-// used).  `bicubic_swin_kernel` (default) stages the source footprint of a 256-element x 32-row output tile in shared
-// memory with coalesced cp.async and lets every thread slide a 4-row register window of horizontal-pass results down
-// its output column; `bicubic_stream_kernel` is the same loop reading global memory, for strong down-scaling.
+// used).  `bicubic_quad_kernel` (default) stages the source footprint of a 1,024-element x up-to-64-row output tile in
+// shared memory and lets every thread slide a 4-row register window of horizontal-pass results down four adjacent
+// output columns (packed fp32x2 math, 16-byte stores); `bicubic_stream_kernel` is the one-column loop reading global
+// memory, for strong down-scaling where the footprint does not fit.
 //
 // float path  : t from double, FMA-contracted coefficient polynomial, FMA accumulation in tap order
 //               (OpenCV's default dispatch to <= 1e-6; uint8 = saturate(rint(.)) of the same path).
@@ -131,96 +132,192 @@ bicubic_stream_kernel(const T* __restrict__ src, T* __restrict__ dst, const Axis
   }
 }
 
-// Shared-memory sliding-window variant (the default): stage 1 of the tiled kernel (coalesced cp.async of the source
-// footprint) feeds the register window of the streaming kernel, so the horizontal pass reads shared memory instead of
-// global memory and there is no horizontal-result buffer: per output element an up-scale by s costs 4/s shared gathers
-// + 2 uniform shared loads (row coefficients, row base) + 1 coalesced store, and ~20 KB of shared memory per block.
-template <typename T, bool FIXED>
-__global__ void __launch_bounds__(kTE)
-bicubic_swin_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
-                    const AxisTap* __restrict__ ytab, const int* __restrict__ ybase, int src_h, int src_w, int C,
-                    int dst_h, int dst_w, int tile_rows, int max_src_rows, int max_src_cols, int clip01) {
-  extern __shared__ __align__(16) float wsm_[];
-  float* S = wsm_;                                               // [max_src_rows][max_src_cols]
-  float4* cy = reinterpret_cast<float4*>(S + (size_t)max_src_rows * max_src_cols);   // [tile_rows] vertical coefficients
-  int* ub = reinterpret_cast<int*>(cy + tile_rows);              // [tile_rows] first (unclamped) tap row, tile-relative
+// Shared-memory quad kernel (the default).  A block owns kQT * kQE = 1,024 interleaved output elements (x*C + c) by
+// `tile_rows` output rows.  Stage 1 copies the source footprint of the tile into shared memory as float with 16-byte
+// (uint8: 4-byte) vector accesses; rows and columns outside the image are filled with the clamped (replicated) border
+// pixels there, so the main loop needs no index clamps.  Every thread then produces kQE = 4 consecutive output
+// elements per row - one 16-byte (uint8: 4-byte) coalesced store - and slides a 4-row register window of
+// horizontal-pass results down its columns: an up-scale by s costs (16 shared gathers + 8 packed FMAs) / s + 8 packed
+// FMAs + 1 store per four output elements.  The arithmetic is fp32x2 packed (FMUL2 / FFMA2), which is the same IEEE
+// operation per lane as the scalar code, so the results are bit-identical to the streaming kernel:
+//   float path : FMA chain in tap order (OpenCV default dispatch to <= 1e-6);
+//   fixed path : the integer horizontal pass is evaluated in fp32 (|sum| < 2^24, so every product and sum is exact),
+//                the vertical pass is OpenCV's float32 multiply-then-add with coefficients scaled by 2^-22.
+constexpr int kQT = 256;   // threads per block
+constexpr int kQE = 4;     // interleaved output elements per thread
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+};
+template <> struct Vec4<uint8_t> {
+  static __device__ __forceinline__ float4 load(const uint8_t* p) {
+    const uchar4 v = __ldg(reinterpret_cast<const uchar4*>(p));
+    return make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  }
+};
+
+template <typename T, bool FIXED, int KC>    // KC: compile-time channel count (tap offsets become immediates), 0 = run time
+__global__ void __launch_bounds__(kQT)
+bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
+                    const int* __restrict__ xbase, const AxisTap* __restrict__ ytab, const int* __restrict__ ybase,
+                    int src_h, int src_w, int C_rt, int dst_h, int dst_w, int tile_rows, int max_src_rows, int pitch,
+                    int vec_src, int vec_dst, int clip01) {
+  const int C = KC ? KC : C_rt;
+  extern __shared__ __align__(16) float qsm_[];
+  float* S = qsm_;                                                          // [max_src_rows][pitch]
+  float4* cyv = reinterpret_cast<float4*>(S + (size_t)max_src_rows * pitch);  // [tile_rows] vertical coefficients
+  int* ub = reinterpret_cast<int*>(cyv + tile_rows);                        // [tile_rows] first tap row, tile-relative
   const int t = threadIdx.x;
   const int DE = dst_w * C, SE = src_w * C;
-  const int e0 = blockIdx.x * kTE;
-  const int e = e0 + t;
+  const int e0 = blockIdx.x * (kQT * kQE);
   const int y0 = blockIdx.y * tile_rows;
-  const int y1 = min(y0 + tile_rows, dst_h);
-  const size_t src_img = (size_t)blockIdx.z * src_h * SE;
-  const int u0 = __ldg(ybase + y0);                              // unclamped first source row of the tile
-  const int nr = min(__ldg(ybase + y1 - 1) + 4 - u0, max_src_rows);
-  const int x_first = e0 / C, x_last = (min(e0 + kTE, DE) - 1) / C;
-  const int c_lo = xtab[x_first].idx[0] * C;
-  const int nc = min(xtab[x_last].idx[3] * C + C - c_lo, max_src_cols);
+  const int rows = min(tile_rows, dst_h - y0);
+  const int u0 = __ldg(ybase + y0);                                         // unclamped first source row of the tile
+  const int nr = min(__ldg(ybase + y0 + rows - 1) + 4 - u0, max_src_rows);
+  const int x_first = e0 / C, x_last = (min(e0 + kQT * kQE, DE) - 1) / C;
+  const int c_lo = (__ldg(xbase + x_first) * C) & ~3;                       // floor to a multiple of 4 (may be negative)
+  const int nc4 = min(((__ldg(xbase + x_last) + 4) * C - c_lo + 3) >> 2, pitch >> 2);
+  const T* simg = src + (size_t)blockIdx.z * src_h * SE;
 
-  // stage 1: rows u0 .. u0+nr-1 (clamped to the image) x columns c_lo .. c_lo+nc-1 -> shared memory
-  for (int r = 0; r < nr; ++r) {
-    const int gr = min(max(u0 + r, 0), src_h - 1);
-    const T* row = src + src_img + (size_t)gr * SE + c_lo;
-    for (int i = t; i < nc; i += kTE) {
-      if (sizeof(T) == 4) {
-        const uint32_t d = (uint32_t)__cvta_generic_to_shared(S + r * max_src_cols + i);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(row + i) : "memory");
+  // stage 1: source rows u0 .. u0+nr-1 x elements c_lo .. c_lo+4*nc4-1, border-replicated, as float.  The (row, chunk)
+  // space is flattened over the block (row = idx / nc4 by multiply-high); interior float chunks go through cp.async so
+  // that every load of the tile is in flight at once.
+  {
+    const uint32_t total = (uint32_t)(nr * nc4);
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nc4 + 1u;                // exact quotient for idx < 2^32 / nc4
+    for (uint32_t idx = t; idx < total; idx += kQT) {
+      const int r = (int)__umulhi(idx, magic);
+      const int i = (int)idx - r * nc4;
+      const int gr = min(max(u0 + r, 0), src_h - 1);
+      const T* row = simg + (size_t)gr * SE;
+      float* sdst = S + r * pitch + 4 * i;
+      const int q = c_lo + 4 * i;
+      if (vec_src && q >= 0 && q + 4 <= SE) {
+        if (sizeof(T) == 4) {
+          const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(row + q) : "memory");
+        } else {
+          *reinterpret_cast<float4*>(sdst) = Vec4<T>::load(row + q);
+        }
       } else {
-        S[r * max_src_cols + i] = px_load(row + i);
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int qq = q + k;
+          int px = (qq + 8 * C) / C - 8;                                    // floor division (qq >= -2C - 3)
+          const int ch = qq - px * C;
+          px = min(max(px, 0), src_w - 1);
+          f[k] = px_load(row + px * C + ch);
+        }
+        *reinterpret_cast<float4*>(sdst) = make_float4(f[0], f[1], f[2], f[3]);
       }
     }
-  }
-  for (int i = t; i < y1 - y0; i += kTE) {
-    cy[i] = __ldg(reinterpret_cast<const float4*>(ytab[y0 + i].coef));
-    ub[i] = __ldg(ybase + y0 + i) - u0;
-  }
-  if (sizeof(T) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  if (e >= DE) return;
-
-  const int x = e / C, c = e - x * C;
-  const AxisTap xt = xtab[x];
-  const int o0 = xt.idx[0] * C + c - c_lo, o1 = xt.idx[1] * C + c - c_lo, o2 = xt.idx[2] * C + c - c_lo,
-            o3 = xt.idx[3] * C + c - c_lo;
-  auto hrow = [&](int r) -> float {                    // horizontal pass of tile row r for this column
-    const float* row = S + min(r, nr - 1) * max_src_cols;
-    if (FIXED) {
-      const int v = (int)row[o0] * (int)xt.coef[0] + (int)row[o1] * (int)xt.coef[1] +
-                    (int)row[o2] * (int)xt.coef[2] + (int)row[o3] * (int)xt.coef[3];
-      return __int_as_float(v);
+    for (int i = t; i < rows; i += kQT) {
+      float4 k = __ldg(reinterpret_cast<const float4*>(ytab[y0 + i].coef));
+      if (FIXED) {
+        const float sc = 1.f / (2048.f * 2048.f);
+        k = make_float4(__fmul_rn(k.x, sc), __fmul_rn(k.y, sc), __fmul_rn(k.z, sc), __fmul_rn(k.w, sc));
+      }
+      cyv[i] = k;
+      ub[i] = __ldg(ybase + y0 + i) - u0;
     }
-    float v = __fmul_rn(row[o0], xt.coef[0]);
-    v = __fmaf_rn(row[o1], xt.coef[1], v);
-    v = __fmaf_rn(row[o2], xt.coef[2], v);
-    v = __fmaf_rn(row[o3], xt.coef[3], v);
-    return v;
+    if (sizeof(T) == 4) asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+  __syncthreads();
+  // Element mapping.  float: lane l of warp w owns elements e0 + 128 w + 32 j + l (j = 0..3), so one shared gather of a
+  // warp covers 32 consecutive output elements (<= 32 consecutive source floats when up-scaling: no bank conflicts) and
+  // each of the four 4-byte stores is a fully coalesced 128-byte line.  uint8: thread t owns the four consecutive
+  // elements e0 + 4 t + j and packs them into one 4-byte store.
+  constexpr bool kStrided = sizeof(T) == 4;
+  const int ef = kStrided ? e0 + (t >> 5) * (32 * kQE) + (t & 31) : e0 + kQE * t;   // first of this thread's elements
+  constexpr int kStep = kStrided ? 32 : 1;
+  if (ef >= DE) return;
+
+  // per-element tap origin (unclamped: the staged tile replicates the borders) and packed horizontal coefficients
+  int ob[kQE];
+  float2 cx[4][kQE / 2];
+#pragma unroll
+  for (int j = 0; j < kQE; ++j) {
+    const int e = min(ef + j * kStep, DE - 1);                              // (past the row end: repeat the last element)
+    const int x = e / C, c = e - x * C;
+    const float4 k = __ldg(reinterpret_cast<const float4*>(xtab[x].coef));
+    ob[j] = __ldg(xbase + x) * C + c - c_lo;
+    if (j & 1) { cx[0][j >> 1].y = k.x; cx[1][j >> 1].y = k.y; cx[2][j >> 1].y = k.z; cx[3][j >> 1].y = k.w; }
+    else       { cx[0][j >> 1].x = k.x; cx[1][j >> 1].x = k.y; cx[2][j >> 1].x = k.z; cx[3][j >> 1].x = k.w; }
+  }
+  auto hrow = [&](int r, float2 (&w)[kQE / 2]) {                            // horizontal pass of tile row r
+    const float* row = S + min(r, nr - 1) * pitch;
+#pragma unroll
+    for (int p = 0; p < kQE / 2; ++p) {
+      const float* a = row + ob[2 * p];
+      const float* b = row + ob[2 * p + 1];
+      float2 v = __fmul2_rn(make_float2(a[0], b[0]), cx[0][p]);
+      v = __ffma2_rn(make_float2(a[C], b[C]), cx[1][p], v);
+      v = __ffma2_rn(make_float2(a[2 * C], b[2 * C]), cx[2][p], v);
+      v = __ffma2_rn(make_float2(a[3 * C], b[3 * C]), cx[3][p], v);
+      w[p] = v;
+    }
   };
+  float2 w0[kQE / 2], w1[kQE / 2], w2[kQE / 2], w3[kQE / 2];
+  hrow(0, w0); hrow(1, w1); hrow(2, w2); hrow(3, w3);
   int u = 0;
-  float w0 = hrow(0), w1 = hrow(1), w2 = hrow(2), w3 = hrow(3);
-  T* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
-  for (int i = 0; i < y1 - y0; ++i, out += DE) {
-    const int un = ub[i];                              // block-uniform
-    while (u < un) { w0 = w1; w1 = w2; w2 = w3; ++u; w3 = hrow(u + 3); }
-    const float4 k = cy[i];
-    float v;
-    if (FIXED) {
-      const float sc = 1.f / (2048.f * 2048.f);
-      v = __fmul_rn((float)__float_as_int(w0), __fmul_rn(k.x, sc));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w1), __fmul_rn(k.y, sc)));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w2), __fmul_rn(k.z, sc)));
-      v = __fadd_rn(v, __fmul_rn((float)__float_as_int(w3), __fmul_rn(k.w, sc)));
-    } else {
-      v = __fmul_rn(w0, k.x);
-      v = __fmaf_rn(w1, k.y, v);
-      v = __fmaf_rn(w2, k.z, v);
-      v = __fmaf_rn(w3, k.w, v);
+  const bool all4 = ef + (kQE - 1) * kStep < DE;
+  T* out = dst + ((size_t)blockIdx.z * dst_h + y0) * DE + ef;
+  for (int i = 0; i < rows; ++i, out += DE) {
+    const int un = ub[i];                                                   // block-uniform
+    while (u < un) {
+#pragma unroll
+      for (int p = 0; p < kQE / 2; ++p) { w0[p] = w1[p]; w1[p] = w2[p]; w2[p] = w3[p]; }
+      ++u;
+      hrow(u + 3, w3);
+    }
+    const float4 k = cyv[i];
+    float v[kQE];
+#pragma unroll
+    for (int p = 0; p < kQE / 2; ++p) {
+      float2 a;
+      if (FIXED) {
+        // scalar on purpose: the product and the sum round separately (OpenCV's float32 vertical pass), and ptxas
+        // contracts the packed mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 even when written as inline PTX
+        a.x = __fmul_rn(w0[p].x, k.x);                    a.y = __fmul_rn(w0[p].y, k.x);
+        a.x = __fadd_rn(a.x, __fmul_rn(w1[p].x, k.y));    a.y = __fadd_rn(a.y, __fmul_rn(w1[p].y, k.y));
+        a.x = __fadd_rn(a.x, __fmul_rn(w2[p].x, k.z));    a.y = __fadd_rn(a.y, __fmul_rn(w2[p].y, k.z));
+        a.x = __fadd_rn(a.x, __fmul_rn(w3[p].x, k.w));    a.y = __fadd_rn(a.y, __fmul_rn(w3[p].y, k.w));
+      } else {
+        a = __fmul2_rn(w0[p], make_float2(k.x, k.x));
+        a = __ffma2_rn(w1[p], make_float2(k.y, k.y), a);
+        a = __ffma2_rn(w2[p], make_float2(k.z, k.z), a);
+        a = __ffma2_rn(w3[p], make_float2(k.w, k.w), a);
+      }
+      v[2 * p] = a.x; v[2 * p + 1] = a.y;
     }
     if (sizeof(T) == 1) {
-      const int qv = __float2int_rn(v);                      // round-half-even, then saturate
-      *reinterpret_cast<uint8_t*>(out) = (uint8_t)min(max(qv, 0), 255);
+      // saturate, then round half to even with the 1.5 * 2^23 trick (== saturate_cast<uchar>(rint(v)) on [0, 255])
+      uint32_t b[kQE];
+#pragma unroll
+      for (int j = 0; j < kQE; ++j)
+        b[j] = (uint32_t)__float_as_int(__fadd_rn(fminf(fmaxf(v[j], 0.f), 255.f), 12582912.f)) & 0xFFu;
+      if (vec_dst) {
+        *reinterpret_cast<uint32_t*>(out) = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kQE; ++j)
+          if (ef + j < DE) reinterpret_cast<uint8_t*>(out)[j] = (uint8_t)b[j];
+      }
     } else {
-      if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
-      *reinterpret_cast<float*>(out) = v;
+      if (clip01) {
+#pragma unroll
+        for (int j = 0; j < kQE; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 1.f);
+      }
+      if (all4) {
+#pragma unroll
+        for (int j = 0; j < kQE; ++j) reinterpret_cast<float*>(out)[j * kStep] = v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < kQE; ++j)
+          if (ef + j * kStep < DE) reinterpret_cast<float*>(out)[j * kStep] = v[j];
+      }
     }
   }
 }
@@ -232,31 +329,46 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
   SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "bicubic: bad geometry");
   if (batch == 0) return SRB_OK;
   AxisTap* tabs = nullptr;
-  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh) + sizeof(int) * (size_t)dh, stream));
+  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh) + sizeof(int) * ((size_t)dh + dw), stream));
   int* ybase = reinterpret_cast<int*>(tabs + (size_t)dw + dh);
+  int* xbase = ybase + dh;
   AxisTap* xtab = tabs;
   AxisTap* ytab = tabs + dw;
-  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, nullptr, sw, dw, FIXED ? 1 : 0);
+  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, xbase, sw, dw, FIXED ? 1 : 0);
   bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, ybase, sh, dh, FIXED ? 1 : 0);
   int rc = launch_check("bicubic_tables");
   if (rc) return rc;
   {
-    // default: shared-memory sliding window
-    const double ratio = (double)sw / (double)dw;
-    const int src_px = (int)((kTE / C + 2) * (ratio > 1.0 ? ratio : 1.0)) + 6;
-    const int msc = ((src_px * C) + 3) & ~3;
-    int tr = 32;
-    auto rows_needed = [&](int n) { return (int)(((long)n * sh + dh - 1) / dh) + 6; };
-    auto need = [&](int n) { return (size_t)rows_needed(n) * msc * sizeof(float) + (size_t)n * (sizeof(float4) + sizeof(int)); };
-    while (tr > 4 && need(tr) > 40 * 1024) tr >>= 1;
+    // default: shared-memory quad kernel; a block's source footprint is bounded from the scale ratios
+    const int DE = dw * C, SE = sw * C;
+    const double rx = (double)sw / (double)dw, ry = (double)sh / (double)dh;
+    const int out_px = (kQT * kQE + C - 1) / C + 1;                       // output pixels a block can touch
+    const int span_px = (int)(out_px * rx) + 7;                           // source pixels under their taps
+    const int pitch = ((span_px * C + 4) + 3) & ~3;                       // (+4: c_lo is rounded down to a multiple of 4)
+    auto rows_needed = [&](int n) { return (int)(n * ry) + 6; };
+    auto need = [&](int n) { return (size_t)rows_needed(n) * pitch * sizeof(float) + (size_t)n * (sizeof(float4) + sizeof(int)); };
+    int tr = 64;
+    while (tr > 4 && (need(tr) > 48 * 1024 || tr >= 2 * dh)) tr >>= 1;
     if (need(tr) <= 96 * 1024) {
       const size_t smem = need(tr);
-      SRB_CUDA(cudaFuncSetAttribute(bicubic_swin_kernel<T, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      dim3 grid((dw * C + kTE - 1) / kTE, (dh + tr - 1) / tr, batch);
+      static size_t configured = 0;                                       // (per template instantiation)
+      if (smem > configured) {
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+      }
+      const uintptr_t salign = sizeof(T) == 4 ? 15u : 3u;
+      const int vec_src = (SE % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & salign) == 0);
+      const int vec_dst = (DE % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & salign) == 0);
+      dim3 grid((DE + kQT * kQE - 1) / (kQT * kQE), (dh + tr - 1) / tr, batch);
       SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
-      bicubic_swin_kernel<T, FIXED><<<grid, kTE, smem, stream>>>(src, dst, xtab, ytab, ybase, sh, sw, C, dh, dw, tr,
-                                                                 rows_needed(tr), msc, clip01);
-      rc = launch_check("bicubic_swin_kernel");
+      auto kern = C == 3 ? bicubic_quad_kernel<T, FIXED, 3> : C == 1 ? bicubic_quad_kernel<T, FIXED, 1>
+                : C == 4 ? bicubic_quad_kernel<T, FIXED, 4> : bicubic_quad_kernel<T, FIXED, 0>;
+      kern<<<grid, kQT, smem, stream>>>(src, dst, xtab, xbase, ytab, ybase, sh, sw, C, dh, dw, tr, rows_needed(tr), pitch,
+                                        vec_src, vec_dst, clip01);
+      rc = launch_check("bicubic_quad_kernel");
     } else {
       // strong down-scaling: stream straight from global memory
       int rows = 64;

@@ -52,6 +52,8 @@ struct TcParams {
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
+  int debug;             // diagnostics (SRB_TC_DEBUG): 1 = epilogue only releases TMEM (no math / stores: wrong results),
+                         // 2 = the MMA warp issues no MMAs (commits only: wrong results)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -396,7 +398,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (q.fold) {
         // dx folded into N: D[input pixel, (dx, co)] += sum over dy of A shifted by dy halo rows (1,024-B aligned)
         const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
-        if (elect_one()) {
+        if (q.debug == 2) {
+          if (elect_one()) { commit(empty_bar(s)); commit(tfull_bar(acc)); }
+        } else if (elect_one()) {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
             const uint64_t ad = a_desc0 + (uint64_t)(dy * a_dy), bd = b_desc0 + (uint64_t)dy * b_tap_step;
@@ -424,7 +428,22 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       } else if (q.base_off_mode == 0) {
         // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
         const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
-        if (elect_one()) {
+        if (q.debug == 2) {
+          if (elect_one()) { commit(empty_bar(s)); commit(tfull_bar(acc)); }
+        } else if (q.debug == 3) {          // timing probe: consecutive MMAs alternate between the two accumulators
+          const uint32_t d_alt = tmem_base + (uint32_t)((acc ^ 1) * q.n_tile);
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
+              const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) mma((k & 1) ? d_alt : d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
+            }
+            commit(empty_bar(s));
+            commit(tfull_bar(acc));
+          }
+        } else if (elect_one()) {
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
             const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
@@ -580,7 +599,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      if (!active) {                                    // chunk too narrow to split: this warp only keeps the protocol
+      if (!active || q.debug == 1 || q.debug == 3) {                    // chunk too narrow to split: this warp only keeps the protocol
         release_tmem(acc);
         continue;
       }
@@ -952,6 +971,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
     if (!stage_cap) { const char* e = getenv("SRB_TC_STAGES"); stage_cap = e ? atoi(e) : kMaxStages; if (stage_cap < 1 || stage_cap > kMaxStages) stage_cap = kMaxStages; }
+    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SRB_TC_DEBUG"); dbg = e ? atoi(e) : 0; } q.debug = dbg; }
     q.stages = stage_cap;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);

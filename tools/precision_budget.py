@@ -14,6 +14,9 @@ torch.set_num_threads(8)
 def rnd(t, kind):
     if kind=='bf16': return t.bfloat16().float()
     if kind=='fp16': return t.half().float()
+    if kind=='fp16+e5m2':      # hi = fp16(t), lo = e5m2(t - hi): the two-tensor trunk of precision="fp16", trunk="pair8"
+        hi = t.half().float()
+        return hi + (t - hi).to(torch.float8_e5m2).float()
     return t
 def conv(x, w, name, wk):
     k = torch.from_numpy(w[name+'/kernel']).permute(3,2,0,1).contiguous()
@@ -24,8 +27,9 @@ def edsr(w, x, nb, wk_body, ak_body, trunk, wk_late, ak_late):
     head = rnd(h, trunk)
     h = head
     for i in range(nb):
-        t = rnd(F.relu(conv(rnd(h,ak_body), w, f'rb{i}_c1', wk_body)), ak_body)
+        t = rnd(F.relu(conv(rnd(h,ak_body), w, f'rb{i}_c1', wk_body)), ak_body)   # (rnd(h, fp16) of an fp16+e5m2 trunk = its hi half)
         h = rnd(h + 0.1*conv(t, w, f'rb{i}_c2', wk_body), trunk)
+    if trunk=='fp16+e5m2': h = h.half().float()      # the next conv's operand is the hi half alone
     h = rnd(conv(rnd(h,ak_late), w, 'body', wk_late) + head, ak_late)
     h = rnd(oc.depth_to_space(conv(h, w, 'up0', wk_late),2), ak_late)
     h = rnd(oc.depth_to_space(conv(h, w, 'up1', wk_late),2), ak_late)
@@ -48,3 +52,4 @@ report('all fp16 (trunk fp16)', wk_body='fp16', ak_body='fp16', trunk='fp16', wk
 report('fp16, fp32 trunk', wk_body='fp16', ak_body='fp16', trunk=None, wk_late='fp16', ak_late='fp16')
 report('weights bf16 only', wk_body='bf16', ak_body=None, trunk=None, wk_late='bf16', ak_late=None)
 report('acts bf16 only', wk_body=None, ak_body='bf16', trunk='bf16', wk_late=None, ak_late='bf16')
+report('fp16, fp16+e5m2 trunk (pair8)', wk_body='fp16', ak_body='fp16', trunk='fp16+e5m2', wk_late='fp16', ak_late='fp16')
