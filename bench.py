@@ -288,8 +288,8 @@ def main():
     ap.add_argument("--tile", type=int, default=192)
     ap.add_argument("--micro-batch", type=int, default=32)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--trunk", default="fp32", choices=["fp32", "pair", "half"],
-                    help="residual trunk storage: fp32 (default), compensated 16-bit pair, or plain 16-bit")
+    ap.add_argument("--trunk", default="pair8", choices=["pair8", "fp32", "pair", "half"],
+                    help="residual trunk storage: 16-bit + e5m2 rounding-error pair (default), fp32, compensated 16-bit pair, or plain 16-bit")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

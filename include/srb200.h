@@ -33,7 +33,7 @@ typedef void* srb_stream_t;          /* cudaStream_t */
 typedef struct srb_conv_weights srb_conv_weights;   /* opaque, device-resident packed kernel */
 
 enum { SRB_OK = 0, SRB_E_INVALID = -1, SRB_E_UNSUPPORTED = -2, SRB_E_CUDA = -3, SRB_E_NOMEM = -4 };
-enum { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2, SRB_F16 = 3 };
+enum { SRB_F32 = 0, SRB_BF16 = 1, SRB_U8 = 2, SRB_F16 = 3, SRB_F8E5M2 = 4 };
 enum { SRB_ACT_NONE = 0, SRB_ACT_RELU = 1, SRB_ACT_PRELU = 2, SRB_ACT_LEAKY = 3, SRB_ACT_TANH = 4 };
 /* conv engine selection: AUTO picks tcgen05 when the shape is eligible, else the CUDA-core path */
 enum { SRB_ENGINE_AUTO = 0, SRB_ENGINE_DIRECT = 1, SRB_ENGINE_TCGEN05 = 2 };
@@ -87,7 +87,9 @@ typedef struct srb_conv_args {
                                                                            (fp32 trunk next to the 16-bit operand);
                                                                            mode 1 = v - round_to_y_dtype(v), the
                                                                            rounding error of y, so that y + y2 carries
-                                                                           ~22 bits in two 16-bit tensors */
+                                                                           ~22 bits in two 16-bit tensors, or ~14 bits in
+                                                                           3 bytes when y2 is SRB_F8E5M2 (allowed for y2,
+                                                                           res1 and res2 only) */
   int batch, height, width;
   const srb_conv_weights* weights;
   int act;              float act_slope;               const float* prelu;   /* [cout / d2s^2] */

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -62,7 +63,7 @@ __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   }
 }
 
-inline size_t dtype_size(int dt) { return dt == SRB_F32 ? 4 : (dt == SRB_BF16 || dt == SRB_F16) ? 2 : 1; }
+inline size_t dtype_size(int dt) { return dt == SRB_F32 ? 4 : (dt == SRB_BF16 || dt == SRB_F16) ? 2 : 1; }   // (u8, e5m2: 1)
 
 }  // namespace srb
 

@@ -95,11 +95,12 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   const srb_conv_weights* w = a->weights;
   SRB_REQUIRE(a->batch >= 0 && a->height > 0 && a->width > 0, "conv2d: bad geometry %dx%dx%d", a->batch, a->height, a->width);
   auto float_dt = [](int d) { return d == SRB_F32 || d == SRB_BF16 || d == SRB_F16; };
+  auto float_or_f8 = [&](int d) { return float_dt(d) || d == SRB_F8E5M2; };   // e5m2: second output / residuals only
   SRB_REQUIRE(float_dt(a->x_dtype), "conv2d: x dtype must be f32, bf16 or f16");
   SRB_REQUIRE(float_dt(a->y_dtype), "conv2d: y dtype must be f32, bf16 or f16");
-  SRB_REQUIRE(!a->y2 || float_dt(a->y2_dtype), "conv2d: y2 dtype must be f32, bf16 or f16");
-  SRB_REQUIRE(!a->res1 || float_dt(a->res1_dtype), "conv2d: res1 dtype must be f32, bf16 or f16");
-  SRB_REQUIRE(!a->res2 || float_dt(a->res2_dtype), "conv2d: res2 dtype must be f32, bf16 or f16");
+  SRB_REQUIRE(!a->y2 || float_or_f8(a->y2_dtype), "conv2d: y2 dtype must be f32, bf16, f16 or e5m2");
+  SRB_REQUIRE(!a->res1 || float_or_f8(a->res1_dtype), "conv2d: res1 dtype must be f32, bf16, f16 or e5m2");
+  SRB_REQUIRE(!a->res2 || float_or_f8(a->res2_dtype), "conv2d: res2 dtype must be f32, bf16, f16 or e5m2");
   const int d2s = a->d2s <= 0 ? 1 : a->d2s;
   SRB_REQUIRE(d2s >= 1 && d2s <= 4, "conv2d: depth_to_space factor must be 1..4 (got %d)", a->d2s);
   SRB_REQUIRE(w->cout % (d2s * d2s) == 0, "conv2d: cout %d is not divisible by d2s^2 = %d", w->cout, d2s * d2s);

@@ -26,12 +26,26 @@ struct ConvParams {
 __device__ __forceinline__ float load_elem(const void* base, int dtype, size_t idx) {
   if (dtype == SRB_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
   if (dtype == SRB_F16) return __half2float(reinterpret_cast<const __half*>(base)[idx]);
+  if (dtype == SRB_F8E5M2) {                                  // e5m2 = the upper byte of an IEEE half
+    const __half_raw h = {(unsigned short)(reinterpret_cast<const uint8_t*>(base)[idx] << 8)};
+    return __half2float(__half(h));
+  }
   return __ldg(reinterpret_cast<const float*>(base) + idx);
+}
+
+// (e5m2 is rare on the scalar paths: kept out of line so that the common stores stay small)
+__device__ __noinline__ void store_e5m2(void* base, size_t idx, float v) {
+  reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2);
+}
+__device__ __noinline__ float round_e5m2(float v) {
+  const __half_raw h = {(unsigned short)(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2) << 8)};
+  return __half2float(__half(h));
 }
 
 __device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, float v) {
   if (dtype == SRB_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
   else if (dtype == SRB_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+  else if (dtype == SRB_F8E5M2) store_e5m2(base, idx, v);
   else reinterpret_cast<float*>(base)[idx] = v;
 }
 
@@ -39,6 +53,7 @@ __device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, fl
 __device__ __forceinline__ float round_to(int dtype, float v) {
   if (dtype == SRB_BF16) return __bfloat162float(__float2bfloat16_rn(v));
   if (dtype == SRB_F16) return __half2float(__float2half_rn(v));
+  if (dtype == SRB_F8E5M2) return round_e5m2(v);
   return v;
 }
 

@@ -18,6 +18,10 @@ constexpr int kHaloW = kHT_W + 2, kHaloH = kHT_H + 2;
 __device__ __forceinline__ void head_store4(void* base, int dtype, size_t idx, const float (&v)[4]) {
   if (dtype == SRB_F32) {
     *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+  } else if (dtype == SRB_F8E5M2) {
+    const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(v[0], v[1]), __NV_SATFINITE, __NV_E5M2);
+    const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(v[2], v[3]), __NV_SATFINITE, __NV_E5M2);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(base) + idx) = lo | (hi << 16);
   } else if (dtype == SRB_BF16) {
     const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
     *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(base) + idx) =
@@ -150,14 +154,14 @@ conv_head_kernel(const ConvParams p, int tiles_x, int tiles_y) {
 }
 
 static bool head_aligned(const void* ptr, int dtype, int cstride, int coffset) {
-  const size_t es = dtype == SRB_F32 ? 4 : 2;
+  const size_t es = dtype == SRB_F32 ? 4 : dtype == SRB_F8E5M2 ? 1 : 2;
   return ((reinterpret_cast<uintptr_t>(ptr) + (size_t)coffset * es) % (4 * es) == 0) && (cstride % 4 == 0);
 }
 
 bool conv_head_eligible(const ConvParams& p) {
   if (p.kh != 3 || p.kw != 3 || p.cin != 3 || p.x_dtype != SRB_F32) return false;
   if (p.cout % 4 || p.cout > 128 || (32 % (p.cout / 4)) != 0) return false;
-  if (p.d2s != 1 || p.res1 || p.res2) return false;
+  if (p.d2s != 1 || p.res1 || p.res2 || p.y_dtype == SRB_F8E5M2) return false;
   if (!head_aligned(p.y, p.y_dtype, p.y_cstride, p.y_coffset)) return false;
   if (p.y2 && !head_aligned(p.y2, p.y2_dtype, p.y2_cstride, 0)) return false;
   return true;

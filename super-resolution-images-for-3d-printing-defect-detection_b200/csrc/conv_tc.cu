@@ -19,6 +19,8 @@
 #include "conv_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
+#include <type_traits>
 
 namespace srb {
 
@@ -52,9 +54,13 @@ struct TcParams {
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
+  int tma_epi;           // staged epilogue moves its rows with TMA (residual loads, output stores) instead of per-lane copies
   int debug;             // diagnostics (SRB_TC_DEBUG): 1 = epilogue only releases TMEM (no math / stores: wrong results),
                          // 2 = the MMA warp issues no MMAs (commits only: wrong results)
 };
+
+// tensor maps of the TMA epilogue: y / y2 outputs and res1 / res2 residuals, boxes of {warp columns, 8, 4, 1}
+struct EpiMaps { CUtensorMap y, y2, r1, r2; };
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -106,6 +112,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -264,6 +278,19 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int dtype) {
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// four e5m2 bytes -> two half2 words (e5m2 is the upper byte of an IEEE half)
+__device__ __forceinline__ void e5m2x4_to_float4(uint32_t w, float (&f)[4]) {
+  const uint32_t lo = __byte_perm(w, 0u, 0x1404u), hi = __byte_perm(w, 0u, 0x3424u);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+}
+__device__ __forceinline__ uint32_t float4_to_e5m2x4(float a, float b, float c, float d) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E5M2);
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E5M2);
+  return lo | (hi << 16);
+}
+
 __device__ __noinline__ float act_generic(float v, int act, float slope) { return apply_act(v, act, slope); }
 
 // generic per-element epilogue, kept out of line so that the staged path stays small in the instruction cache
@@ -276,13 +303,15 @@ __device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, 
 //   0 generic (all flags read at run time)      1 act none, 16-bit y            2 ReLU, 16-bit y
 //   3 fp32 residual, fp32 y + 16-bit y2         4 fp32 residual, 16-bit y
 //   5 16-bit (hi, lo) residual pair -> 16-bit y + its rounding error y2 (compensated trunk, all in the F rows)
+//   6 (16-bit hi, e5m2 lo) residual pair -> 16-bit y + its rounding error y2 in e5m2 ("pair8" trunk: 3 bytes per
+//     channel carry ~14 significant bits; staging = one 16-bit and one 8-bit row region per prefetch buffer)
 // k2: cta_group::2 - a cluster of two CTAs issues M = 256 MMAs (128 pixels per CTA) from the leader; each CTA keeps
 // only half of the weight rows (the tensor cores fetch the other half from the peer), which cuts the per-CTA
 // B-operand shared-memory traffic and the resident weight footprint in half.
 template <int kSpec, bool k2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                  const TcParams q, const ConvParams p) {
+                  const __grid_constant__ EpiMaps em, const TcParams q, const ConvParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is what the 128-byte swizzle pattern of TMA and UMMA is anchored to
   const uint32_t raw = smem_u32(smem_raw);
@@ -307,6 +336,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 3 + a); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile], 16-byte aligned
+  const uint32_t rbar0 = smem_u32(bias_s) + (uint32_t)q.n_tile * 4u;       // [kEpiWarps][2] residual-landed barriers (TMA epilogue)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work units: a CTA (or a CTA pair) owns channel chunk `unit % n_chunks` and every (units / n_chunks)-th tile (pair)
@@ -326,10 +356,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // one arrival per participating epilogue warp (an elected lane, after the warp's TMEM reads have completed)
       mbar_init(tempty_bar(a), ((q.n_tile < 32 && q.epi_mode != 1) ? kEpiWarps / 2 : kEpiWarps) * (k2 ? 2 : 1));
     }
+    if (q.tma_epi) for (int i = 0; i < 2 * kEpiWarps; ++i) mbar_init(rbar0 + 8u * (uint32_t)i, 1);
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+  if (warp == 2 && lane == 0 && q.tma_epi) {
+    prefetch_tmap(&em.y);
+    if (kSpec == 6) { prefetch_tmap(&em.r1); prefetch_tmap(&em.r2); if (p.y2) prefetch_tmap(&em.y2); }
+  }
   if (warp == 1) { if (k2) tmem_alloc_2sm(smem_u32(tmem_slot), q.tmem_cols); else tmem_alloc(smem_u32(tmem_slot), q.tmem_cols); }
   tc_fence_before();
   if (k2) cluster_sync_all(); else __syncthreads();   // barrier inits must be visible to the peer before it signals them
@@ -471,6 +506,134 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
     }
+  } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6) && !k2 && q.tma_epi) {
+    // ===================== epilogue, TMA flavour (16-bit y, d2s = 1, 64- or 128-channel chunks) =====================
+    // Warp (quadrant, column half) owns 4 tile rows x 8 pixels x ncols channels.  Its staging rows are laid out exactly as
+    // the {ncols, 8, 4, 1} TMA box with the 32/64/128-byte swizzle of the row size, so one elected lane moves the whole
+    // block with one bulk-tensor copy: residual (hi, lo) loads one tile ahead into alternating buffers, signalled on a
+    // per-warp mbarrier, and output stores tracked by the bulk async-group of that lane.  Out-of-image pixels are
+    // clipped (stores) or zero-filled (loads) by the TMA unit - no per-lane address arithmetic or bounds predicates.
+    constexpr bool P8 = kSpec == 6;
+    const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
+    const int ncols = q.n_tile >> 1, col0 = half * ncols;
+    const int c_out0 = co_base + col0;
+    const uint32_t hb = (uint32_t)ncols * 2u, lb = (uint32_t)ncols;          // row bytes: 16-bit rows, e5m2 rows
+    const uint32_t h_sh = hb == 128u ? 0u : 1u, h_mask = (hb >> 4) - 1u;      // swizzle: chunk ^= (row >> sh) & mask
+    const uint32_t l_sh = lb == 64u ? 1u : 2u, l_mask = (lb >> 4) - 1u;
+    const uint32_t buf_bytes = 32u * hb + (P8 ? 32u * lb : 0u);
+    const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
+    const uint32_t row = (uint32_t)lane;
+    const uint32_t h_row = row * hb, h_x = (row >> h_sh) & h_mask;
+    const uint32_t l_row = 32u * hb + row * lb, l_x = (row >> l_sh) & l_mask;
+    const uint32_t my_rbar = rbar0 + 16u * (uint32_t)ew;
+    const float alpha = p.alpha, beta1 = p.beta1, beta2 = p.beta2;
+    const bool bf = p.y_dtype == SRB_BF16;
+    auto release_tmem = [&](int acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    };
+    auto coords = [&](int tile, int& b, int& y0, int& x0) {
+      b = tile / tiles_per_img;
+      const int rr_ = tile - b * tiles_per_img;
+      const int ty = rr_ / q.tiles_x;
+      y0 = ty * kTileH + quad * 4;                      // first image row of this warp's quadrant
+      x0 = (rr_ - ty * q.tiles_x) * kTileW;
+    };
+    auto load_res = [&](int tile, uint32_t nb) {        // lane 0: residual (hi, lo) of `tile` into buffer nb
+      int b, y0, x0;
+      coords(tile, b, y0, x0);
+      const uint32_t buf = my_epi + nb * buf_bytes, bar = my_rbar + 8u * nb;
+      mbar_expect_tx(bar, 32u * (hb + lb));
+      tma_load_4d(buf, &em.r1, bar, c_out0, x0, y0, b);
+      tma_load_4d(buf + 32u * hb, &em.r2, bar, c_out0, x0, y0, b);
+    };
+    int it = 0;
+    if (P8 && lane == 0 && first_tile < q.total_tiles) load_res(first_tile, 0u);
+    for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
+      int b, y0, x0;
+      coords(tile, b, y0, x0);
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      const uint32_t buf = my_epi + (P8 ? (uint32_t)(it & 1) * buf_bytes : 0u);
+      if (lane == 0) {
+        bulk_wait_read0();                              // this lane's earlier stores have finished reading the staging rows
+        if (P8 && tile + tile_step < q.total_tiles) load_res(tile + tile_step, (uint32_t)((it + 1) & 1));
+      }
+      __syncwarp();
+      mbar_wait(tfull_bar(acc), acc_ph);
+      tc_fence_after();
+      if (P8) mbar_wait(my_rbar + 8u * (uint32_t)(it & 1), acc_ph);
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
+#pragma unroll 1
+      for (int c0 = 0; c0 < ncols; c0 += 16) {
+        uint32_t rr[16];
+        float4 bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_s + col0 + c0 + 4 * j);
+        __syncwarp();
+        tmem_ld16(t_row + (uint32_t)c0, rr);
+        tmem_ld_wait();
+        if (c0 + 16 >= ncols) release_tmem(acc);
+        const float bb[16] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
+                              bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w};
+        const uint32_t c16 = (uint32_t)c0 >> 4;
+        const uint32_t a_h0 = buf + h_row + (((2u * c16) ^ h_x) << 4), a_h1 = buf + h_row + (((2u * c16 + 1u) ^ h_x) << 4);
+        uint32_t oh[8];
+        if (!P8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0 = __uint_as_float(rr[2 * i]) + bb[2 * i], v1 = __uint_as_float(rr[2 * i + 1]) + bb[2 * i + 1];
+            if (kSpec == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
+          }
+        } else {
+          // pair8 trunk: v = alpha * (acc + bias) + beta1 * hi + beta2 * lo;  y = round16(v), y2 = e5m2(v - y)
+          const uint32_t a_l = buf + l_row + ((c16 ^ l_x) << 4);
+          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
+          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
+          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+          uint32_t ol[4];
+          auto half_block = [&](auto is_bf) {
+            constexpr bool kBf = decltype(is_bf)::value;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              float lo4[4], er[4];
+              e5m2x4_to_float4(wl[i4], lo4);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int e0 = 4 * i4 + 2 * hh;
+                float2 fh;
+                if (kBf) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
+                else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
+                const float a0 = (__uint_as_float(rr[e0]) + bb[e0]) * alpha, a1 = (__uint_as_float(rr[e0 + 1]) + bb[e0 + 1]) * alpha;
+                const float v0 = fmaf(beta2, lo4[2 * hh], fmaf(beta1, fh.x, a0));
+                const float v1 = fmaf(beta2, lo4[2 * hh + 1], fmaf(beta1, fh.y, a1));
+                const uint32_t pk = pack2(v0, v1, kBf ? SRB_BF16 : SRB_F16);
+                oh[2 * i4 + hh] = pk;
+                float2 back;
+                if (kBf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+                else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                er[2 * hh] = v0 - back.x; er[2 * hh + 1] = v1 - back.y;
+              }
+              ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
+            }
+          };
+          if (bf) half_block(std::true_type{}); else half_block(std::false_type{});
+          sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+        }
+        sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+        sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
+      }
+      fence_proxy_async_smem();                         // generic-proxy writes of the rows -> visible to the TMA unit
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_4d(&em.y, buf, c_out0, x0, y0, b);
+        if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, c_out0, x0, y0, b);
+        bulk_commit();
+      }
+    }
+    if (lane == 0) bulk_wait0();                        // all stores complete before the CTA's shared memory goes away
   } else {
     // ===================== epilogue: TMEM -> registers -> (smem transpose) -> global =====================
     // 8 warps: warp w may only touch TMEM lanes [32 * (w % 4), +32); the two warps of a lane quadrant split the
@@ -519,7 +682,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const bool has_res2 = G && p.res2 != nullptr && !pair;
     const bool do_clip = G && p.clip01;
     const bool f_on = G ? f_dst != 0 : kSpec == 3;
-    const bool h_on = G ? h_dst != 0 : kSpec != 5;
+    const bool h_on = G ? h_dst != 0 : (kSpec != 5 && kSpec != 6);
+    constexpr bool P8 = kSpec == 6;
+    // pair8 staging geometry (per prefetch buffer): 32 rows of 16-bit hi (ncols * 2 B), then 32 rows of e5m2 lo (ncols B)
+    const uint32_t p8_hb = (uint32_t)ncols * 2u, p8_lb = (uint32_t)ncols;
+    const uint32_t p8_hc = p8_hb >> 4, p8_lc = p8_lb >> 4;        // 16-byte chunks per row: (4, 2) or (8, 4)
+    const uint32_t p8_hlg = 31u - (uint32_t)__clz((int)p8_hc), p8_llg = 31u - (uint32_t)__clz((int)p8_lc);
+    const uint32_t p8_buf_bytes = 32u * (p8_hb + p8_lb);
+    auto p8_hi = [&](uint32_t buf, uint32_t row, uint32_t chunk) { return buf + row * p8_hb + ((chunk ^ (row & (p8_hc - 1u))) << 4); };
+    auto p8_lo = [&](uint32_t buf, uint32_t row, uint32_t chunk) { return buf + 32u * p8_hb + row * p8_lb + ((chunk ^ (row & (p8_lc - 1u))) << 4); };
     const int epi_mode = G ? q.epi_mode : 1;
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
@@ -527,6 +698,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const size_t tp = tile_pixel(b, y0, x0);
+      if (P8) {
+        const uint32_t buf = my_epi + (uint32_t)fb * p8_buf_bytes;
+        {
+          const uint32_t ch = (uint32_t)lane & (p8_hc - 1u), rsub = (uint32_t)lane >> p8_hlg;
+          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.res1) + (tp * (size_t)p.res1_cstride + c_out0) * 2u + ch * 16u;
+          const uint32_t pix_bytes = (uint32_t)p.res1_cstride * 2u;
+#pragma unroll 4
+          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_hlg) {
+            const int mm = quad * 32 + (int)row;
+            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
+              cp_async16(p8_hi(buf, row, ch), src0 + (size_t)pix_off(mm) * pix_bytes);
+          }
+        }
+        {
+          const uint32_t ch = (uint32_t)lane & (p8_lc - 1u), rsub = (uint32_t)lane >> p8_llg;
+          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.res2) + (tp * (size_t)p.res2_cstride + c_out0) + ch * 16u;
+          const uint32_t pix_bytes = (uint32_t)p.res2_cstride;
+#pragma unroll 2
+          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_llg) {
+            const int mm = quad * 32 + (int)row;
+            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
+              cp_async16(p8_lo(buf, row, ch), src0 + (size_t)pix_off(mm) * pix_bytes);
+          }
+        }
+        return;
+      }
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
       const uint32_t rows_per_it = 32u >> f_lg;
       const uint32_t ch = (uint32_t)lane & (f_cpr - 1u), rsub = (uint32_t)lane >> f_lg;
@@ -595,7 +792,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         cp_async_commit();
         cp_async_wait1();                               // this tile's residual rows have landed
         __syncwarp();
-        f_buf = my_epi + (uint32_t)(it & 1) * 32u * f_rb;
+        f_buf = my_epi + (uint32_t)(it & 1) * (P8 ? p8_buf_bytes : 32u * f_rb);
       }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
@@ -652,7 +849,48 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tmem_ld16(t_row + (uint32_t)c0, rr);
         tmem_ld_wait();
         if (c0 + 16 >= ncols) release_tmem(acc);        // last read of this accumulator: hand it back to the MMA warp
-        if (epi_mode == 1) {
+        if (P8) {
+          // pair8 trunk: v = alpha * (acc + bias) + beta1 * hi + beta2 * lo;  y = round16(v), y2 = e5m2(v - y), in place
+          const uint32_t c16 = (uint32_t)c0 >> 4;
+          const uint32_t a_h0 = p8_hi(f_buf, my_row_sw, 2u * c16), a_h1 = p8_hi(f_buf, my_row_sw, 2u * c16 + 1u);
+          const uint32_t a_l = p8_lo(f_buf, my_row_sw, c16);
+          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
+          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
+          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+          const float bb[16] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
+                                bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w};
+          uint32_t oh[8], ol[4];
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {              // four channels at a time
+            float lo4[4], hi4[4], v4[4], er[4];
+            e5m2x4_to_float4(wl[i4], lo4);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float2 fh;
+              if (p.y_dtype == SRB_BF16) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
+              else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
+              hi4[2 * hh] = fh.x; hi4[2 * hh + 1] = fh.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float a = (__uint_as_float(rr[4 * i4 + e]) + bb[4 * i4 + e]) * p.alpha;
+              v4[e] = fmaf(p.beta2, lo4[e], fmaf(p.beta1, hi4[e], a));
+            }
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const uint32_t pk = pack2(v4[2 * hh], v4[2 * hh + 1], p.y_dtype);
+              oh[2 * i4 + hh] = pk;
+              float2 back;
+              if (p.y_dtype == SRB_BF16) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+              else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+              er[2 * hh] = v4[2 * hh] - back.x; er[2 * hh + 1] = v4[2 * hh + 1] - back.y;
+            }
+            ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
+          }
+          sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+          sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
+          if (p.y2) sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+        } else if (epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cc = c0 + g * 8;                  // channel offset inside this warp's column range
@@ -802,7 +1040,32 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (epi_mode == 1 && pair) {
+      if (P8) {
+        __syncwarp();
+        {
+          const uint32_t ch = (uint32_t)lane & (p8_hc - 1u), rsub = (uint32_t)lane >> p8_hlg;
+          uint8_t* dst0 = reinterpret_cast<uint8_t*>(p.y) + (tpix * (size_t)p.y_cstride + (size_t)(p.y_coffset + c_out0)) * 2u + ch * 16u;
+          const uint32_t pix_bytes = (uint32_t)p.y_cstride * 2u;
+#pragma unroll 4
+          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_hlg) {
+            const int mm = quad * 32 + (int)row;
+            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
+              *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes) = lds128(p8_hi(f_buf, row, ch));
+          }
+        }
+        if (p.y2) {
+          const uint32_t ch = (uint32_t)lane & (p8_lc - 1u), rsub = (uint32_t)lane >> p8_llg;
+          uint8_t* dst0 = reinterpret_cast<uint8_t*>(p.y2) + (tpix * (size_t)p.y2_cstride + (size_t)c_out0) + ch * 16u;
+          const uint32_t pix_bytes = (uint32_t)p.y2_cstride;
+#pragma unroll 2
+          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_llg) {
+            const int mm = quad * 32 + (int)row;
+            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
+              *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes) = lds128(p8_lo(f_buf, row, ch));
+          }
+        }
+        __syncwarp();
+      } else if (epi_mode == 1 && pair) {
         __syncwarp();
         // chunks [0, cpr/2) of every staged row -> y, chunks [cpr/2, cpr) -> y2 (both 16-bit)
         const uint32_t hcn = f_cpr >> 1;
@@ -879,7 +1142,7 @@ bool conv_tc_eligible(const ConvParams& p) {
 
 // 8 consecutive channels per access: one 16-byte vector for 16-bit types, two for fp32
 static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
-  const int per16 = dtype == SRB_F32 ? 4 : 8;
+  const int per16 = dtype == SRB_F32 ? 4 : dtype == SRB_F8E5M2 ? 16 : 8;
   return aligned16(ptr) && (cstride % per16 == 0) && (coffset % per16 == 0);
 }
 
@@ -949,7 +1212,13 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     // (y2 may be absent: the layer that leaves the trunk only needs the rounded sum)
     const bool pair = dt16(p.y_dtype) && (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == p.y_dtype)) && p.res1 && p.res2 &&
                       p.res1_dtype == p.y_dtype && p.res2_dtype == p.y_dtype && p.act == SRB_ACT_NONE && !p.clip01;
-    if (p.y2 && !pair && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
+    // pair8 trunk: 16-bit hi + e5m2 lo residual pair in, 16-bit y + e5m2 rounding error out
+    const bool pair8 = dt16(p.y_dtype) && p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
+                       (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == SRB_F8E5M2)) && p.act == SRB_ACT_NONE && !p.clip01 && p.d2s == 1;
+    const bool any_f8 = p.y_dtype == SRB_F8E5M2 || (p.y2 && p.y2_dtype == SRB_F8E5M2) || (p.res1 && p.res1_dtype == SRB_F8E5M2) ||
+                        (p.res2 && p.res2_dtype == SRB_F8E5M2);
+    if (any_f8 && !pair8) vec = false;                 // (the generic scalar epilogue handles e5m2 element by element)
+    if (p.y2 && !pair && !pair8 && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
     if (fold) { vec = false; q.epi_mode = 3; }
@@ -963,11 +1232,21 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.h_dst = dt16(p.y_dtype) ? 1 : (p.y2 && dt16(p.y2_dtype) ? 2 : 0);
       q.res_prefetch = (p.res1 && p.res1_dtype == SRB_F32) ? 1 : 0;
       if (pair) { q.res_prefetch = 2; q.f_dst = 0; q.h_dst = 0; }
+      if (pair8) { q.res_prefetch = 3; q.f_dst = 0; q.h_dst = 0; }
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
+      if (pair8) q.epi_warp_bytes = (uint32_t)(2 * 32 * warp_cols * 3);
+      // TMA epilogue: 16-bit y without depth_to_space, 64- or 128-channel chunks, the plain / ReLU / pair8 layer types
+      static const bool tma_enabled = getenv("SRB_TC_NO_TMA_EPI") == nullptr && !(getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")));
+      const bool plain16 = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && q.h_dst == 1 && q.f_dst == 0 &&
+                           (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU);
+      if (tma_enabled && !k2c && p.d2s == 1 && (nt == 64 || nt == 128) && dt16(p.y_dtype) && (plain16 || pair8)) {
+        q.tma_epi = 1;
+        q.epi_warp_bytes = (uint32_t)(pair8 ? 2 * 32 * warp_cols * 3 : 32 * warp_cols * 2);   // multiples of 1,024 bytes
+      }
     }
     const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
-    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float);
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
     if (!stage_cap) { const char* e = getenv("SRB_TC_STAGES"); stage_cap = e ? atoi(e) : kMaxStages; if (stage_cap < 1 || stage_cap > kMaxStages) stage_cap = kMaxStages; }
@@ -1003,8 +1282,37 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
   }
 
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (q.tma_epi) {
+    const int wc = q.n_tile / 2;
+    auto encode_epi = [&](CUtensorMap* m, const void* ptr, int coffset, int cstride, bool f8) -> bool {
+      const size_t es = f8 ? 1 : 2;
+      const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+      const cuuint64_t strides[3] = {(cuuint64_t)cstride * es, (cuuint64_t)p.W * cstride * es, (cuuint64_t)p.H * p.W * cstride * es};
+      const cuuint32_t box[4] = {(cuuint32_t)wc, (cuuint32_t)kTileW, 4, 1};
+      const cuuint32_t es1[4] = {1, 1, 1, 1};
+      const size_t row_bytes = (size_t)wc * es;
+      const CUtensorMapSwizzle sw = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                                    : CU_TENSOR_MAP_SWIZZLE_32B;
+      const CUtensorMapDataType dt = f8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                        : (p.y_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+      void* g = (void*)((const uint8_t*)ptr + (size_t)coffset * es);
+      return encode(m, dt, 4, g, dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = encode_epi(&em.y, p.y, p.y_coffset, p.y_cstride, false);
+    if (q.res_prefetch == 3) {
+      ok = ok && encode_epi(&em.r1, p.res1, 0, p.res1_cstride, false) && encode_epi(&em.r2, p.res2, 0, p.res2_cstride, true);
+      if (p.y2) ok = ok && encode_epi(&em.y2, p.y2, 0, p.y2_cstride, true);
+    }
+    if (!ok) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
+  }
+
   int spec = 0;
-  if (q.epi_mode == 1 && q.res_prefetch == 2) {
+  if (q.epi_mode == 1 && q.res_prefetch == 3) {
+    spec = 6;
+  } else if (q.epi_mode == 1 && q.res_prefetch == 2) {
     spec = 5;
   } else if (q.epi_mode == 1 && !p.res2 && !p.clip01) {
     if (!p.res1 && p.alpha == 1.f && q.f_dst == 0 && q.h_dst == 1 && !p.y2) {
@@ -1015,13 +1323,13 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       else if (q.f_dst == 0 && q.h_dst == 1 && !p.y2) spec = 4;
     }
   }
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const TcParams, const ConvParams);
-  static const KernelFn kernels[2][6] = {
-      {conv3x3_tc_kernel<0, false>, conv3x3_tc_kernel<1, false>, conv3x3_tc_kernel<2, false>,
-       conv3x3_tc_kernel<3, false>, conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>},
-      {conv3x3_tc_kernel<0, true>, conv3x3_tc_kernel<1, true>, conv3x3_tc_kernel<2, true>,
-       conv3x3_tc_kernel<3, true>, conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>}};
-  static size_t configured[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const TcParams, const ConvParams);
+  static const KernelFn kernels[2][7] = {
+      {conv3x3_tc_kernel<0, false>, conv3x3_tc_kernel<1, false>, conv3x3_tc_kernel<2, false>, conv3x3_tc_kernel<3, false>,
+       conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>, conv3x3_tc_kernel<6, false>},
+      {conv3x3_tc_kernel<0, true>, conv3x3_tc_kernel<1, true>, conv3x3_tc_kernel<2, true>, conv3x3_tc_kernel<3, true>,
+       conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>}};
+  static size_t configured[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
   if (smem > configured[k2][spec]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[k2][spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1043,9 +1351,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    SRB_CUDA(cudaLaunchKernelEx(&cfg, kernels[1][spec], tmx, tmw, q, p));
+    SRB_CUDA(cudaLaunchKernelEx(&cfg, kernels[1][spec], tmx, tmw, em, q, p));
   } else {
-    kernels[0][spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, q, p);
+    kernels[0][spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, em, q, p);
   }
   return launch_check("conv3x3_tc_kernel");
 }

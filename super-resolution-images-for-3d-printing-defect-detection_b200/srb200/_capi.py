@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 
 SRB_OK, SRB_E_INVALID, SRB_E_UNSUPPORTED, SRB_E_CUDA, SRB_E_NOMEM = 0, -1, -2, -3, -4
-F32, BF16, U8, F16 = 0, 1, 2, 3
+F32, BF16, U8, F16, F8E5M2 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 ACTIVATIONS = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "prelu": ACT_PRELU,
@@ -139,6 +139,8 @@ def dtype_code(t):
         return F16
     if t.dtype == torch.uint8:
         return U8
+    if t.dtype == torch.float8_e5m2:
+        return F8E5M2
     raise TypeError(f"unsupported tensor dtype {t.dtype}")
 
 

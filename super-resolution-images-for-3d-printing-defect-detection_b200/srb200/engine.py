@@ -39,10 +39,13 @@ class DeviceModel:
         self.precision = precision
         self.act_dtype = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
         # how the residual trunk is carried in the 16-bit modes:
-        #   "fp32" - fp32 trunk next to a 16-bit operand copy (default);  "half" - plain 16-bit trunk
+        #   "fp32" - fp32 trunk next to a 16-bit operand copy;  "half" - plain 16-bit trunk
         #   "pair" - compensated: h = round16(x) plus e = round16(x - h), two 16-bit tensors (~22 bits, 17 % fewer
-        #            HBM bytes per res-block, same speed on B200 because conv2 is shared-memory-pipe bound)
-        self.trunk = "fp32" if precision != "fp32" else "none"
+        #            HBM bytes per res-block than fp32)
+        #   "pair8" - as "pair" with e stored as float8 e5m2: 3 bytes per channel carry ~14 significant bits, which on
+        #            EDSR x4 is as accurate as the fp32 trunk (tools/precision_budget.py) for a third fewer HBM bytes, and
+        #            its rows move through TMA in the tcgen05 epilogue (default)
+        self.trunk = "pair8" if precision != "fp32" else "none"
         self.fp32_trunk = False
         self.weights = {k: np.asarray(v, dtype=np.float32) for k, v in weights.items()}
         self.layers = {}
@@ -152,8 +155,8 @@ class EDSRNet(DeviceModel):
             raise ValueError(f"Scale factor {scale_factor} not supported. Use 2, 3, or 4.")
         super().__init__(weights, precision)
         if trunk is not None and precision != "fp32":
-            if trunk not in ("pair", "fp32", "half"):
-                raise ValueError("trunk must be 'pair', 'fp32' or 'half'")
+            if trunk not in ("pair", "pair8", "fp32", "half"):
+                raise ValueError("trunk must be 'pair8', 'pair', 'fp32' or 'half'")
             self.trunk = trunk
         self.scale_factor, self.num_res_blocks, self.res_scaling = scale_factor, num_res_blocks, float(res_scaling)
 
@@ -163,16 +166,17 @@ class EDSRNet(DeviceModel):
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        if self.trunk == "pair":
+        if self.trunk in ("pair", "pair8"):
             # compensated 16-bit trunk: (h, e) with h the tensor-core operand of the next conv and h + e the trunk value
-            head, head_e = ops.conv2d(x, L["head"], out_dtype=dt, out2_dtype=dt, out2_error=True)
+            et = torch.float8_e5m2 if self.trunk == "pair8" else dt
+            head, head_e = ops.conv2d(x, L["head"], out_dtype=dt, out2_dtype=et, out2_error=True)
             if self.event_hook:
                 self.event_hook("tc_begin")
             h, e = head, head_e
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
                 h, e = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, res2=e, out_dtype=dt,
-                                  out2_dtype=dt, out2_error=True)
+                                  out2_dtype=et, out2_error=True)
             h = ops.conv2d(h, L["body"], res1=head, res2=head_e, out_dtype=dt)
         elif self.trunk == "fp32":
             # trunk in fp32 (y), 16-bit copy (y2) as the next conv's tensor-core operand
@@ -254,12 +258,13 @@ class SRResNetNet(DeviceModel):
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        if self.trunk == "pair":
-            head, head_e = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt, out2_dtype=dt, out2_error=True)
+        if self.trunk in ("pair", "pair8"):
+            et = torch.float8_e5m2 if self.trunk == "pair8" else dt
+            head, head_e = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt, out2_dtype=et, out2_error=True)
             h, e = head, head_e
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="prelu", out_dtype=dt)
-                h, e = ops.conv2d(t, L[f"rb{i}_c2"], res1=h, res2=e, out_dtype=dt, out2_dtype=dt, out2_error=True)
+                h, e = ops.conv2d(t, L[f"rb{i}_c2"], res1=h, res2=e, out_dtype=dt, out2_dtype=et, out2_error=True)
             h = ops.conv2d(h, L["body"], res1=head, res2=head_e, out_dtype=dt)
         else:
             head = ops.conv2d(x, L["head"], act="prelu", out_dtype=dt)

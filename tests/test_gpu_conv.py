@@ -163,6 +163,7 @@ def test_edsr_full_depth_vs_oracle():
     lr = synth.area_downsample(synth.hr_batch(2, 96, 96), 4)
     want = oc.edsr_forward(w, lr, 4, 16, dtype=torch.float64)
     for precision, trunk, tol in (("fp32", None, FP32_TOL), ("fp16", "pair", HALF_TOL), ("fp16", "fp32", HALF_TOL),
+                                  ("fp16", "pair8", HALF_TOL),
                                   ("fp16", "half", 2 * HALF_TOL), ("bf16", "pair", BF16_BUDGET)):
         got = engine.EDSRNet(w, 4, 16, precision=precision, trunk=trunk).predict(lr)
         err = np.abs(got - want).max()

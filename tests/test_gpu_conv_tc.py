@@ -153,6 +153,39 @@ def test_compensated_trunk_pair(kind, shape):
         assert torch.equal(y_only, y)                                           # trunk exit: same rounded sum, no y2
 
 
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [(2, 32, 24), (1, 19, 21)])
+def test_compensated_trunk_pair8(kind, shape):
+    """"pair8" trunk: residual = 16-bit hi + float8-e5m2 lo; output y = round16(v) and y2 = e5m2(v - y).  y + y2 must
+    carry ~3 more bits than y alone (e5m2 keeps 2-3 significant bits of the rounding error), on both engines, and the
+    tensor-core kernel must agree with the scalar engine."""
+    from srb200 import ops, _capi
+    B, H, W = shape
+    dt = DT[kind]
+    x = _round(_rand((B, H, W, 64), 1), kind)
+    kern = _round(_rand((3, 3, 64, 64), 2, -0.1, 0.1), kind)
+    bias = _rand((64,), 3, -0.1, 0.1)
+    trunk = _rand((B, H, W, 64), 5, -2.0, 2.0)
+    hi_t = torch.from_numpy(trunk).to(dt)
+    lo_t = (torch.from_numpy(trunk) - hi_t.float()).to(torch.float8_e5m2)
+    want = 0.1 * oc.conv2d_same_numpy(x, kern, bias) + (hi_t.double().numpy() + lo_t.double().numpy())
+    w = ops.ConvWeights(kern, bias)
+    xd = torch.from_numpy(x).cuda().to(dt)
+    res = {}
+    for engine in (_capi.ENGINE_TCGEN05, _capi.ENGINE_DIRECT):
+        y, y2 = ops.conv2d(xd, w, alpha=0.1, res1=hi_t.cuda(), res2=lo_t.cuda(), out_dtype=dt, out2_dtype=torch.float8_e5m2,
+                           out2_error=True, engine=engine)
+        assert y2.dtype == torch.float8_e5m2
+        e1 = np.abs(y.double().cpu().numpy() - want).max()
+        e2 = np.abs(y.double().cpu().numpy() + y2.double().cpu().numpy() - want).max()
+        assert e2 <= e1 / 3, (engine, e1, e2)                                   # the e5m2 term buys >= ~2 bits
+        y_only = ops.conv2d(xd, w, alpha=0.1, res1=hi_t.cuda(), res2=lo_t.cuda(), out_dtype=dt, engine=engine)
+        assert torch.equal(y_only, y)
+        res[engine] = (y, y2)
+    ya, yb = res[_capi.ENGINE_TCGEN05][0].float(), res[_capi.ENGINE_DIRECT][0].float()
+    assert (ya - yb).abs().max().item() <= (4e-3 if kind == "fp16" else 3.2e-2)  # <= 1-2 ulp of the 16-bit format at |v| <= 4
+
+
 @pytest.mark.parametrize("shape", [(2, 32, 24, 64), (1, 21, 13, 64), (1, 24, 24, 256), (3, 16, 8, 64)])
 def test_cta_pairs_match_single_cta(shape):
     """cta_group::2 launch (cluster of two CTAs, M = 256 MMAs, weights split across the pair, odd tile counts give

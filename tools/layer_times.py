@@ -57,7 +57,7 @@ def main():
         in_b = npx * w.cin * (4 if w.cin == 3 else 2)
         out_b = npx * w.cout * (2 if kw.get("out_dtype") != torch.float32 else 4)
         if kw.get("out2_dtype") is not None:
-            out_b += npx * w.cout * 2
+            out_b += npx * w.cout * torch.empty((), dtype=kw["out2_dtype"]).element_size()
         for rk in ("res1", "res2"):
             if kw.get(rk) is not None:
                 in_b += npx * w.cout * kw[rk].element_size()
