@@ -34,10 +34,10 @@ __device__ __forceinline__ float load_elem(const void* base, int dtype, size_t i
 }
 
 // (e5m2 is rare on the scalar paths: kept out of line so that the common stores stay small)
-__device__ __noinline__ void store_e5m2(void* base, size_t idx, float v) {
+static __device__ __noinline__ void store_e5m2(void* base, size_t idx, float v) {
   reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2);
 }
-__device__ __noinline__ float round_e5m2(float v) {
+static __device__ __noinline__ float round_e5m2(float v) {
   const __half_raw h = {(unsigned short)(__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E5M2) << 8)};
   return __half2float(__half(h));
 }
