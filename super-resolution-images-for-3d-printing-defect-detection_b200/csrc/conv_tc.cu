@@ -116,6 +116,10 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -516,7 +520,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     constexpr bool P8 = kSpec == 6;
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
     const int ncols = q.n_tile >> 1, col0 = half * ncols;
-    const int c_out0 = co_base + col0;
+    // depth_to_space(2): this warp's columns are one (i, j) sub-pixel; the output map is 5-D {c, j, x, i, (b, y)}
+    const int d2s = p.d2s;
+    int c_out0 = co_base + col0, sub_i = 0, sub_j = 0;
+    if (d2s > 1) { const int qq = c_out0 / p.c_post; c_out0 -= qq * p.c_post; sub_i = qq / d2s; sub_j = qq - sub_i * d2s; }
     const uint32_t hb = (uint32_t)ncols * 2u, lb = (uint32_t)ncols;          // row bytes: 16-bit rows, e5m2 rows
     const uint32_t h_sh = hb == 128u ? 0u : 1u, h_mask = (hb >> 4) - 1u;      // swizzle: chunk ^= (row >> sh) & mask
     const uint32_t l_sh = lb == 64u ? 1u : 2u, l_mask = (lb >> 4) - 1u;
@@ -628,7 +635,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       fence_proxy_async_smem();                         // generic-proxy writes of the rows -> visible to the TMA unit
       __syncwarp();
       if (lane == 0) {
-        tma_store_4d(&em.y, buf, c_out0, x0, y0, b);
+        if (d2s > 1) tma_store_5d(&em.y, buf, c_out0, sub_j, x0, sub_i, b * p.H + y0);
+        else tma_store_4d(&em.y, buf, c_out0, x0, y0, b);
         if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, c_out0, x0, y0, b);
         bulk_commit();
       }
@@ -1240,7 +1248,10 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       static const bool tma_enabled = getenv("SRB_TC_NO_TMA_EPI") == nullptr && !(getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")));
       const bool plain16 = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && q.h_dst == 1 && q.f_dst == 0 &&
                            (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU);
-      if (tma_enabled && !k2c && p.d2s == 1 && (nt == 64 || nt == 128) && dt16(p.y_dtype) && (plain16 || pair8)) {
+      // (depth_to_space: plain layers whose warp columns are whole sub-pixels, images made of whole 16-row tiles because
+      //  the 5-D output map merges the image and row dimensions)
+      const bool d2s_ok = p.d2s == 1 || (plain16 && p.c_post % warp_cols == 0 && p.H % kTileH == 0 && p.y_coffset == 0 && p.y_cstride == p.c_post);
+      if (tma_enabled && !k2c && d2s_ok && (nt == 64 || nt == 128) && dt16(p.y_dtype) && (plain16 || pair8)) {
         q.tma_epi = 1;
         q.epi_warp_bytes = (uint32_t)(pair8 ? 2 * 32 * warp_cols * 3 : 32 * warp_cols * 2);   // multiples of 1,024 bytes
       }
@@ -1301,7 +1312,20 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       return encode(m, dt, 4, g, dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
     };
-    bool ok = encode_epi(&em.y, p.y, p.y_coffset, p.y_cstride, false);
+    bool ok;
+    if (p.d2s > 1) {
+      // out[b, y*r + i, x*r + j, c]: dims {c, j, x, i, (b, y)}; a warp stores {wc, 1, 8, 1, 4}
+      const cuuint64_t r = (cuuint64_t)p.d2s, pix = (cuuint64_t)p.c_post * 2, orow = (cuuint64_t)p.W * r * pix;
+      const cuuint64_t dims[5] = {(cuuint64_t)p.c_post, r, (cuuint64_t)p.W, r, (cuuint64_t)p.H * p.B};
+      const cuuint64_t strides[4] = {pix, r * pix, orow, r * orow};
+      const cuuint32_t box[5] = {(cuuint32_t)wc, 1, (cuuint32_t)kTileW, 1, 4};
+      const cuuint32_t es1[5] = {1, 1, 1, 1, 1};
+      const CUtensorMapSwizzle sw = wc * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      ok = encode(&em.y, p.y_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, p.y, dims, strides,
+                  box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    } else {
+      ok = encode_epi(&em.y, p.y, p.y_coffset, p.y_cstride, false);
+    }
     if (q.res_prefetch == 3) {
       ok = ok && encode_epi(&em.r1, p.res1, 0, p.res1_cstride, false) && encode_epi(&em.r2, p.res2, 0, p.res2_cstride, true);
       if (p.y2) ok = ok && encode_epi(&em.y2, p.y2, 0, p.y2_cstride, true);

@@ -95,6 +95,22 @@ def test_fused_epilogues(kind):
     assert np.abs(got - want).max() <= 2e-3
 
 
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+def test_tma_epilogue_paths(kind):
+    """Layer shapes that take the TMA epilogue (16-bit output, 64/128-channel chunks): plain and ReLU stores with tiles
+    clipped at the right / bottom image edge, several images, and depth_to_space(2) through the 5-D output map
+    (needs whole 16-row tiles)."""
+    tol16 = 2e-2 if kind == "bf16" else 4e-3
+    for (B, H, W) in ((2, 32, 24), (3, 19, 21), (1, 40, 13)):
+        got, want = _run(kind, B, H, W, 64, act="relu", out_dtype=DT[kind])
+        assert np.abs(got - want).max() <= tol16, (B, H, W)
+        got, want = _run(kind, B, H, W, 128, out_dtype=DT[kind])
+        assert np.abs(got - want).max() <= tol16, (B, H, W)
+    for (B, H, W) in ((2, 32, 24), (1, 16, 21), (3, 48, 8)):
+        got, want = _run(kind, B, H, W, 256, d2s=2, out_dtype=DT[kind])
+        assert got.shape == (B, 2 * H, 2 * W, 64) and np.abs(got - want).max() <= tol16, (B, H, W)
+
+
 def test_second_output_copy_and_channel_slice():
     from srb200 import ops, _capi
     x = _round(_rand((1, 16, 16, 64), 1), "fp16")
