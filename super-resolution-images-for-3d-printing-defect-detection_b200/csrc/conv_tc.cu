@@ -1113,6 +1113,309 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   }
 }
 
+
+// ===================================================================================================================
+// Wide-tile, dx-folded kernel for 3x3 layers with few output channels per MMA (Cout = 64 and the RGB tails).
+//
+// A tcgen05.mma with M = 128 spends ~64 cycles fetching its 128 x 16 A block from shared memory whatever N is (measured:
+// N = 16, 64 and 128 all issue at ~60-64 cycles per instruction), so the 36-MMA, N = 64 formulation of a 64 -> 64 layer
+// cannot pass 50 % of the tensor peak.  Folding the three horizontal taps into N makes the instruction three times wider
+// and the tile three times shorter:
+//     D[input pixel p, (dx, co)] = sum over dy, ci of  X[p_y + dy - 1, p_x, ci] * W[dy, dx, ci, co]      (N = 3 * Cout, 12 MMAs)
+//     out[y, x, co] = D[(y, x - 1), (0, co)] + D[(y, x), (1, co)] + D[(y, x + 1), (2, co)]
+// The second line is a sum over neighbouring GEMM rows, i.e. neighbouring TMEM lanes: a tile is 4 image rows x 32
+// consecutive input columns (one row per lane quadrant), lane l of a quadrant holds input column x0 - 1 + l, and the
+// epilogue warp combines own / lane + 1 / lane + 2 with two shuffles per channel; lanes 0..29 hold the 30 output columns.
+// The halo is one TMA box of 64 c x 32 w x 6 h; the dy shift is 4,096 bytes (swizzle-atom aligned).  Output rows move with
+// TMA exactly as in the staged epilogue above (boxes of {32 channels, 30 pixels, 1 row}).
+// Modes: 0 plain 16-bit y, 1 ReLU 16-bit y, 2 pair8 trunk (16-bit hi + e5m2 lo residual in, y + rounding error out),
+//        3 few channels (Cout <= 4, groups of 5 columns): bias / activation / alpha / clip, stored element-wise.
+// ===================================================================================================================
+constexpr int kFW = 32, kFH = 4, kFOut = 30;
+constexpr uint32_t kFStage = 6u * kFW * 128u;     // 24,576 bytes
+constexpr int kFoldEpiWarps = 16;
+constexpr int kFoldThreads = 64 + 32 * kFoldEpiWarps;
+
+struct FoldParams {
+  int n;                 // MMA N: 192 (3 x 64) or 16 (3 x 5, padded)
+  int gw;                // accumulator columns per dx group: 64 or 5
+  int tiles_x, tiles_y, total_tiles;
+  int stages;
+  uint32_t tmem_cols, idesc, epi_warp_bytes;
+};
+
+template <int kMode>
+__global__ void __launch_bounds__(kFoldThreads, 1)
+conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                    const __grid_constant__ EpiMaps em, const FoldParams q, const ConvParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t w_bytes = 3u * (uint32_t)q.n * 128u;
+  const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
+  const uint32_t w_smem = base, a_smem = base + w_span;
+  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * kFStage;
+  uint8_t* tail = smem + w_span + (size_t)q.stages * kFStage + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(kMaxStages + s); };
+  const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxStages);
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 1 + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 3 + a); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [64]
+  const uint32_t rbar0 = smem_u32(bias_s) + 64u * 4u;                        // [kFoldEpiWarps][2]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(wfull_bar, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kMode == 3 ? 4 : kFoldEpiWarps); }
+    for (int i = 0; i < 2 * kFoldEpiWarps; ++i) mbar_init(rbar0 + 8u * (uint32_t)i, 1);
+    fence_barrier_init();
+  }
+  for (int i = threadIdx.x; i < 64; i += kFoldThreads) bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
+  if (warp == 2 && lane == 0 && kMode != 3) {
+    prefetch_tmap(&em.y);
+    if (kMode == 2) { prefetch_tmap(&em.r1); prefetch_tmap(&em.r2); if (p.y2) prefetch_tmap(&em.y2); }
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), q.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_img = q.tiles_x * q.tiles_y;
+  const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
+  auto coords = [&](int tile, int& b, int& y0, int& x0) {
+    b = tile / tiles_per_img;
+    const int rr_ = tile - b * tiles_per_img;
+    const int ty = rr_ / q.tiles_x;
+    y0 = ty * kFH;
+    x0 = (rr_ - ty * q.tiles_x) * kFOut;
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_expect_tx(wfull_bar, w_bytes);
+      for (int dy = 0; dy < 3; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
+    }
+    __syncwarp();
+    int s = 0; uint32_t ph = 0;
+    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
+      int b, y0, x0;
+      coords(tile, b, y0, x0);
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      if (elect_one()) {
+        mbar_expect_tx(full_bar(s), kFStage);
+        tma_load_4d(a_smem + (uint32_t)s * kFStage, &tmap_x, full_bar(s), 0, x0 - 1, y0 - 1, b);
+      }
+      __syncwarp();
+      if (++s == q.stages) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: 3 vertical taps x 4 k-steps, N = 3 * group width =====================
+    mbar_wait(wfull_bar, 0);
+    int s = 0; uint32_t ph = 0; int it = 0;
+    const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
+    const uint32_t b_dy = ((uint32_t)q.n * 128u) >> 4;
+    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * kFStage, 1024u, 0);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n);
+      if (elect_one()) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(acc));
+      }
+      __syncwarp();
+      if (++s == q.stages) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int ew = warp - 2, quad = warp & 3, cq = ew >> 2;   // cq: warp set (mode 3) / 16-channel quarter (modes 0-2)
+    auto release_tmem = [&](int acc) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    };
+    if (kMode == 3) {
+      // few channels: the two warp sets take alternate tiles; element-wise stores (lanes 0..29 = output columns x0 + lane)
+      int it = 0;
+      for (int tile = first_tile; tile < q.total_tiles && cq < 2; tile += tile_step, ++it) {
+        const int acc = it & 1;
+        if (acc != cq) continue;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        int b, y0, x0;
+        coords(tile, b, y0, x0);
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        uint32_t rr[16];
+        __syncwarp();
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n), rr);
+        tmem_ld_wait();
+        release_tmem(acc);
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[5 + e]), 1);
+          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[10 + e]), 2);
+          v[e] = bias_s[e] + __uint_as_float(rr[e]) + mid + right;
+        }
+        const int oy = y0 + quad, ox = x0 + lane;
+        if (lane < kFOut && oy < p.H && ox < p.W) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
+            else if (p.act != SRB_ACT_NONE)
+              v[e] = act_generic(v[e], p.act, (p.act == SRB_ACT_PRELU && e < p.cout) ? __ldg(p.prelu + e) : p.act_slope);
+            v[e] *= p.alpha;
+            if (p.clip01) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
+          }
+          const size_t o = (((size_t)b * p.H + oy) * p.W + ox) * p.y_cstride + p.y_coffset;
+          if (p.y_dtype == SRB_F32) {
+            float* d = reinterpret_cast<float*>(p.y) + o;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (e < p.cout) d[e] = v[e];
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) if (e < p.cout) store_elem(p.y, p.y_dtype, o + e, v[e]);
+          }
+        }
+      }
+    } else {
+      // 64 output channels, 16-bit y: warp (quadrant = tile row, cq = 16 of the 64 channels); rows move with TMA.
+      // Sixteen epilogue warps (four per scheduler) hide the TMEM-load / shuffle latencies of this role.
+      constexpr bool P8 = kMode == 2;
+      const int col0 = cq * 16;                           // first output channel of this warp
+      constexpr uint32_t hb = 32u, lb = 16u;              // staged row bytes: 16 x 16-bit, 16 x e5m2
+      const uint32_t buf_bytes = 32u * hb + (P8 ? 32u * lb : 0u);
+      const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
+      const uint32_t row = (uint32_t)lane;
+      const uint32_t h_row = row * hb, h_x = (row >> 2) & 1u;            // 32-byte swizzle
+      const uint32_t l_row = 32u * hb + row * lb;                        // 16-byte rows: no swizzle
+      const uint32_t my_rbar = rbar0 + 16u * (uint32_t)ew;
+      const float alpha = p.alpha, beta1 = p.beta1, beta2 = p.beta2;
+      const bool bf = p.y_dtype == SRB_BF16;
+      float bb[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) bb[e] = bias_s[col0 + e];
+      auto load_res = [&](int tile, uint32_t nb) {
+        int b, y0, x0;
+        coords(tile, b, y0, x0);
+        const uint32_t buf = my_epi + nb * buf_bytes, bar = my_rbar + 8u * nb;
+        mbar_expect_tx(bar, (uint32_t)kFOut * (hb + lb));
+        tma_load_4d(buf, &em.r1, bar, col0, x0, y0 + quad, b);
+        tma_load_4d(buf + 32u * hb, &em.r2, bar, col0, x0, y0 + quad, b);
+      };
+      int it = 0;
+      if (P8 && lane == 0 && first_tile < q.total_tiles) load_res(first_tile, 0u);
+      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
+        int b, y0, x0;
+        coords(tile, b, y0, x0);
+        const int acc = it & 1;
+        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
+        const uint32_t buf = my_epi + (P8 ? (uint32_t)(it & 1) * buf_bytes : 0u);
+        if (lane == 0) {
+          bulk_wait_read0();
+          if (P8 && tile + tile_step < q.total_tiles) load_res(tile + tile_step, (uint32_t)((it + 1) & 1));
+        }
+        __syncwarp();
+        mbar_wait(tfull_bar(acc), acc_ph);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n + col0);
+        uint32_t d0[16], d1[16], d2[16];
+        __syncwarp();
+        tmem_ld16(t_row, d0);
+        tmem_ld16(t_row + 64u, d1);
+        tmem_ld16(t_row + 128u, d2);
+        tmem_ld_wait();
+        release_tmem(acc);
+        float a[16];                                      // conv + bias of output column x0 + lane
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[e]), 1);
+          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[e]), 2);
+          a[e] = (__uint_as_float(d0[e]) + mid) + (right + bb[e]);
+        }
+        const uint32_t a_h0 = buf + h_row + ((0u ^ h_x) << 4), a_h1 = buf + h_row + ((1u ^ h_x) << 4);
+        uint32_t oh[8];
+        if (!P8) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float v0 = a[2 * i], v1 = a[2 * i + 1];
+            if (kMode == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
+          }
+        } else {
+          mbar_wait(my_rbar + 8u * (uint32_t)(it & 1), acc_ph);
+          const uint32_t a_l = buf + l_row;
+          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
+          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
+          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+          uint32_t ol[4];
+          auto half_block = [&](auto is_bf) {
+            constexpr bool kBf = decltype(is_bf)::value;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              float lo4[4], er[4];
+              e5m2x4_to_float4(wl[i4], lo4);
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const int e0 = 4 * i4 + 2 * hh;
+                float2 fh;
+                if (kBf) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
+                else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
+                const float v0 = fmaf(beta2, lo4[2 * hh], fmaf(beta1, fh.x, a[e0] * alpha));
+                const float v1 = fmaf(beta2, lo4[2 * hh + 1], fmaf(beta1, fh.y, a[e0 + 1] * alpha));
+                const uint32_t pk = pack2(v0, v1, kBf ? SRB_BF16 : SRB_F16);
+                oh[2 * i4 + hh] = pk;
+                float2 back;
+                if (kBf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+                else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                er[2 * hh] = v0 - back.x; er[2 * hh + 1] = v1 - back.y;
+              }
+              ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
+            }
+          };
+          if (bf) half_block(std::true_type{}); else half_block(std::false_type{});
+          sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+        }
+        sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+        sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&em.y, buf, col0, x0, y0 + quad, b);               // rows 0..29 of the staging block
+          if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, col0, x0, y0 + quad, b);
+          bulk_commit();
+        }
+      }
+      if (lane == 0) bulk_wait0();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, q.tmem_cols);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
@@ -1154,7 +1457,116 @@ static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
   return aligned16(ptr) && (cstride % per16 == 0) && (coffset % per16 == 0);
 }
 
+
+// ---- wide-tile fold kernel: eligibility and launch ----
+static int fold_mode(const ConvParams& p) {          // -1: not eligible
+  static const bool enabled = getenv("SRB_TC_NO_WIDE") == nullptr;
+  if (!enabled || g_variant != 0 || p.kh != 3 || p.kw != 3 || p.cin != 64 || !p.w_tc_fold || p.d2s != 1) return -1;
+  if (getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG"))) return -1;
+  auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
+  if (p.cout <= 4) return (!p.res1 && !p.res2 && !p.y2) ? 3 : -1;
+  if (p.cout != 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
+  if (!p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f) {
+    if (p.act == SRB_ACT_NONE) return 0;
+    if (p.act == SRB_ACT_RELU) return 1;
+    return -1;
+  }
+  const bool pair8 = p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
+                     (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == SRB_F8E5M2)) && p.act == SRB_ACT_NONE && !p.clip01 &&
+                     p.res1_cstride % 8 == 0 && p.res2_cstride % 16 == 0 && (!p.y2 || p.y2_cstride % 16 == 0) &&
+                     aligned16(p.res1) && aligned16(p.res2) && (!p.y2 || aligned16(p.y2));
+  // (the pair8 epilogue on wide tiles is issue-bound by its shuffles and conversions: 0.125 ms per 32 tiles against 0.111 ms for
+  //  the 16 x 8-tile kernel with the same TMA epilogue, so it is opt-in)
+  static const bool wide_p8 = getenv("SRB_TC_WIDE_P8") != nullptr;
+  return (pair8 && wide_p8) ? 2 : -1;
+}
+
+static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) {
+  EncodeTiledFn encode = encode_fn();
+  if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
+  FoldParams q{};
+  q.gw = mode == 3 ? 5 : 64;
+  q.n = mode == 3 ? 16 : 192;
+  q.tiles_x = (p.W + kFOut - 1) / kFOut;
+  q.tiles_y = (p.H + kFH - 1) / kFH;
+  const long total = (long)p.B * q.tiles_x * q.tiles_y;
+  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
+  q.total_tiles = (int)total;
+  q.tmem_cols = 32;
+  while (q.tmem_cols < (uint32_t)(2 * q.n)) q.tmem_cols <<= 1;
+  const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;
+  q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+  q.epi_warp_bytes = mode == 3 ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
+  int dev = 0, max_smem = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const size_t w_bytes = ((size_t)3 * q.n * 128 + 1023) & ~(size_t)1023;
+  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 64 * sizeof(float) + 2 * kFoldEpiWarps * 8;
+  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * kFStage + (size_t)kFoldEpiWarps * q.epi_warp_bytes + tail_bytes; };
+  q.stages = 4;
+  while (q.stages > 2 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
+  const size_t smem = smem_need(q.stages);
+  if (smem > (size_t)max_smem) { set_error("conv(tcgen05, fold): staging does not fit shared memory"); return SRB_E_UNSUPPORTED; }
+
+  const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUtensorMap tmx, tmw;
+  {
+    const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2, (cuuint64_t)p.H * p.W * p.x_cstride * 2};
+    const cuuint32_t box[4] = {64, (cuuint32_t)kFW, (cuuint32_t)(kFH + 2), 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    void* gptr = (void*)((const uint16_t*)p.x + p.x_coffset);
+    CUresult r = encode(&tmx, tdt, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
+  }
+  {
+    const cuuint64_t dims[2] = {64, (cuuint64_t)3 * q.n};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {64, (cuuint32_t)q.n};
+    const cuuint32_t es[2] = {1, 1};
+    CUresult r = encode(&tmw, tdt, 2, (void*)p.w_tc_fold, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
+  }
+  EpiMaps em;
+  memset(&em, 0, sizeof(em));
+  if (mode != 3) {
+    auto encode_epi = [&](CUtensorMap* m, const void* ptr, int coffset, int cstride, bool f8) -> bool {
+      const size_t es = f8 ? 1 : 2;
+      const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+      const cuuint64_t strides[3] = {(cuuint64_t)cstride * es, (cuuint64_t)p.W * cstride * es, (cuuint64_t)p.H * p.W * cstride * es};
+      const cuuint32_t box[4] = {16, (cuuint32_t)kFOut, 1, 1};
+      const cuuint32_t es1[4] = {1, 1, 1, 1};
+      const CUtensorMapDataType dt = f8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
+                                        : (p.y_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+      void* g = (void*)((const uint8_t*)ptr + (size_t)coffset * es);
+      return encode(m, dt, 4, g, dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    f8 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+    };
+    bool ok = encode_epi(&em.y, p.y, p.y_coffset, p.y_cstride, false);
+    if (mode == 2) {
+      ok = ok && encode_epi(&em.r1, p.res1, 0, p.res1_cstride, false) && encode_epi(&em.r2, p.res2, 0, p.res2_cstride, true);
+      if (p.y2) ok = ok && encode_epi(&em.y2, p.y2, 0, p.y2_cstride, true);
+    }
+    if (!ok) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
+  }
+  typedef void (*FoldFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FoldParams, const ConvParams);
+  static const FoldFn kernels[4] = {conv3x3_fold_kernel<0>, conv3x3_fold_kernel<1>, conv3x3_fold_kernel<2>, conv3x3_fold_kernel<3>};
+  static size_t configured[4] = {0, 0, 0, 0};
+  if (smem > configured[mode]) {
+    SRB_CUDA(cudaFuncSetAttribute(kernels[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[mode] = smem;
+  }
+  int grid = sm_count();
+  if ((long)grid > total) grid = (int)total;
+  kernels[mode]<<<grid, kFoldThreads, smem, stream>>>(tmx, tmw, em, q, p);
+  return launch_check("conv3x3_fold_kernel");
+}
+
 int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
+  { const int fm = fold_mode(p); if (fm >= 0) return conv_fold_launch(p, fm, stream); }
   EncodeTiledFn encode = encode_fn();
   if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
 
