@@ -307,6 +307,7 @@ __device__ __noinline__ void epilogue_store_generic(const ConvParams& p, int b, 
 //   0 generic (all flags read at run time)      1 act none, 16-bit y            2 ReLU, 16-bit y
 //   3 fp32 residual, fp32 y + 16-bit y2         4 fp32 residual, 16-bit y
 //   5 16-bit (hi, lo) residual pair -> 16-bit y + its rounding error y2 (compensated trunk, all in the F rows)
+//   7 PReLU / leaky ReLU, 16-bit y (TMA epilogue only; slopes staged in shared memory)
 //   6 (16-bit hi, e5m2 lo) residual pair -> 16-bit y + its rounding error y2 in e5m2 ("pair8" trunk: 3 bytes per
 //     channel carry ~14 significant bits; staging = one 16-bit and one 8-bit row region per prefetch buffer)
 // k2: cta_group::2 - a cluster of two CTAs issues M = 256 MMAs (128 pixels per CTA) from the leader; each CTA keeps
@@ -341,6 +342,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [n_tile], 16-byte aligned
   const uint32_t rbar0 = smem_u32(bias_s) + (uint32_t)q.n_tile * 4u;       // [kEpiWarps][2] residual-landed barriers (TMA epilogue)
+  float* slope_s = bias_s + q.n_tile + 4 * kEpiWarps;                      // [n_tile] PReLU / leaky slopes (kSpec 7)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work units: a CTA (or a CTA pair) owns channel chunk `unit % n_chunks` and every (units / n_chunks)-th tile (pair)
@@ -364,6 +366,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     fence_barrier_init();
   }
   for (int i = threadIdx.x; i < q.n_tile; i += kThreads) bias_s[i] = (co_base + i < p.cout) ? p.bias[co_base + i] : 0.f;
+  if (kSpec == 7) {
+    for (int i = threadIdx.x; i < q.n_tile; i += kThreads) {
+      const int co = co_base + i;
+      slope_s[i] = (p.act == SRB_ACT_PRELU && co < p.cout) ? p.prelu[p.d2s > 1 ? co % p.c_post : co] : p.act_slope;
+    }
+  }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
   if (warp == 2 && lane == 0 && q.tma_epi) {
     prefetch_tmap(&em.y);
@@ -510,7 +518,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
     }
-  } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6) && !k2 && q.tma_epi) {
+  } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6 || kSpec == 7) && !k2 && q.tma_epi) {
     // ===================== epilogue, TMA flavour (16-bit y, d2s = 1, 64- or 128-channel chunks) =====================
     // Warp (quadrant, column half) owns 4 tile rows x 8 pixels x ncols channels.  Its staging rows are laid out exactly as
     // the {ncols, 8, 4, 1} TMA box with the 32/64/128-byte swizzle of the row size, so one elected lane moves the whole
@@ -592,6 +600,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           for (int i = 0; i < 8; ++i) {
             float v0 = __uint_as_float(rr[2 * i]) + bb[2 * i], v1 = __uint_as_float(rr[2 * i + 1]) + bb[2 * i + 1];
             if (kSpec == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (kSpec == 7) {                             // PReLU / leaky: max(v, 0) + slope * min(v, 0)
+              const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + c0 + 2 * i);
+              v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
+            }
             oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
           }
         } else {
@@ -1128,7 +1140,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 // epilogue warp combines own / lane + 1 / lane + 2 with two shuffles per channel; lanes 0..29 hold the 30 output columns.
 // The halo is one TMA box of 64 c x 32 w x 6 h; the dy shift is 4,096 bytes (swizzle-atom aligned).  Output rows move with
 // TMA exactly as in the staged epilogue above (boxes of {32 channels, 30 pixels, 1 row}).
-// Modes: 0 plain 16-bit y, 1 ReLU 16-bit y, 2 pair8 trunk (16-bit hi + e5m2 lo residual in, y + rounding error out),
+// Modes: 0 plain 16-bit y, 1 ReLU 16-bit y, 4 PReLU / leaky 16-bit y, 2 pair8 trunk (16-bit hi + e5m2 lo residual in, y + rounding error out),
 //        3 few channels (Cout <= 4, groups of 5 columns): bias / activation / alpha / clip, stored element-wise.
 // ===================================================================================================================
 constexpr int kFW = 32, kFH = 4, kFOut = 30;
@@ -1167,6 +1179,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [64]
   const uint32_t rbar0 = smem_u32(bias_s) + 64u * 4u;                        // [kFoldEpiWarps][2]
+  float* slope_s = bias_s + 64 + 4 * kFoldEpiWarps;                          // [64] PReLU / leaky slopes (mode 4)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -1176,7 +1189,10 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     for (int i = 0; i < 2 * kFoldEpiWarps; ++i) mbar_init(rbar0 + 8u * (uint32_t)i, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 64; i += kFoldThreads) bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < 64; i += kFoldThreads) {
+    bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
+    if (kMode == 4) slope_s[i] = (p.act == SRB_ACT_PRELU && i < p.cout) ? p.prelu[i] : p.act_slope;
+  }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
   if (warp == 2 && lane == 0 && kMode != 3) {
     prefetch_tmap(&em.y);
@@ -1312,6 +1328,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       float bb[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) bb[e] = bias_s[col0 + e];
+      __syncwarp();
       auto load_res = [&](int tile, uint32_t nb) {
         int b, y0, x0;
         coords(tile, b, y0, x0);
@@ -1357,6 +1374,10 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int i = 0; i < 8; ++i) {
             float v0 = a[2 * i], v1 = a[2 * i + 1];
             if (kMode == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            if (kMode == 4) {
+              const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + 2 * i);
+              v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
+            }
             oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
           }
         } else {
@@ -1469,6 +1490,7 @@ static int fold_mode(const ConvParams& p) {          // -1: not eligible
   if (!p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f) {
     if (p.act == SRB_ACT_NONE) return 0;
     if (p.act == SRB_ACT_RELU) return 1;
+    if (p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu)) return 4;
     return -1;
   }
   const bool pair8 = p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
@@ -1501,7 +1523,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const size_t w_bytes = ((size_t)3 * q.n * 128 + 1023) & ~(size_t)1023;
-  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 64 * sizeof(float) + 2 * kFoldEpiWarps * 8;
+  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * 64 * sizeof(float) + 2 * kFoldEpiWarps * 8;
   auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * kFStage + (size_t)kFoldEpiWarps * q.epi_warp_bytes + tail_bytes; };
   q.stages = 4;
   while (q.stages > 2 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
@@ -1553,8 +1575,9 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
     if (!ok) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
   }
   typedef void (*FoldFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FoldParams, const ConvParams);
-  static const FoldFn kernels[4] = {conv3x3_fold_kernel<0>, conv3x3_fold_kernel<1>, conv3x3_fold_kernel<2>, conv3x3_fold_kernel<3>};
-  static size_t configured[4] = {0, 0, 0, 0};
+  static const FoldFn kernels[5] = {conv3x3_fold_kernel<0>, conv3x3_fold_kernel<1>, conv3x3_fold_kernel<2>, conv3x3_fold_kernel<3>,
+                                    conv3x3_fold_kernel<4>};
+  static size_t configured[5] = {0, 0, 0, 0, 0};
   if (smem > configured[mode]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[mode] = smem;
@@ -1658,8 +1681,9 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       if (pair8) q.epi_warp_bytes = (uint32_t)(2 * 32 * warp_cols * 3);
       // TMA epilogue: 16-bit y without depth_to_space, 64- or 128-channel chunks, the plain / ReLU / pair8 layer types
       static const bool tma_enabled = getenv("SRB_TC_NO_TMA_EPI") == nullptr && !(getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")));
+      const bool slope_act = p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu);
       const bool plain16 = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && q.h_dst == 1 && q.f_dst == 0 &&
-                           (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU);
+                           (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || slope_act);
       // (depth_to_space: plain layers whose warp columns are whole sub-pixels, images made of whole 16-row tiles because
       //  the 5-D output map merges the image and row dimensions)
       const bool d2s_ok = p.d2s == 1 || (plain16 && p.c_post % warp_cols == 0 && p.H % kTileH == 0 && p.y_coffset == 0 && p.y_cstride == p.c_post);
@@ -1669,7 +1693,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       }
     }
     const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
-    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
+    const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
     if (!stage_cap) { const char* e = getenv("SRB_TC_STAGES"); stage_cap = e ? atoi(e) : kMaxStages; if (stage_cap < 1 || stage_cap > kMaxStages) stage_cap = kMaxStages; }
@@ -1754,18 +1778,19 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (!p.res1 && p.alpha == 1.f && q.f_dst == 0 && q.h_dst == 1 && !p.y2) {
       if (p.act == SRB_ACT_NONE) spec = 1;
       else if (p.act == SRB_ACT_RELU) spec = 2;
+      else if (q.tma_epi && (p.act == SRB_ACT_LEAKY || p.act == SRB_ACT_PRELU)) spec = 7;   // (TMA epilogue only)
     } else if (q.res_prefetch && p.act == SRB_ACT_NONE) {
       if (q.f_dst == 1 && q.h_dst == 2) spec = 3;
       else if (q.f_dst == 0 && q.h_dst == 1 && !p.y2) spec = 4;
     }
   }
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const TcParams, const ConvParams);
-  static const KernelFn kernels[2][7] = {
+  static const KernelFn kernels[2][8] = {
       {conv3x3_tc_kernel<0, false>, conv3x3_tc_kernel<1, false>, conv3x3_tc_kernel<2, false>, conv3x3_tc_kernel<3, false>,
-       conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>, conv3x3_tc_kernel<6, false>},
+       conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>, conv3x3_tc_kernel<6, false>, conv3x3_tc_kernel<7, false>},
       {conv3x3_tc_kernel<0, true>, conv3x3_tc_kernel<1, true>, conv3x3_tc_kernel<2, true>, conv3x3_tc_kernel<3, true>,
-       conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>}};
-  static size_t configured[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
+       conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>, conv3x3_tc_kernel<0, true>}};
+  static size_t configured[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
   if (smem > configured[k2][spec]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[k2][spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

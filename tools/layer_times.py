@@ -22,9 +22,19 @@ def main():
     ap.add_argument("--tile", type=int, default=192)
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--trunk", default="fp32")
+    ap.add_argument("--trunk", default="pair8")
+    ap.add_argument("--net", default="edsr", choices=["edsr", "espcn", "srresnet", "srcnn", "vgg16"])
     a = ap.parse_args()
-    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=a.dtype, trunk=a.trunk)
+    if a.net == "edsr":
+        net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=a.dtype, trunk=a.trunk)
+    elif a.net == "espcn":
+        net = engine.ESPCNNet(weights.espcn_weights(4), 4, precision=a.dtype)
+    elif a.net == "srresnet":
+        net = engine.SRResNetNet(weights.srresnet_weights(4), 4, 16, precision=a.dtype)
+    elif a.net == "srcnn":
+        net = engine.SRCNNNet(weights.srcnn_weights(), precision=a.dtype)
+    else:
+        net = engine.VGG16ClassifierNet(weights.vgg16_classifier_weights(2), precision=a.dtype)
     x = torch.rand((a.batch, a.tile, a.tile, 3), device="cuda")
     records = []
     orig = ops.conv2d
@@ -62,7 +72,7 @@ def main():
             if kw.get(rk) is not None:
                 in_b += npx * w.cout * kw[rk].element_size()
         print(f"{i:3d} {w.kh}x{w.kw} {w.cin:3d}->{w.cout:3d} {npx:10d} {ms:8.3f} {flop / ms / 1e9:9.1f} {(in_b + out_b) / ms / 1e6:10.1f}")
-    print(f"total {total:.3f} ms for {a.batch} tiles -> {a.batch * (a.tile * 4) ** 2 / 1e6 / (total / 1e3):.1f} MP/s")
+    print(f"total {total:.3f} ms (conv layers) for {a.batch} tiles of {a.tile}x{a.tile}")
 
 
 if __name__ == "__main__":
