@@ -261,8 +261,12 @@ def run_gpu(args):
                     "api": "EDSRNet.predict(host NHWC float32, out=pinned host)"},
             "gpu_launches": launches * world,
             "clocks": clk.result,
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel", "achieved": achieved, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": None,
+            # traffic: dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over the 36 tcgen05 launches of one
+            # 32-tile forward (ncu --set full, profiles/r01_ncu_conv_final.txt): 16 x (0.260 + 0.572) + 0.503 + 0.697 + 2.977 + 2.641 GB
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel + conv3x3_fold_kernel (tcgen05 implicit GEMM, all 36 launches of a forward)",
+                         "achieved": achieved, "peak": peaks["tflops"],
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": 0.559e9 * (mb / 32.0),
+                         "traffic_unit": "bytes per launch (ncu dram read + write, mean over the launches of a forward)",
                          "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                          "flop_per_launch": tc_flops / max(n_tc_launches, 1),
                          "avg_launch_ms": tc_ms / max(n_tc_launches, 1), "launches": n_tc_launches,
