@@ -78,4 +78,7 @@ struct srb_conv_weights {
   int tc_cout_pad;        // rows per tap in `tc` (multiple of 16)
   __nv_bfloat16* tc_fold; // cout <= 4 only: [dy][16 rows = dx*5+co][cin] (horizontal taps folded into N) or nullptr
   __half* tc_fold_f16;
+  __nv_bfloat16* tc_head; // cin == 3, cout == 64 only: im2col GEMM operand [n_kb][64 cout rows][64 k], k = (dy*kw + dx)*3 + c, or nullptr
+  __half* tc_head_f16;
+  int tc_head_kb;         // 64-wide K blocks
 };

@@ -33,6 +33,27 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
     srb_conv_weights_destroy(w);
     return cuda_fail(e, "conv_weights_create");
   }
+  // RGB head layers (cin == 3, cout == 64): im2col GEMM operand for the tcgen05 head kernel
+  if (cin == 3 && cout == 64 && kh <= 9 && kw <= 9) {
+    const int K = taps * 3, kpad = (K + 15) & ~15, n_kb = (kpad + 63) / 64;
+    w->tc_head_kb = n_kb;
+    std::vector<__nv_bfloat16> hb((size_t)n_kb * 64 * 64, __float2bfloat16_rn(0.f));
+    std::vector<__half> hh((size_t)n_kb * 64 * 64, __float2half_rn(0.f));
+    for (int k = 0; k < K; ++k)
+      for (int o = 0; o < cout; ++o) {
+        const float v = hwio[(size_t)k * cout + o];               // k = (dy*kw + dx)*3 + c is the HWIO flattening itself
+        const size_t idx = ((size_t)(k / 64) * 64 + o) * 64 + (k % 64);
+        hb[idx] = __float2bfloat16_rn(v);
+        hh[idx] = __float2half_rn(v);
+      }
+    if ((e = cudaMalloc(&w->tc_head, hb.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc_head, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&w->tc_head_f16, hh.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc_head_f16, hh.data(), hh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      srb_conv_weights_destroy(w);
+      return cuda_fail(e, "conv_weights_create(tc head)");
+    }
+  }
   // tensor-core copies: [tap][cout_pad16][cin] K(cin)-major rows in bf16 and fp16, for cin == 64
   if (cin == 64) {
     const int rows = (cout + 15) & ~15;
@@ -106,6 +127,8 @@ extern "C" void srb_conv_weights_destroy(srb_conv_weights* w) {
   if (w->tc_f16) cudaFree(w->tc_f16);
   if (w->tc_fold) cudaFree(w->tc_fold);
   if (w->tc_fold_f16) cudaFree(w->tc_fold_f16);
+  if (w->tc_head) cudaFree(w->tc_head);
+  if (w->tc_head_f16) cudaFree(w->tc_head_f16);
   free(w);
 }
 
@@ -139,6 +162,7 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.w_hwio = w->hwio; p.w_cout_pad = w->cout_pad4;
   p.w_tc = a->x_dtype == SRB_F16 ? (const void*)w->tc_f16 : (const void*)w->tc; p.w_tc_rows = w->tc_cout_pad;
   p.w_tc_fold = a->x_dtype == SRB_F16 ? (const void*)w->tc_fold_f16 : (const void*)w->tc_fold;
+  p.w_tc_head = a->y_dtype == SRB_F16 ? (const void*)w->tc_head_f16 : (const void*)w->tc_head; p.w_tc_head_kb = w->tc_head_kb;
   p.bias = w->bias;
   p.act = a->act; p.act_slope = a->act_slope; p.prelu = a->prelu;
   SRB_REQUIRE(a->act >= SRB_ACT_NONE && a->act <= SRB_ACT_TANH, "conv2d: unknown activation %d", a->act);
@@ -155,7 +179,7 @@ extern "C" int srb_conv2d_engine(const srb_conv_args* a) {
   ConvParams p;
   int rc = fill_params(a, p);
   if (rc) return rc;
-  return conv_tc_eligible(p) ? SRB_ENGINE_TCGEN05 : SRB_ENGINE_DIRECT;
+  return (conv_tc_eligible(p) || conv_headtc_eligible(p)) ? SRB_ENGINE_TCGEN05 : SRB_ENGINE_DIRECT;
 }
 
 extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
@@ -165,6 +189,10 @@ extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
   if (rc) return rc;
   if (p.B == 0) return SRB_OK;
   const bool tc_ok = conv_tc_eligible(p);
+  if (a->engine != SRB_ENGINE_DIRECT && !tc_ok && conv_headtc_eligible(p)) {       // RGB head layers: im2col GEMM on the tensor cores
+    rc = conv_headtc_launch(p, (cudaStream_t)stream);
+    if (rc != SRB_E_UNSUPPORTED || a->engine == SRB_ENGINE_TCGEN05) return rc;
+  }
   if (a->engine == SRB_ENGINE_TCGEN05 && !tc_ok) {
     set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, cin == 64, odd filter up to 9x9)");
     return SRB_E_UNSUPPORTED;

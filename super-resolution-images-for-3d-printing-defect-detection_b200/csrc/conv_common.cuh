@@ -12,7 +12,8 @@ struct ConvParams {
   int kh, kw, cin, cout;
   const float* w_hwio; int w_cout_pad;      // direct engine weights
   const void* w_tc; int w_tc_rows;          // tcgen05 engine weights [tap][rows][cin] in the dtype of x
-  const void* w_tc_fold;                    // [dy][16][cin] dx-folded weights for cout <= 4, or nullptr
+  const void* w_tc_fold;                    // dx-folded weights ([dy][16][cin] for cout <= 4, [dy][192][cin] for cout == 64), or nullptr
+  const void* w_tc_head; int w_tc_head_kb;  // cin == 3 im2col weights in the 16-bit dtype of y, or nullptr
   const float* bias;                        // [cout], never null
   int act; float act_slope; const float* prelu;
   float alpha;
@@ -97,6 +98,8 @@ int conv_direct_launch(const ConvParams& p, cudaStream_t stream);
 int conv_head_launch(const ConvParams& p, cudaStream_t stream);
 bool conv_head_eligible(const ConvParams& p);
 int conv_tc_launch(const ConvParams& p, cudaStream_t stream);
+int conv_headtc_launch(const ConvParams& p, cudaStream_t stream);
+bool conv_headtc_eligible(const ConvParams& p);
 bool conv_tc_eligible(const ConvParams& p);
 
 }  // namespace srb

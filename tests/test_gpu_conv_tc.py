@@ -111,6 +111,42 @@ def test_tma_epilogue_paths(kind):
         assert got.shape == (B, 2 * H, 2 * W, 64) and np.abs(got - want).max() <= tol16, (B, H, W)
 
 
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("ksize", [3, 5, 9])
+def test_rgb_head_on_tensor_cores(kind, ksize):
+    """K x K, 3 -> 64 head layers as an im2col GEMM on tcgen05 (fp32 image in, 16-bit out): against the fp64 oracle on
+    operands rounded to the 16-bit type, with edge-clipped tiles, several images, the activations the networks use, and
+    the pair8 second output (e5m2 rounding error of y)."""
+    from srb200 import ops, _capi
+    dt = DT[kind]
+    tol = 3e-2 if kind == "bf16" else 4e-3
+    kern = _rand((ksize, ksize, 3, 64), 2, -0.2, 0.2)
+    bias = _rand((64,), 3, -0.1, 0.1)
+    slopes = _rand((64,), 4, 0.05, 0.4)
+    w = ops.ConvWeights(kern, bias, slopes)
+    for (B, H, W, act) in ((2, 32, 24, "relu"), (3, 19, 21, None), (1, 40, 13, "prelu"), (1, 16, 8, "tanh")):
+        x = _rand((B, H, W, 3), 10 + H, 0.0, 1.0)
+        want = oc.conv2d_same_numpy(_round(x, kind), _round(kern, kind), bias)
+        if act == "relu":
+            want = np.maximum(want, 0)
+        elif act == "prelu":
+            want = np.where(want >= 0, want, want * slopes)
+        elif act == "tanh":
+            want = np.tanh(want)
+        xd = torch.from_numpy(x).cuda()
+        got = ops.conv2d(xd, w, act=act, out_dtype=dt, engine=_capi.ENGINE_TCGEN05)
+        assert got.dtype == dt and np.abs(got.float().cpu().numpy() - want).max() <= tol, (B, H, W, act)
+        ref = ops.conv2d(xd, w, act=act, out_dtype=dt, engine=_capi.ENGINE_DIRECT)      # exact fp32 CUDA-core engine
+        assert (got.float() - ref.float()).abs().max().item() <= tol
+    x = _rand((2, 24, 24, 3), 7, 0.0, 1.0)
+    xd = torch.from_numpy(x).cuda()
+    y, e = ops.conv2d(xd, w, out_dtype=dt, out2_dtype=torch.float8_e5m2, out2_error=True, engine=_capi.ENGINE_TCGEN05)
+    want = oc.conv2d_same_numpy(_round(x, kind), _round(kern, kind), bias)
+    e1 = np.abs(y.double().cpu().numpy() - want).max()
+    e2 = np.abs(y.double().cpu().numpy() + e.double().cpu().numpy() - want).max()
+    assert e.dtype == torch.float8_e5m2 and e2 <= max(e1 / 3, 2e-4), (e1, e2)
+
+
 def test_second_output_copy_and_channel_slice():
     from srb200 import ops, _capi
     x = _round(_rand((1, 16, 16, 64), 1), "fp16")
