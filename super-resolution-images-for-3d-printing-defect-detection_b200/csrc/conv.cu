@@ -94,17 +94,19 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
         return cuda_fail(e, "conv_weights_create(tc fold 64)");
       }
     }
-    if (kh == 3 && kw == 3 && cout <= 5) {
-      // few-channel layers (RGB tails): fold the horizontal taps into N so that a tile needs 12 instead of 36 MMAs
-      std::vector<__nv_bfloat16> fb((size_t)3 * 16 * cin, __float2bfloat16_rn(0.f));
-      std::vector<__half> fh((size_t)3 * 16 * cin, __float2half_rn(0.f));
-      for (int dy = 0; dy < 3; ++dy)
-        for (int dx = 0; dx < 3; ++dx)
+    if (cout <= 4 && kh <= 9 && kw <= 9) {
+      // few-channel layers (RGB tails, any odd filter up to 9 x 9): the horizontal taps are folded into N, row = dx * 4 + co,
+      // N = kw * 4 rounded up to 16 rows per vertical tap (wide-tile kernel, mode 3)
+      const int n = (kw * 4 + 15) & ~15;
+      std::vector<__nv_bfloat16> fb((size_t)kh * n * cin, __float2bfloat16_rn(0.f));
+      std::vector<__half> fh((size_t)kh * n * cin, __float2half_rn(0.f));
+      for (int dy = 0; dy < kh; ++dy)
+        for (int dx = 0; dx < kw; ++dx)
           for (int o = 0; o < cout; ++o)
             for (int c = 0; c < cin; ++c) {
-              const float v = hwio[((size_t)(dy * 3 + dx) * cin + c) * cout + o];
-              fb[((size_t)dy * 16 + dx * 5 + o) * cin + c] = __float2bfloat16_rn(v);
-              fh[((size_t)dy * 16 + dx * 5 + o) * cin + c] = __float2half_rn(v);
+              const float v = hwio[((size_t)(dy * kw + dx) * cin + c) * cout + o];
+              fb[((size_t)dy * n + dx * 4 + o) * cin + c] = __float2bfloat16_rn(v);
+              fh[((size_t)dy * n + dx * 4 + o) * cin + c] = __float2half_rn(v);
             }
       if ((e = cudaMalloc(&w->tc_fold, fb.size() * 2)) != cudaSuccess ||
           (e = cudaMemcpy(w->tc_fold, fb.data(), fb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||

@@ -15,6 +15,7 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 
 namespace srb {
 
@@ -203,6 +204,10 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
     const int act = p.act;
     const float alpha = p.alpha;
     const bool clip = p.clip01 != 0, err_out = q.y2_f8 != 0;
+    const bool scaled = alpha != 1.f || clip;
+    float bias_r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) bias_r[i] = bias_s[col0 + i];
     int it = 0;
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
       int b, y0, x0;
@@ -223,37 +228,44 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+      // the activation is a warp-uniform switch around the fully unrolled 32-channel block (one code copy per kind)
+      auto finish = [&](auto kind) {
+        constexpr int kAct = decltype(kind)::value;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t oh[8], ol[4];
+        for (int c = 0; c < 2; ++c) {
+          uint32_t oh[8], ol[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float v[2];
+          for (int i = 0; i < 8; ++i) {
+            float v[2];
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int ch = col0 + 16 * c + 2 * i + u;
-            float t = __uint_as_float(rr[c][2 * i + u]) + bias_s[ch];
-            if (act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
-            else if (act == SRB_ACT_PRELU || act == SRB_ACT_LEAKY) t = fmaf(slope_s[ch], fminf(t, 0.f), fmaxf(t, 0.f));
-            else if (act == SRB_ACT_TANH) t = tanhf(t);
-            t *= alpha;
-            if (clip) t = fminf(fmaxf(t, 0.f), 1.f);
-            v[u] = t;
+            for (int u = 0; u < 2; ++u) {
+              const int ci = 16 * c + 2 * i + u;
+              float t = __uint_as_float(rr[c][2 * i + u]) + bias_r[ci];
+              if (kAct == SRB_ACT_RELU) t = fmaxf(t, 0.f);
+              else if (kAct == SRB_ACT_PRELU) t = fmaf(slope_s[col0 + ci], fminf(t, 0.f), fmaxf(t, 0.f));
+              else if (kAct == SRB_ACT_TANH) t = tanhf(t);
+              if (scaled) { t *= alpha; if (clip) t = fminf(fmaxf(t, 0.f), 1.f); }
+              v[u] = t;
+            }
+            const uint32_t pk = bf ? pack2(v[0], v[1], SRB_BF16) : pack2(v[0], v[1], SRB_F16);
+            oh[i] = pk;
+            if (err_out) {
+              float2 back;
+              if (bf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+              else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+              const uint32_t e2 = __nv_cvt_float2_to_fp8x2(make_float2(v[0] - back.x, v[1] - back.y), __NV_SATFINITE, __NV_E5M2);
+              if (i & 1) ol[i >> 1] |= e2 << 16; else ol[i >> 1] = e2;
+            }
           }
-          const uint32_t pk = bf ? pack2(v[0], v[1], SRB_BF16) : pack2(v[0], v[1], SRB_F16);
-          oh[i] = pk;
-          if (err_out) {
-            float2 back;
-            if (bf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-            else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-            const uint32_t e2 = __nv_cvt_float2_to_fp8x2(make_float2(v[0] - back.x, v[1] - back.y), __NV_SATFINITE, __NV_E5M2);
-            if (i & 1) ol[i >> 1] |= e2 << 16; else ol[i >> 1] = e2;
-          }
+          sts128(buf + h_row + (((2u * (uint32_t)c) ^ h_x) << 4), make_uint4(oh[0], oh[1], oh[2], oh[3]));
+          sts128(buf + h_row + (((2u * (uint32_t)c + 1u) ^ h_x) << 4), make_uint4(oh[4], oh[5], oh[6], oh[7]));
+          if (err_out) sts128(buf + l_row + (((uint32_t)c ^ l_x) << 4), make_uint4(ol[0], ol[1], ol[2], ol[3]));
         }
-        sts128(buf + h_row + (((2u * (uint32_t)c) ^ h_x) << 4), make_uint4(oh[0], oh[1], oh[2], oh[3]));
-        sts128(buf + h_row + (((2u * (uint32_t)c + 1u) ^ h_x) << 4), make_uint4(oh[4], oh[5], oh[6], oh[7]));
-        if (err_out) sts128(buf + l_row + (((uint32_t)c ^ l_x) << 4), make_uint4(ol[0], ol[1], ol[2], ol[3]));
-      }
+      };
+      if (act == SRB_ACT_RELU) finish(std::integral_constant<int, SRB_ACT_RELU>{});
+      else if (act == SRB_ACT_PRELU || act == SRB_ACT_LEAKY) finish(std::integral_constant<int, SRB_ACT_PRELU>{});
+      else if (act == SRB_ACT_TANH) finish(std::integral_constant<int, SRB_ACT_TANH>{});
+      else finish(std::integral_constant<int, SRB_ACT_NONE>{});
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {

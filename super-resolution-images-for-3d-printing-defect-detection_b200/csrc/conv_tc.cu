@@ -54,6 +54,8 @@ struct TcParams {
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
+  int reverse;           // walk the tiles from the last to the first (alternate launches: the next layer starts on the
+                         // rows the previous one wrote last, which are still in L2)
   int tma_epi;           // staged epilogue moves its rows with TMA (residual loads, output stores) instead of per-lane copies
   int debug;             // diagnostics (SRB_TC_DEBUG): 1 = epilogue only releases TMEM (no math / stores: wrong results),
                          // 2 = the MMA warp issues no MMAs (commits only: wrong results)
@@ -214,7 +216,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     __syncwarp();
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
-      const int b = tile / tiles_per_img, r = tile - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
+      const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
+      const int b = tl / tiles_per_img, r = tl - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
       const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * q.tile_cols_out;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
@@ -361,8 +364,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     };
     auto coords = [&](int tile, int& b, int& y0, int& x0) {
-      b = tile / tiles_per_img;
-      const int rr_ = tile - b * tiles_per_img;
+      const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
+      b = tl / tiles_per_img;
+      const int rr_ = tl - b * tiles_per_img;
       const int ty = rr_ / q.tiles_x;
       y0 = ty * kTileH + quad * 4;                      // first image row of this warp's quadrant
       x0 = (rr_ - ty * q.tiles_x) * kTileW;
@@ -526,7 +530,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const int epi_mode = G ? q.epi_mode : 1;
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
-      const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
+      const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
+      const int b = tl / tiles_per_img, rr_ = tl - b * tiles_per_img;
       const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const size_t tp = tile_pixel(b, y0, x0);
@@ -611,7 +616,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     };
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
       const bool live = tile < q.total_tiles;           // (k2: the pair's odd CTA may hold a dummy tile)
-      const int b = tile / tiles_per_img, rr_ = tile - b * tiles_per_img;
+      const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
+      const int b = tl / tiles_per_img, rr_ = tl - b * tiles_per_img;
       const int y0 = live ? (rr_ / q.tiles_x) * kTileH : p.H, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
@@ -956,16 +962,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 //        3 few channels (Cout <= 4, groups of 5 columns): bias / activation / alpha / clip, stored element-wise.
 // ===================================================================================================================
 constexpr int kFW = 32, kFH = 4, kFOut = 30;
-constexpr uint32_t kFStage = 6u * kFW * 128u;     // 24,576 bytes
 constexpr int kFoldEpiWarps = 16;
 constexpr int kFoldThreads = 64 + 32 * kFoldEpiWarps;
 
 struct FoldParams {
-  int n;                 // MMA N: 192 (3 x 64) or 16 (3 x 5, padded)
-  int gw;                // accumulator columns per dx group: 64 or 5
+  int n;                 // MMA N: 192 (3 x 64), or kw x 4 rounded up to 16 for the few-channel layers (16 / 32 / 48)
+  int gw;                // accumulator columns per dx group: 64 or 4
+  int kh, kw;            // filter size (3 x 3 for the 64-channel modes; odd, <= 9 for mode 3)
+  int out_cols;          // output columns per tile row: 32 - (kw - 1)
+  uint32_t stage_bytes;  // (kFH + kh - 1) halo rows x 32 columns x 128 B
   int tiles_x, tiles_y, total_tiles;
   int stages;
   uint32_t tmem_cols, idesc, epi_warp_bytes;
+  int reverse;           // as TcParams::reverse
 };
 
 template <int kMode>
@@ -976,11 +985,11 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t w_bytes = 3u * (uint32_t)q.n * 128u;
+  const uint32_t w_bytes = (uint32_t)q.kh * (uint32_t)q.n * 128u;
   const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base, a_smem = base + w_span;
-  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * kFStage;
-  uint8_t* tail = smem + w_span + (size_t)q.stages * kFStage + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
+  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * q.stage_bytes;
+  uint8_t* tail = smem + w_span + (size_t)q.stages * q.stage_bytes + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -1018,18 +1027,19 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int tiles_per_img = q.tiles_x * q.tiles_y;
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
-    b = tile / tiles_per_img;
-    const int rr_ = tile - b * tiles_per_img;
+    const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
+    b = tl / tiles_per_img;
+    const int rr_ = tl - b * tiles_per_img;
     const int ty = rr_ / q.tiles_x;
     y0 = ty * kFH;
-    x0 = (rr_ - ty * q.tiles_x) * kFOut;
+    x0 = (rr_ - ty * q.tiles_x) * q.out_cols;
   };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(wfull_bar, w_bytes);
-      for (int dy = 0; dy < 3; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
+      for (int dy = 0; dy < q.kh; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
     }
     __syncwarp();
     int s = 0; uint32_t ph = 0;
@@ -1038,8 +1048,8 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       coords(tile, b, y0, x0);
       mbar_wait(empty_bar(s), ph ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(full_bar(s), kFStage);
-        tma_load_4d(a_smem + (uint32_t)s * kFStage, &tmap_x, full_bar(s), 0, x0 - 1, y0 - 1, b);
+        mbar_expect_tx(full_bar(s), q.stage_bytes);
+        tma_load_4d(a_smem + (uint32_t)s * q.stage_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1), y0 - (q.kh >> 1), b);
       }
       __syncwarp();
       if (++s == q.stages) { s = 0; ph ^= 1u; }
@@ -1056,11 +1066,21 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * kFStage, 1024u, 0);
+      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, 1024u, 0);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n);
-      if (elect_one()) {
+      if (kMode != 3 || q.kh == 3) {                     // 3 x 3: twelve MMAs, fully unrolled (descriptors in uniform registers)
+        if (elect_one()) {
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
+          }
+          umma_commit(empty_bar(s));
+          umma_commit(tfull_bar(acc));
+        }
+      } else if (elect_one()) {                          // taller filters (5 x 5, 9 x 9 tails): rolled over the vertical taps
+        for (int dy = 0; dy < q.kh; ++dy) {
           const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
@@ -1090,20 +1110,40 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         coords(tile, b, y0, x0);
         mbar_wait(tfull_bar(acc), acc_ph);
         tc_fence_after();
-        uint32_t rr[16];
-        __syncwarp();
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n), rr);
-        tmem_ld_wait();
-        release_tmem(acc);
         float v[4];
+        const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n);
+        if (q.kw == 3) {                                  // the hot case (RGB tail of EDSR): one TMEM load, two shuffles per channel
+          uint32_t rr[16];                                // columns dx * 4 + co
+          __syncwarp();
+          tmem_ld16(t_acc, rr);
+          tmem_ld_wait();
+          release_tmem(acc);
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[5 + e]), 1);
-          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[10 + e]), 2);
-          v[e] = bias_s[e] + __uint_as_float(rr[e]) + mid + right;
+          for (int e = 0; e < 4; ++e) {
+            const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[4 + e]), 1);
+            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[8 + e]), 2);
+            v[e] = (bias_s[e] + __uint_as_float(rr[e])) + (mid + right);
+          }
+        } else {
+          uint32_t rr[48];
+          __syncwarp();
+          tmem_ld16(t_acc, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
+          if (q.n > 16) tmem_ld16(t_acc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
+          if (q.n > 32) tmem_ld16(t_acc + 32u, *reinterpret_cast<uint32_t(*)[16]>(&rr[32]));
+          tmem_ld_wait();
+          release_tmem(acc);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[e] = bias_s[e] + __uint_as_float(rr[e]);
+#pragma unroll
+          for (int dx = 1; dx < 9; ++dx) {
+            if (dx < q.kw) {                              // (uniform) tap dx of output column l sits in lane l + dx
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(rr[dx * 4 + e]), dx);
+            }
+          }
         }
         const int oy = y0 + quad, ox = x0 + lane;
-        if (lane < kFOut && oy < p.H && ox < p.W) {
+        if (lane < q.out_cols && oy < p.H && ox < p.W) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
@@ -1253,6 +1293,13 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // host side
 // ---------------------------------------------------------------------------------------------------
 static int g_variant = 0;
+static int g_snake = -1;        // -1: read SRB_TC_SNAKE on first use (default on); alternate the tile walk direction of successive
+                                // launches: +1.5 % on the EDSR bench, the next layer starts on what is still in L2
+static unsigned g_launch_parity = 0;
+static int next_reverse() {
+  if (g_snake < 0) { const char* e = getenv("SRB_TC_SNAKE"); g_snake = e ? atoi(e) : 1; }
+  return g_snake ? (int)(g_launch_parity++ & 1u) : 0;
+}
 static int g_two_cta = -1;      // -1: read SRB_TC_2CTA on first use
 
 EncodeTiledFn tc_encode_fn() {
@@ -1290,10 +1337,11 @@ static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
 // ---- wide-tile fold kernel: eligibility and launch ----
 static int fold_mode(const ConvParams& p) {          // -1: not eligible
   static const bool enabled = getenv("SRB_TC_NO_WIDE") == nullptr;
-  if (!enabled || g_variant != 0 || p.kh != 3 || p.kw != 3 || p.cin != 64 || !p.w_tc_fold || p.d2s != 1) return -1;
+  if (!enabled || g_variant != 0 || p.cin != 64 || !p.w_tc_fold || p.d2s != 1 || p.kh > 9 || p.kw > 9) return -1;
   if (getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG"))) return -1;
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
   if (p.cout <= 4) return (!p.res1 && !p.res2 && !p.y2) ? 3 : -1;
+  if (p.kh != 3 || p.kw != 3) return -1;
   if (p.cout != 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
   if (!p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f) {
     if (p.act == SRB_ACT_NONE) return 0;
@@ -1315,9 +1363,12 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   EncodeTiledFn encode = tc_encode_fn();
   if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
   FoldParams q{};
-  q.gw = mode == 3 ? 5 : 64;
-  q.n = mode == 3 ? 16 : 192;
-  q.tiles_x = (p.W + kFOut - 1) / kFOut;
+  q.gw = mode == 3 ? 4 : 64;
+  q.kh = p.kh; q.kw = p.kw;
+  q.n = mode == 3 ? ((p.kw * 4 + 15) & ~15) : 192;
+  q.out_cols = kFW - (p.kw - 1);
+  q.stage_bytes = (uint32_t)(kFH + p.kh - 1) * kFW * 128u;
+  q.tiles_x = (p.W + q.out_cols - 1) / q.out_cols;
   q.tiles_y = (p.H + kFH - 1) / kFH;
   const long total = (long)p.B * q.tiles_x * q.tiles_y;
   SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
@@ -1327,12 +1378,13 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   q.epi_warp_bytes = mode == 3 ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
+  q.reverse = next_reverse();
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t w_bytes = ((size_t)3 * q.n * 128 + 1023) & ~(size_t)1023;
+  const size_t w_bytes = ((size_t)p.kh * q.n * 128 + 1023) & ~(size_t)1023;
   const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * 64 * sizeof(float) + 2 * kFoldEpiWarps * 8;
-  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * kFStage + (size_t)kFoldEpiWarps * q.epi_warp_bytes + tail_bytes; };
+  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kFoldEpiWarps * q.epi_warp_bytes + tail_bytes; };
   q.stages = 4;
   while (q.stages > 2 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
   const size_t smem = smem_need(q.stages);
@@ -1343,7 +1395,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   {
     const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2, (cuuint64_t)p.H * p.W * p.x_cstride * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)kFW, (cuuint32_t)(kFH + 2), 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)kFW, (cuuint32_t)(kFH + p.kh - 1), 1};
     const cuuint32_t es[4] = {1, 1, 1, 1};
     void* gptr = (void*)((const uint16_t*)p.x + p.x_coffset);
     CUresult r = encode(&tmx, tdt, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1351,7 +1403,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)3 * q.n};
+    const cuuint64_t dims[2] = {64, (cuuint64_t)p.kh * q.n};
     const cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {64, (cuuint32_t)q.n};
     const cuuint32_t es[2] = {1, 1};
@@ -1409,7 +1461,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   const int variant = g_variant;
   static const bool fold_enabled = getenv("SRB_TC_NOFOLD") == nullptr;
-  const bool fold = fold_enabled && variant == 0 && p.kh == 3 && p.kw == 3 && p.w_tc_fold && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2;
+  (void)fold_enabled;
+  const bool fold = false;      // (the 16 x 6 dx-folded tile of this kernel is superseded by conv3x3_fold_kernel's wide tiles)
   const int cols_out = fold ? kTileW - 2 : kTileW;
   const long total = (long)p.B * ((p.W + cols_out - 1) / cols_out) * ((p.H + kTileH - 1) / kTileH);
   SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
@@ -1600,6 +1653,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
        conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>, conv3x3_tc_kernel<0, true>}};
   static size_t configured[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
+  q.reverse = k2 ? 0 : next_reverse();
   if (smem > configured[k2][spec]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[k2][spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[k2][spec] = smem;
