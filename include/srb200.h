@@ -123,6 +123,10 @@ int srb_conv_tc_set_cta_pairs(int on);
 /* ---- small layout / elementwise helpers used between layers -------------------------------------- */
 int srb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, float shift,
              srb_stream_t stream);                                   /* dst = src * scale + shift */
+/* dst = max(src * scale + shift, 0): the ReLU that follows a convolution whose input channels were accumulated in
+ * several passes of srb_conv2d_nhwc (64-channel slices of a wider input, fp32 partial sums through res1) */
+int srb_cast_relu(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, float shift,
+                  srb_stream_t stream);
 int srb_maxpool2x2_nhwc(const void* x, int dtype, int batch, int height, int width, int channels, void* y,
                         srb_stream_t stream);                        /* VGG16_model.py:69 (MaxPooling2D) */
 int srb_gap_dense_softmax(const void* x, int dtype, int batch, int hw, int channels,

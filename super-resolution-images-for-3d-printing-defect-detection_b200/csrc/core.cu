@@ -32,10 +32,13 @@ int sm_count() {
 
 // dst = src * scale + shift with dtype conversion; 4 elements per thread when aligned
 template <typename S, typename D>
-__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n, float scale, float shift) {
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, size_t n, float scale, float shift, int relu) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-    store_from_float<D>(dst + i, fmaf(load_as_float<S>(src + i), scale, shift));
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float v = fmaf(load_as_float<S>(src + i), scale, shift);
+    if (relu) v = fmaxf(v, 0.f);
+    store_from_float<D>(dst + i, v);
+  }
 }
 
 template <typename T>
@@ -190,13 +193,24 @@ extern "C" int srb_device_info(int* sm, int* cc_major, int* cc_minor) {
   return SRB_OK;
 }
 
+static int cast_impl(const void* src, int sdt, void* dst, int ddt, size_t n, float scale, float shift, int relu, srb_stream_t stream_);
+
 extern "C" int srb_cast(const void* src, int sdt, void* dst, int ddt, size_t n, float scale, float shift,
                         srb_stream_t stream_) {
+  return cast_impl(src, sdt, dst, ddt, n, scale, shift, 0, stream_);
+}
+
+extern "C" int srb_cast_relu(const void* src, int sdt, void* dst, int ddt, size_t n, float scale, float shift,
+                             srb_stream_t stream_) {
+  return cast_impl(src, sdt, dst, ddt, n, scale, shift, 1, stream_);
+}
+
+static int cast_impl(const void* src, int sdt, void* dst, int ddt, size_t n, float scale, float shift, int relu, srb_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   SRB_REQUIRE(src && dst, "cast: null pointer");
   if (n == 0) return SRB_OK;
   const int g = grid_for(n, 256);
-#define SRB_CAST(S, D) cast_kernel<S, D><<<g, 256, 0, stream>>>((const S*)src, (D*)dst, n, scale, shift)
+#define SRB_CAST(S, D) cast_kernel<S, D><<<g, 256, 0, stream>>>((const S*)src, (D*)dst, n, scale, shift, relu)
 #define SRB_CAST_FROM(S)                                                                       \
   if (ddt == SRB_F32) SRB_CAST(S, float);                                                      \
   else if (ddt == SRB_BF16) SRB_CAST(S, __nv_bfloat16);                                        \

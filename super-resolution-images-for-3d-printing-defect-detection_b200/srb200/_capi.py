@@ -63,6 +63,7 @@ _SIGNATURES = {
     "srb_conv2d_nhwc": (C.c_int, [C.POINTER(ConvArgs), C.c_void_p]),
     "srb_conv2d_engine": (C.c_int, [C.POINTER(ConvArgs)]),
     "srb_cast": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_void_p]),
+    "srb_cast_relu": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_float, C.c_void_p]),
     "srb_maxpool2x2_nhwc": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p]),
     "srb_gap_dense_softmax": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

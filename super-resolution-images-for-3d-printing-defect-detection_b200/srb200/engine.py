@@ -347,13 +347,32 @@ class VGG16ClassifierNet(DeviceModel):
         torch = _torch()
         self.dense = {k: torch.from_numpy(self.weights[k]).cuda() for k in
                       ("dense/kernel", "dense/bias", "predictions/kernel", "predictions/bias")}
+        # 16-bit modes: the tcgen05 engine takes 64 input channels per launch, so a layer with Cin = 64 s is run as s
+        # passes over 64-channel slices of its input (x_coffset), partial sums accumulated in one fp32 tensor through the
+        # residual input, followed by one ReLU + cast (the direct engine would run these layers at ~30 TFLOP/s)
+        self.slices = {}
+        if precision != "fp32":
+            for name, w in self.layers.items():
+                if w.cin > 64 and w.cin % 64 == 0 and w.kh == 3:
+                    k, b = self.weights[name + "/kernel"], self.weights.get(name + "/bias")
+                    self.slices[name] = [ops.ConvWeights(k[:, :, 64 * i:64 * (i + 1), :], b if i == 0 else None)
+                                         for i in range(w.cin // 64)]
+
+    def _conv_relu(self, h, name):
+        torch = _torch()
+        sl = self.slices.get(name)
+        if sl is None:
+            return ops.conv2d(h, self.layers[name], act="relu", out_dtype=self.act_dtype)
+        acc = ops.conv2d(h, sl[0], x_coffset=0, out_dtype=torch.float32)
+        for i in range(1, len(sl)):
+            ops.conv2d(h, sl[i], x_coffset=64 * i, res1=acc, out=acc)
+        return ops.cast(acc, self.act_dtype, relu=True)
 
     def forward_device(self, x):
-        L, dt = self.layers, self.act_dtype
         h = x
         for blk, n in self.CFG:
             for j in range(1, n + 1):
-                h = ops.conv2d(h, L[f"block{blk}_conv{j}"], act="relu", out_dtype=dt)
+                h = self._conv_relu(h, f"block{blk}_conv{j}")
             h = ops.maxpool2x2(h)
         d = self.dense
         return ops.gap_dense_softmax(h, d["dense/kernel"], d["dense/bias"], d["predictions/kernel"],

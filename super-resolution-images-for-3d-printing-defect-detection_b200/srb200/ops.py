@@ -223,14 +223,16 @@ def conv2d_engine(x, w: ConvWeights, d2s=1):
     return rc
 
 
-def cast(x, dtype, scale=1.0, shift=0.0):
-    """dst = x * scale + shift converted to ``dtype`` (float32 <-> bfloat16)."""
+def cast(x, dtype, scale=1.0, shift=0.0, relu=False):
+    """dst = x * scale + shift (then max(., 0) with ``relu``) converted to ``dtype``."""
     torch = _torch()
     x = x.contiguous()
     out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    fn = capi.lib().srb_cast_relu if relu else capi.lib().srb_cast
     with torch.cuda.device(x.device):
-        capi.check(capi.lib().srb_cast(capi.ptr(x), capi.dtype_code(x), capi.ptr(out), capi.dtype_code(out),
-                                       x.numel(), float(scale), float(shift), capi.stream_ptr()))
+        capi.check(fn(capi.ptr(x), capi.dtype_code(x), capi.ptr(out), capi.dtype_code(out),
+                      x.numel(), float(scale), float(shift), capi.stream_ptr()))
+    _LAUNCHES[0] += 1
     return out
 
 

@@ -156,6 +156,20 @@ def test_vgg16_classifier_vs_oracle():
     assert np.abs(got - want).max() <= 2e-3 and np.array_equal(got.argmax(1), want.argmax(1))
 
 
+def test_vgg16_classifier_16bit_sliced_layers():
+    """16-bit VGG16: layers with Cin = 128/256/512 run as passes over 64-channel input slices on the tcgen05 engine with
+    fp32 partial sums (srb_conv2d_nhwc x_coffset + res1, then srb_cast_relu).  SURVEY C4: softmax probabilities within
+    2e-2 of the oracle and the same argmax."""
+    from srb200 import engine, weights
+    w = weights.vgg16_classifier_weights(2, bias_scale=0.05)
+    x = np.random.default_rng(1).random((5, 32, 32, 3), dtype=np.float32)
+    want = oc.vgg16_classifier_forward(w, x)
+    net = engine.VGG16ClassifierNet(w, precision="fp16")
+    assert len(net.slices) == 10 and len(net.slices["block5_conv3"]) == 8
+    got = net.predict(x)
+    assert np.abs(got - want).max() <= 2e-2 and np.array_equal(got.argmax(1), want.argmax(1))
+
+
 def test_edsr_full_depth_vs_oracle():
     """The benchmark network (16 blocks, x4) on a small tile, both precisions, oracle computed live."""
     from srb200 import engine, weights, synth
