@@ -977,7 +977,7 @@ struct FoldParams {
   int reverse;           // as TcParams::reverse
 };
 
-template <int kMode>
+template <int kMode, bool kGen>   // kGen: filter size from q.kh / q.kw (mode 3 only); otherwise 3 x 3 with compile-time geometry
 __global__ void __launch_bounds__(kFoldThreads, 1)
 conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                     const __grid_constant__ EpiMaps em, const FoldParams q, const ConvParams p) {
@@ -985,11 +985,14 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t w_bytes = (uint32_t)q.kh * (uint32_t)q.n * 128u;
+  const int f_kh = kGen ? q.kh : 3, f_kw = kGen ? q.kw : 3;
+  const int f_out = kGen ? q.out_cols : kFOut;
+  const uint32_t f_stage = kGen ? q.stage_bytes : 6u * kFW * 128u;
+  const uint32_t w_bytes = (uint32_t)f_kh * (uint32_t)q.n * 128u;
   const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base, a_smem = base + w_span;
-  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * q.stage_bytes;
-  uint8_t* tail = smem + w_span + (size_t)q.stages * q.stage_bytes + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
+  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * f_stage;
+  uint8_t* tail = smem + w_span + (size_t)q.stages * f_stage + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
@@ -1032,14 +1035,14 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int rr_ = tl - b * tiles_per_img;
     const int ty = rr_ / q.tiles_x;
     y0 = ty * kFH;
-    x0 = (rr_ - ty * q.tiles_x) * q.out_cols;
+    x0 = (rr_ - ty * q.tiles_x) * f_out;
   };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       mbar_expect_tx(wfull_bar, w_bytes);
-      for (int dy = 0; dy < q.kh; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
+      for (int dy = 0; dy < f_kh; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
     }
     __syncwarp();
     int s = 0; uint32_t ph = 0;
@@ -1048,8 +1051,8 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       coords(tile, b, y0, x0);
       mbar_wait(empty_bar(s), ph ^ 1u);
       if (elect_one()) {
-        mbar_expect_tx(full_bar(s), q.stage_bytes);
-        tma_load_4d(a_smem + (uint32_t)s * q.stage_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1), y0 - (q.kh >> 1), b);
+        mbar_expect_tx(full_bar(s), f_stage);
+        tma_load_4d(a_smem + (uint32_t)s * f_stage, &tmap_x, full_bar(s), 0, x0 - (f_kw >> 1), y0 - (f_kh >> 1), b);
       }
       __syncwarp();
       if (++s == q.stages) { s = 0; ph ^= 1u; }
@@ -1066,9 +1069,9 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       mbar_wait(full_bar(s), ph);
       tc_fence_after();
-      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, 1024u, 0);
+      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * f_stage, 1024u, 0);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n);
-      if (kMode != 3 || q.kh == 3) {                     // 3 x 3: twelve MMAs, fully unrolled (descriptors in uniform registers)
+      if (!kGen) {                                        // 3 x 3: twelve MMAs, fully unrolled (descriptors in uniform registers)
         if (elect_one()) {
 #pragma unroll
           for (int dy = 0; dy < 3; ++dy) {
@@ -1080,7 +1083,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           umma_commit(tfull_bar(acc));
         }
       } else if (elect_one()) {                          // taller filters (5 x 5, 9 x 9 tails): rolled over the vertical taps
-        for (int dy = 0; dy < q.kh; ++dy) {
+        for (int dy = 0; dy < f_kh; ++dy) {
           const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
 #pragma unroll
           for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
@@ -1112,7 +1115,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tc_fence_after();
         float v[4];
         const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n);
-        if (q.kw == 3) {                                  // the hot case (RGB tail of EDSR): one TMEM load, two shuffles per channel
+        if (!kGen) {                                      // the hot case (RGB tail of EDSR): one TMEM load, two shuffles per channel
           uint32_t rr[16];                                // columns dx * 4 + co
           __syncwarp();
           tmem_ld16(t_acc, rr);
@@ -1136,14 +1139,14 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           for (int e = 0; e < 4; ++e) v[e] = bias_s[e] + __uint_as_float(rr[e]);
 #pragma unroll
           for (int dx = 1; dx < 9; ++dx) {
-            if (dx < q.kw) {                              // (uniform) tap dx of output column l sits in lane l + dx
+            if (dx < f_kw) {                              // (uniform) tap dx of output column l sits in lane l + dx
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(rr[dx * 4 + e]), dx);
             }
           }
         }
         const int oy = y0 + quad, ox = x0 + lane;
-        if (lane < q.out_cols && oy < p.H && ox < p.W) {
+        if (lane < f_out && oy < p.H && ox < p.W) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
@@ -1435,16 +1438,17 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
     if (!ok) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
   }
   typedef void (*FoldFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FoldParams, const ConvParams);
-  static const FoldFn kernels[5] = {conv3x3_fold_kernel<0>, conv3x3_fold_kernel<1>, conv3x3_fold_kernel<2>, conv3x3_fold_kernel<3>,
-                                    conv3x3_fold_kernel<4>};
-  static size_t configured[5] = {0, 0, 0, 0, 0};
-  if (smem > configured[mode]) {
-    SRB_CUDA(cudaFuncSetAttribute(kernels[mode], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[mode] = smem;
+  static const FoldFn kernels[6] = {conv3x3_fold_kernel<0, false>, conv3x3_fold_kernel<1, false>, conv3x3_fold_kernel<2, false>,
+                                    conv3x3_fold_kernel<3, false>, conv3x3_fold_kernel<4, false>, conv3x3_fold_kernel<3, true>};
+  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+  const int ki = (mode == 3 && (p.kh != 3 || p.kw != 3)) ? 5 : mode;
+  if (smem > configured[ki]) {
+    SRB_CUDA(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[ki] = smem;
   }
   int grid = sm_count();
   if ((long)grid > total) grid = (int)total;
-  kernels[mode]<<<grid, kFoldThreads, smem, stream>>>(tmx, tmw, em, q, p);
+  kernels[ki]<<<grid, kFoldThreads, smem, stream>>>(tmx, tmw, em, q, p);
   return launch_check("conv3x3_fold_kernel");
 }
 
