@@ -29,6 +29,11 @@ constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM r
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
+// n / d by multiply-high with magic = ceil(2^32 / d) (exact while n * d < 2^32: checked on the host, which passes 0 otherwise)
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  return magic ? (int)__umulhi((uint32_t)n, magic) : n / d;
+}
+
 struct TcParams {
   int n_tile;            // output channels per CTA (multiple of 16, <= 128)
   int n_chunks;          // ceil(cout_pad / n_tile); CTA c owns chunk c % n_chunks
@@ -54,6 +59,7 @@ struct TcParams {
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
+  uint32_t magic_tpi, magic_tx;   // ceil(2^32 / tiles_per_img), ceil(2^32 / tiles_x) for multiply-high division, or 0
   int reverse;           // walk the tiles from the last to the first (alternate launches: the next layer starts on the
                          // rows the previous one wrote last, which are still in L2)
   int tma_epi;           // staged epilogue moves its rows with TMA (residual loads, output stores) instead of per-lane copies
@@ -217,8 +223,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-      const int b = tl / tiles_per_img, r = tl - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
-      const int y0 = (r / q.tiles_x) * kTileH, x0 = (r % q.tiles_x) * q.tile_cols_out;
+      const int b = fast_div(tl, tiles_per_img, q.magic_tpi), r = tl - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
+      const int ty_ = fast_div(r, q.tiles_x, q.magic_tx);
+      const int y0 = ty_ * kTileH, x0 = (r - ty_ * q.tiles_x) * q.tile_cols_out;
       mbar_wait(empty_bar(s), ph ^ 1u);
       const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
       if (elect_one()) {
@@ -365,9 +372,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     };
     auto coords = [&](int tile, int& b, int& y0, int& x0) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-      b = tl / tiles_per_img;
+      b = fast_div(tl, tiles_per_img, q.magic_tpi);
       const int rr_ = tl - b * tiles_per_img;
-      const int ty = rr_ / q.tiles_x;
+      const int ty = fast_div(rr_, q.tiles_x, q.magic_tx);
       y0 = ty * kTileH + quad * 4;                      // first image row of this warp's quadrant
       x0 = (rr_ - ty * q.tiles_x) * kTileW;
     };
@@ -975,6 +982,7 @@ struct FoldParams {
   int stages;
   uint32_t tmem_cols, idesc, epi_warp_bytes;
   int reverse;           // as TcParams::reverse
+  uint32_t magic_tpi, magic_tx;   // as TcParams
 };
 
 template <int kMode, bool kGen>   // kGen: filter size from q.kh / q.kw (mode 3 only); otherwise 3 x 3 with compile-time geometry
@@ -1031,9 +1039,9 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
     const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-    b = tl / tiles_per_img;
+    b = fast_div(tl, tiles_per_img, q.magic_tpi);
     const int rr_ = tl - b * tiles_per_img;
-    const int ty = rr_ / q.tiles_x;
+    const int ty = fast_div(rr_, q.tiles_x, q.magic_tx);
     y0 = ty * kFH;
     x0 = (rr_ - ty * q.tiles_x) * f_out;
   };
@@ -1295,6 +1303,10 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+static uint32_t div_magic(long max_n, int d) {      // 0: not representable / not exact -> the kernel divides
+  if (d <= 1 || max_n * (long)d >= (1L << 32)) return 0;
+  return (uint32_t)(((1UL << 32) + (unsigned long)d - 1) / (unsigned long)d);
+}
 static int g_variant = 0;
 static int g_snake = -1;        // -1: read SRB_TC_SNAKE on first use (default on); alternate the tile walk direction of successive
                                 // launches: +1.5 % on the EDSR bench, the next layer starts on what is still in L2
@@ -1382,6 +1394,8 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
   q.epi_warp_bytes = mode == 3 ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
   q.reverse = next_reverse();
+  q.magic_tpi = div_magic(total + 1, q.tiles_x * q.tiles_y);
+  q.magic_tx = div_magic((long)q.tiles_x * q.tiles_y, q.tiles_x);
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
@@ -1658,6 +1672,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   static size_t configured[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
   q.reverse = k2 ? 0 : next_reverse();
+  q.magic_tpi = div_magic((long)q.total_tiles + 2, q.tiles_x * q.tiles_y);
+  q.magic_tx = div_magic((long)q.tiles_x * q.tiles_y, q.tiles_x);
   if (smem > configured[k2][spec]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[k2][spec], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[k2][spec] = smem;
