@@ -1223,12 +1223,16 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         tmem_ld16(t_row + 128u, d2);
         tmem_ld_wait();
         release_tmem(acc);
-        float a[16];                                      // conv + bias of output column x0 + lane
+        float a[16];                                      // conv + bias of output column x0 + lane (packed fp32x2 adds)
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(d1[e]), 1);
-          const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[e]), 2);
-          a[e] = (__uint_as_float(d0[e]) + mid) + (right + bb[e]);
+        for (int i = 0; i < 8; ++i) {
+          const float2 mid = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(d1[2 * i]), 1),
+                                         __shfl_down_sync(0xffffffffu, __uint_as_float(d1[2 * i + 1]), 1));
+          const float2 right = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(d2[2 * i]), 2),
+                                           __shfl_down_sync(0xffffffffu, __uint_as_float(d2[2 * i + 1]), 2));
+          const float2 sum = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1])), mid),
+                                        __fadd2_rn(right, make_float2(bb[2 * i], bb[2 * i + 1])));
+          a[2 * i] = sum.x; a[2 * i + 1] = sum.y;
         }
         const uint32_t a_h0 = buf + h_row + ((0u ^ h_x) << 4), a_h1 = buf + h_row + ((1u ^ h_x) << 4);
         uint32_t oh[8];
@@ -1236,12 +1240,16 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             float v0 = a[2 * i], v1 = a[2 * i + 1];
-            if (kMode == 1) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
             if (kMode == 4) {
               const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + 2 * i);
               v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
             }
-            oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
+            uint32_t pk = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
+            if (kMode == 1) {                              // ReLU on the packed pair (rounding is monotonic and 0 is exact)
+              if (bf) { const __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&pk), __float2bfloat162_rn(0.f)); pk = *reinterpret_cast<const uint32_t*>(&r2); }
+              else { const __half2 r2 = __hmax2(*reinterpret_cast<const __half2*>(&pk), __float2half2_rn(0.f)); pk = *reinterpret_cast<const uint32_t*>(&r2); }
+            }
+            oh[i] = pk;
           }
         } else {
           mbar_wait(my_rbar + 8u * (uint32_t)(it & 1), acc_ph);
