@@ -340,7 +340,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
     }
-  } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6 || kSpec == 7) && !k2 && q.tma_epi) {
+  } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6 || kSpec == 7) && !(k2 && kSpec == 6) && q.tma_epi) {
     // ===================== epilogue, TMA flavour (16-bit y, d2s = 1, 64- or 128-channel chunks) =====================
     // Warp (quadrant, column half) owns 4 tile rows x 8 pixels x ncols channels.  Its staging rows are laid out exactly as
     // the {ncols, 8, 4, 1} TMA box with the 32/64/128-byte swizzle of the row size, so one elected lane moves the whole
@@ -349,11 +349,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // clipped (stores) or zero-filled (loads) by the TMA unit - no per-lane address arithmetic or bounds predicates.
     constexpr bool P8 = kSpec == 6;
     const int ew = warp - 2, quad = warp & 3, half = ew >> 2;
-    const int ncols = q.n_tile >> 1, col0 = half * ncols;
-    // depth_to_space(2): this warp's columns are one (i, j) sub-pixel; the output map is 5-D {c, j, x, i, (b, y)}
+    // a warp's columns are handled in sub-blocks of at most 64 channels (one 128-byte swizzle row): one for the 64- and
+    // 128-channel chunks, two for the 256-channel chunks of CTA pairs
+    const int wcols = q.n_tile >> 1, ncols = wcols > 64 ? 64 : wcols, n_sb = wcols / ncols;
+    // depth_to_space(2): a sub-block's columns are one (i, j) sub-pixel; the output map is 5-D {c, j, x, i, (b, y)}
     const int d2s = p.d2s;
-    int c_out0 = co_base + col0, sub_i = 0, sub_j = 0;
-    if (d2s > 1) { const int qq = c_out0 / p.c_post; c_out0 -= qq * p.c_post; sub_i = qq / d2s; sub_j = qq - sub_i * d2s; }
     const uint32_t hb = (uint32_t)ncols * 2u, lb = (uint32_t)ncols;          // row bytes: 16-bit rows, e5m2 rows
     const uint32_t h_sh = hb == 128u ? 0u : 1u, h_mask = (hb >> 4) - 1u;      // swizzle: chunk ^= (row >> sh) & mask
     const uint32_t l_sh = lb == 64u ? 1u : 2u, l_mask = (lb >> 4) - 1u;
@@ -365,10 +365,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint32_t my_rbar = rbar0 + 16u * (uint32_t)ew;
     const float alpha = p.alpha, beta1 = p.beta1, beta2 = p.beta2;
     const bool bf = p.y_dtype == SRB_BF16;
-    auto release_tmem = [&](int acc) {
+    auto release_tmem = [&](int acc) {                  // (k2: the MMA warp of the pair's leader waits for both CTAs)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) { if (k2 && rank != 0) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
     };
     auto coords = [&](int tile, int& b, int& y0, int& x0) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
@@ -378,19 +378,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       y0 = ty * kTileH + quad * 4;                      // first image row of this warp's quadrant
       x0 = (rr_ - ty * q.tiles_x) * kTileW;
     };
+    const int c_res0 = co_base + half * wcols;          // (pair8: d2s = 1, one sub-block)
     auto load_res = [&](int tile, uint32_t nb) {        // lane 0: residual (hi, lo) of `tile` into buffer nb
       int b, y0, x0;
       coords(tile, b, y0, x0);
       const uint32_t buf = my_epi + nb * buf_bytes, bar = my_rbar + 8u * nb;
       mbar_expect_tx(bar, 32u * (hb + lb));
-      tma_load_4d(buf, &em.r1, bar, c_out0, x0, y0, b);
-      tma_load_4d(buf + 32u * hb, &em.r2, bar, c_out0, x0, y0, b);
+      tma_load_4d(buf, &em.r1, bar, c_res0, x0, y0, b);
+      tma_load_4d(buf + 32u * hb, &em.r2, bar, c_res0, x0, y0, b);
     };
     int it = 0;
     if (P8 && lane == 0 && first_tile < q.total_tiles) load_res(first_tile, 0u);
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
+      const bool live = tile < q.total_tiles;           // (k2: the pair's odd CTA may hold a dummy tile past the end)
       int b, y0, x0;
-      coords(tile, b, y0, x0);
+      coords(live ? tile : 0, b, y0, x0);
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       const uint32_t buf = my_epi + (P8 ? (uint32_t)(it & 1) * buf_bytes : 0u);
@@ -402,78 +404,87 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
       if (P8) mbar_wait(my_rbar + 8u * (uint32_t)(it & 1), acc_ph);
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
-#pragma unroll 1
-      for (int c0 = 0; c0 < ncols; c0 += 16) {
-        uint32_t rr[16];
-        float4 bv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_s + col0 + c0 + 4 * j);
-        __syncwarp();
-        tmem_ld16(t_row + (uint32_t)c0, rr);
-        tmem_ld_wait();
-        if (c0 + 16 >= ncols) release_tmem(acc);
-        const float bb[16] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
-                              bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w};
-        const uint32_t c16 = (uint32_t)c0 >> 4;
-        const uint32_t a_h0 = buf + h_row + (((2u * c16) ^ h_x) << 4), a_h1 = buf + h_row + (((2u * c16 + 1u) ^ h_x) << 4);
-        uint32_t oh[8];
-        if (!P8) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v0 = __uint_as_float(rr[2 * i]) + bb[2 * i], v1 = __uint_as_float(rr[2 * i + 1]) + bb[2 * i + 1];
-            if (kSpec == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
-            if (kSpec == 7) {                             // PReLU / leaky: max(v, 0) + slope * min(v, 0)
-              const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + c0 + 2 * i);
-              v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
-            }
-            oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
-          }
-        } else {
-          // pair8 trunk: v = alpha * (acc + bias) + beta1 * hi + beta2 * lo;  y = round16(v), y2 = e5m2(v - y)
-          const uint32_t a_l = buf + l_row + ((c16 ^ l_x) << 4);
-          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
-          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
-          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
-          uint32_t ol[4];
-          auto half_block = [&](auto is_bf) {
-            constexpr bool kBf = decltype(is_bf)::value;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              float lo4[4], er[4];
-              e5m2x4_to_float4(wl[i4], lo4);
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int e0 = 4 * i4 + 2 * hh;
-                float2 fh;
-                if (kBf) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
-                else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
-                const float a0 = (__uint_as_float(rr[e0]) + bb[e0]) * alpha, a1 = (__uint_as_float(rr[e0 + 1]) + bb[e0 + 1]) * alpha;
-                const float v0 = fmaf(beta2, lo4[2 * hh], fmaf(beta1, fh.x, a0));
-                const float v1 = fmaf(beta2, lo4[2 * hh + 1], fmaf(beta1, fh.y, a1));
-                const uint32_t pk = pack2(v0, v1, kBf ? SRB_BF16 : SRB_F16);
-                oh[2 * i4 + hh] = pk;
-                float2 back;
-                if (kBf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-                else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-                er[2 * hh] = v0 - back.x; er[2 * hh + 1] = v1 - back.y;
-              }
-              ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
-            }
-          };
-          if (bf) half_block(std::true_type{}); else half_block(std::false_type{});
-          sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+      for (int sb = 0; sb < n_sb; ++sb) {
+        const int col0 = half * wcols + sb * ncols;     // first accumulator column of this sub-block
+        int c_out0 = co_base + col0, sub_i = 0, sub_j = 0;
+        if (d2s > 1) { const int qq = c_out0 / p.c_post; c_out0 -= qq * p.c_post; sub_i = qq / d2s; sub_j = qq - sub_i * d2s; }
+        if (sb > 0) {                                   // the staging rows are reused: the previous sub-block's store must have read them
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
         }
-        sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
-        sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
-      }
-      fence_proxy_async_smem();                         // generic-proxy writes of the rows -> visible to the TMA unit
-      __syncwarp();
-      if (lane == 0) {
-        if (d2s > 1) tma_store_5d(&em.y, buf, c_out0, sub_j, x0, sub_i, b * p.H + y0);
-        else tma_store_4d(&em.y, buf, c_out0, x0, y0, b);
-        if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, c_out0, x0, y0, b);
-        bulk_commit();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n_tile + col0);
+#pragma unroll 1
+        for (int c0 = 0; c0 < ncols; c0 += 16) {
+          uint32_t rr[16];
+          float4 bv[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const float4*>(bias_s + col0 + c0 + 4 * j);
+          __syncwarp();
+          tmem_ld16(t_row + (uint32_t)c0, rr);
+          tmem_ld_wait();
+          if (sb == n_sb - 1 && c0 + 16 >= ncols) release_tmem(acc);
+          const float bb[16] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
+                                bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w};
+          const uint32_t c16 = (uint32_t)c0 >> 4;
+          const uint32_t a_h0 = buf + h_row + (((2u * c16) ^ h_x) << 4), a_h1 = buf + h_row + (((2u * c16 + 1u) ^ h_x) << 4);
+          uint32_t oh[8];
+          if (!P8) {
+  #pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float v0 = __uint_as_float(rr[2 * i]) + bb[2 * i], v1 = __uint_as_float(rr[2 * i + 1]) + bb[2 * i + 1];
+              if (kSpec == 2) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+              if (kSpec == 7) {                             // PReLU / leaky: max(v, 0) + slope * min(v, 0)
+                const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + c0 + 2 * i);
+                v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
+              }
+              oh[i] = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
+            }
+          } else {
+            // pair8 trunk: v = alpha * (acc + bias) + beta1 * hi + beta2 * lo;  y = round16(v), y2 = e5m2(v - y)
+            const uint32_t a_l = buf + l_row + ((c16 ^ l_x) << 4);
+            const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
+            const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
+            const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+            uint32_t ol[4];
+            auto half_block = [&](auto is_bf) {
+              constexpr bool kBf = decltype(is_bf)::value;
+  #pragma unroll
+              for (int i4 = 0; i4 < 4; ++i4) {
+                float lo4[4], er[4];
+                e5m2x4_to_float4(wl[i4], lo4);
+  #pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const int e0 = 4 * i4 + 2 * hh;
+                  float2 fh;
+                  if (kBf) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
+                  else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
+                  const float a0 = (__uint_as_float(rr[e0]) + bb[e0]) * alpha, a1 = (__uint_as_float(rr[e0 + 1]) + bb[e0 + 1]) * alpha;
+                  const float v0 = fmaf(beta2, lo4[2 * hh], fmaf(beta1, fh.x, a0));
+                  const float v1 = fmaf(beta2, lo4[2 * hh + 1], fmaf(beta1, fh.y, a1));
+                  const uint32_t pk = pack2(v0, v1, kBf ? SRB_BF16 : SRB_F16);
+                  oh[2 * i4 + hh] = pk;
+                  float2 back;
+                  if (kBf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
+                  else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
+                  er[2 * hh] = v0 - back.x; er[2 * hh + 1] = v1 - back.y;
+                }
+                ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
+              }
+            };
+            if (bf) half_block(std::true_type{}); else half_block(std::false_type{});
+            sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
+          }
+          sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+          sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
+        }
+        fence_proxy_async_smem();                       // generic-proxy writes of the rows -> visible to the TMA unit
+        __syncwarp();
+        if (lane == 0 && live) {
+          if (d2s > 1) tma_store_5d(&em.y, buf, c_out0, sub_j, x0, sub_i, b * p.H + y0);
+          else tma_store_4d(&em.y, buf, c_out0, x0, y0, b);
+          if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, c_out0, x0, y0, b);
+          bulk_commit();
+        }
       }
     }
     if (lane == 0) bulk_wait0();                        // all stores complete before the CTA's shared memory goes away
@@ -1311,6 +1322,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+static bool g_debug_env() { static const bool on = getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")); return on; }
 static uint32_t div_magic(long max_n, int d) {      // 0: not representable / not exact -> the kernel divides
   if (d <= 1 || max_n * (long)d >= (1L << 32)) return 0;
   return (uint32_t)(((1UL << 32) + (unsigned long)d - 1) / (unsigned long)d);
@@ -1502,11 +1514,18 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   // >= 2 A stages and epilogue staging fit shared memory (N = 128 halves the A-operand smem traffic per FLOP)
   TcParams q{};
   size_t smem = 0;
-  const int cand[4] = {128, 64, rows < 64 ? rows : 16, 16};
+  // 256-channel chunks exist only as CTA pairs (each CTA holds 128 weight rows) with the TMA epilogue, for plain 16-bit
+  // layers with >= 256 output channels (the up-sampling convs): halves the B-operand shared-memory traffic per CTA that
+  // the epilogue competes with.  SRB_TC_PAIRS256=0 turns the choice off.
+  static const bool pairs256 = !(getenv("SRB_TC_PAIRS256") && atoi(getenv("SRB_TC_PAIRS256")) == 0);
+  const bool plain_layer = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && dt16(p.y_dtype) &&
+                           (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu));
+  const int cand[5] = {256, 128, 64, rows < 64 ? rows : 16, 16};
   bool found = false;
-  for (int ci = 0; ci < 4 && !found; ++ci) {
+  for (int ci = 0; ci < 5 && !found; ++ci) {
     const int nt = fold ? 16 : cand[ci];
-    if (!fold && (nt > ntile_max || rows % nt)) continue;
+    if (!fold && ((nt > ntile_max && nt != 256) || rows % nt)) continue;
+    if (nt == 256 && !(pairs256 && plain_layer && variant == 0 && p.kh == 3 && p.kw == 3 && !g_debug_env())) continue;
     q = TcParams{};
     q.fold = fold ? 1 : 0;
     q.kh = p.kh; q.kw = p.kw;
@@ -1528,13 +1547,14 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.tmem_cols = 32;
     while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
     const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
-    const bool k2c = two_cta && !fold && variant == 0 && nt >= 32;
+    const bool k2c = (two_cta || nt == 256) && !fold && variant == 0 && nt >= 32;
     q.two_cta = k2c ? 1 : 0;
     q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)((k2c ? 2 * kTileM : kTileM) >> 4) << 24);
     // staged vector epilogue: one fp32 and/or one 16-bit destination; a warp's columns map to one d2s sub-pixel
     const int warp_cols = nt >= 32 ? nt / 2 : nt;
-    bool vec = (nt == 16 || nt == 32 || nt == 64 || nt == 128) && (p.cout % nt == 0) &&
-               (p.d2s == 1 || p.c_post % warp_cols == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
+    const int sb_cols = warp_cols > 64 ? 64 : warp_cols;      // TMA epilogue sub-block width (256-channel chunks: two per warp)
+    bool vec = (nt == 16 || nt == 32 || nt == 64 || nt == 128 || nt == 256) && (p.cout % nt == 0) &&
+               (p.d2s == 1 || p.c_post % (nt == 256 ? sb_cols : warp_cols) == 0) && vec_ok_for(p.y, p.y_dtype, p.y_cstride, p.y_coffset) &&
                (!p.y2 || vec_ok_for(p.y2, p.y2_dtype, p.y2_cstride, 0)) &&
                (!p.res1 || vec_ok_for(p.res1, p.res1_dtype, p.res1_cstride, 0)) &&
                (!p.res2 || vec_ok_for(p.res2, p.res2_dtype, p.res2_cstride, 0));
@@ -1573,12 +1593,13 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
                            (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || slope_act);
       // (depth_to_space: plain layers whose warp columns are whole sub-pixels, images made of whole 16-row tiles because
       //  the 5-D output map merges the image and row dimensions)
-      const bool d2s_ok = p.d2s == 1 || (plain16 && p.c_post % warp_cols == 0 && p.H % kTileH == 0 && p.y_coffset == 0 && p.y_cstride == p.c_post);
-      if (tma_enabled && !k2c && d2s_ok && (nt == 64 || nt == 128) && dt16(p.y_dtype) && (plain16 || pair8)) {
+      const bool d2s_ok = p.d2s == 1 || (plain16 && p.c_post % sb_cols == 0 && p.H % kTileH == 0 && p.y_coffset == 0 && p.y_cstride == p.c_post);
+      if (tma_enabled && d2s_ok && (nt == 64 || nt == 128 || nt == 256) && dt16(p.y_dtype) && ((plain16) || (pair8 && !k2c))) {
         q.tma_epi = 1;
-        q.epi_warp_bytes = (uint32_t)(pair8 ? 2 * 32 * warp_cols * 3 : 32 * warp_cols * 2);   // multiples of 1,024 bytes
+        q.epi_warp_bytes = (uint32_t)(pair8 ? 2 * 32 * warp_cols * 3 : 32 * sb_cols * 2);   // multiples of 1,024 bytes
       }
     }
+    if (nt == 256 && !q.tma_epi) continue;                    // (256-channel chunks only exist with the TMA epilogue)
     const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
@@ -1588,7 +1609,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.stages = stage_cap;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);
-    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16 || ci == 3);
+    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16 || ci == 4);
   }
   if (!found) { set_error("conv(tcgen05): weights + one pipeline stage + epilogue staging do not fit shared memory"); return SRB_E_UNSUPPORTED; }
 
@@ -1619,7 +1640,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   EpiMaps em;
   memset(&em, 0, sizeof(em));
   if (q.tma_epi) {
-    const int wc = q.n_tile / 2;
+    const int wc = q.n_tile / 2 > 64 ? 64 : q.n_tile / 2;
     auto encode_epi = [&](CUtensorMap* m, const void* ptr, int coffset, int cstride, bool f8) -> bool {
       const size_t es = f8 ? 1 : 2;
       const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
@@ -1676,7 +1697,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       {conv3x3_tc_kernel<0, false>, conv3x3_tc_kernel<1, false>, conv3x3_tc_kernel<2, false>, conv3x3_tc_kernel<3, false>,
        conv3x3_tc_kernel<4, false>, conv3x3_tc_kernel<5, false>, conv3x3_tc_kernel<6, false>, conv3x3_tc_kernel<7, false>},
       {conv3x3_tc_kernel<0, true>, conv3x3_tc_kernel<1, true>, conv3x3_tc_kernel<2, true>, conv3x3_tc_kernel<3, true>,
-       conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>, conv3x3_tc_kernel<0, true>}};
+       conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>, conv3x3_tc_kernel<7, true>}};
   static size_t configured[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
   q.reverse = k2 ? 0 : next_reverse();
