@@ -225,6 +225,7 @@ class ESPCNNet(DeviceModel):
             k3p = np.zeros((k3.shape[0], k3.shape[1], 64, k3.shape[3]), np.float32)
             k3p[:, :, :32, :] = k3
             self._pad3 = ops.ConvWeights(k3p, self.weights.get("conv3/bias"))
+        self._wide = {}
 
     def output_scale(self):
         return self.scale_factor
@@ -235,7 +236,11 @@ class ESPCNNet(DeviceModel):
         h = ops.conv2d(x, L["conv1"], act=self.activation, out_dtype=dt)
         if self._pad3 is not None:
             B, H, W, _ = h.shape
-            wide = torch.zeros((B, H, W, 64), dtype=dt, device=h.device)
+            key = (B, H, W, dt, h.device)
+            wide = self._wide.get(key)
+            if wide is None:                          # the zero upper half is written once; conv2 only touches channels [0, 32)
+                self._wide.clear()
+                wide = self._wide[key] = torch.zeros((B, H, W, 64), dtype=dt, device=h.device)
             ops.conv2d(h, L["conv2"], act=self.activation, out=wide, out_coffset=0)
             return ops.conv2d(wide, self._pad3, d2s=self.scale_factor, out_dtype=torch.float32)
         h = ops.conv2d(h, L["conv2"], act=self.activation, out_dtype=dt)
