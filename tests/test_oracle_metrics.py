@@ -49,3 +49,33 @@ def test_evaluate_means_shape():
     b = rng.random((3, 12, 12, 3), dtype=np.float32)
     loss, p, s = om.evaluate_means(a, b)
     assert abs(loss - np.mean((a - b) ** 2)) < 1e-7 and -1 < s < 1 and p > 0
+
+
+def test_ssim_against_independent_scipy_evaluation():
+    """Independent code path: the Wang et al. SSIM with tf.image.ssim's constants, written directly on
+    scipy.ndimage's separable correlation (no shared code with oracle/metrics.py), float64.  Pins the restatement's
+    window, VALID cropping, c1 / c2 and the (mean over pixels, then over channels) reduction."""
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    a = rng.random((2, 40, 37, 3))
+    b = np.clip(a + 0.1 * rng.standard_normal(a.shape), 0, 1)
+    x = np.arange(11) - 5.0
+    w = np.exp(-x * x / (2 * 1.5 ** 2)); w /= w.sum()
+
+    def filt(img):                                   # [H, W] -> VALID 11x11 Gaussian
+        f = ndimage.correlate1d(ndimage.correlate1d(img, w, axis=0, mode="constant"), w, axis=1, mode="constant")
+        return f[5:-5, 5:-5]
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    want = []
+    for i in range(a.shape[0]):
+        per_c = []
+        for c in range(3):
+            p, q = a[i, :, :, c], b[i, :, :, c]
+            mp, mq = filt(p), filt(q)
+            spp, sqq, spq = filt(p * p) - mp * mp, filt(q * q) - mq * mq, filt(p * q) - mp * mq
+            per_c.append((((2 * mp * mq + c1) * (2 * spq + c2)) / ((mp * mp + mq * mq + c1) * (spp + sqq + c2))).mean())
+        want.append(np.mean(per_c))
+    got = om.ssim(a.astype(np.float32), b.astype(np.float32), dtype=np.float64)
+    assert np.abs(got - np.array(want)).max() < 1e-6
+    mse = ((a.astype(np.float32).astype(np.float64) - b.astype(np.float32).astype(np.float64)) ** 2).mean(axis=(1, 2, 3))
+    assert np.abs(om.psnr(a.astype(np.float32), b.astype(np.float32), dtype=np.float64) - (-10 * np.log10(mse))).max() < 1e-9
