@@ -17,5 +17,7 @@ Pinning status:
               the architecture known-answers of the reference notebooks (parameter counts) and
               cross-checked fp32 vs fp64 and torch-conv vs explicit numpy im2col.
 * PSNR/SSIM - parity unpinned by execution (tf.image absent); anchored on analytic
-              known-answers listed in SURVEY.md section 8c.
+              known-answers listed in SURVEY.md section 8c and cross-checked against an
+              independent scipy.ndimage evaluation of the same published definition
+              (tests/test_oracle_metrics.py).
 """
