@@ -18,7 +18,10 @@ namespace srb {
 
 struct AxisTap { int idx[4]; float coef[4]; };   // 32 bytes
 
-__global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base_out, int n_src, int n_dst, int fixed) {
+// mode: 0 cubic (float path), 1 cubic (OpenCV 11-bit fixed-point coefficients), 2 bilinear, 3 bilinear with INTER_AREA's
+// up-scaling coefficients (cv2.resize treats INTER_AREA as that when the image grows).  The bilinear modes fill the same
+// four-tap table with (0, 1 - t, t, 0), so every kernel below serves them unchanged.
+__global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base_out, int n_src, int n_dst, int mode) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_dst) return;
   const double scale = 1.0 / ((double)n_dst / (double)n_src);
@@ -26,7 +29,25 @@ __global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base
   const float A = -0.75f;
   int s;
   float c0, c1, c2, c3;
-  if (fixed) {
+  if (mode >= 2) {
+    // OpenCV resize.cpp, linear branch: fx in float, taps sx and sx + 1, both ends clamp to a pure copy
+    float t;
+    int sx;
+    if (mode == 2) {
+      const float f = (float)fd;
+      sx = (int)floorf(f);
+      t = __fsub_rn(f, (float)sx);
+    } else {
+      const double inv_scale = (double)n_dst / (double)n_src;
+      sx = (int)floor((double)d * scale);
+      t = (float)((double)(d + 1) - (double)(sx + 1) * inv_scale);
+      t = t <= 0.f ? 0.f : __fsub_rn(t, floorf(t));
+    }
+    if (sx < 0) { t = 0.f; sx = 0; }
+    if (sx >= n_src - 1) { t = 0.f; sx = n_src - 1; }
+    s = sx;
+    c0 = 0.f; c1 = __fsub_rn(1.f, t); c2 = t; c3 = 0.f;
+  } else if (mode == 1) {
     const float f = (float)fd;
     s = (int)floorf(f);
     const float t = __fsub_rn(f, (float)s);
@@ -324,7 +345,7 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
 
 template <typename T, bool FIXED>
 static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, int dh, int dw, int clip01,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int table_mode = FIXED ? 1 : 0) {
   SRB_REQUIRE(src && dst, "bicubic: null pointer");
   SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "bicubic: bad geometry");
   if (batch == 0) return SRB_OK;
@@ -334,8 +355,8 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
   int* xbase = ybase + dh;
   AxisTap* xtab = tabs;
   AxisTap* ytab = tabs + dw;
-  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, xbase, sw, dw, FIXED ? 1 : 0);
-  bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, ybase, sh, dh, FIXED ? 1 : 0);
+  bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, xbase, sw, dw, table_mode);
+  bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, ybase, sh, dh, table_mode);
   int rc = launch_check("bicubic_tables");
   if (rc) return rc;
   {
@@ -391,6 +412,21 @@ using namespace srb;
 extern "C" int srb_bicubic_f32(const float* src, int batch, int src_h, int src_w, int channels,
                                float* dst, int dst_h, int dst_w, int clip01, srb_stream_t stream) {
   return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream);
+}
+
+extern "C" int srb_resize_f32(const float* src, int batch, int src_h, int src_w, int channels,
+                              float* dst, int dst_h, int dst_w, int interpolation, int clip01, srb_stream_t stream) {
+  if (interpolation == SRB_INTER_CUBIC)
+    return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream);
+  if (interpolation == SRB_INTER_LINEAR)
+    return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream, 2);
+  if (interpolation == SRB_INTER_AREA) {
+    SRB_REQUIRE(dst_h >= src_h && dst_w >= src_w, "resize: INTER_AREA is built for up-scaling only (the reference's use); got %dx%d -> %dx%d",
+                src_w, src_h, dst_w, dst_h);
+    return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream, 3);
+  }
+  set_error("resize: unsupported interpolation code %d (cubic = 2, linear = 1, area = 3)", interpolation);
+  return SRB_E_UNSUPPORTED;
 }
 
 extern "C" int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,

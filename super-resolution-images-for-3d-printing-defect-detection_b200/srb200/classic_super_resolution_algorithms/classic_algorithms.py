@@ -58,6 +58,32 @@ def _not_on_path(name):
     return f
 
 
-interpolate_bilinear = _not_on_path("interpolate_bilinear")
-interpolate_area = _not_on_path("interpolate_area")
+def _resize_float(img, target_shape, code):
+    torch = capi.require_cuda()
+    was_numpy = not isinstance(img, torch.Tensor)
+    t = torch.from_numpy(np.ascontiguousarray(img)).cuda() if was_numpy else (img if img.is_cuda else img.cuda())
+    if t.dtype != torch.float32:
+        raise NotImplementedError("bilinear / area resizing is built for float32 images (the reference's [0, 1] data); "
+                                  "uint8 uses OpenCV's fixed-point filter, which only the bicubic kernel reproduces")
+    nd = t.dim()
+    t4 = t[None, :, :, None] if nd == 2 else t[None] if nd == 3 else t
+    w, h = int(target_shape[0]), int(target_shape[1])
+    if w <= 0 or h <= 0:
+        raise ValueError("target_shape must be (width, height) with positive entries")
+    out = ops.resize(t4.contiguous(), h, w, interpolation=code)
+    out = out[0, :, :, 0] if nd == 2 else out[0] if nd == 3 else out
+    return out.cpu().numpy() if was_numpy else out
+
+
+def interpolate_bilinear(lr_img, target_shape: Tuple[int, int]):
+    """Bilinear upscaling (== cv2.resize(lr_img, target_shape, interpolation=cv2.INTER_LINEAR), classic_algorithms.py:7-9)."""
+    return _resize_float(lr_img, target_shape, capi.INTER_LINEAR)
+
+
+def interpolate_area(lr_img, target_shape: Tuple[int, int]):
+    """Area upscaling (== cv2.resize(..., interpolation=cv2.INTER_AREA) when the image grows, classic_algorithms.py:15-17)."""
+    return _resize_float(lr_img, target_shape, capi.INTER_AREA)
+
+
+
 interpolate_lanczos = _not_on_path("interpolate_lanczos")

@@ -11,8 +11,8 @@ Documented differences:
 * ``load_dataset_as_patches(mode='srcnn', interpolation_map_path=None)`` raises ``NameError`` in the reference because
   ``interpolation_map`` is only bound when a path is given (``:110-113`` vs ``:134``); here a missing map simply means
   bicubic for every image.
-* interpolation codes other than ``cv2.INTER_CUBIC`` (``:133-145``) are resized by OpenCV on the host, exactly as the
-  reference does; only the bicubic case is on the hot path.
+* ``INTER_CUBIC``, ``INTER_LINEAR`` and (up-scaling) ``INTER_AREA`` entries of the interpolation map (``:133-145``) run
+  on the device; ``INTER_LANCZOS4`` is resized by OpenCV on the host, exactly as the reference does.
 * ``load_defects_dataset_as_patches`` walks the *unpadded* extent (``:276-277``), so the padding it adds is never
   visited; reproduced as is.
 """
@@ -118,9 +118,10 @@ def load_dataset_as_patches(hr_root, lr_root, mode="srcnn", patch_size=33, strid
                     code = by_name.get(chosen, cv2.INTER_CUBIC)
                 elif isinstance(chosen, int):
                     code = chosen
-            if code == cv2.INTER_CUBIC:
+            grows = hr_h >= lr_img.shape[0] and hr_w >= lr_img.shape[1]
+            if code in (cv2.INTER_CUBIC, cv2.INTER_LINEAR) or (code == cv2.INTER_AREA and grows):
                 lr_dev = torch.from_numpy(lr_img).cuda()[None]
-                lr_up = ops.bicubic(lr_dev, hr_h, hr_w, clip01=True)[0]              # resize + np.clip in one kernel
+                lr_up = ops.resize(lr_dev, hr_h, hr_w, interpolation=code, clip01=True)[0]   # resize + np.clip in one kernel
             else:
                 lr_up = np.clip(cv2.resize(lr_img, (hr_w, hr_h), interpolation=code), 0.0, 1.0)
             Y.append(_device_patches(hr_img, patch_size, stride))

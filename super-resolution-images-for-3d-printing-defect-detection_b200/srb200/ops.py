@@ -87,6 +87,22 @@ def bicubic(src, dst_h, dst_w, clip01=False, fixed_point=False):
     return dst
 
 
+def resize(src, dst_h, dst_w, interpolation=capi.INTER_CUBIC, clip01=False):
+    """cv2.resize(src, (dst_w, dst_h), interpolation) for float32 NHWC CUDA tensors; INTER_CUBIC, INTER_LINEAR and
+    (up-scaling) INTER_AREA share the bicubic kernels through the four-tap table."""
+    torch = _torch()
+    _check_nhwc(src, "src")
+    if src.dtype != torch.float32:
+        raise TypeError(f"resize supports float32, got {src.dtype}")
+    B, H, W, Cc = src.shape
+    dst = torch.empty((B, int(dst_h), int(dst_w), Cc), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        capi.check(capi.lib().srb_resize_f32(capi.ptr(src), B, H, W, Cc, capi.ptr(dst), int(dst_h), int(dst_w),
+                                             int(interpolation), int(bool(clip01)), capi.stream_ptr()))
+    _LAUNCHES[0] += 3
+    return dst
+
+
 # ---------------------------------------------------------------------------------------------
 # tiling  (loading_methods.py:6-26, EDSR_model.py:201-256)
 # ---------------------------------------------------------------------------------------------

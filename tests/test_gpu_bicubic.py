@@ -86,3 +86,21 @@ def test_downscale_uses_streaming_fallback():
     u = rng.integers(0, 256, (300, 300, 3), dtype=np.uint8)
     assert np.array_equal(resize_cubic(u, (23, 17), fixed_point=True), ob.resize_cubic_u8(u, (23, 17), "scalar"))
     assert np.abs(interpolate_bicubic(f, (250, 200)) - ob.cv2_resize(f, (250, 200))).max() <= 2e-6   # mild x0.5 (smem path)
+
+
+def test_bilinear_and_area_vs_cv2_golden(golden_dir):
+    """interpolate_bilinear / interpolate_area (classic_algorithms.py:7-17) against cv2.resize outputs: the bilinear taps
+    ride in the four-tap table of the bicubic kernels."""
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_area, interpolate_bilinear
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw = (int(v) for v in g[f"c{n}_shape"])
+        src = g[f"c{n}_in"]
+        lin = interpolate_bilinear(src, (dw, dh))
+        assert lin.dtype == np.float32 and lin.shape == (dh, dw, 3)
+        assert np.abs(lin - g[f"c{n}_linear"]).max() <= 1e-6, n
+        assert np.abs(interpolate_area(src, (dw, dh)) - g[f"c{n}_area"]).max() <= 1e-6, n
+    with pytest.raises(NotImplementedError):
+        interpolate_bilinear(np.zeros((8, 8, 3), np.uint8), (16, 16))
+    with pytest.raises(ValueError):
+        interpolate_area(np.zeros((16, 16, 3), np.float32), (8, 8))          # down-scaling area resampling is not built
