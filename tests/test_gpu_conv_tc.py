@@ -109,6 +109,11 @@ def test_tma_epilogue_paths(kind):
     for (B, H, W) in ((2, 32, 24), (1, 16, 21), (3, 48, 8)):
         got, want = _run(kind, B, H, W, 256, d2s=2, out_dtype=DT[kind])
         assert got.shape == (B, 2 * H, 2 * W, 64) and np.abs(got - want).max() <= tol16, (B, H, W)
+    # 256-channel chunks run as CTA pairs (cta_group::2) with two 64-channel epilogue sub-blocks per warp: odd tile
+    # counts (dummy tile of the pair), clipped tiles, with and without depth_to_space
+    for (B, H, W) in ((1, 19, 21), (3, 16, 8), (2, 40, 13)):
+        got, want = _run(kind, B, H, W, 256, act="relu", out_dtype=DT[kind])
+        assert got.shape == (B, H, W, 256) and np.abs(got - want).max() <= tol16, (B, H, W)
 
 
 @pytest.mark.parametrize("kind", ["fp16", "bf16"])
