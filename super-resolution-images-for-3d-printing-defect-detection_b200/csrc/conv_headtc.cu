@@ -86,6 +86,8 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp != kHProd) pdl_wait();                     // producers read the image, epilogue warps write the outputs (the MMA warp touches neither)
   const int tiles_per_img = q.tiles_x * q.tiles_y;
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
@@ -359,7 +361,7 @@ int conv_headtc_launch(const ConvParams& p, cudaStream_t stream) {
   }
   int grid = sm_count();
   if ((long)grid > total) grid = (int)total;
-  conv_headtc_kernel<<<grid, kHThreads, smem, stream>>>(tmw, em, q, p);
+  SRB_CUDA(tc_launch(conv_headtc_kernel, grid, kHThreads, smem, stream, false, tmw, em, q, p));
   return launch_check("conv_headtc_kernel");
 }
 

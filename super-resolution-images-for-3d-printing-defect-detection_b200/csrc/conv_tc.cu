@@ -202,8 +202,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (k2) cluster_sync_all(); else __syncthreads();   // barrier inits must be visible to the peer before it signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();                            // the next layer may begin its prologue as SMs free up
 
   const int tiles_per_img = q.tiles_x * q.tiles_y;
+  // (the weights do not depend on the previous launch; everything else read or written below does: the producer waits
+  //  after queueing the weight loads, the epilogue warps before their first global access)
+  if (warp >= 2) pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -220,6 +224,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     }
     __syncwarp();
+    pdl_wait();
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
@@ -1046,6 +1051,8 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  if (warp >= 2) pdl_wait();                          // epilogue warps: before their first global access
   const int tiles_per_img = q.tiles_x * q.tiles_y;
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
@@ -1064,6 +1071,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       for (int dy = 0; dy < f_kh; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
     }
     __syncwarp();
+    pdl_wait();                                       // (the weight loads above do not depend on the previous launch)
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
       int b, y0, x0;
@@ -1482,7 +1490,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   }
   int grid = sm_count();
   if ((long)grid > total) grid = (int)total;
-  kernels[ki]<<<grid, kFoldThreads, smem, stream>>>(tmx, tmw, em, q, p);
+  SRB_CUDA(tc_launch(kernels[ki], grid, kFoldThreads, smem, stream, false, tmx, tmw, em, q, p));
   return launch_check("conv3x3_fold_kernel");
 }
 
@@ -1713,20 +1721,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   if (grid < unit) grid = unit;
   const long work = ((long)(k2 ? (q.total_tiles + 1) / 2 : q.total_tiles)) * unit;
   if ((long)grid > work) grid = (int)work;
-  if (k2) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    SRB_CUDA(cudaLaunchKernelEx(&cfg, kernels[1][spec], tmx, tmw, em, q, p));
-  } else {
-    kernels[0][spec]<<<grid, kThreads, smem, stream>>>(tmx, tmw, em, q, p);
-  }
+  SRB_CUDA(tc_launch(kernels[k2][spec], grid, kThreads, smem, stream, k2 != 0, tmx, tmw, em, q, p));
   return launch_check("conv3x3_tc_kernel");
 }
 
