@@ -349,6 +349,21 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
   SRB_REQUIRE(src && dst, "bicubic: null pointer");
   SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "bicubic: bad geometry");
   if (batch == 0) return SRB_OK;
+  {
+    // the tap tables come from the stream-ordered allocator: keep its pool from handing memory back to the driver at every
+    // synchronisation (the default release threshold is 0), which showed up as millisecond hiccups between launches
+    static bool pool_set[64] = {};
+    int dev = 0;
+    SRB_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_set[dev] = true;
+    }
+  }
   AxisTap* tabs = nullptr;
   SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh) + sizeof(int) * ((size_t)dh + dw), stream));
   int* ybase = reinterpret_cast<int*>(tabs + (size_t)dw + dh);
