@@ -61,10 +61,11 @@ int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int
 int srb_bicubic_f32(const float* src, int batch, int src_h, int src_w, int channels,
                     float* dst, int dst_h, int dst_w, int clip01, srb_stream_t stream);
 /* cv2.resize(src, (dst_w, dst_h), interpolation) for the other codes of the reference's interpolation map
- * (classic_algorithms.py:7-17, loading_methods.py:133-147): SRB_INTER_LINEAR, SRB_INTER_AREA (up-scaling, where OpenCV
+ * (classic_algorithms.py:7-21, loading_methods.py:133-147): SRB_INTER_LINEAR, SRB_INTER_AREA (up-scaling, where OpenCV
  * evaluates it as a bilinear filter with area coefficients) and SRB_INTER_CUBIC (== srb_bicubic_f32).  Same kernels:
- * the bilinear taps are (0, 1 - t, t, 0) in the four-tap table. */
-enum { SRB_INTER_LINEAR = 1, SRB_INTER_CUBIC = 2, SRB_INTER_AREA = 3 };   /* OpenCV's codes */
+ * the bilinear taps are (0, 1 - t, t, 0) in the four-tap table.  SRB_INTER_LANCZOS4 (classic_algorithms.py:19-21, 58-62)
+ * is OpenCV's 8-tap interpolateLanczos4 filter on its own eight-tap table and streaming kernel. */
+enum { SRB_INTER_LINEAR = 1, SRB_INTER_CUBIC = 2, SRB_INTER_AREA = 3, SRB_INTER_LANCZOS4 = 4 };   /* OpenCV's codes */
 int srb_resize_f32(const float* src, int batch, int src_h, int src_w, int channels,
                    float* dst, int dst_h, int dst_w, int interpolation, int clip01, srb_stream_t stream);
 int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,

@@ -343,6 +343,130 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
   }
 }
 
+// ---- cv2.resize(..., INTER_LANCZOS4) (classic_algorithms.py:19-21, 58-62; the interpolation map of
+// loading_methods.py:133-145) ----------------------------------------------------------------------------------------
+// Separable 8-tap Lanczos (a = 4) as OpenCV's interpolateLanczos4 evaluates it: position and fraction in float32, the
+// eight sinc weights from one sin/cos pair in double through the pi/4 rotation table, 1e30 at a zero argument (which the
+// normalisation turns into a one-hot row), float32 normalisation by the reciprocal of the float32 sum; taps
+// floor(f) - 3 .. floor(f) + 4 with index clamping.
+struct AxisTap8 { int idx[8]; float coef[8]; };   // 64 bytes
+
+__global__ void lanczos4_tables(AxisTap8* __restrict__ tab, int* __restrict__ base_out, int n_src, int n_dst) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_dst) return;
+  const double scale = 1.0 / ((double)n_dst / (double)n_src);
+  const float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  const int s = (int)floorf(f);
+  const float t = __fsub_rn(f, (float)s);
+  const double s45 = 0.70710678118654752440084436210485;
+  const double cs[8][2] = {{1, 0}, {-s45, -s45}, {0, 1}, {s45, -s45}, {-1, 0}, {s45, s45}, {0, -1}, {-s45, s45}};
+  const double kPi = 3.1415926535897932384626433832795;
+  const double y0 = -((double)t + 3.0) * kPi * 0.25;
+  const double s0 = sin(y0), c0 = cos(y0);
+  float c[8], sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float yi = __fsub_rn(__fadd_rn(t, 3.f), (float)i);
+    if (fabsf(yi) >= 1e-6f) {
+      const double y = -(double)yi * kPi * 0.25;
+      c[i] = (float)((cs[i][0] * s0 + cs[i][1] * c0) / (y * y));
+    } else {
+      c[i] = 1e30f;
+    }
+    sum = __fadd_rn(sum, c[i]);
+  }
+  sum = __fdiv_rn(1.f, sum);
+  AxisTap8 a;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a.idx[i] = min(max(s - 3 + i, 0), n_src - 1);
+    a.coef[i] = __fmul_rn(c[i], sum);
+  }
+  tab[d] = a;
+  base_out[d] = s - 3;
+}
+
+// One interleaved output column per thread over a strip of output rows, with the horizontal-pass results of the eight
+// source rows under the vertical taps kept in a register window (the 8-tap sibling of bicubic_stream_kernel).
+__global__ void __launch_bounds__(kTE)
+lanczos4_stream_kernel(const float* __restrict__ src, float* __restrict__ dst, const AxisTap8* __restrict__ xtab,
+                       const AxisTap8* __restrict__ ytab, const int* __restrict__ ybase, int src_h, int src_w, int C,
+                       int dst_h, int dst_w, int rows_per_block, int clip01) {
+  const int DE = dst_w * C, SE = src_w * C;
+  const int e = blockIdx.x * kTE + threadIdx.x;
+  if (e >= DE) return;
+  const int x = e / C, c = e - x * C;
+  int o[8];
+  float cx[8];
+  {
+    const AxisTap8 xt = xtab[x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { o[k] = xt.idx[k] * C + c; cx[k] = xt.coef[k]; }
+  }
+  const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, dst_h);
+  const float* simg = src + (size_t)blockIdx.z * src_h * SE;
+  float* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
+  auto hrow = [&](int r) -> float {
+    r = min(max(r, 0), src_h - 1);
+    const float* row = simg + (size_t)r * SE;
+    float v = __fmul_rn(__ldg(row + o[0]), cx[0]);
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v = __fmaf_rn(__ldg(row + o[k]), cx[k], v);
+    return v;
+  };
+  int u = __ldg(ybase + y0);
+  float w[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) w[k] = hrow(u + k);
+  for (int y = y0; y < y1; ++y, out += DE) {
+    const int ub = __ldg(ybase + y);                // block-uniform
+    while (u < ub) {
+#pragma unroll
+      for (int k = 0; k < 7; ++k) w[k] = w[k + 1];
+      ++u;
+      w[7] = hrow(u + 7);
+    }
+    const float4 ca = __ldg(reinterpret_cast<const float4*>(ytab[y].coef));
+    const float4 cb = __ldg(reinterpret_cast<const float4*>(ytab[y].coef + 4));
+    float v = __fmul_rn(w[0], ca.x);
+    v = __fmaf_rn(w[1], ca.y, v); v = __fmaf_rn(w[2], ca.z, v); v = __fmaf_rn(w[3], ca.w, v);
+    v = __fmaf_rn(w[4], cb.x, v); v = __fmaf_rn(w[5], cb.y, v); v = __fmaf_rn(w[6], cb.z, v); v = __fmaf_rn(w[7], cb.w, v);
+    if (clip01) v = fminf(fmaxf(v, 0.f), 1.f);
+    *out = v;
+  }
+}
+
+static int run_lanczos4(const float* src, int batch, int sh, int sw, int C, float* dst, int dh, int dw, int clip01,
+                        cudaStream_t stream) {
+  SRB_REQUIRE(src && dst, "lanczos4: null pointer");
+  SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "lanczos4: bad geometry");
+  if (batch == 0) return SRB_OK;
+  AxisTap8* tabs = nullptr;
+  SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap8) * ((size_t)dw + dh) + sizeof(int) * ((size_t)dh + dw), stream));
+  AxisTap8* xtab = tabs;
+  AxisTap8* ytab = tabs + dw;
+  int* ybase = reinterpret_cast<int*>(tabs + (size_t)dw + dh);
+  int* xbase = ybase + dh;
+  lanczos4_tables<<<(dw + 127) / 128, 128, 0, stream>>>(xtab, xbase, sw, dw);
+  lanczos4_tables<<<(dh + 127) / 128, 128, 0, stream>>>(ytab, ybase, sh, dh);
+  int rc = launch_check("lanczos4_tables");
+  if (rc == SRB_OK) {
+    int rows = 64;
+    const long target = 4L * sm_count();
+    while (rows > 8 && (long)((dw * C + kTE - 1) / kTE) * ((dh + rows - 1) / rows) * batch < target) rows >>= 1;
+    dim3 grid((dw * C + kTE - 1) / kTE, (dh + rows - 1) / rows, batch);
+    if (grid.y > 65535 || grid.z > 65535) {
+      set_error("lanczos4: grid too large");
+      rc = SRB_E_INVALID;
+    } else {
+      lanczos4_stream_kernel<<<grid, kTE, 0, stream>>>(src, dst, xtab, ytab, ybase, sh, sw, C, dh, dw, rows, clip01);
+      rc = launch_check("lanczos4_stream_kernel");
+    }
+  }
+  SRB_CUDA(cudaFreeAsync(tabs, stream));
+  return rc;
+}
+
 template <typename T, bool FIXED>
 static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, int dh, int dw, int clip01,
                        cudaStream_t stream, int table_mode = FIXED ? 1 : 0) {
@@ -440,7 +564,9 @@ extern "C" int srb_resize_f32(const float* src, int batch, int src_h, int src_w,
                 src_w, src_h, dst_w, dst_h);
     return run_bicubic<float, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream, 3);
   }
-  set_error("resize: unsupported interpolation code %d (cubic = 2, linear = 1, area = 3)", interpolation);
+  if (interpolation == SRB_INTER_LANCZOS4)
+    return run_lanczos4(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, clip01, (cudaStream_t)stream);
+  set_error("resize: unsupported interpolation code %d (linear = 1, cubic = 2, area = 3, lanczos4 = 4)", interpolation);
   return SRB_E_UNSUPPORTED;
 }
 

@@ -10,6 +10,7 @@
 // from the same loaded lines over a non-overlapping ownership partition of the image.
 // Per-image double-precision accumulators receive one atomicAdd per block and statistic.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace srb {
 
@@ -141,6 +142,169 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
   }
 }
 
+// Wide-image variant: two horizontally adjacent map pixels per thread.  Lines are de-interleaved into channel planes
+// when they are fetched ((a, b) pairs per pixel), and every thread turns the elements it fetched itself into a second
+// plane of (a^2 + b^2, a*b) pairs one row ahead of the arithmetic, so the products are formed once per input element
+// instead of once per tap.  The four maps tf.image.ssim filters (mu_a, mu_b, E[a^2 + b^2], E[ab]) are then exactly two
+// packed fp32x2 FMAs per tap and output in both passes, and a thread's two outputs share 10 of their 11 tap loads
+// (six 16-byte shared loads per plane and row).  A block is Q pixel pairs x C channels (thread = (channel, pair), warps
+// are channel-uniform so the 16-byte loads of a warp are contiguous).
+template <int C, int Q>
+__global__ void __launch_bounds__(Q * C, 2)
+psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
+                      float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
+  constexpr int T = Q * C;
+  constexpr int PX = 2 * Q;                        // map pixels per block row
+  constexpr int LW = PX + 10;                      // line width in pixels (even: 16-byte aligned planes)
+  constexpr int kAhead = 8;                        // rows in flight = line buffers (a line is refilled after the barrier that retires it)
+  constexpr int kSlots = (LW * C + T - 1) / T;     // fetch slots per thread: 2 cover the block's own pixels, the 3rd the halo
+  static_assert(kSlots == 3 && (Q % 32) == 0, "geometry");
+  __shared__ __align__(16) float2 sab[kAhead][C][LW];   // (a, b)
+  __shared__ __align__(16) float2 ssp[2][C][LW];        // (a^2 + b^2, a*b)
+  __shared__ float red[2][T / 32];
+
+  const int WE = W * C;
+  const int OW = W - 10, OH = H - 10;
+  const int t = threadIdx.x;
+  const int X0 = blockIdx.x * PX;
+  const int y0 = blockIdx.y * rows_per_strip;
+  const int rows_out = min(rows_per_strip, OH - y0);
+  const int nin = rows_out + 10;
+  const bool last_x = (X0 + PX >= OW);
+  const bool last_y = (y0 + rows_per_strip >= OH);
+  const size_t img_off = (size_t)blockIdx.z * H * WE;
+  const int c = t / Q, q = t % Q;
+
+  float2 g2[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_gauss[k], c_gauss[k]);
+
+  // fetch slots (fixed per thread): interleaved element i of the block's line -> plane (i % C), pixel (i / C)
+  uint32_t s_off[kSlots];     // byte offset of the (a, b) pair inside one line buffer; the (s, p) planes use the same offset
+  bool s_in[kSlots], s_ok[kSlots];
+#pragma unroll
+  for (int s = 0; s < kSlots; ++s) {
+    const int i = t + s * T;
+    s_in[s] = i < LW * C;
+    s_ok[s] = s_in[s] && (X0 * C + i) < WE;
+    s_off[s] = (uint32_t)(((i % C) * LW + (i / C)) * sizeof(float2));
+  }
+  for (int i = t; i < kAhead * C * LW; i += T) (&sab[0][0][0])[i] = make_float2(0.f, 0.f);
+  __syncthreads();
+  const uint32_t sab0 = (uint32_t)__cvta_generic_to_shared(&sab[0][0][0]);
+  constexpr uint32_t kLineBytes = C * LW * sizeof(float2);
+  const float* fa = a + img_off + (size_t)y0 * WE + (size_t)X0 * C + t;
+  const float* fb = b + img_off + (size_t)y0 * WE + (size_t)X0 * C + t;
+  auto fetch = [&](int row) {
+    if (row < nin) {
+      const uint32_t d = sab0 + (uint32_t)(row % kAhead) * kLineBytes;
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s)
+        if (s_ok[s]) {
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + s_off[s]), "l"(fa + s * T) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + s_off[s] + 4u), "l"(fb + s * T) : "memory");
+        }
+      fa += WE;
+      fb += WE;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  float sse = 0.f;
+  // products of this thread's own elements of a landed row (its own cp.async groups are complete: no barrier needed)
+  auto products = [&](int row) {
+    if (row < nin) {
+      const bool row_owned = (row < rows_out) || last_y;
+      const char* lab = reinterpret_cast<const char*>(&sab[row % kAhead][0][0]);
+      char* lsp = reinterpret_cast<char*>(&ssp[row & 1][0][0]);
+#pragma unroll
+      for (int s = 0; s < kSlots; ++s)
+        if (s_in[s]) {
+          const float2 v = *reinterpret_cast<const float2*>(lab + s_off[s]);
+          const float2 sq = __fmul2_rn(v, v);
+          *reinterpret_cast<float2*>(lsp + s_off[s]) = make_float2(sq.x + sq.y, v.x * v.y);
+          if (row_owned && (s < 2 || last_x)) { const float d = v.x - v.y; sse = fmaf(d, d, sse); }
+        }
+    }
+  };
+
+  float2 rab0[11], rab1[11], rsp0[11], rsp1[11];
+#pragma unroll
+  for (int k = 0; k < 11; ++k) rab0[k] = rab1[k] = rsp0[k] = rsp1[k] = make_float2(0.f, 0.f);
+  float2 ssim2 = make_float2(0.f, 0.f);
+  const float2 valid2 = make_float2((X0 + 2 * q) < OW ? 1.f : 0.f, (X0 + 2 * q + 1) < OW ? 1.f : 0.f);
+  const float2 c1_2 = make_float2(c1, c1), c2_2 = make_float2(c2, c2), two2 = make_float2(2.f, 2.f);
+
+#pragma unroll
+  for (int r = 0; r < kAhead; ++r) fetch(r);
+  asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
+  products(0);
+  __syncthreads();
+
+  for (int r = 0; r < nin; r += 11) {
+#pragma unroll
+    for (int j = 0; j < 11; ++j) {
+      const int row = r + j;              // block-uniform
+      if (row < nin) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 2) : "memory");   // this thread's part of row + 1 has landed
+        products(row + 1);
+        const float4* lab = reinterpret_cast<const float4*>(&sab[row % kAhead][c][2 * q]);
+        const float4* lsp = reinterpret_cast<const float4*>(&ssp[row & 1][c][2 * q]);
+        float2 hab0 = make_float2(0.f, 0.f), hab1 = hab0, hsp0 = hab0, hsp1 = hab0;
+#pragma unroll
+        for (int m = 0; m < 6; ++m) {
+          const float4 va = lab[m], vs = lsp[m];
+          const float2 a0 = make_float2(va.x, va.y), a1 = make_float2(va.z, va.w);
+          const float2 p0 = make_float2(vs.x, vs.y), p1 = make_float2(vs.z, vs.w);
+          hab0 = __ffma2_rn(g2[2 * m], a0, hab0);
+          hsp0 = __ffma2_rn(g2[2 * m], p0, hsp0);
+          if (m >= 1) { hab1 = __ffma2_rn(g2[2 * m - 1], a0, hab1); hsp1 = __ffma2_rn(g2[2 * m - 1], p0, hsp1); }
+          if (m <= 4) { hab0 = __ffma2_rn(g2[2 * m + 1], a1, hab0); hsp0 = __ffma2_rn(g2[2 * m + 1], p1, hsp0); }
+          hab1 = __ffma2_rn(g2[2 * m], a1, hab1);
+          hsp1 = __ffma2_rn(g2[2 * m], p1, hsp1);
+        }
+        rab0[j] = hab0; rab1[j] = hab1; rsp0[j] = hsp0; rsp1[j] = hsp1;
+        if (row >= 10) {
+          float2 mab0 = make_float2(0.f, 0.f), mab1 = mab0, esp0 = mab0, esp1 = mab0;
+#pragma unroll
+          for (int k = 0; k < 11; ++k) {
+            const int slot = (j + 1 + k) % 11;   // oldest row first
+            mab0 = __ffma2_rn(g2[k], rab0[slot], mab0);
+            mab1 = __ffma2_rn(g2[k], rab1[slot], mab1);
+            esp0 = __ffma2_rn(g2[k], rsp0[slot], esp0);
+            esp1 = __ffma2_rn(g2[k], rsp1[slot], esp1);
+          }
+          // point function for both outputs at once
+          const float2 ma = make_float2(mab0.x, mab1.x), mb = make_float2(mab0.y, mab1.y);
+          const float2 es = make_float2(esp0.x, esp1.x), ep = make_float2(esp0.y, esp1.y);
+          const float2 mm = __fmul2_rn(ma, mb);                       // mu_a mu_b
+          const float2 den0 = __ffma2_rn(ma, ma, __fmul2_rn(mb, mb)); // mu_a^2 + mu_b^2
+          const float2 ln = __ffma2_rn(two2, mm, c1_2);
+          const float2 cn = __ffma2_rn(two2, make_float2(ep.x - mm.x, ep.y - mm.y), c2_2);
+          const float2 ld = make_float2(den0.x + c1, den0.y + c1);
+          const float2 cd = make_float2((es.x - den0.x) + c2, (es.y - den0.y) + c2);
+          const float2 num = __fmul2_rn(ln, cn), den = __fmul2_rn(ld, cd);
+          ssim2 = __ffma2_rn(make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y)), valid2, ssim2);
+        }
+        __syncthreads();                  // row is retired by every thread; row + 1 (both planes) is visible
+        fetch(row + kAhead);
+      }
+    }
+  }
+
+  sse = warp_sum(sse);
+  float ssim_sum = warp_sum(ssim2.x + ssim2.y);
+  if ((t & 31) == 0) { red[0][t >> 5] = sse; red[1][t >> 5] = ssim_sum; }
+  __syncthreads();
+  if (t == 0) {
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+    for (int w = 0; w < T / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+    atomicAdd(&acc[2 * blockIdx.z + 0], s0);
+    atomicAdd(&acc[2 * blockIdx.z + 1], s1);
+  }
+}
+
 __global__ void psnr_ssim_finalize(const double* __restrict__ acc, int B, double n_pix, double n_map,
                                    float max_val, float* psnr, float* ssim, float* mse_out, double* sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,12 +357,33 @@ extern "C" int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int 
   double* acc = (double*)workspace;
   SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
   const int OH = height - 10, OE = (width - 10) * channels;
+  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
+  static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
+  if (width - 10 >= 96 && !force_narrow) {   // wide images: two map pixels per thread
+    const int OW = width - 10;
+    const int px = channels == 1 ? 256 : channels == 4 ? 64 : 128;     // map pixels per block row (2 * Q)
+    const int gxp = (OW + px - 1) / px;
+    int rows = 128;
+    const long target = 4L * sm_count();
+    while (rows > 16 && (long)gxp * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
+    dim3 grid(gxp, (OH + rows - 1) / rows, batch);
+    switch (channels) {
+      case 1: psnr_ssim_pair_kernel<1, 128><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 2: psnr_ssim_pair_kernel<2, 64><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 3: psnr_ssim_pair_kernel<3, 64><<<grid, 192, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      default: psnr_ssim_pair_kernel<4, 32><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+    }
+    rc = launch_check("psnr_ssim_pair_kernel");
+    if (rc) return rc;
+    psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(
+        acc, batch, (double)height * width * channels, (double)OH * OE, max_val, psnr, ssim, mse, sums);
+    return launch_check("psnr_ssim_finalize");
+  }
   const int gx = (OE + kCols - 1) / kCols;
   int rows = 64;
   const long target = 2L * sm_count();
   while (rows > 16 && (long)gx * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
   dim3 grid(gx, (OH + rows - 1) / rows, batch);
-  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
   switch (channels) {
     case 1: psnr_ssim_kernel<1><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
     case 2: psnr_ssim_kernel<2><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;

@@ -1,5 +1,5 @@
-"""``interpolate_bicubic`` with the reference's signature
-(SRModels/classic_super_resolution_algorithms/classic_algorithms.py:11-13), computed on the GPU.
+"""``interpolate_bicubic`` / ``interpolate_bilinear`` / ``interpolate_area`` / ``interpolate_lanczos`` with the reference's
+signatures (SRModels/classic_super_resolution_algorithms/classic_algorithms.py:7-21), computed on the GPU.
 
 ``target_shape`` is ``(width, height)`` exactly as for ``cv2.resize``; dtype is preserved (uint8 or
 float32); float results are not clipped.  Accepts ``[H, W, C]`` / ``[H, W]`` images or an
@@ -53,7 +53,7 @@ def interpolate_bicubic(lr_img, target_shape: Tuple[int, int]):
 def _not_on_path(name):
     def f(*_a, **_k):
         raise NotImplementedError(
-            f"{name} is outside the B200 hot path (SURVEY.md section 8f rank 3); only interpolate_bicubic is built")
+            f"{name} is outside the B200 hot path (SURVEY.md section 8f): only the four cv2.resize interpolators are built")
     f.__name__ = name
     return f
 
@@ -63,7 +63,7 @@ def _resize_float(img, target_shape, code):
     was_numpy = not isinstance(img, torch.Tensor)
     t = torch.from_numpy(np.ascontiguousarray(img)).cuda() if was_numpy else (img if img.is_cuda else img.cuda())
     if t.dtype != torch.float32:
-        raise NotImplementedError("bilinear / area resizing is built for float32 images (the reference's [0, 1] data); "
+        raise NotImplementedError("bilinear / area / Lanczos resizing is built for float32 images (the reference's [0, 1] data); "
                                   "uint8 uses OpenCV's fixed-point filter, which only the bicubic kernel reproduces")
     nd = t.dim()
     t4 = t[None, :, :, None] if nd == 2 else t[None] if nd == 3 else t
@@ -86,4 +86,6 @@ def interpolate_area(lr_img, target_shape: Tuple[int, int]):
 
 
 
-interpolate_lanczos = _not_on_path("interpolate_lanczos")
+def interpolate_lanczos(lr_img, target_shape: Tuple[int, int]):
+    """Lanczos-4 upscaling (== cv2.resize(..., interpolation=cv2.INTER_LANCZOS4), classic_algorithms.py:19-21)."""
+    return _resize_float(lr_img, target_shape, capi.INTER_LANCZOS4)

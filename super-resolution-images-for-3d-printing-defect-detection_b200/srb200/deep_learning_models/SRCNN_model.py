@@ -51,21 +51,27 @@ class SRCNNModel:
         return results
 
     def super_resolve_image(self, lr_img, hr_h, hr_w, patch_size=33, stride=14, interpolation=INTER_CUBIC):
-        """Bicubic-upscale the LR image to (hr_w, hr_h), then patch-wise SRCNN with overlap averaging.
+        """Upscale the LR image to (hr_w, hr_h) with the given cv2 interpolation (bicubic by default), then patch-wise SRCNN with overlap averaging.
         Returns (float32 RGB in [0,1] of shape (hr_h, hr_w, 3), inference_metrics)."""
         if not self._trained:
             raise RuntimeError("Model has not been trained.")
         if lr_img is None or not isinstance(lr_img, np.ndarray):
             raise ValueError("lr_img must be a numpy array (RGB).")
-        if interpolation != INTER_CUBIC:
-            raise NotImplementedError("only cv2.INTER_CUBIC is built on the device (SURVEY.md section 8f rank 3)")
+        if interpolation not in (capi.INTER_LINEAR, capi.INTER_CUBIC, capi.INTER_AREA, capi.INTER_LANCZOS4):
+            raise NotImplementedError(f"cv2 interpolation code {interpolation} is not built on the device "
+                                      "(INTER_LINEAR, INTER_CUBIC, INTER_AREA and INTER_LANCZOS4 are)")
+        if interpolation != INTER_CUBIC and lr_img.dtype == np.uint8:
+            raise NotImplementedError("uint8 input is built for cv2.INTER_CUBIC only (OpenCV's fixed-point filters)")
         torch = capi.require_cuda()
         if lr_img.dtype == np.uint8:
             # cv2.resize keeps uint8; the network then sees 0..255 values, exactly as in the reference
             src = torch.from_numpy(np.ascontiguousarray(lr_img)).cuda()
         else:
             src = common.as_device_image(lr_img)
-        up = ops.bicubic(src[None], hr_h, hr_w)[0].float()
+        if interpolation == INTER_CUBIC:
+            up = ops.bicubic(src[None], hr_h, hr_w)[0].float()
+        else:
+            up = ops.resize(src[None], hr_h, hr_w, interpolation=interpolation)[0]
         sr, metrics = common.tiled_super_resolve(self.model, up, patch_size, stride, 1)
         return sr.cpu().numpy(), metrics
 

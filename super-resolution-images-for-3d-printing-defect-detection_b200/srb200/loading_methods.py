@@ -11,8 +11,8 @@ Documented differences:
 * ``load_dataset_as_patches(mode='srcnn', interpolation_map_path=None)`` raises ``NameError`` in the reference because
   ``interpolation_map`` is only bound when a path is given (``:110-113`` vs ``:134``); here a missing map simply means
   bicubic for every image.
-* ``INTER_CUBIC``, ``INTER_LINEAR`` and (up-scaling) ``INTER_AREA`` entries of the interpolation map (``:133-145``) run
-  on the device; ``INTER_LANCZOS4`` is resized by OpenCV on the host, exactly as the reference does.
+* ``INTER_CUBIC``, ``INTER_LINEAR``, ``INTER_LANCZOS4`` and (up-scaling) ``INTER_AREA`` entries of the interpolation map
+  (``:133-145``) run on the device; a down-scaling ``INTER_AREA`` is resized by OpenCV on the host, as the reference does.
 * ``load_defects_dataset_as_patches`` walks the *unpadded* extent (``:276-277``), so the padding it adds is never
   visited; reproduced as is.
 """
@@ -119,7 +119,7 @@ def load_dataset_as_patches(hr_root, lr_root, mode="srcnn", patch_size=33, strid
                 elif isinstance(chosen, int):
                     code = chosen
             grows = hr_h >= lr_img.shape[0] and hr_w >= lr_img.shape[1]
-            if code in (cv2.INTER_CUBIC, cv2.INTER_LINEAR) or (code == cv2.INTER_AREA and grows):
+            if code in (cv2.INTER_CUBIC, cv2.INTER_LINEAR, cv2.INTER_LANCZOS4) or (code == cv2.INTER_AREA and grows):
                 lr_dev = torch.from_numpy(lr_img).cuda()[None]
                 lr_up = ops.resize(lr_dev, hr_h, hr_w, interpolation=code, clip01=True)[0]   # resize + np.clip in one kernel
             else:

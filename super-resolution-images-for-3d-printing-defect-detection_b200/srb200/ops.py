@@ -89,7 +89,7 @@ def bicubic(src, dst_h, dst_w, clip01=False, fixed_point=False):
 
 def resize(src, dst_h, dst_w, interpolation=capi.INTER_CUBIC, clip01=False):
     """cv2.resize(src, (dst_w, dst_h), interpolation) for float32 NHWC CUDA tensors; INTER_CUBIC, INTER_LINEAR and
-    (up-scaling) INTER_AREA share the bicubic kernels through the four-tap table."""
+    (up-scaling) INTER_AREA share the bicubic kernels through the four-tap table; INTER_LANCZOS4 has an eight-tap one."""
     torch = _torch()
     _check_nhwc(src, "src")
     if src.dtype != torch.float32:

@@ -1,5 +1,5 @@
-"""cv2.resize golden outputs for the bilinear and (up-scaling) area modes (OpenCV 4.13.0 of the build image) - the
-reference's interpolate_bilinear / interpolate_area (classic_algorithms.py:7-17).
+"""cv2.resize golden outputs for the bilinear, (up-scaling) area and Lanczos-4 modes (OpenCV 4.13.0 of the build image) -
+the reference's interpolate_bilinear / interpolate_area / interpolate_lanczos (classic_algorithms.py:7-21).
 
     python tests/golden/make_resize_golden.py
 """
@@ -18,6 +18,7 @@ for n, (h, w, dh, dw) in enumerate(cases):
     out[f"c{n}_in"] = f
     out[f"c{n}_linear"] = cv2.resize(f, (dw, dh), interpolation=cv2.INTER_LINEAR)
     out[f"c{n}_area"] = cv2.resize(f, (dw, dh), interpolation=cv2.INTER_AREA)
+    out[f"c{n}_lanczos4"] = cv2.resize(f, (dw, dh), interpolation=cv2.INTER_LANCZOS4)
 out["n_cases"] = np.array(len(cases))
 np.savez_compressed(os.path.join(HERE, "resize_cv2.npz"), **out)
 print("wrote", len(cases), "cases")

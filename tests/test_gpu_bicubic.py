@@ -104,3 +104,29 @@ def test_bilinear_and_area_vs_cv2_golden(golden_dir):
         interpolate_bilinear(np.zeros((8, 8, 3), np.uint8), (16, 16))
     with pytest.raises(ValueError):
         interpolate_area(np.zeros((16, 16, 3), np.float32), (8, 8))          # down-scaling area resampling is not built
+
+
+def test_lanczos4_vs_cv2_golden_and_oracle(golden_dir):
+    """interpolate_lanczos (classic_algorithms.py:19-21) against cv2.resize(INTER_LANCZOS4) outputs and the restatement;
+    batch, grayscale, strip boundaries (more rows than one block owns) and the clip of the loaders."""
+    import torch
+    from srb200 import ops, _capi
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import interpolate_lanczos
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw = (int(v) for v in g[f"c{n}_shape"])
+        got = interpolate_lanczos(g[f"c{n}_in"], (dw, dh))
+        assert got.dtype == np.float32 and got.shape == (dh, dw, 3)
+        assert np.abs(got - g[f"c{n}_lanczos4"]).max() <= 2e-6, n
+    rng = np.random.default_rng(3)
+    f = rng.random((3, 41, 29, 3), dtype=np.float32)
+    got = interpolate_lanczos(f, (87, 300))                                  # 300 output rows: several row strips
+    for i in range(3):
+        assert np.abs(got[i] - ob.resize_lanczos4_f32(f[i], (87, 300))).max() <= 2e-6
+    gray = rng.random((20, 33), dtype=np.float32)
+    assert np.abs(interpolate_lanczos(gray, (66, 40)) - ob.resize_lanczos4_f32(gray, (66, 40))).max() <= 2e-6
+    t = torch.from_numpy(f).cuda()
+    clipped = ops.resize(t, 82, 58, interpolation=_capi.INTER_LANCZOS4, clip01=True).cpu().numpy()
+    assert np.abs(clipped - np.clip(np.stack([ob.resize_lanczos4_f32(x, (58, 82)) for x in f]), 0, 1)).max() <= 2e-6
+    with pytest.raises(NotImplementedError):
+        interpolate_lanczos(np.zeros((8, 8, 3), np.uint8), (16, 16))

@@ -68,3 +68,19 @@ def test_grayscale_and_identity():
     g = rng.random((9, 11), dtype=np.float32)
     assert ob.resize_cubic_f32(g, (22, 18)).shape == (18, 22)
     assert np.array_equal(ob.resize_cubic_f32(g, (11, 9)), g)   # t == 0 -> taps (0,1,0,0)
+
+
+def test_lanczos4_restatement_against_cv2_golden(golden_dir):
+    """interpolate_lanczos (classic_algorithms.py:19-21): the 8-tap restatement against cv2.resize(INTER_LANCZOS4) outputs
+    (up-scaling, down-scaling along one axis, identity) and its known answers (one-hot rows up to the 1e30 sentinel, symmetry, unit sum)."""
+    g = np.load(os.path.join(golden_dir, "resize_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw = (int(v) for v in g[f"c{n}_shape"])
+        got = ob.resize_lanczos4_f32(g[f"c{n}_in"], (dw, dh))
+        assert got.shape == (dh, dw, 3)
+        assert np.abs(got - g[f"c{n}_lanczos4"]).max() <= 2e-6, n
+    c = ob.lanczos4_coeffs(np.array([0.0, 0.5, 1e-7], np.float32))
+    assert np.allclose(c[0], np.eye(8, dtype=np.float32)[3], atol=1e-29) and np.allclose(c[2], c[0], atol=1e-29)
+    assert np.allclose(c[1], c[1][::-1], atol=1e-7) and abs(float(c[1].sum()) - 1.0) <= 1e-6
+    idx, _ = ob.lanczos4_axis_table(10, 20)
+    assert idx.min() == 0 and idx.max() == 9 and idx.shape == (20, 8)
