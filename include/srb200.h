@@ -53,6 +53,16 @@ size_t srb_psnr_ssim_workspace(int batch);
 int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int width, int channels,
                       float max_val, float* psnr, float* ssim, float* mse, double* sums,
                       void* workspace, size_t workspace_bytes, srb_stream_t stream);
+/* Same pass with the window chosen: SRB_SSIM_TF = srb_psnr_ssim_f32; SRB_SSIM_SKIMAGE = the metric definitions the
+ * reference's classical benchmark uses (super_resolucion_clasica.ipynb cell 7: skimage.metrics.peak_signal_noise_ratio
+ * and structural_similarity(..., data_range, channel_axis=2) with their defaults - 7 x 7 uniform window, sample
+ * covariance N/(N-1), K1 = 0.01, K2 = 0.03, borders cropped by 3): psnr = 10 log10(max_val^2 / mse), ssim = mean over the
+ * (H-6) x (W-6) valid windows and channels.  Needs H, W >= 7. */
+enum { SRB_SSIM_TF = 0, SRB_SSIM_SKIMAGE = 1 };
+int srb_psnr_ssim_window_f32(const float* a, const float* b, int batch, int height, int width, int channels,
+                             float max_val, int window, float* psnr /* [B] or NULL */, float* ssim /* [B] or NULL */,
+                             float* mse /* [B] or NULL */, double* sums /* [4] or NULL, accumulated */,
+                             void* workspace, size_t workspace_bytes, srb_stream_t stream);
 
 /* ---- bicubic resampling == cv2.resize(src, (dst_w, dst_h), INTER_CUBIC) ------------------------
  * NHWC interleaved, any channel count, any ratio.  clip01: clamp to [0,1] (loading_methods.py:148).

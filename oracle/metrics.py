@@ -94,3 +94,38 @@ def evaluate_means(y_true, y_pred):
     loss = np.mean((y_true - y_pred) ** 2, dtype=np.float64)
     return [float(loss), float(np.mean(psnr(y_true, y_pred), dtype=np.float64)),
             float(np.mean(ssim(y_true, y_pred), dtype=np.float64))]
+
+
+# ---- skimage.metrics definitions (super_resolucion_clasica.ipynb cell 7 lines 213-214 / 278-279, EDA.ipynb:235,254) ----
+# scikit-image is unpinned by the reference and absent here ("parity unpinned"): restated from its published algorithm
+# (skimage/metrics/_structural_similarity.py, simple_metrics.py), on the same scipy.ndimage.uniform_filter primitive
+# skimage itself calls; pinned by known answers and an independent windowed evaluation in tests/test_oracle_metrics.py.
+def skimage_psnr(image_true, image_test, data_range):
+    """peak_signal_noise_ratio: 10 log10(data_range^2 / mean((a - b)^2)) in float64 over the whole array."""
+    a = np.asarray(image_true, dtype=np.float64)
+    b = np.asarray(image_test, dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        return float(10.0 * np.log10(float(data_range) ** 2 / np.mean((a - b) ** 2)))
+
+
+def skimage_ssim(im1, im2, data_range, channel_axis=None, win_size=7, k1=0.01, k2=0.03):
+    """structural_similarity with its defaults: uniform win_size^2 window (uniform_filter, reflect borders), sample
+    covariance (N / (N - 1)), mean over the map cropped by (win_size - 1) // 2, then over channels."""
+    from scipy.ndimage import uniform_filter
+    a = np.asarray(im1, dtype=np.float64)
+    b = np.asarray(im2, dtype=np.float64)
+    if channel_axis is not None:
+        a, b = np.moveaxis(a, channel_axis, -1), np.moveaxis(b, channel_axis, -1)
+        return float(np.mean([skimage_ssim(a[..., c], b[..., c], data_range, None, win_size, k1, k2)
+                              for c in range(a.shape[-1])]))
+    if min(a.shape) < win_size:
+        raise ValueError("win_size exceeds image extent")
+    n = win_size ** a.ndim
+    cov_norm = n / (n - 1.0)
+    ux, uy = uniform_filter(a, size=win_size), uniform_filter(b, size=win_size)
+    uxx, uyy, uxy = uniform_filter(a * a, size=win_size), uniform_filter(b * b, size=win_size), uniform_filter(a * b, size=win_size)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    s = ((2 * ux * uy + c1) * (2 * vxy + c2)) / ((ux ** 2 + uy ** 2 + c1) * (vx + vy + c2))
+    pad = (win_size - 1) // 2
+    return float(s[pad:a.shape[0] - pad, pad:a.shape[1] - pad].mean(dtype=np.float64))

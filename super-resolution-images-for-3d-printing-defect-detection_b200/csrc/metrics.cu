@@ -14,27 +14,27 @@
 
 namespace srb {
 
-__constant__ float c_gauss[11];
+__constant__ float c_win[2][11];   // [0]: 11-tap Gaussian (sigma 1.5), [1]: 7-tap uniform window
 
 constexpr int kCols = 128;  // output elements (threads) per block
 
-template <int C>
+template <int C, int K>   // K: window taps per axis (11: tf.image.ssim's Gaussian, 7: skimage's uniform window)
 __global__ void __launch_bounds__(kCols)
 psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
-                 float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
-  constexpr int kLine = kCols + 10 * C;
+                 float c1, float c2, float cov_norm, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
+  constexpr int kLine = kCols + (K - 1) * C;
   constexpr int kAhead = 4, kRing = 8;               // rows in flight / line buffers (power of two >= kAhead + 1)
   __shared__ float2 sab[kRing][kLine];               // (a, b) interleaved: one 8-byte shared load per tap
   __shared__ float red[2][kCols / 32];
 
   const int WE = W * C;            // interleaved floats per image row
-  const int OE = (W - 10) * C;     // SSIM-map elements per row
-  const int OH = H - 10;
+  const int OE = (W - (K - 1)) * C;     // SSIM-map elements per row
+  const int OH = H - (K - 1);
   const int t = threadIdx.x;
   const int e0 = blockIdx.x * kCols;
   const int y0 = blockIdx.y * rows_per_strip;
   const int rows_out = min(rows_per_strip, OH - y0);
-  const int nin = rows_out + 10;
+  const int nin = rows_out + (K - 1);
   const bool last_x = (e0 + kCols >= OE);
   const bool last_y = (y0 + rows_per_strip >= OH);
   const size_t img_off = (size_t)blockIdx.z * H * WE;
@@ -44,14 +44,14 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
 
   // packed fp32x2 arithmetic (FFMA2 / FMUL2, sm_100): the maps are carried as (mu_a, mu_b), (E[a^2], E[b^2]) pairs
   // plus E[ab]; tf.image.ssim's E[a^2 + b^2] is the sum of the second pair
-  float2 g2[11];
+  float2 g2[K];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_gauss[k], c_gauss[k]);
+  for (int k = 0; k < K; ++k) g2[k] = make_float2(c_win[K == 11 ? 0 : 1][k], c_win[K == 11 ? 0 : 1][k]);
 
-  float2 rab[11], rqq[11];
-  float rp[11];
+  float2 rab[K], rqq[K];
+  float rp[K];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) { rab[k] = rqq[k] = make_float2(0.f, 0.f); rp[k] = 0.f; }
+  for (int k = 0; k < K; ++k) { rab[k] = rqq[k] = make_float2(0.f, 0.f); rp[k] = 0.f; }
 
   float sse = 0.f, ssim_sum = 0.f;
 
@@ -84,9 +84,9 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
 #pragma unroll
   for (int r = 0; r < kAhead; ++r) fetch(r);
 
-  for (int r = 0; r < nin; r += 11) {
+  for (int r = 0; r < nin; r += K) {
 #pragma unroll
-    for (int j = 0; j < 11; ++j) {
+    for (int j = 0; j < K; ++j) {
       const int row = r + j;              // block-uniform
       if (row < nin) {
         const int buf = row & (kRing - 1);
@@ -96,24 +96,24 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
         fetch(row + kAhead);
         if (row_owned) {                  // squared error: every element of the row exactly once
           { const float2 v = sab[buf][t]; const float d = v.x - v.y; sse = fmaf(d, d, sse); }
-          if (last_x && t < 10 * C) { const float2 v = sab[buf][kCols + t]; const float d = v.x - v.y; sse = fmaf(d, d, sse); }
+          if (last_x && t < (K - 1) * C) { const float2 v = sab[buf][kCols + t]; const float d = v.x - v.y; sse = fmaf(d, d, sse); }
         }
         float2 hab = make_float2(0.f, 0.f), hqq = make_float2(0.f, 0.f);
         float hp = 0.f;
 #pragma unroll
-        for (int k = 0; k < 11; ++k) {
+        for (int k = 0; k < K; ++k) {
           const float2 v = sab[buf][t + k * C];
           hab = __ffma2_rn(g2[k], v, hab);
           hqq = __ffma2_rn(g2[k], __fmul2_rn(v, v), hqq);
           hp = fmaf(g2[k].x, v.x * v.y, hp);
         }
         rab[j] = hab; rqq[j] = hqq; rp[j] = hp;
-        if (row >= 10 && col_valid) {
+        if (row >= K - 1 && col_valid) {
           float2 mab = make_float2(0.f, 0.f), eqq = make_float2(0.f, 0.f);
           float ep = 0.f;
 #pragma unroll
-          for (int k = 0; k < 11; ++k) {
-            const int slot = (j + 1 + k) % 11;   // oldest row first
+          for (int k = 0; k < K; ++k) {
+            const int slot = (j + 1 + k) % K;    // oldest row first
             mab = __ffma2_rn(g2[k], rab[slot], mab);
             eqq = __ffma2_rn(g2[k], rqq[slot], eqq);
             ep = fmaf(g2[k].x, rp[slot], ep);
@@ -121,8 +121,9 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
           const float ma = mab.x, mb = mab.y, es = eqq.x + eqq.y;
           const float num0 = 2.f * ma * mb;
           const float den0 = fmaf(ma, ma, mb * mb);
-          const float num = (num0 + c1) * (2.f * ep - num0 + c2);
-          const float den = (den0 + c1) * (es - den0 + c2);
+          // cov_norm = 1 (tf.image.ssim, population moments) or N / (N - 1) (skimage's sample covariance)
+          const float num = (num0 + c1) * fmaf(cov_norm, 2.f * ep - num0, c2);
+          const float den = (den0 + c1) * fmaf(cov_norm, es - den0, c2);
           ssim_sum += num / den;
         }
       }
@@ -177,7 +178,7 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
 
   float2 g2[11];
 #pragma unroll
-  for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_gauss[k], c_gauss[k]);
+  for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_win[0][k], c_win[0][k]);
 
   // fetch slots (fixed per thread): interleaved element i of the block's line -> plane (i % C), pixel (i / C)
   uint32_t s_off[kSlots];     // byte offset of the (a, b) pair inside one line buffer; the (s, p) planes use the same offset
@@ -306,12 +307,14 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
 }
 
 __global__ void psnr_ssim_finalize(const double* __restrict__ acc, int B, double n_pix, double n_map,
-                                   float max_val, float* psnr, float* ssim, float* mse_out, double* sums) {
+                                   float max_val, int skimage, float* psnr, float* ssim, float* mse_out, double* sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B) return;
   const double mse = acc[2 * i] / n_pix;
-  // tf.image.psnr: 20*log(max)/log(10) - 10/log(10)*log(mse), evaluated in float32
-  const float p = 20.f * log10f(max_val) - 10.f * log10f((float)mse);
+  // tf.image.psnr: 20*log(max)/log(10) - 10/log(10)*log(mse), evaluated in float32;
+  // skimage.metrics.peak_signal_noise_ratio: 10*log10(data_range^2 / mse) in float64
+  const float p = skimage ? (float)(10.0 * log10((double)max_val * (double)max_val / mse))
+                          : 20.f * log10f(max_val) - 10.f * log10f((float)mse);
   const float s = (float)(acc[2 * i + 1] / n_map);
   if (psnr) psnr[i] = p;
   if (ssim) ssim[i] = s;
@@ -324,17 +327,86 @@ __global__ void psnr_ssim_finalize(const double* __restrict__ acc, int B, double
   }
 }
 
-static bool g_gauss_ready = false;
+static bool g_win_ready[64] = {};
 
-static int upload_gauss() {
-  if (g_gauss_ready) return SRB_OK;
+static int upload_windows() {
+  int dev = 0;
+  SRB_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && g_win_ready[dev]) return SRB_OK;
   double g[11], sum = 0.0;
   for (int i = 0; i < 11; ++i) { const double c = i - 5.0; g[i] = exp(-0.5 * c * c / (1.5 * 1.5)); sum += g[i]; }
-  float gf[11];
-  for (int i = 0; i < 11; ++i) gf[i] = (float)(g[i] / sum);
-  SRB_CUDA(cudaMemcpyToSymbol(c_gauss, gf, sizeof(gf)));
-  g_gauss_ready = true;
+  float wf[2][11] = {};
+  for (int i = 0; i < 11; ++i) wf[0][i] = (float)(g[i] / sum);
+  for (int i = 0; i < 7; ++i) wf[1][i] = (float)(1.0 / 7.0);
+  SRB_CUDA(cudaMemcpyToSymbol(c_win, wf, sizeof(wf)));
+  if (dev >= 0 && dev < 64) g_win_ready[dev] = true;
   return SRB_OK;
+}
+
+// window: SRB_SSIM_TF (11-tap Gaussian, population moments) or SRB_SSIM_SKIMAGE (7 x 7 uniform, sample covariance)
+static int run_psnr_ssim(const float* a, const float* b, int batch, int height, int width, int channels, float max_val,
+                         int window, float* psnr, float* ssim, float* mse, double* sums, void* workspace,
+                         size_t workspace_bytes, cudaStream_t stream) {
+  SRB_REQUIRE(a && b && workspace, "psnr_ssim: null pointer");
+  SRB_REQUIRE(window == SRB_SSIM_TF || window == SRB_SSIM_SKIMAGE, "psnr_ssim: unknown window kind %d", window);
+  SRB_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4, "psnr_ssim: channels must be 1..4 (got %d)", channels);
+  const int K = window == SRB_SSIM_TF ? 11 : 7;
+  SRB_REQUIRE(height >= K && width >= K, "psnr_ssim: image dimensions must be at least %dx%d (got %dx%d)", K, K, height, width);
+  SRB_REQUIRE(workspace_bytes >= srb_psnr_ssim_workspace(batch), "psnr_ssim: workspace too small");
+  if (batch == 0) return SRB_OK;
+  int rc = upload_windows();
+  if (rc) return rc;
+  double* acc = (double*)workspace;
+  SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
+  const int OH = height - (K - 1), OW = width - (K - 1), OE = OW * channels;
+  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
+  const float cov_norm = window == SRB_SSIM_TF ? 1.f : (float)(49.0 / 48.0);
+  static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
+  if (window == SRB_SSIM_TF && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread
+    const int px = channels == 1 ? 256 : channels == 4 ? 64 : 128;     // map pixels per block row (2 * Q)
+    const int gxp = (OW + px - 1) / px;
+    int rows = 128;
+    const long target = 4L * sm_count();
+    while (rows > 16 && (long)gxp * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
+    dim3 grid(gxp, (OH + rows - 1) / rows, batch);
+    SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "psnr_ssim: grid too large");
+    switch (channels) {
+      case 1: psnr_ssim_pair_kernel<1, 128><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 2: psnr_ssim_pair_kernel<2, 64><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 3: psnr_ssim_pair_kernel<3, 64><<<grid, 192, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      default: psnr_ssim_pair_kernel<4, 32><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+    }
+    rc = launch_check("psnr_ssim_pair_kernel");
+  } else {
+    const int gx = (OE + kCols - 1) / kCols;
+    int rows = 64;
+    const long target = 2L * sm_count();
+    while (rows > 16 && (long)gx * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
+    dim3 grid(gx, (OH + rows - 1) / rows, batch);
+    SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "psnr_ssim: grid too large");
+#define SRB_SSIM_LAUNCH(CH, KK) psnr_ssim_kernel<CH, KK><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, cov_norm, acc)
+    if (K == 11) {
+      switch (channels) {
+        case 1: SRB_SSIM_LAUNCH(1, 11); break;
+        case 2: SRB_SSIM_LAUNCH(2, 11); break;
+        case 3: SRB_SSIM_LAUNCH(3, 11); break;
+        default: SRB_SSIM_LAUNCH(4, 11); break;
+      }
+    } else {
+      switch (channels) {
+        case 1: SRB_SSIM_LAUNCH(1, 7); break;
+        case 2: SRB_SSIM_LAUNCH(2, 7); break;
+        case 3: SRB_SSIM_LAUNCH(3, 7); break;
+        default: SRB_SSIM_LAUNCH(4, 7); break;
+      }
+    }
+#undef SRB_SSIM_LAUNCH
+    rc = launch_check("psnr_ssim_kernel");
+  }
+  if (rc) return rc;
+  psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(
+      acc, batch, (double)height * width * channels, (double)OH * OE, max_val, window == SRB_SSIM_SKIMAGE, psnr, ssim, mse, sums);
+  return launch_check("psnr_ssim_finalize");
 }
 
 }  // namespace srb
@@ -345,54 +417,14 @@ extern "C" size_t srb_psnr_ssim_workspace(int batch) { return (size_t)(batch > 0
 
 extern "C" int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int width, int channels,
                                  float max_val, float* psnr, float* ssim, float* mse, double* sums,
-                                 void* workspace, size_t workspace_bytes, srb_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  SRB_REQUIRE(a && b && workspace, "psnr_ssim: null pointer");
-  SRB_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4, "psnr_ssim: channels must be 1..4 (got %d)", channels);
-  SRB_REQUIRE(height >= 11 && width >= 11, "psnr_ssim: image dimensions must be at least 11x11 (got %dx%d)", height, width);
-  SRB_REQUIRE(workspace_bytes >= srb_psnr_ssim_workspace(batch), "psnr_ssim: workspace too small");
-  if (batch == 0) return SRB_OK;
-  int rc = upload_gauss();
-  if (rc) return rc;
-  double* acc = (double*)workspace;
-  SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
-  const int OH = height - 10, OE = (width - 10) * channels;
-  const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
-  static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
-  if (width - 10 >= 96 && !force_narrow) {   // wide images: two map pixels per thread
-    const int OW = width - 10;
-    const int px = channels == 1 ? 256 : channels == 4 ? 64 : 128;     // map pixels per block row (2 * Q)
-    const int gxp = (OW + px - 1) / px;
-    int rows = 128;
-    const long target = 4L * sm_count();
-    while (rows > 16 && (long)gxp * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
-    dim3 grid(gxp, (OH + rows - 1) / rows, batch);
-    switch (channels) {
-      case 1: psnr_ssim_pair_kernel<1, 128><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      case 2: psnr_ssim_pair_kernel<2, 64><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      case 3: psnr_ssim_pair_kernel<3, 64><<<grid, 192, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      default: psnr_ssim_pair_kernel<4, 32><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-    }
-    rc = launch_check("psnr_ssim_pair_kernel");
-    if (rc) return rc;
-    psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(
-        acc, batch, (double)height * width * channels, (double)OH * OE, max_val, psnr, ssim, mse, sums);
-    return launch_check("psnr_ssim_finalize");
-  }
-  const int gx = (OE + kCols - 1) / kCols;
-  int rows = 64;
-  const long target = 2L * sm_count();
-  while (rows > 16 && (long)gx * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
-  dim3 grid(gx, (OH + rows - 1) / rows, batch);
-  switch (channels) {
-    case 1: psnr_ssim_kernel<1><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-    case 2: psnr_ssim_kernel<2><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-    case 3: psnr_ssim_kernel<3><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-    default: psnr_ssim_kernel<4><<<grid, kCols, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-  }
-  rc = launch_check("psnr_ssim_kernel");
-  if (rc) return rc;
-  psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(
-      acc, batch, (double)height * width * channels, (double)OH * OE, max_val, psnr, ssim, mse, sums);
-  return launch_check("psnr_ssim_finalize");
+                                 void* workspace, size_t workspace_bytes, srb_stream_t stream) {
+  return run_psnr_ssim(a, b, batch, height, width, channels, max_val, SRB_SSIM_TF, psnr, ssim, mse, sums, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int srb_psnr_ssim_window_f32(const float* a, const float* b, int batch, int height, int width, int channels,
+                                        float max_val, int window, float* psnr, float* ssim, float* mse, double* sums,
+                                        void* workspace, size_t workspace_bytes, srb_stream_t stream) {
+  return run_psnr_ssim(a, b, batch, height, width, channels, max_val, window, psnr, ssim, mse, sums, workspace,
+                       workspace_bytes, (cudaStream_t)stream);
 }

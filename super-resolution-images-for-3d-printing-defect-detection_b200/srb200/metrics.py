@@ -4,6 +4,8 @@
 per-image float32 vectors ``[B]`` (a scalar for a single ``[H, W, C]`` image).  Inputs may be numpy
 arrays (copied to the device, result returned as numpy) or CUDA torch tensors (result stays on
 the device).  Both functions run the same fused one-pass kernel; ``psnr_ssim`` returns both at once.
+``peak_signal_noise_ratio`` / ``structural_similarity`` are the skimage.metrics definitions the classical
+benchmark notebook uses (7 x 7 uniform window), on the same kernel.
 """
 from __future__ import annotations
 
@@ -52,3 +54,60 @@ def psnr(y_true, y_pred):
 
 def ssim(y_true, y_pred):
     return psnr_ssim(y_true, y_pred, 1.0)[1]
+
+
+# ---------------------------------------------------------------------------------------------
+# skimage.metrics definitions, as the classical benchmark calls them
+# (super_resolucion_clasica.ipynb cell 7: psnr(hr_f, sr_f, data_range=1.0), ssim(hr_f, sr_f, channel_axis=2,
+#  data_range=1.0), grayscale: ssim(hr_g, sr_g, data_range=dr); EDA.ipynb: data_range=255 on uint8)
+# ---------------------------------------------------------------------------------------------
+def _skimage_pair(im1, im2, data_range, channel_axis):
+    torch = capi.require_cuda()
+    tensors = []
+    for im in (im1, im2):
+        t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
+        t = t.cuda() if not t.is_cuda else t
+        if t.dim() == 2 and channel_axis is None:
+            t = t[:, :, None]
+        elif t.dim() == 3 and channel_axis is not None:
+            t = t.movedim(channel_axis, -1)
+        else:
+            raise ValueError("expected a 2-D image (channel_axis=None) or a 3-D image with channel_axis given, "
+                             f"got shape {tuple(t.shape)} with channel_axis={channel_axis}")
+        tensors.append(t)
+    a, b = tensors
+    if a.shape != b.shape:
+        raise ValueError("Input images must have the same dimensions.")
+    if data_range is None:
+        if a.dtype.is_floating_point:
+            raise ValueError("data_range must be given for floating-point images (skimage >= 0.19 requires it for SSIM)")
+        data_range = 255.0
+    # both metrics are invariant under a common scale when data_range scales with it: evaluate on [0, 1]
+    scale = 1.0 / float(data_range)
+    a = (a.to(torch.float32) * scale).contiguous()[None]
+    b = (b.to(torch.float32) * scale).contiguous()[None]
+    return a, b
+
+
+def peak_signal_noise_ratio(image_true, image_test, *, data_range=None):
+    """skimage.metrics.peak_signal_noise_ratio: 10 log10(data_range^2 / mse) over the whole array -> float."""
+    a, b = _skimage_pair(image_true, image_test, data_range, None if np.ndim(image_true) == 2 else -1)
+    if a.shape[1] < 7 or a.shape[2] < 7:      # the fused pass also evaluates the 7 x 7 windows
+        return float(10.0 * np.log10(1.0 / float(((a - b) ** 2).double().mean().item())))
+    p, _ = ops.psnr_ssim(a, b, 1.0, window=capi.SSIM_SKIMAGE)
+    return float(p[0].item())
+
+
+def structural_similarity(im1, im2, *, win_size=None, data_range=None, channel_axis=None, gaussian_weights=False,
+                          full=False):
+    """skimage.metrics.structural_similarity with its defaults (7 x 7 uniform window, sample covariance, K1 = 0.01,
+    K2 = 0.03, mean over the border-cropped map and then over channels) -> float."""
+    if gaussian_weights or full or (win_size not in (None, 7)):
+        raise NotImplementedError("only skimage's default window (win_size=7, uniform, full=False) is built")
+    a, b = _skimage_pair(im1, im2, data_range, channel_axis)
+    if a.shape[1] < 7 or a.shape[2] < 7:
+        raise ValueError("win_size exceeds image extent. Either ensure that your images are at least 7x7; or pass "
+                         "win_size explicitly in the function call, with an odd value less than or equal to the "
+                         "smaller side of your images.")
+    _, s = ops.psnr_ssim(a, b, 1.0, window=capi.SSIM_SKIMAGE)
+    return float(s[0].item())

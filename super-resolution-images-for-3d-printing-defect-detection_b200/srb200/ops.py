@@ -40,8 +40,11 @@ def _check_nhwc(t, name):
 # ---------------------------------------------------------------------------------------------
 # PSNR / SSIM  (metrics.py:3-7)
 # ---------------------------------------------------------------------------------------------
-def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False):
+def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False, window=capi.SSIM_TF):
     """a, b: [B,H,W,C] float32 CUDA tensors -> (psnr [B], ssim [B][, mse [B]]) float32.
+
+    ``window``: ``SSIM_TF`` (tf.image definitions, metrics.py:3-7) or ``SSIM_SKIMAGE`` (skimage.metrics definitions
+    with their defaults, as used by super_resolucion_clasica.ipynb cell 7).
 
     ``sums`` (optional float64[4] CUDA tensor) is accumulated with (sum psnr, sum ssim, count,
     sum mse) for sharded evaluation."""
@@ -58,9 +61,9 @@ def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False):
     ws_bytes = capi.lib().srb_psnr_ssim_workspace(B)
     ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=a.device)
     with torch.cuda.device(a.device):
-        capi.check(capi.lib().srb_psnr_ssim_f32(capi.ptr(a), capi.ptr(b), B, H, W, Cc, float(max_val),
-                                                capi.ptr(psnr), capi.ptr(ssim), capi.ptr(mse), capi.ptr(sums),
-                                                capi.ptr(ws), ws_bytes, capi.stream_ptr()))
+        capi.check(capi.lib().srb_psnr_ssim_window_f32(capi.ptr(a), capi.ptr(b), B, H, W, Cc, float(max_val), int(window),
+                                                       capi.ptr(psnr), capi.ptr(ssim), capi.ptr(mse), capi.ptr(sums),
+                                                       capi.ptr(ws), ws_bytes, capi.stream_ptr()))
     _LAUNCHES[0] += 2
     return (psnr, ssim, mse) if want_mse else (psnr, ssim)
 

@@ -33,6 +33,12 @@ def test_srcnn_super_resolve_image_config1_flow():
     assert sr.shape == (96, 80, 3) and sr.dtype == np.float32
     assert np.abs(sr - want).max() <= 1e-3
     assert set(info) == {"time_sec", "gpu_mean_current_mb", "gpu_peak_mb"}
+    # the `interpolation` argument (SRCNN_model.py:111, :191): Lanczos-4 pre-upsampling through the same flow
+    sr4, _ = m.super_resolve_image(lr, 96, 80, patch_size=33, stride=14, interpolation=4)     # cv2.INTER_LANCZOS4
+    want4 = _oracle_tiled(lambda p: oc.srcnn_forward(w, p), ob.resize_lanczos4_f32(lr, (80, 96)), 33, 14, 1)
+    assert np.abs(sr4 - want4).max() <= 1e-3
+    with pytest.raises(NotImplementedError):
+        m.super_resolve_image(lr, 96, 80, interpolation=0)                                    # cv2.INTER_NEAREST
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-3), ("fp16", 2e-2)])

@@ -86,3 +86,38 @@ def test_full_size_properties():
     assert (p1 > p2).all() and (s1 > s2).all()
     mse = ((a - n1) ** 2).mean(dim=(1, 2, 3))
     assert torch.allclose(p1, -10 * torch.log10(mse), atol=PSNR_TOL)
+
+
+@pytest.mark.parametrize("shape", [(7, 7, 3), (24, 24, 3), (61, 150, 3), (130, 47), (239, 478, 3)])
+def test_skimage_definitions_against_oracle(shape):
+    """peak_signal_noise_ratio / structural_similarity as super_resolucion_clasica.ipynb cell 7 and EDA.ipynb call them
+    (float [0, 1] with data_range=1.0 and channel_axis=2; grayscale; uint8 with data_range=255)."""
+    from srb200 import metrics, synth
+    gray = len(shape) == 2
+    hr = synth.hr_batch(1, shape[0], shape[1], channels=1 if gray else 3, first_index=shape[1])[0]
+    rng = np.random.default_rng(shape[0])
+    sr = np.clip(hr + 0.04 * rng.standard_normal(hr.shape).astype(np.float32), 0, 1)
+    if gray:
+        hr, sr = hr[:, :, 0], sr[:, :, 0]
+    ax = None if gray else 2
+    s = metrics.structural_similarity(hr, sr, channel_axis=ax, data_range=1.0)
+    p = metrics.peak_signal_noise_ratio(hr, sr, data_range=1.0)
+    assert isinstance(s, float) and isinstance(p, float)
+    assert abs(s - om.skimage_ssim(hr, sr, 1.0, channel_axis=ax)) <= SSIM_TOL
+    assert abs(p - om.skimage_psnr(hr, sr, 1.0)) <= PSNR_TOL
+    hu, su = np.rint(hr * 255).astype(np.uint8), np.rint(sr * 255).astype(np.uint8)
+    assert abs(metrics.structural_similarity(hu, su, channel_axis=ax, data_range=255) - om.skimage_ssim(hu, su, 255, channel_axis=ax)) <= SSIM_TOL
+    assert abs(metrics.peak_signal_noise_ratio(hu, su, data_range=255) - om.skimage_psnr(hu, su, 255)) <= PSNR_TOL
+
+
+def test_skimage_definitions_errors_and_identity():
+    from srb200 import metrics
+    x = np.random.default_rng(0).random((20, 20, 3)).astype(np.float32)
+    assert abs(metrics.structural_similarity(x, x, channel_axis=2, data_range=1.0) - 1.0) <= 1e-6
+    assert np.isinf(metrics.peak_signal_noise_ratio(x, x, data_range=1.0))
+    with pytest.raises(ValueError):
+        metrics.structural_similarity(x[:6], x[:6], channel_axis=2, data_range=1.0)
+    with pytest.raises(ValueError):
+        metrics.structural_similarity(x, x, channel_axis=2)                   # float images need data_range
+    with pytest.raises(NotImplementedError):
+        metrics.structural_similarity(x, x, channel_axis=2, data_range=1.0, gaussian_weights=True)

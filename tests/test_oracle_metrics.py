@@ -79,3 +79,34 @@ def test_ssim_against_independent_scipy_evaluation():
     assert np.abs(got - np.array(want)).max() < 1e-6
     mse = ((a.astype(np.float32).astype(np.float64) - b.astype(np.float32).astype(np.float64)) ** 2).mean(axis=(1, 2, 3))
     assert np.abs(om.psnr(a.astype(np.float32), b.astype(np.float32), dtype=np.float64) - (-10 * np.log10(mse))).max() < 1e-9
+
+
+def test_skimage_definitions_known_answers_and_windowed_evaluation():
+    """skimage.metrics restatement (super_resolucion_clasica.ipynb cell 7): known answers plus a direct evaluation of
+    every valid 7 x 7 window with numpy's own sample (co)variance."""
+    a = np.full((16, 20), 0.3)
+    b = np.full((16, 20), 0.6)
+    assert abs(om.skimage_ssim(a, b, 1.0) - 0.80004443) <= 1e-7
+    assert abs(om.skimage_psnr(a, b, 1.0) - 10.4575749) <= 1e-6
+    rng = np.random.default_rng(5)
+    x = rng.random((19, 23, 3))
+    y = np.clip(x + 0.1 * rng.standard_normal(x.shape), 0, 1)
+    assert om.skimage_ssim(x, x, 1.0, channel_axis=2) == 1.0 and np.isinf(om.skimage_psnr(x, x, 1.0))
+    c1, c2 = 0.01 ** 2, 0.03 ** 2
+    per_channel = []
+    for c in range(3):
+        vals = []
+        for i in range(19 - 6):
+            for j in range(23 - 6):
+                wx, wy = x[i:i + 7, j:j + 7, c].ravel(), y[i:i + 7, j:j + 7, c].ravel()
+                cov = np.cov(wx, wy, ddof=1)
+                mx, my = wx.mean(), wy.mean()
+                vals.append((2 * mx * my + c1) * (2 * cov[0, 1] + c2) / ((mx * mx + my * my + c1) * (cov[0, 0] + cov[1, 1] + c2)))
+        per_channel.append(np.mean(vals))
+    assert abs(om.skimage_ssim(x, y, 1.0, channel_axis=2) - np.mean(per_channel)) <= 1e-12
+    # uint8 with data_range = 255 (EDA.ipynb) is the same function of the scaled images
+    xu, yu = np.rint(x * 255).astype(np.uint8), np.rint(y * 255).astype(np.uint8)
+    assert abs(om.skimage_ssim(xu, yu, 255, channel_axis=2) - om.skimage_ssim(xu / 255.0, yu / 255.0, 1.0, channel_axis=2)) <= 1e-12
+    assert abs(om.skimage_psnr(xu, yu, 255) - om.skimage_psnr(xu / 255.0, yu / 255.0, 1.0)) <= 1e-9
+    with pytest.raises(ValueError):
+        om.skimage_ssim(np.zeros((6, 9)), np.zeros((6, 9)), 1.0)
