@@ -207,31 +207,64 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
   {
     const uint32_t total = (uint32_t)(nr * nc4);
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nc4 + 1u;                // exact quotient for idx < 2^32 / nc4
-    for (uint32_t idx = t; idx < total; idx += kQT) {
-      const int r = (int)__umulhi(idx, magic);
-      const int i = (int)idx - r * nc4;
-      const int gr = min(max(u0 + r, 0), src_h - 1);
-      const T* row = simg + (size_t)gr * SE;
-      float* sdst = S + r * pitch + 4 * i;
-      const int q = c_lo + 4 * i;
-      if (vec_src && q >= 0 && q + 4 <= SE) {
-        if (sizeof(T) == 4) {
+    auto slow_chunk = [&](const T* row, int q, float* sdst) {               // border / unaligned chunk: clamped scalar gathers
+      float f[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int qq = q + k;
+        int px = (qq + 8 * C) / C - 8;                                      // floor division (qq >= -2C - 3)
+        const int ch = qq - px * C;
+        px = min(max(px, 0), src_w - 1);
+        f[k] = px_load(row + px * C + ch);
+      }
+      *reinterpret_cast<float4*>(sdst) = make_float4(f[0], f[1], f[2], f[3]);
+    };
+    if (sizeof(T) == 4) {
+      for (uint32_t idx = t; idx < total; idx += kQT) {
+        const int r = (int)__umulhi(idx, magic);
+        const int i = (int)idx - r * nc4;
+        const int gr = min(max(u0 + r, 0), src_h - 1);
+        const T* row = simg + (size_t)gr * SE;
+        float* sdst = S + r * pitch + 4 * i;
+        const int q = c_lo + 4 * i;
+        if (vec_src && q >= 0 && q + 4 <= SE) {
           const uint32_t d = (uint32_t)__cvta_generic_to_shared(sdst);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(row + q) : "memory");
         } else {
-          *reinterpret_cast<float4*>(sdst) = Vec4<T>::load(row + q);
+          slow_chunk(row, q, sdst);
         }
-      } else {
-        float f[4];
+      }
+    } else {
+      // uint8: four chunks per thread and pass, all 4-byte loads issued before the first conversion (the loads of a
+      // pass are independent; converting each right after its load serialised the whole stage on memory latency)
+      constexpr int kU = 4;
+      for (uint32_t base = t; base < total; base += kQT * kU) {
+        uint32_t raw[kU];
+        float* sd[kU];
+        bool fast[kU];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int qq = q + k;
-          int px = (qq + 8 * C) / C - 8;                                    // floor division (qq >= -2C - 3)
-          const int ch = qq - px * C;
-          px = min(max(px, 0), src_w - 1);
-          f[k] = px_load(row + px * C + ch);
+        for (int u = 0; u < kU; ++u) {
+          const uint32_t idx = base + (uint32_t)u * kQT;
+          fast[u] = false;
+          sd[u] = nullptr;
+          raw[u] = 0u;
+          if (idx < total) {
+            const int r = (int)__umulhi(idx, magic);
+            const int i = (int)idx - r * nc4;
+            const int gr = min(max(u0 + r, 0), src_h - 1);
+            const T* row = simg + (size_t)gr * SE;
+            const int q = c_lo + 4 * i;
+            sd[u] = S + r * pitch + 4 * i;
+            fast[u] = vec_src && q >= 0 && q + 4 <= SE;
+            if (fast[u]) raw[u] = __ldg(reinterpret_cast<const uint32_t*>(row + q));
+            else slow_chunk(row, q, sd[u]);
+          }
         }
-        *reinterpret_cast<float4*>(sdst) = make_float4(f[0], f[1], f[2], f[3]);
+#pragma unroll
+        for (int u = 0; u < kU; ++u)
+          if (fast[u])
+            *reinterpret_cast<float4*>(sd[u]) = make_float4((float)(raw[u] & 0xFFu), (float)((raw[u] >> 8) & 0xFFu),
+                                                            (float)((raw[u] >> 16) & 0xFFu), (float)(raw[u] >> 24));
       }
     }
     for (int i = t; i < rows; i += kQT) {
