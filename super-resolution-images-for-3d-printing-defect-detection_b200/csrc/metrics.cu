@@ -143,68 +143,69 @@ psnr_ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, int H
   }
 }
 
-// Wide-image variant: two horizontally adjacent map pixels per thread.  Lines are de-interleaved into channel planes
-// when they are fetched ((a, b) pairs per pixel), and every thread turns the elements it fetched itself into a second
-// plane of (a^2 + b^2, a*b) pairs one row ahead of the arithmetic, so the products are formed once per input element
-// instead of once per tap.  The four maps tf.image.ssim filters (mu_a, mu_b, E[a^2 + b^2], E[ab]) are then exactly two
-// packed fp32x2 FMAs per tap and output in both passes, and a thread's two outputs share 10 of their 11 tap loads
-// (six 16-byte shared loads per plane and row).  A block is Q pixel pairs x C channels (thread = (channel, pair), warps
-// are channel-uniform so the 16-byte loads of a warp are contiguous).
-template <int C, int Q>
-__global__ void __launch_bounds__(Q * C, 2)
+// Wide-image variant: two horizontally adjacent map pixels per thread, one warp per (channel, 64-pixel column block).
+// A warp de-interleaves its own channel plane when it fetches a line ((a, b) pairs per pixel, cp.async a few rows ahead),
+// and every lane turns the pixels it fetched itself into a second plane of (a^2 + b^2, a*b) pairs one row ahead of the
+// arithmetic, so the products are formed once per input element instead of once per tap.  The four maps tf.image.ssim
+// filters (mu_a, mu_b, E[a^2 + b^2], E[ab]) are then exactly two packed fp32x2 FMAs per tap and output in both passes,
+// and a lane's two outputs share 10 of their 11 tap loads (six contiguous 16-byte shared loads per plane and row).
+// Warps never exchange data, so the row loop synchronises with __syncwarp only; the strided 4-byte fetches of the three
+// channel warps of a block meet in L1.
+constexpr int kPairPx = 64;                        // map pixels per warp row (2 per lane)
+constexpr int kPairLW = kPairPx + 10;              // line width in pixels (even: 16-byte aligned planes)
+constexpr int kPairAhead = 8;                      // rows in flight = line buffers (refilled after the row is retired)
+
+template <int C>
+__global__ void __launch_bounds__((C == 3 ? 3 : 4) * 32, 3)
 psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,
                       float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
-  constexpr int T = Q * C;
-  constexpr int PX = 2 * Q;                        // map pixels per block row
-  constexpr int LW = PX + 10;                      // line width in pixels (even: 16-byte aligned planes)
-  constexpr int kAhead = 8;                        // rows in flight = line buffers (a line is refilled after the barrier that retires it)
-  constexpr int kSlots = (LW * C + T - 1) / T;     // fetch slots per thread: 2 cover the block's own pixels, the 3rd the halo
-  static_assert(kSlots == 3 && (Q % 32) == 0, "geometry");
-  __shared__ __align__(16) float2 sab[kAhead][C][LW];   // (a, b)
-  __shared__ __align__(16) float2 ssp[2][C][LW];        // (a^2 + b^2, a*b)
-  __shared__ float red[2][T / 32];
+  constexpr int NW = C == 3 ? 3 : 4;               // warps per block
+  constexpr int CB = NW / C;                       // column blocks per block (4, 2, 1, 1 for C = 1..4)
+  constexpr int LW = kPairLW, kAhead = kPairAhead;
+  __shared__ __align__(16) float2 sab[NW][kAhead][LW];   // (a, b)
+  __shared__ __align__(16) float2 ssp[NW][2][LW];        // (a^2 + b^2, a*b)
+  __shared__ float red[2][NW];
 
   const int WE = W * C;
   const int OW = W - 10, OH = H - 10;
-  const int t = threadIdx.x;
-  const int X0 = blockIdx.x * PX;
+  const int t = threadIdx.x, wid = t >> 5, lane = t & 31;
+  const int c = wid % C;
+  const int X0 = (blockIdx.x * CB + wid / C) * kPairPx;
   const int y0 = blockIdx.y * rows_per_strip;
   const int rows_out = min(rows_per_strip, OH - y0);
-  const int nin = rows_out + 10;
-  const bool last_x = (X0 + PX >= OW);
+  const int nin = X0 < OW ? rows_out + 10 : 0;     // (a warp past the right edge only joins the final reduction)
+  const bool last_x = (X0 + kPairPx >= OW);
   const bool last_y = (y0 + rows_per_strip >= OH);
   const size_t img_off = (size_t)blockIdx.z * H * WE;
-  const int c = t / Q, q = t % Q;
 
   float2 g2[11];
 #pragma unroll
   for (int k = 0; k < 11; ++k) g2[k] = make_float2(c_win[0][k], c_win[0][k]);
 
-  // fetch slots (fixed per thread): interleaved element i of the block's line -> plane (i % C), pixel (i / C)
-  uint32_t s_off[kSlots];     // byte offset of the (a, b) pair inside one line buffer; the (s, p) planes use the same offset
-  bool s_in[kSlots], s_ok[kSlots];
-#pragma unroll
-  for (int s = 0; s < kSlots; ++s) {
-    const int i = t + s * T;
-    s_in[s] = i < LW * C;
-    s_ok[s] = s_in[s] && (X0 * C + i) < WE;
-    s_off[s] = (uint32_t)(((i % C) * LW + (i / C)) * sizeof(float2));
-  }
-  for (int i = t; i < kAhead * C * LW; i += T) (&sab[0][0][0])[i] = make_float2(0.f, 0.f);
-  __syncthreads();
-  const uint32_t sab0 = (uint32_t)__cvta_generic_to_shared(&sab[0][0][0]);
-  constexpr uint32_t kLineBytes = C * LW * sizeof(float2);
-  const float* fa = a + img_off + (size_t)y0 * WE + (size_t)X0 * C + t;
-  const float* fb = b + img_off + (size_t)y0 * WE + (size_t)X0 * C + t;
+  // fetch slots: pixels lane, lane + 32 (the warp's own 64) and lane + 64 (the 10-pixel halo) of the warp's plane
+  const bool in2 = lane < LW - 64;
+  const bool ok0 = X0 + lane < W, ok1 = X0 + lane + 32 < W, ok2 = in2 && X0 + lane + 64 < W;
+  for (int i = lane; i < kAhead * LW; i += 32) (&sab[wid][0][0])[i] = make_float2(0.f, 0.f);
+  __syncwarp();
+  const uint32_t sab0 = (uint32_t)__cvta_generic_to_shared(&sab[wid][0][lane]);
+  constexpr uint32_t kLineBytes = LW * sizeof(float2);
+  const float* fa = a + img_off + (size_t)y0 * WE + (size_t)(X0 + lane) * C + c;
+  const float* fb = b + img_off + (size_t)y0 * WE + (size_t)(X0 + lane) * C + c;
   auto fetch = [&](int row) {
     if (row < nin) {
-      const uint32_t d = sab0 + (uint32_t)(row % kAhead) * kLineBytes;
-#pragma unroll
-      for (int s = 0; s < kSlots; ++s)
-        if (s_ok[s]) {
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + s_off[s]), "l"(fa + s * T) : "memory");
-          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + s_off[s] + 4u), "l"(fb + s * T) : "memory");
-        }
+      const uint32_t d = sab0 + (uint32_t)(row & (kAhead - 1)) * kLineBytes;
+      if (ok0) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(fa) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 4u), "l"(fb) : "memory");
+      }
+      if (ok1) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 256u), "l"(fa + 32 * C) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 260u), "l"(fb + 32 * C) : "memory");
+      }
+      if (ok2) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 512u), "l"(fa + 64 * C) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d + 516u), "l"(fb + 64 * C) : "memory");
+      }
       fa += WE;
       fb += WE;
     }
@@ -212,18 +213,18 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   };
 
   float sse = 0.f;
-  // products of this thread's own elements of a landed row (its own cp.async groups are complete: no barrier needed)
+  // products of this lane's own pixels of a landed row (its own cp.async groups are complete: no barrier needed)
   auto products = [&](int row) {
     if (row < nin) {
       const bool row_owned = (row < rows_out) || last_y;
-      const char* lab = reinterpret_cast<const char*>(&sab[row % kAhead][0][0]);
-      char* lsp = reinterpret_cast<char*>(&ssp[row & 1][0][0]);
+      const float2* lab = &sab[wid][row & (kAhead - 1)][lane];
+      float2* lsp = &ssp[wid][row & 1][lane];
 #pragma unroll
-      for (int s = 0; s < kSlots; ++s)
-        if (s_in[s]) {
-          const float2 v = *reinterpret_cast<const float2*>(lab + s_off[s]);
+      for (int s = 0; s < 3; ++s)
+        if (s < 2 || in2) {
+          const float2 v = lab[32 * s];
           const float2 sq = __fmul2_rn(v, v);
-          *reinterpret_cast<float2*>(lsp + s_off[s]) = make_float2(sq.x + sq.y, v.x * v.y);
+          lsp[32 * s] = make_float2(sq.x + sq.y, v.x * v.y);
           if (row_owned && (s < 2 || last_x)) { const float d = v.x - v.y; sse = fmaf(d, d, sse); }
         }
     }
@@ -233,24 +234,24 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
 #pragma unroll
   for (int k = 0; k < 11; ++k) rab0[k] = rab1[k] = rsp0[k] = rsp1[k] = make_float2(0.f, 0.f);
   float2 ssim2 = make_float2(0.f, 0.f);
-  const float2 valid2 = make_float2((X0 + 2 * q) < OW ? 1.f : 0.f, (X0 + 2 * q + 1) < OW ? 1.f : 0.f);
+  const float2 valid2 = make_float2((X0 + 2 * lane) < OW ? 1.f : 0.f, (X0 + 2 * lane + 1) < OW ? 1.f : 0.f);
   const float2 c1_2 = make_float2(c1, c1), c2_2 = make_float2(c2, c2), two2 = make_float2(2.f, 2.f);
 
 #pragma unroll
   for (int r = 0; r < kAhead; ++r) fetch(r);
   asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 1) : "memory");
   products(0);
-  __syncthreads();
+  __syncwarp();
 
   for (int r = 0; r < nin; r += 11) {
 #pragma unroll
     for (int j = 0; j < 11; ++j) {
-      const int row = r + j;              // block-uniform
+      const int row = r + j;              // warp-uniform
       if (row < nin) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 2) : "memory");   // this thread's part of row + 1 has landed
+        asm volatile("cp.async.wait_group %0;" ::"n"(kAhead - 2) : "memory");   // this lane's part of row + 1 has landed
         products(row + 1);
-        const float4* lab = reinterpret_cast<const float4*>(&sab[row % kAhead][c][2 * q]);
-        const float4* lsp = reinterpret_cast<const float4*>(&ssp[row & 1][c][2 * q]);
+        const float4* lab = reinterpret_cast<const float4*>(&sab[wid][row & (kAhead - 1)][2 * lane]);
+        const float4* lsp = reinterpret_cast<const float4*>(&ssp[wid][row & 1][2 * lane]);
         float2 hab0 = make_float2(0.f, 0.f), hab1 = hab0, hsp0 = hab0, hsp1 = hab0;
 #pragma unroll
         for (int m = 0; m < 6; ++m) {
@@ -287,20 +288,20 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
           const float2 num = __fmul2_rn(ln, cn), den = __fmul2_rn(ld, cd);
           ssim2 = __ffma2_rn(make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y)), valid2, ssim2);
         }
-        __syncthreads();                  // row is retired by every thread; row + 1 (both planes) is visible
+        __syncwarp();                     // row is retired by every lane; row + 1 (both planes) is visible
         fetch(row + kAhead);
       }
     }
   }
 
   sse = warp_sum(sse);
-  float ssim_sum = warp_sum(ssim2.x + ssim2.y);
-  if ((t & 31) == 0) { red[0][t >> 5] = sse; red[1][t >> 5] = ssim_sum; }
+  const float ssim_sum = warp_sum(ssim2.x + ssim2.y);
+  if (lane == 0) { red[0][wid] = sse; red[1][wid] = ssim_sum; }
   __syncthreads();
   if (t == 0) {
     double s0 = 0.0, s1 = 0.0;
 #pragma unroll
-    for (int w = 0; w < T / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+    for (int w = 0; w < NW; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
     atomicAdd(&acc[2 * blockIdx.z + 0], s0);
     atomicAdd(&acc[2 * blockIdx.z + 1], s1);
   }
@@ -362,19 +363,19 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
   const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
   const float cov_norm = window == SRB_SSIM_TF ? 1.f : (float)(49.0 / 48.0);
   static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
-  if (window == SRB_SSIM_TF && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread
-    const int px = channels == 1 ? 256 : channels == 4 ? 64 : 128;     // map pixels per block row (2 * Q)
+  if (window == SRB_SSIM_TF && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread, one warp per plane
+    const int px = kPairPx * (channels == 1 ? 4 : channels == 2 ? 2 : 1);   // map pixels per block row
     const int gxp = (OW + px - 1) / px;
     int rows = 128;
-    const long target = 4L * sm_count();
+    const long target = 6L * sm_count();
     while (rows > 16 && (long)gxp * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
     dim3 grid(gxp, (OH + rows - 1) / rows, batch);
     SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "psnr_ssim: grid too large");
     switch (channels) {
-      case 1: psnr_ssim_pair_kernel<1, 128><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      case 2: psnr_ssim_pair_kernel<2, 64><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      case 3: psnr_ssim_pair_kernel<3, 64><<<grid, 192, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
-      default: psnr_ssim_pair_kernel<4, 32><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 1: psnr_ssim_pair_kernel<1><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 2: psnr_ssim_pair_kernel<2><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      case 3: psnr_ssim_pair_kernel<3><<<grid, 96, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
+      default: psnr_ssim_pair_kernel<4><<<grid, 128, 0, stream>>>(a, b, height, width, rows, c1, c2, acc); break;
     }
     rc = launch_check("psnr_ssim_pair_kernel");
   } else {
