@@ -625,6 +625,19 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
     };
 
+    // depth_to_space-to-image epilogue (epi_mode 4): float offset of every 4-column group inside its pixel's r x r block
+    // (sub-row i = channel / (r * c_post), then the position inside the sub-row), and whether the point function is bias-only
+    uint32_t epi4_off[8] = {};
+    const bool epi4_plain = p.act == SRB_ACT_NONE && p.alpha == 1.f && !p.clip01;
+    if (epi_mode == 4) {
+      const int rg = r * p.c_post;                      // floats per output sub-row (a multiple of 4)
+      const uint32_t sub_row = (uint32_t)OW * (uint32_t)p.c_post;   // floats between output rows
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const int cb = c_first + 4 * c4, i = cb / rg;
+        epi4_off[c4] = (uint32_t)i * sub_row + (uint32_t)(cb - i * rg);
+      }
+    }
     int it = 0;
     const bool staged = epi_mode == 1 && active;
     const bool prefetch = staged && res_pref;
@@ -674,27 +687,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tmem_ld_wait();
         release_tmem(acc);
         if (valid) {
-          const int rg = r * p.c_post;                  // floats per output sub-row (a multiple of 4)
           const int oy = y0 + (m >> 3), ox = x0 + (m & 7);
           float* drow = reinterpret_cast<float*>(p.y) + (((size_t)b * OH + (size_t)oy * r) * OW + (size_t)ox * r) * p.c_post;
-          const size_t sub_row = OW * (size_t)p.c_post;  // floats between output rows
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {              // static register indices: groups of 4 columns
             if (4 * c4 < ncols) {
+              const float4 bv = *reinterpret_cast<const float4*>(bias_s + col0 + 4 * c4);
               float v[4];
+              v[0] = __uint_as_float(c4 < 4 ? ra[(4 * c4) & 15] : rb[(4 * c4) & 15]) + bv.x;
+              v[1] = __uint_as_float(c4 < 4 ? ra[(4 * c4 + 1) & 15] : rb[(4 * c4 + 1) & 15]) + bv.y;
+              v[2] = __uint_as_float(c4 < 4 ? ra[(4 * c4 + 2) & 15] : rb[(4 * c4 + 2) & 15]) + bv.z;
+              v[3] = __uint_as_float(c4 < 4 ? ra[(4 * c4 + 3) & 15] : rb[(4 * c4 + 3) & 15]) + bv.w;
+              if (!epi4_plain) {                        // (ESPCN's last layer is linear: warp-uniform skip)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int cidx = 4 * c4 + u;
-                float t = __uint_as_float(cidx < 16 ? ra[cidx & 15] : rb[cidx & 15]) + bias_s[col0 + cidx];
-                if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
-                else if (p.act != SRB_ACT_NONE) t = act_generic(t, p.act, p.act_slope);
-                t *= p.alpha;
-                if (p.clip01) t = fminf(fmaxf(t, 0.f), 1.f);
-                v[u] = t;
+                for (int u = 0; u < 4; ++u) {
+                  float t = v[u];
+                  if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
+                  else if (p.act != SRB_ACT_NONE) t = act_generic(t, p.act, p.act_slope);
+                  t *= p.alpha;
+                  if (p.clip01) t = fminf(fmaxf(t, 0.f), 1.f);
+                  v[u] = t;
+                }
               }
-              const int cb = c_first + 4 * c4;          // conv-domain channel of v[0]
-              const int i = cb / rg, off = cb - i * rg;
-              *reinterpret_cast<float4*>(drow + (size_t)i * sub_row + off) = make_float4(v[0], v[1], v[2], v[3]);
+              *reinterpret_cast<float4*>(drow + epi4_off[c4]) = make_float4(v[0], v[1], v[2], v[3]);
             }
           }
         }

@@ -366,8 +366,8 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
   if (window == SRB_SSIM_TF && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread, one warp per plane
     const int px = kPairPx * (channels == 1 ? 4 : channels == 2 ? 2 : 1);   // map pixels per block row
     const int gxp = (OW + px - 1) / px;
-    int rows = 128;
-    const long target = 6L * sm_count();
+    int rows = 256;                                // (10 halo rows per strip: 4 % extra horizontal work at 256)
+    const long target = 8L * sm_count();
     while (rows > 16 && (long)gxp * ((OH + rows - 1) / rows) * batch < target) rows >>= 1;
     dim3 grid(gxp, (OH + rows - 1) / rows, batch);
     SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "psnr_ssim: grid too large");
