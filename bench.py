@@ -262,10 +262,11 @@ def run_gpu(args):
             "gpu_launches": launches * world,
             "clocks": clk.result,
             # traffic: dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over the 36 tcgen05 launches of one
-            # 32-tile forward (ncu --set full, profiles/r01_ncu_conv_final.txt): 16 x (0.260 + 0.572) + 0.503 + 0.697 + 2.977 + 2.641 GB
+            # 32-tile forward (ncu dram__bytes_* per launch, profiles/r01_launches_final.md): 16 x 0.563 (res-block 2nd conv) +
+            # 17 x 0.256 (1st conv, body end) + 2 x 1.830 (up-sampling) + 2.635 (RGB tail) = 19.64 GB / 36
             "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel + conv3x3_fold_kernel (tcgen05 implicit GEMM, all 36 launches of a forward)",
                          "achieved": achieved, "peak": peaks["tflops"],
-                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": 0.559e9 * (mb / 32.0),
+                         "unit": "TFLOP/s", "frac": achieved / peaks["tflops"], "traffic": 0.546e9 * (mb / 32.0),
                          "traffic_unit": "bytes per launch (ncu dram read + write, mean over the launches of a forward)",
                          "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                          "flop_per_launch": tc_flops / max(n_tc_launches, 1),
