@@ -31,6 +31,7 @@ struct HeadTcParams {
   int K, kpad, n_kb;
   int halo_w, halo_h, halo_n;
   int tiles_x, tiles_y, total_tiles;
+  uint32_t magic_img, magic_x;                           // multiply-high reciprocals of tiles_per_img and tiles_x (0: divide)
   uint32_t idesc, tmem_cols, a_stage_bytes;
   int y2_f8;
 };
@@ -91,9 +92,16 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   const int tiles_per_img = q.tiles_x * q.tiles_y;
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
-    b = tile / tiles_per_img;
-    const int rr_ = tile - b * tiles_per_img;
-    const int ty = rr_ / q.tiles_x;
+    int rr_, ty;
+    if (q.magic_img) {                                  // exact for every tile index of this launch (checked on the host)
+      b = (int)__umulhi((uint32_t)tile, q.magic_img);
+      rr_ = tile - b * tiles_per_img;
+      ty = (int)__umulhi((uint32_t)rr_, q.magic_x);
+    } else {
+      b = tile / tiles_per_img;
+      rr_ = tile - b * tiles_per_img;
+      ty = rr_ / q.tiles_x;
+    }
     y0 = ty * kHTileH;
     x0 = (rr_ - ty * q.tiles_x) * kHTileW;
   };
@@ -105,32 +113,35 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       mbar_expect_tx(wfull_bar, w_bytes);
       for (int kb = 0; kb < q.n_kb; ++kb) tma_load_2d(w_smem + (uint32_t)kb * 8192u, &tmap_w, wfull_bar, 0, kb * 64);
     }
-    // tile-invariant halo positions of this thread
-    int h_idx[kHMaxHalo], h_dy[kHMaxHalo], h_dx[kHMaxHalo], h_c[kHMaxHalo];
+    // tile-invariant halo positions of this thread: offset of the element relative to the tile's first pixel
+    int h_idx[kHMaxHalo], h_dy[kHMaxHalo], h_dx[kHMaxHalo], h_rel[kHMaxHalo];
 #pragma unroll
     for (int j = 0; j < kHMaxHalo; ++j) {
       const int i = tid + j * kHProdThreads;
       const int hp = i / 3;
       h_idx[j] = i < q.halo_n ? i : -1;
-      h_c[j] = i - hp * 3;
       h_dx[j] = hp % q.halo_w - (p.kw >> 1);
       h_dy[j] = hp / q.halo_w - (p.kh >> 1);
+      h_rel[j] = (h_dy[j] * p.W + h_dx[j]) * p.x_cstride + p.x_coffset + (i - hp * 3);
     }
     const float* xin = reinterpret_cast<const float*>(p.x);
     auto fetch = [&](int tile, int buf) {
       if (tile < q.total_tiles) {
         int b, y0, x0;
         coords(tile, b, y0, x0);
+        const float* tile0 = xin + (((size_t)b * p.H + y0) * p.W + x0) * p.x_cstride;
+        const uint32_t d0 = smem_u32(halo + buf * q.halo_n);
+        // interior tiles (the whole halo inside the image) skip the per-element range checks
+        const bool inside = y0 >= (p.kh >> 1) && y0 + kHTileH + (p.kh >> 1) <= p.H && x0 >= (p.kw >> 1) && x0 + kHTileW + (p.kw >> 1) <= p.W;
 #pragma unroll
         for (int j = 0; j < kHMaxHalo; ++j) {
           if (h_idx[j] >= 0) {
-            float* d = halo + buf * q.halo_n + h_idx[j];
+            const uint32_t d = d0 + 4u * (uint32_t)h_idx[j];
             const int gy = y0 + h_dy[j], gx = x0 + h_dx[j];
-            if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-              const float* src = xin + (((size_t)b * p.H + gy) * p.W + gx) * p.x_cstride + p.x_coffset + h_c[j];
-              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(d)), "l"(src) : "memory");
+            if (inside || (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)) {
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(tile0 + h_rel[j]) : "memory");
             } else {
-              *d = 0.f;
+              asm volatile("st.shared.f32 [%0], %1;" ::"r"(d), "f"(0.f) : "memory");
             }
           }
         }
@@ -314,6 +325,13 @@ int conv_headtc_launch(const ConvParams& p, cudaStream_t stream) {
   const long total = (long)p.B * q.tiles_x * q.tiles_y;
   SRB_REQUIRE(total < (1L << 30), "conv(head, tcgen05): too many tiles");
   q.total_tiles = (int)total;
+  {
+    // multiply-high division (idx * magic >> 32 with magic = floor((2^32 - 1) / d) + 1) is exact while idx * d < 2^32
+    const uint64_t tpi = (uint64_t)q.tiles_x * q.tiles_y;
+    const bool ok = (uint64_t)total * tpi < (1ull << 32) && tpi * (uint64_t)q.tiles_x < (1ull << 32) && tpi > 1 && q.tiles_x > 1;
+    q.magic_img = ok ? (uint32_t)(0xFFFFFFFFull / tpi) + 1u : 0u;
+    q.magic_x = ok ? (uint32_t)(0xFFFFFFFFull / (uint64_t)q.tiles_x) + 1u : 0u;
+  }
   const uint32_t fmt = p.y_dtype == SRB_BF16 ? 1u : 0u;
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   q.tmem_cols = 128;

@@ -134,12 +134,50 @@ class DeviceModel:
 
 
 class SRCNNNet(DeviceModel):
-    """conv9x9x96 relu -> conv1x1x32 relu -> conv5x5x3 linear; no clip (SRCNN_model.py:45-53)."""
+    """conv9x9x96 relu -> conv1x1x32 relu -> conv5x5x3 linear; no clip (SRCNN_model.py:45-53).
+
+    fp32: three launches of the exact CUDA-core engine.  16-bit modes: the same network on the tcgen05 kernels, composed
+    from their 64-channel shapes - conv1's 96 filters run as two passes of the RGB head kernel (filters [0, 64) and
+    [64, 96) + zero filters) into one 128-channel buffer, the 1x1 layer as two passes over its 64-channel input slices
+    with the partial sums in fp32 (its 32 outputs zero-padded to 64), then ReLU + cast, and the 5x5x32 -> 3 layer on the
+    wide-tile few-channel kernel with zero rows for the padded input channels."""
     arch = "SRCNN"
+
+    def __init__(self, weights, precision="fp32"):
+        super().__init__(weights, precision)
+        self._tc = None
+        k1, k2, k3 = (self.weights[f"conv{i}/kernel"] for i in (1, 2, 3))
+        c1, c2 = k1.shape[3], k2.shape[3]
+        if (precision != "fp32" and k1.shape[2] == 3 and 64 < c1 <= 128 and k2.shape[2] == c1 and c2 <= 64
+                and k3.shape[2] == c2 and k3.shape[3] <= 4 and max(k1.shape[0], k2.shape[0], k3.shape[0]) <= 9):
+            def pad(a, axis, n):
+                width = [(0, 0)] * a.ndim
+                width[axis] = (0, n - a.shape[axis])
+                return np.pad(a, width)
+            b1 = self.weights.get("conv1/bias", np.zeros(c1, np.float32))
+            b2 = self.weights.get("conv2/bias", np.zeros(c2, np.float32))
+            k2p = pad(pad(k2, 2, 128), 3, 64)
+            self._tc = {
+                "c1a": ops.ConvWeights(k1[..., :64], b1[:64]),
+                "c1b": ops.ConvWeights(pad(k1[..., 64:], 3, 64), pad(b1[64:], 0, 64)),
+                "c2a": ops.ConvWeights(k2p[:, :, :64, :], pad(b2, 0, 64)),
+                "c2b": ops.ConvWeights(k2p[:, :, 64:, :], None),
+                "c3": ops.ConvWeights(pad(k3, 2, 64), self.weights.get("conv3/bias")),
+            }
 
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
+        if self._tc is not None:
+            T = self._tc
+            B, H, W, _ = x.shape
+            h1 = torch.empty((B, H, W, 128), dtype=dt, device=x.device)
+            ops.conv2d(x, T["c1a"], act="relu", out=h1, out_coffset=0)
+            ops.conv2d(x, T["c1b"], act="relu", out=h1, out_coffset=64)
+            acc = ops.conv2d(h1, T["c2a"], x_coffset=0, out_dtype=torch.float32)
+            ops.conv2d(h1, T["c2b"], x_coffset=64, res1=acc, out=acc)
+            h2 = ops.cast(acc, dt, relu=True)
+            return ops.conv2d(h2, T["c3"], out_dtype=torch.float32)
         h = ops.conv2d(x, L["conv1"], act="relu", out_dtype=dt)
         h = ops.conv2d(h, L["conv2"], act="relu", out_dtype=dt)
         return ops.conv2d(h, L["conv3"], out_dtype=torch.float32)

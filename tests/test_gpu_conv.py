@@ -183,3 +183,26 @@ def test_edsr_full_depth_vs_oracle():
         err = np.abs(got - want).max()
         print(f"EDSR x4 16 blocks {precision}/{trunk}: max-abs {err:.4f}")
         assert err <= tol, (precision, trunk, err)
+
+
+def test_srcnn_16bit_runs_on_the_tensor_core_kernels():
+    """SRCNN 9-1-5 in the 16-bit modes (SRCNN_model.py:45-53): the 96-filter head as two RGB-head passes, the 1x1 layer as
+    two 64-channel slice passes with fp32 partial sums, the 5x5x32 -> 3 layer on the few-channel kernel; odd sizes, biases."""
+    import torch
+    from srb200 import engine, ops, weights, _capi
+    w = weights.srcnn_weights(bias_scale=0.1)
+    x = np.random.default_rng(7).random((3, 45, 70, 3), dtype=np.float32)
+    want = oc.srcnn_forward(w, x)
+    net = engine.SRCNNNet(w, precision="fp16")
+    assert net._tc is not None
+    h1 = torch.zeros((1, 16, 16, 128), dtype=torch.float16, device="cuda")
+    assert ops.conv2d_engine(h1, net._tc["c2a"]) == _capi.ENGINE_TCGEN05      # 1x1, Cin = 64 slice
+    assert ops.conv2d_engine(h1[..., :64].contiguous(), net._tc["c3"]) == _capi.ENGINE_TCGEN05
+    got = net.predict(x)
+    assert got.shape == want.shape and np.abs(got - want).max() <= HALF_TOL
+    # a 64-filter variant keeps the plain three-launch path
+    w2 = {k: v for k, v in w.items()}
+    w2["conv1/kernel"], w2["conv1/bias"] = w["conv1/kernel"][..., :64], w["conv1/bias"][:64]
+    w2["conv2/kernel"] = w["conv2/kernel"][:, :, :64, :]
+    assert engine.SRCNNNet(w2, precision="fp16")._tc is None
+    assert np.abs(engine.SRCNNNet(w2, precision="fp16").predict(x) - oc.srcnn_forward(w2, x)).max() <= HALF_TOL

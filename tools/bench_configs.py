@@ -46,6 +46,9 @@ def main():
         return ops.psnr_ssim(hr, net.forward_device(up))
     ms = timed(c1)
     rows.append({"config": "C1 bicubic + SRCNN 9-1-5 + PSNR/SSIM, 64 x 128x128 (fp32)", "ms": ms, "out_MPps": 64 * 128 * 128 / ms / 1e3})
+    net = engine.SRCNNNet(weights.srcnn_weights(), precision="fp16")
+    ms = timed(c1)
+    rows.append({"config": "C1 bicubic + SRCNN 9-1-5 + PSNR/SSIM, 64 x 128x128 (fp16 operands, tcgen05)", "ms": ms, "out_MPps": 64 * 128 * 128 / ms / 1e3})
 
     # C2: ESPCN x4, 256 tiles of 256x256
     x = torch.rand((256, 256, 256, 3), device="cuda", generator=g)
