@@ -291,7 +291,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--tile", type=int, default=192)
-    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--micro-batch", type=int, default=128)
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--trunk", default="pair8", choices=["pair8", "fp32", "pair", "half"],
                     help="residual trunk storage: 16-bit + e5m2 rounding-error pair (default), fp32, compensated 16-bit pair, or plain 16-bit")
