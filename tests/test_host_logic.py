@@ -80,3 +80,13 @@ def test_gloo_world2_allreduce(tmp_path):
     means, vec = eval(line[len("RESULT"):])
     assert means == pytest.approx([0.0045, 24.5, 0.45])
     assert vec == [0.0] * 5 + [1.0] * 5
+
+
+def test_constants_keep_the_reference_names():
+    """SRModels/constants.py:1-14: same names and values, exported from the per-family table."""
+    from srb200 import constants as c
+    assert (c.SRCNN_PATCH_SIZE, c.SRCNN_STRIDE) == (24, 12)
+    assert (c.EDSR_PATCH_SIZE, c.EDSR_STRIDE, c.EDSR_SCALE_FACTOR) == (24, 12, 2)
+    assert (c.ESRGAN_PATCH_SIZE, c.ESRGAN_STRIDE, c.ESRGAN_SCALE_FACTOR) == (24, 12, 2)
+    assert (c.VGG_PATCH_SIZE, c.VGG_STRIDE, c.RANDOM_SEED) == (96, 48, 42)
+    assert not hasattr(c, "SRCNN_SCALE_FACTOR") and not hasattr(c, "VGG_SCALE_FACTOR")
