@@ -48,7 +48,9 @@ int srb_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * per-image mean squared error (the Keras "mean_squared_error" loss of SRCNN_model.py:59).
  * sums: optional [4] float64 {sum psnr, sum ssim, count, sum mse}, ACCUMULATED (not overwritten) so
  * that sharded evaluation can all-reduce one 4-vector.  workspace: >= srb_psnr_ssim_workspace(B) bytes.
- * H and W must be >= 11 (tf.image.ssim raises otherwise) -> SRB_E_INVALID. */
+ * H and W must be >= 11 (tf.image.ssim raises otherwise) -> SRB_E_INVALID.
+ * With ssim == NULL only the squared error is evaluated (tf.image.psnr alone, metrics.py:3-4): a streaming reduction at
+ * the HBM roofline, any image size; the ssim entry of `sums` then receives nothing. */
 size_t srb_psnr_ssim_workspace(int batch);
 int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int width, int channels,
                       float max_val, float* psnr, float* ssim, float* mse, double* sums,

@@ -307,6 +307,54 @@ psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, 
   }
 }
 
+// PSNR alone (ssim == NULL at the C ABI): the squared error is a pure streaming reduction - 24 B per RGB pixel, 16-byte
+// loads, eight independent loads in flight per thread - and runs at the HBM roofline instead of the SSIM kernel's FP32 bound.
+constexpr int kSseThreads = 256, kSseUnroll = 4;
+
+__global__ void __launch_bounds__(kSseThreads)
+sse_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t n_per_image, int vec, double* __restrict__ acc) {
+  __shared__ float red[kSseThreads / 32];
+  const float* pa = a + (size_t)blockIdx.y * n_per_image;
+  const float* pb = b + (size_t)blockIdx.y * n_per_image;
+  float s0 = 0.f, s1 = 0.f;
+  if (vec) {
+    const size_t n4 = n_per_image >> 2;
+    const float4* va = reinterpret_cast<const float4*>(pa);
+    const float4* vb = reinterpret_cast<const float4*>(pb);
+    const size_t step = (size_t)gridDim.x * kSseThreads;
+    size_t i = (size_t)blockIdx.x * kSseThreads + threadIdx.x;
+    for (; i + (kSseUnroll - 1) * step < n4; i += kSseUnroll * step) {
+      float4 x[kSseUnroll], y[kSseUnroll];
+#pragma unroll
+      for (int u = 0; u < kSseUnroll; ++u) { x[u] = __ldcs(va + i + u * step); y[u] = __ldcs(vb + i + u * step); }
+#pragma unroll
+      for (int u = 0; u < kSseUnroll; ++u) {
+        const float d0 = x[u].x - y[u].x, d1 = x[u].y - y[u].y, d2 = x[u].z - y[u].z, d3 = x[u].w - y[u].w;
+        s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s0 = fmaf(d2, d2, s0); s1 = fmaf(d3, d3, s1);
+      }
+    }
+    for (; i < n4; i += step) {
+      const float4 x = __ldcs(va + i), y = __ldcs(vb + i);
+      const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+      s0 = fmaf(d0, d0, s0); s1 = fmaf(d1, d1, s1); s0 = fmaf(d2, d2, s0); s1 = fmaf(d3, d3, s1);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * kSseThreads + threadIdx.x; i < n_per_image; i += (size_t)gridDim.x * kSseThreads) {
+      const float d = __ldg(pa + i) - __ldg(pb + i);
+      s0 = fmaf(d, d, s0);
+    }
+  }
+  const float w = warp_sum(s0 + s1);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = w;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < kSseThreads / 32; ++k) t += red[k];
+    atomicAdd(&acc[2 * blockIdx.y], t);
+  }
+}
+
 __global__ void psnr_ssim_finalize(const double* __restrict__ acc, int B, double n_pix, double n_map,
                                    float max_val, int skimage, float* psnr, float* ssim, float* mse_out, double* sums) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -352,12 +400,33 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
   SRB_REQUIRE(window == SRB_SSIM_TF || window == SRB_SSIM_SKIMAGE, "psnr_ssim: unknown window kind %d", window);
   SRB_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4, "psnr_ssim: channels must be 1..4 (got %d)", channels);
   const int K = window == SRB_SSIM_TF ? 11 : 7;
-  SRB_REQUIRE(height >= K && width >= K, "psnr_ssim: image dimensions must be at least %dx%d (got %dx%d)", K, K, height, width);
   SRB_REQUIRE(workspace_bytes >= srb_psnr_ssim_workspace(batch), "psnr_ssim: workspace too small");
+  double* acc = (double*)workspace;
+  if (!ssim) {
+    // PSNR / MSE only: streaming squared-error reduction (no window, so no minimum image size either)
+    SRB_REQUIRE(height >= 1 && width >= 1, "psnr: bad geometry %dx%d", height, width);
+    if (batch == 0) return SRB_OK;
+    SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
+    const size_t n = (size_t)height * width * channels;
+    const int vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) && ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
+    const size_t work = vec ? n / 4 : n;                                   // loads per image and array
+    long per_image = (long)((work + (size_t)kSseThreads * kSseUnroll * 4 - 1) / ((size_t)kSseThreads * kSseUnroll * 4));
+    const long cap = (32L * sm_count() + batch - 1) / batch;              // enough blocks to fill the chip, few atomics
+    if (per_image > cap) per_image = cap;
+    if (per_image < 1) per_image = 1;
+    SRB_REQUIRE(batch <= 65535, "psnr: batch too large for one launch");
+    dim3 grid((unsigned)per_image, batch);
+    sse_kernel<<<grid, kSseThreads, 0, stream>>>(a, b, n, vec, acc);
+    int rc = launch_check("sse_kernel");
+    if (rc) return rc;
+    psnr_ssim_finalize<<<(batch + 127) / 128, 128, 0, stream>>>(acc, batch, (double)n, 1.0, max_val,
+                                                                 window == SRB_SSIM_SKIMAGE, psnr, nullptr, mse, sums);
+    return launch_check("psnr_ssim_finalize");
+  }
+  SRB_REQUIRE(height >= K && width >= K, "psnr_ssim: image dimensions must be at least %dx%d (got %dx%d)", K, K, height, width);
   if (batch == 0) return SRB_OK;
   int rc = upload_windows();
   if (rc) return rc;
-  double* acc = (double*)workspace;
   SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
   const int OH = height - (K - 1), OW = width - (K - 1), OE = OW * channels;
   const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);

@@ -49,7 +49,15 @@ def psnr_ssim(y_true, y_pred, max_val=1.0):
 
 
 def psnr(y_true, y_pred):
-    return psnr_ssim(y_true, y_pred, 1.0)[0]
+    """tf.image.psnr(y_true, y_pred, max_val=1.0) (metrics.py:3-4): the squared-error reduction alone, any image size."""
+    a, np_a, single = _to_device(y_true)
+    b, np_b, _ = _to_device(y_pred)
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch: {tuple(a.shape)} vs {tuple(b.shape)}")
+    p = ops.psnr(a, b, 1.0)
+    if single:
+        p = p[0]
+    return p.cpu().numpy() if (np_a and np_b) else p
 
 
 def ssim(y_true, y_pred):
@@ -92,10 +100,7 @@ def _skimage_pair(im1, im2, data_range, channel_axis):
 def peak_signal_noise_ratio(image_true, image_test, *, data_range=None):
     """skimage.metrics.peak_signal_noise_ratio: 10 log10(data_range^2 / mse) over the whole array -> float."""
     a, b = _skimage_pair(image_true, image_test, data_range, None if np.ndim(image_true) == 2 else -1)
-    if a.shape[1] < 7 or a.shape[2] < 7:      # the fused pass also evaluates the 7 x 7 windows
-        return float(10.0 * np.log10(1.0 / float(((a - b) ** 2).double().mean().item())))
-    p, _ = ops.psnr_ssim(a, b, 1.0, window=capi.SSIM_SKIMAGE)
-    return float(p[0].item())
+    return float(ops.psnr(a, b, 1.0, window=capi.SSIM_SKIMAGE)[0].item())
 
 
 def structural_similarity(im1, im2, *, win_size=None, data_range=None, channel_axis=None, gaussian_weights=False,

@@ -40,6 +40,28 @@ def _check_nhwc(t, name):
 # ---------------------------------------------------------------------------------------------
 # PSNR / SSIM  (metrics.py:3-7)
 # ---------------------------------------------------------------------------------------------
+def psnr(a, b, max_val=1.0, want_mse=False, window=capi.SSIM_TF):
+    """a, b: [B,H,W,C] float32 CUDA tensors -> psnr [B] (and mse [B]): the squared-error reduction alone (no SSIM windows),
+    a streaming kernel at the HBM roofline; any image size (tf.image.psnr has no minimum)."""
+    torch = _torch()
+    _check_nhwc(a, "y_true"); _check_nhwc(b, "y_pred")
+    if a.shape != b.shape:
+        raise ValueError(f"shape mismatch: {tuple(a.shape)} vs {tuple(b.shape)}")
+    if a.dtype != torch.float32 or b.dtype != torch.float32:
+        raise TypeError("psnr inputs must be float32")
+    B, H, W, Cc = a.shape
+    p = torch.empty(B, dtype=torch.float32, device=a.device)
+    mse = torch.empty(B, dtype=torch.float32, device=a.device) if want_mse else None
+    ws_bytes = capi.lib().srb_psnr_ssim_workspace(B)
+    ws = torch.empty(max(ws_bytes, 8), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        capi.check(capi.lib().srb_psnr_ssim_window_f32(capi.ptr(a), capi.ptr(b), B, H, W, Cc, float(max_val), int(window),
+                                                       capi.ptr(p), None, capi.ptr(mse), None,
+                                                       capi.ptr(ws), ws_bytes, capi.stream_ptr()))
+    _LAUNCHES[0] += 2
+    return (p, mse) if want_mse else p
+
+
 def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False, window=capi.SSIM_TF):
     """a, b: [B,H,W,C] float32 CUDA tensors -> (psnr [B], ssim [B][, mse [B]]) float32.
 

@@ -121,3 +121,26 @@ def test_skimage_definitions_errors_and_identity():
         metrics.structural_similarity(x, x, channel_axis=2)                   # float images need data_range
     with pytest.raises(NotImplementedError):
         metrics.structural_similarity(x, x, channel_axis=2, data_range=1.0, gaussian_weights=True)
+
+
+@pytest.mark.parametrize("shape", [(3, 5, 7, 3), (2, 33, 33, 3), (1, 130, 47, 1), (2, 64, 300, 4), (1, 478, 478, 3)])
+def test_psnr_alone_streaming_reduction(shape):
+    """metrics.psnr (tf.image.psnr, metrics.py:3-4) runs the squared-error reduction alone: any size (no 11 x 11 minimum),
+    vector and scalar paths, same values as the fused pass."""
+    import torch
+    from srb200 import metrics, ops
+    a, b = _pair(shape, seed=shape[2])
+    p = metrics.psnr(a, b)
+    assert p.dtype == np.float32 and p.shape == (shape[0],)
+    assert np.abs(p - om.psnr(a, b, dtype=np.float64)).max() <= PSNR_TOL
+    ta, tb = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    p2, m2 = ops.psnr(ta, tb, want_mse=True)
+    assert np.allclose(m2.cpu().numpy(), ((a - b) ** 2).mean(axis=(1, 2, 3)), rtol=1e-5)
+    if shape[1] >= 11 and shape[2] >= 11:
+        assert np.abs(p2.cpu().numpy() - ops.psnr_ssim(ta, tb)[0].cpu().numpy()).max() <= 1e-4
+    # unaligned views take the scalar path
+    n = (ta.numel() - 1) // 3 * 3
+    va, vb = ta.flatten()[1:1 + n].view(1, 1, n // 3, 3), tb.flatten()[1:1 + n].view(1, 1, n // 3, 3)
+    want = -10 * np.log10(((a.ravel()[1:1 + n].astype(np.float64) - b.ravel()[1:1 + n]) ** 2).mean())
+    assert abs(float(ops.psnr(va, vb)[0]) - want) <= PSNR_TOL
+    assert np.all(np.isinf(metrics.psnr(a, a)))

@@ -67,6 +67,9 @@ def main():
         alg = batch * oh * ow * 24
         rows.append({"op": "psnr_ssim_f32", "out": f"{ow}x{oh}", "batch": batch, "ms": ms, "GBps": alg / ms / 1e6,
                      "frac": alg / ms / 1e6 / peak, "out_MPps": batch * oh * ow / ms / 1e3})
+        ms = timed(lambda: ops.psnr(aimg, bimg), a.reps)
+        rows.append({"op": "psnr_f32", "out": f"{ow}x{oh}", "batch": batch, "ms": ms, "GBps": alg / ms / 1e6,
+                     "frac": alg / ms / 1e6 / peak, "out_MPps": batch * oh * ow / ms / 1e3})
         del aimg, bimg
     print(f"{'op':18s} {'size':>10s} {'batch':>5s} {'ms':>8s} {'GB/s':>8s} {'of HBM':>7s} {'MP/s':>9s}")
     for r in rows:
