@@ -143,7 +143,7 @@ def run_reference(args):
     val = mp / dt
     cores = torch.get_num_threads()
     sample = f"{per_step} of the {args.batch} LR tiles ({tile}x{tile}) per step, fp32 oracle port (torch CPU conv2d), {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "sr_output_megapixels_per_sec", "value": val, "unit": "MP/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -151,7 +151,7 @@ def run_reference(args):
         "cpu_baseline": {"value": val, "unit": "MP/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference engine (TensorFlow/Keras 2.10) is not installable offline; CPU arm = oracle restatement",
-    }))
+    })
 
 
 def workload_config(args, micro_batch):
@@ -282,12 +282,35 @@ def run_gpu(args):
             mp_s, cores, secs = cpu_edsr_mp_per_s(n_cpu, tile)
             line["cpu_baseline"] = {"value": mp_s, "unit": "MP/s", "cores": cores, "kind": "port",
                                     "sample": f"first {n_cpu} of the {args.batch} LR tiles, fp32 oracle port (torch CPU), {secs:.1f} s"}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under torchrun), so
+    file descriptor 1 is pointed at stderr for the whole run and the result line is written to the saved descriptor."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
