@@ -51,14 +51,53 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clocks / throttle reasons / power sampled DURING the timed region: NVML polled from a thread every few
+    milliseconds (the timed region of a multi-GPU run is a few tens of milliseconds - shorter than nvidia-smi's start-up),
+    with `nvidia-smi -lms` as the fallback when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
-        self.index, self.proc = index, None
+        self.index, self.proc, self.thread = index, None, None
+        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid if not uuid.startswith("GPU-") else uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll(self, nv, h):
+        import threading  # noqa: F401
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                watts = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self._samples.append((sm, mask, watts))
+            except Exception:
+                pass
+            self._stop.wait(0.003)
 
     def __enter__(self):
+        import threading
+        self._stop, self._samples = threading.Event(), []
+        try:
+            nv, h = self._nvml_handle()
+            self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -68,7 +107,18 @@ class ClockSampler:
         return self
 
     def __exit__(self, *exc):
-        self.result = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            if self._samples:
+                sm = [s[0] for s in self._samples]
+                mask = 0
+                for s in self._samples:
+                    mask |= int(s[1])
+                self.result = {"sm_mhz": float(statistics.median(sm)), "sm_max_mhz": float(self._max),
+                               "reasons": sorted(n for n, bit in self.REASONS if mask & bit), "samples": len(sm),
+                               "power_w_max": max(s[2] for s in self._samples), "source": "nvml"}
+            return
         if not self.proc:
             return
         self.proc.terminate()
@@ -92,7 +142,7 @@ class ClockSampler:
                     reasons.add(name)
         if sm:
             self.result = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                           "samples": len(sm), "power_w_max": max(watts)}
+                           "samples": len(sm), "power_w_max": max(watts), "source": "nvidia-smi"}
 
 
 def lr_tiles(lo, hi, size):
@@ -176,6 +226,9 @@ def run_gpu(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # opt-in: on the 4-GPU boxes measured (all GPUs on NUMA node 0) binding the ranks to the GPU's CPU set did not help
+    # (e2e 7,352 MP/s bound vs 8,090 unbound); the e2e line at N >= 4 is limited by the host side of the 3.6 GB/step read-back
+    numa_bound = D.bind_host_to_gpu(local) if (world > 1 and os.environ.get("SRB_NUMA_BIND")) else False
     lo, hi = D.shard_bounds(args.batch, rank, world)
     n_local = hi - lo
     tile, out_px = args.tile, (args.tile * 4) ** 2
@@ -262,7 +315,8 @@ def run_gpu(args):
             "config": workload_config(args, mb),
             "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": args.batch * tile * tile * 3 * 4,
                     "d2h_bytes_per_step": args.batch * out_px * 3 * 4, "ms_per_step": e2e_ms / args.steps,
-                    "api": "EDSRNet.predict(host NHWC float32, out=pinned host)", "micro_batch": e2e_mb},
+                    "api": "EDSRNet.predict(host NHWC float32, out=pinned host)", "micro_batch": e2e_mb,
+                    "host_bound_to_gpu_numa_node": bool(numa_bound)},
             "gpu_launches": launches * world,
             "clocks": clk.result,
             # traffic: dram__bytes_read + dram__bytes_write per launch, launch-weighted mean over the 36 tcgen05 launches of one
