@@ -66,6 +66,16 @@ class EDSR:
         sr, metrics = common.tiled_super_resolve(self.model, img, patch_size_lr, stride, self.scale_factor)
         return sr.cpu().numpy(), metrics
 
+    def super_resolve_image_whole(self, lr_img):
+        """Fast path without tiling: one fully-convolutional pass over the whole LR image (see
+        ``_common.whole_image_super_resolve`` for how it relates to the tiled flow).  Same return convention."""
+        if not self.trained:
+            raise RuntimeError("Model has not been trained.")
+        if self.scale_factor is None:
+            raise ValueError("scale_factor is not set. Call setup_model first.")
+        sr, metrics = common.whole_image_super_resolve(self.model, common.as_device_image(lr_img))
+        return sr.cpu().numpy(), metrics
+
     def super_resolve_batch(self, lr_batch):
         """Whole-image fully-convolutional fast path (the network's input is (None, None, 3),
         EDSR_model.py:98): NHWC float32 batch in, NHWC float32 batch out, no tiling."""

@@ -40,3 +40,14 @@ class ESRGAN:
         sr, metrics = common.tiled_super_resolve(self.generator, img, patch_size_lr, stride, self.scale_factor,
                                                  pre=(2.0, -1.0), post=(0.5, 0.5))
         return sr.cpu().numpy(), metrics
+
+    def super_resolve_image_whole(self, lr_img):
+        """Fast path without tiling: one pass of the generator over the whole LR image ([-1, 1] mapping as in the tiled
+        flow).  The two SelfAttention layers then attend over the whole image instead of one patch."""
+        if not self.trained:
+            raise RuntimeError("Model has not been trained.")
+        if self.scale_factor is None:
+            raise ValueError("scale_factor is not set. Call setup_model first.")
+        sr, metrics = common.whole_image_super_resolve(self.generator, common.as_device_image(lr_img),
+                                                       pre=(2.0, -1.0), post=(0.5, 0.5))
+        return sr.cpu().numpy(), metrics

@@ -75,6 +75,17 @@ class SRCNNModel:
         sr, metrics = common.tiled_super_resolve(self.model, up, patch_size, stride, 1)
         return sr.cpu().numpy(), metrics
 
+    def super_resolve_image_whole(self, lr_img, hr_h, hr_w, interpolation=INTER_CUBIC):
+        """Fast path without tiling: pre-upsample, then one fully-convolutional pass over the whole image."""
+        if not self._trained:
+            raise RuntimeError("Model has not been trained.")
+        if lr_img is None or not isinstance(lr_img, np.ndarray):
+            raise ValueError("lr_img must be a numpy array (RGB).")
+        src = common.as_device_image(lr_img)
+        up = ops.resize(src[None], hr_h, hr_w, interpolation=interpolation)[0]
+        sr, metrics = common.whole_image_super_resolve(self.model, up)
+        return sr.cpu().numpy(), metrics
+
     def save(self, directory, timestamp):
         if not self._trained:
             raise RuntimeError("Cannot save an untrained model.")

@@ -65,6 +65,23 @@ def tiled_super_resolve(model: engine.DeviceModel, image_dev, patch, stride, sca
     return sr, metrics
 
 
+def whole_image_super_resolve(model: engine.DeviceModel, image_dev, pre=None, post=None):
+    """Fully-convolutional fast path: the network runs once over the whole image instead of
+    over overlapping patches - no padding, no patch loop, no overlap averaging - then ``clip(0, 1)``.  Every reference
+    network is built with ``input_shape=(None, None, C)`` (EDSR_model.py:98), so this is the same function of the image
+    wherever a pixel's receptive field lies inside one patch of the tiled flow; near patch borders the tiled flow sees
+    zero padding and averages overlapping predictions, which this path does not reproduce (it is an additional entry
+    point, not a replacement for ``super_resolve_image``).
+    Returns (sr [H*scale, W*scale, C] float32 CUDA, inference_metrics)."""
+    x = image_dev[None].contiguous()
+    if pre is not None:
+        x = ops.cast(x, x.dtype, pre[0], pre[1])
+    preds, metrics = engine.timed_predict(model, x)
+    if post is not None:
+        preds = ops.cast(preds, preds.dtype, post[0], post[1])
+    return preds[0].clamp_(0.0, 1.0), metrics
+
+
 def evaluate_arrays(model: engine.DeviceModel, X, Y, micro_batch=64, sums=None):
     """Forward X in micro-batches and accumulate (sum psnr, sum ssim, count, sum mse) on the device.
 

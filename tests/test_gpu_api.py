@@ -88,3 +88,34 @@ def test_vgg16_classify_defects_method():
     patches, _ = ot.extract_patches(padded, 32, 16)
     want = vote(oc.vgg16_classifier_forward(w, patches))
     assert cls == want[0] and abs(conf - want[1]) <= 2e-3
+
+
+def test_whole_image_fast_path():
+    """super_resolve_image_whole: one fully-convolutional pass (no tiling) against the oracle network on the whole image,
+    and agreement with the tiled flow away from patch borders."""
+    from srb200 import synth, weights
+    from srb200.deep_learning_models.EDSR_model import EDSR
+    from srb200.deep_learning_models.SRCNN_model import SRCNNModel
+    hr = synth.hr_image(120, 88, 3)
+    lr = synth.area_downsample(hr, 2)
+    w = weights.edsr_weights(2, num_res_blocks=2, bias_scale=0.05)
+    m = EDSR()
+    m.setup_model(scale_factor=2, num_res_blocks=2, precision="fp32")
+    with pytest.raises(RuntimeError):
+        m.super_resolve_image_whole(lr)
+    m.load_weights(w)
+    sr, info = m.super_resolve_image_whole(lr)
+    want = np.clip(oc.edsr_forward(w, lr[None], 2, 2)[0], 0, 1)
+    assert sr.shape == (120, 88, 3) and sr.dtype == np.float32 and np.abs(sr - want).max() <= 1e-3
+    assert set(info) == {"time_sec", "gpu_mean_current_mb", "gpu_peak_mb"}
+    tiled, _ = m.super_resolve_image(lr, patch_size_lr=24, stride=12)
+    # receptive field: head + 2 blocks + body-end + up-conv = 7 LR pixels (+ the HR tail).  LR pixels 8..10 are covered by
+    # the first patch only (the next one starts at 12) and see no patch border, so both flows compute the same function
+    assert np.abs(sr[16:22, 16:22] - tiled[16:22, 16:22]).max() <= 1e-3
+    ws = weights.srcnn_weights(bias_scale=0.05)
+    s = SRCNNModel()
+    s.setup_model(input_shape=(33, 33, 3))
+    s.load_weights(ws)
+    out, _ = s.super_resolve_image_whole(lr, 120, 88)
+    want = np.clip(oc.srcnn_forward(ws, ob.cv2_resize(lr, (88, 120))[None])[0], 0, 1)
+    assert out.shape == (120, 88, 3) and np.abs(out - want).max() <= 1e-3
