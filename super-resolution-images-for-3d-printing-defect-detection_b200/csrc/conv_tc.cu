@@ -554,8 +554,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-      const int b = tl / tiles_per_img, rr_ = tl - b * tiles_per_img;
-      const int y0 = (rr_ / q.tiles_x) * kTileH, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
+      const int b = fast_div(tl, tiles_per_img, q.magic_tpi), rr_ = tl - b * tiles_per_img;
+      const int ty_ = fast_div(rr_, q.tiles_x, q.magic_tx);
+      const int y0 = ty_ * kTileH, x0 = (rr_ - ty_ * q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const size_t tp = tile_pixel(b, y0, x0);
       if (P8) {
@@ -652,9 +653,10 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     };
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
       const bool live = tile < q.total_tiles;           // (k2: the pair's odd CTA may hold a dummy tile)
-      const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-      const int b = tl / tiles_per_img, rr_ = tl - b * tiles_per_img;
-      const int y0 = live ? (rr_ / q.tiles_x) * kTileH : p.H, x0 = (rr_ % q.tiles_x) * q.tile_cols_out;
+      const int tl = !live ? 0 : q.reverse ? q.total_tiles - 1 - tile : tile;   // (never negative: multiply-high division)
+      const int b = fast_div(tl, tiles_per_img, q.magic_tpi), rr_ = tl - b * tiles_per_img;
+      const int ty_ = fast_div(rr_, q.tiles_x, q.magic_tx);
+      const int y0 = live ? ty_ * kTileH : p.H, x0 = (rr_ - ty_ * q.tiles_x) * q.tile_cols_out;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
       const int acc = it & 1;
