@@ -74,24 +74,26 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
       srb_conv_weights_destroy(w);
       return cuda_fail(e, "conv_weights_create(tc)");
     }
-    if (kh == 3 && kw == 3 && cout == 64) {
-      // 64 -> 64 layers: horizontal taps folded into N = 192 rows per vertical tap, row = dx * 64 + co (wide-tile kernel)
-      std::vector<__nv_bfloat16> fb((size_t)3 * 192 * cin, __float2bfloat16_rn(0.f));
-      std::vector<__half> fh((size_t)3 * 192 * cin, __float2half_rn(0.f));
+    if (kh == 3 && kw == 3 && cout % 16 == 0 && cout >= 16 && cout <= 64) {
+      // 64 -> 16 / 32 / 48 / 64 layers: horizontal taps folded into N = 3 * cout rows per vertical tap, row = dx * cout + co
+      // (wide-tile kernel)
+      const int n = 3 * cout;
+      std::vector<__nv_bfloat16> fb((size_t)3 * n * cin, __float2bfloat16_rn(0.f));
+      std::vector<__half> fh((size_t)3 * n * cin, __float2half_rn(0.f));
       for (int dy = 0; dy < 3; ++dy)
         for (int dx = 0; dx < 3; ++dx)
           for (int o = 0; o < cout; ++o)
             for (int c = 0; c < cin; ++c) {
               const float v = hwio[((size_t)(dy * 3 + dx) * cin + c) * cout + o];
-              fb[((size_t)dy * 192 + dx * 64 + o) * cin + c] = __float2bfloat16_rn(v);
-              fh[((size_t)dy * 192 + dx * 64 + o) * cin + c] = __float2half_rn(v);
+              fb[((size_t)dy * n + dx * cout + o) * cin + c] = __float2bfloat16_rn(v);
+              fh[((size_t)dy * n + dx * cout + o) * cin + c] = __float2half_rn(v);
             }
       if ((e = cudaMalloc(&w->tc_fold, fb.size() * 2)) != cudaSuccess ||
           (e = cudaMemcpy(w->tc_fold, fb.data(), fb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
           (e = cudaMalloc(&w->tc_fold_f16, fh.size() * 2)) != cudaSuccess ||
           (e = cudaMemcpy(w->tc_fold_f16, fh.data(), fh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
         srb_conv_weights_destroy(w);
-        return cuda_fail(e, "conv_weights_create(tc fold 64)");
+        return cuda_fail(e, "conv_weights_create(tc fold)");
       }
     }
     if (cout <= 4 && kh <= 9 && kw <= 9) {

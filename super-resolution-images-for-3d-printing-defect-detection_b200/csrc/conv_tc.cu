@@ -1211,7 +1211,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
       }
     } else {
-      // 64 output channels, 16-bit y: warp (quadrant = tile row, cq = 16 of the 64 channels); rows move with TMA.
+      // 16 .. 64 output channels, 16-bit y: warp (quadrant = tile row, cq = 16 of the channels); rows move with TMA.
       // Sixteen epilogue warps (four per scheduler) hide the TMEM-load / shuffle latencies of this role.
       constexpr bool P8 = kMode == 2;
       const int col0 = cq * 16;                           // first output channel of this warp
@@ -1244,6 +1244,11 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int acc = it & 1;
         const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
         const uint32_t buf = my_epi + (P8 ? (uint32_t)(it & 1) * buf_bytes : 0u);
+        if (col0 >= p.cout) {                             // layers with fewer than 64 outputs: this channel quarter only keeps the protocol
+          mbar_wait(tfull_bar(acc), acc_ph);
+          release_tmem(acc);
+          continue;
+        }
         if (lane == 0) {
           bulk_wait_read0();
           if (P8 && tile + tile_step < q.total_tiles) load_res(tile + tile_step, (uint32_t)((it + 1) & 1));
@@ -1255,8 +1260,8 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         uint32_t d0[16], d1[16], d2[16];
         __syncwarp();
         tmem_ld16(t_row, d0);
-        tmem_ld16(t_row + 64u, d1);
-        tmem_ld16(t_row + 128u, d2);
+        tmem_ld16(t_row + (uint32_t)q.gw, d1);
+        tmem_ld16(t_row + 2u * (uint32_t)q.gw, d2);
         tmem_ld_wait();
         release_tmem(acc);
         float a[16];                                      // conv + bias of output column x0 + lane (packed fp32x2 adds)
@@ -1402,14 +1407,14 @@ static int fold_mode(const ConvParams& p) {          // -1: not eligible
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
   if (p.cout <= 4) return (!p.res1 && !p.res2 && !p.y2) ? 3 : -1;
   if (p.kh != 3 || p.kw != 3) return -1;
-  if (p.cout != 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
+  if (p.cout % 16 || p.cout < 16 || p.cout > 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
   if (!p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f) {
     if (p.act == SRB_ACT_NONE) return 0;
     if (p.act == SRB_ACT_RELU) return 1;
     if (p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu)) return 4;
     return -1;
   }
-  const bool pair8 = p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
+  const bool pair8 = p.cout == 64 && p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
                      (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == SRB_F8E5M2)) && p.act == SRB_ACT_NONE && !p.clip01 &&
                      p.res1_cstride % 8 == 0 && p.res2_cstride % 16 == 0 && (!p.y2 || p.y2_cstride % 16 == 0) &&
                      aligned16(p.res1) && aligned16(p.res2) && (!p.y2 || aligned16(p.y2));
@@ -1423,9 +1428,9 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   EncodeTiledFn encode = tc_encode_fn();
   if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
   FoldParams q{};
-  q.gw = mode == 3 ? 4 : 64;
+  q.gw = mode == 3 ? 4 : p.cout;                       // 16 / 32 / 48 / 64 output channels: N = 48 / 96 / 144 / 192
   q.kh = p.kh; q.kw = p.kw;
-  q.n = mode == 3 ? ((p.kw * 4 + 15) & ~15) : 192;
+  q.n = mode == 3 ? ((p.kw * 4 + 15) & ~15) : 3 * p.cout;
   q.out_cols = kFW - (p.kw - 1);
   q.stage_bytes = (uint32_t)(kFH + p.kh - 1) * kFW * 128u;
   q.tiles_x = (p.W + q.out_cols - 1) / q.out_cols;

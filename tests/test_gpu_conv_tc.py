@@ -286,3 +286,30 @@ def test_depth_to_space_to_rgb(shape):
     assert got.shape == (B, 4 * H, 4 * W, 3) and np.abs(got - want).max() <= 2e-3
     got, want = _run("fp16", B, H, W, 12, d2s=2, act="relu")
     assert got.shape == (B, 2 * H, 2 * W, 3) and np.abs(got - want).max() <= 2e-3
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("cout", [16, 32, 48])
+@pytest.mark.parametrize("shape,act", [((2, 24, 40), "relu"), ((1, 19, 67), None)])
+def test_wide_tile_kernel_with_fewer_output_channels(kind, cout, shape, act):
+    """3x3 layers with 16 / 32 / 48 outputs and 16-bit results (ESPCN's 64 -> 32 layer) run on the dx-folded wide-tile
+    kernel with N = 3 * cout (the 36-MMA formulation is bound by the A-operand fetch at any N <= 64); odd sizes, tiles
+    clipped in x and y, idle channel quarters."""
+    B, H, W = shape
+    got, want = _run(kind, B, H, W, cout, out_dtype=DT[kind], act=act)
+    tol = (2.0 ** -7 if kind == "bf16" else 2.0 ** -10) * max(1.0, float(np.abs(want).max()))
+    assert got.shape == want.shape and np.abs(got - want).max() <= tol
+
+
+def test_wide_tile_kernel_into_a_channel_slice():
+    """The ESPCN arrangement: 64 -> 32 with ReLU written into channels [0, 32) of a 64-wide buffer whose upper half stays zero."""
+    from srb200 import ops
+    x = _round(_rand((2, 30, 33, 64), 11), "fp16")
+    kern = _round(_rand((3, 3, 64, 32), 12, -0.1, 0.1), "fp16")
+    bias = _rand((32,), 13, -0.1, 0.1)
+    want = np.maximum(oc.conv2d_same_numpy(x, kern, bias), 0)
+    wide = torch.zeros((2, 30, 33, 64), dtype=torch.float16, device="cuda")
+    ops.conv2d(torch.from_numpy(x).cuda().half(), ops.ConvWeights(kern, bias), act="relu", out=wide, out_coffset=0)
+    got = wide.float().cpu().numpy()
+    assert np.abs(got[..., :32] - want).max() <= 2.0 ** -10 * max(1.0, float(np.abs(want).max()))
+    assert not got[..., 32:].any()
