@@ -999,6 +999,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 // The halo is one TMA box of 64 c x 32 w x 6 h; the dy shift is 4,096 bytes (swizzle-atom aligned).  Output rows move with
 // TMA exactly as in the staged epilogue above (boxes of {32 channels, 30 pixels, 1 row}).
 // Modes: 0 plain 16-bit y, 1 ReLU 16-bit y, 4 PReLU / leaky 16-bit y, 2 pair8 trunk (16-bit hi + e5m2 lo residual in, y + rounding error out),
+//        5 depth_to_space straight to a few-channel fp32 image (ESPCN: 48 -> 4 x 4 x RGB), float4 stores,
 //        3 few channels (Cout <= 4, groups of 5 columns): bias / activation / alpha / clip, stored element-wise.
 // ===================================================================================================================
 constexpr int kFW = 32, kFH = 4, kFOut = 30;
@@ -1059,7 +1060,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     if (kMode == 4) slope_s[i] = (p.act == SRB_ACT_PRELU && i < p.cout) ? p.prelu[i] : p.act_slope;
   }
   if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
-  if (warp == 2 && lane == 0 && kMode != 3) {
+  if (warp == 2 && lane == 0 && kMode != 3 && kMode != 5) {
     prefetch_tmap(&em.y);
     if (kMode == 2) { prefetch_tmap(&em.r1); prefetch_tmap(&em.r2); if (p.y2) prefetch_tmap(&em.y2); }
   }
@@ -1227,6 +1228,17 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
       float bb[16];
 #pragma unroll
       for (int e = 0; e < 16; ++e) bb[e] = bias_s[col0 + e];
+      uint32_t d2s_off[4] = {};                           // mode 5: float offset of each 4-channel group inside the r x r block
+      const bool d2s_plain = p.act == SRB_ACT_NONE && p.alpha == 1.f && !p.clip01;
+      if (kMode == 5) {
+        const int rg = p.d2s * p.c_post;                  // floats per output sub-row (a multiple of 4)
+        const uint32_t sub_row = (uint32_t)(p.W * p.d2s) * (uint32_t)p.c_post;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int cb = col0 + 4 * g, i = cb / rg;
+          d2s_off[g] = (uint32_t)i * sub_row + (uint32_t)(cb - i * rg);
+        }
+      }
       __syncwarp();
       auto load_res = [&](int tile, uint32_t nb) {
         int b, y0, x0;
@@ -1249,7 +1261,7 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           release_tmem(acc);
           continue;
         }
-        if (lane == 0) {
+        if (lane == 0 && kMode != 5) {
           bulk_wait_read0();
           if (P8 && tile + tile_step < q.total_tiles) load_res(tile + tile_step, (uint32_t)((it + 1) & 1));
         }
@@ -1274,6 +1286,33 @@ conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
           const float2 sum = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1])), mid),
                                         __fadd2_rn(right, make_float2(bb[2 * i], bb[2 * i + 1])));
           a[2 * i] = sum.x; a[2 * i + 1] = sum.y;
+        }
+        if (kMode == 5) {
+          // depth_to_space straight to the fp32 image: the 16 channels of this warp are four groups of four consecutive
+          // floats inside the pixel's r x r block (offsets precomputed per warp); lanes 0..29 are output columns
+          const int oy = y0 + quad, ox = x0 + lane;
+          if (lane < kFOut && oy < p.H && ox < p.W) {
+            const int r = p.d2s;
+            float* drow = reinterpret_cast<float*>(p.y) +
+                          (((size_t)b * p.H * r + (size_t)oy * r) * ((size_t)p.W * r) + (size_t)ox * r) * p.c_post;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float v[4] = {a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]};
+              if (!d2s_plain) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float t = v[u];
+                  if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
+                  else if (p.act != SRB_ACT_NONE) t = act_generic(t, p.act, p.act_slope);
+                  t *= alpha;
+                  if (p.clip01) t = fminf(fmaxf(t, 0.f), 1.f);
+                  v[u] = t;
+                }
+              }
+              *reinterpret_cast<float4*>(drow + d2s_off[g]) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          }
+          continue;
         }
         const uint32_t a_h0 = buf + h_row + ((0u ^ h_x) << 4), a_h1 = buf + h_row + ((1u ^ h_x) << 4);
         uint32_t oh[8];
@@ -1402,9 +1441,17 @@ static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
 // ---- wide-tile fold kernel: eligibility and launch ----
 static int fold_mode(const ConvParams& p) {          // -1: not eligible
   static const bool enabled = getenv("SRB_TC_NO_WIDE") == nullptr;
-  if (!enabled || g_variant != 0 || p.cin != 64 || !p.w_tc_fold || p.d2s != 1 || p.kh > 9 || p.kw > 9) return -1;
+  if (!enabled || g_variant != 0 || p.cin != 64 || !p.w_tc_fold || p.kh > 9 || p.kw > 9) return -1;
   if (getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG"))) return -1;
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
+  if (p.d2s != 1) {
+    // mode 5: depth_to_space straight to a few-channel fp32 image (ESPCN's last layer: 48 -> 4 x 4 x RGB)
+    const bool ok = p.kh == 3 && p.kw == 3 && p.cout % 16 == 0 && p.cout >= 16 && p.cout <= 64 && p.y_dtype == SRB_F32 &&
+                    !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU && p.y_cstride == p.c_post && p.y_coffset == 0 &&
+                    (p.d2s * p.c_post) % 4 == 0 && aligned16(p.y) &&
+                    (long)p.B * p.H * p.W * p.cout < (1L << 31);          // (32-bit element offsets inside the image batch)
+    return ok ? 5 : -1;
+  }
   if (p.cout <= 4) return (!p.res1 && !p.res2 && !p.y2) ? 3 : -1;
   if (p.kh != 3 || p.kw != 3) return -1;
   if (p.cout % 16 || p.cout < 16 || p.cout > 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
@@ -1442,7 +1489,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   while (q.tmem_cols < (uint32_t)(2 * q.n)) q.tmem_cols <<= 1;
   const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;
   q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  q.epi_warp_bytes = mode == 3 ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
+  q.epi_warp_bytes = (mode == 3 || mode == 5) ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
   q.reverse = next_reverse();
   q.magic_tpi = div_magic(total + 1, q.tiles_x * q.tiles_y);
   q.magic_tx = div_magic((long)q.tiles_x * q.tiles_y, q.tiles_x);
@@ -1480,7 +1527,7 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
   }
   EpiMaps em;
   memset(&em, 0, sizeof(em));
-  if (mode != 3) {
+  if (mode != 3 && mode != 5) {
     auto encode_epi = [&](CUtensorMap* m, const void* ptr, int coffset, int cstride, bool f8) -> bool {
       const size_t es = f8 ? 1 : 2;
       const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
@@ -1502,10 +1549,11 @@ static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) 
     if (!ok) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
   }
   typedef void (*FoldFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FoldParams, const ConvParams);
-  static const FoldFn kernels[6] = {conv3x3_fold_kernel<0, false>, conv3x3_fold_kernel<1, false>, conv3x3_fold_kernel<2, false>,
-                                    conv3x3_fold_kernel<3, false>, conv3x3_fold_kernel<4, false>, conv3x3_fold_kernel<3, true>};
-  static size_t configured[6] = {0, 0, 0, 0, 0, 0};
-  const int ki = (mode == 3 && (p.kh != 3 || p.kw != 3)) ? 5 : mode;
+  static const FoldFn kernels[7] = {conv3x3_fold_kernel<0, false>, conv3x3_fold_kernel<1, false>, conv3x3_fold_kernel<2, false>,
+                                    conv3x3_fold_kernel<3, false>, conv3x3_fold_kernel<4, false>, conv3x3_fold_kernel<3, true>,
+                                    conv3x3_fold_kernel<5, false>};
+  static size_t configured[7] = {0, 0, 0, 0, 0, 0, 0};
+  const int ki = (mode == 3 && (p.kh != 3 || p.kw != 3)) ? 5 : mode == 5 ? 6 : mode;
   if (smem > configured[ki]) {
     SRB_CUDA(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured[ki] = smem;
