@@ -313,3 +313,28 @@ def test_wide_tile_kernel_into_a_channel_slice():
     got = wide.float().cpu().numpy()
     assert np.abs(got[..., :32] - want).max() <= 2.0 ** -10 * max(1.0, float(np.abs(want).max()))
     assert not got[..., 32:].any()
+
+
+def test_espcn_layers_at_benchmark_tile_size():
+    """BASELINE config 2 tile size (256 x 256, 12 tiles: more 4 x 30-pixel tiles than one wave of CTAs): the wide-tile kernel
+    with N = 96 (64 -> 32, ReLU, 16-bit, into a channel slice) and its depth_to_space-to-image mode (64(32) -> 48, fp32)
+    against the exact CUDA-core engine on the same 16-bit inputs, and the whole network against its fp32 mode."""
+    from srb200 import engine, ops, weights, _capi
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = (torch.rand((12, 256, 256, 64), device="cuda", generator=g) * 2 - 1).half()
+    k2 = _round(_rand((3, 3, 64, 32), 2, -0.1, 0.1), "fp16")
+    w2 = ops.ConvWeights(k2, _rand((32,), 3, -0.1, 0.1))
+    a = ops.conv2d(x, w2, act="relu", out_dtype=torch.float16, engine=_capi.ENGINE_TCGEN05)
+    b = ops.conv2d(x, w2, act="relu", out_dtype=torch.float32, engine=_capi.ENGINE_DIRECT)
+    assert (a.float() - b).abs().max().item() <= 4e-3
+    k3 = _round(_rand((3, 3, 64, 48), 4, -0.1, 0.1), "fp16")
+    w3 = ops.ConvWeights(k3, _rand((48,), 5, -0.1, 0.1))
+    a = ops.conv2d(x, w3, d2s=4, out_dtype=torch.float32, engine=_capi.ENGINE_TCGEN05)
+    b = ops.conv2d(x, w3, d2s=4, out_dtype=torch.float32, engine=_capi.ENGINE_DIRECT)
+    assert a.shape == (12, 1024, 1024, 3) and (a - b).abs().max().item() <= 2e-3
+    del a, b, x
+    w = weights.espcn_weights(4, bias_scale=0.05)
+    img = torch.rand((4, 256, 256, 3), device="cuda", generator=g)
+    lo = engine.ESPCNNet(w, 4, precision="fp16").predict_device(img)
+    hi = engine.ESPCNNet(w, 4, precision="fp32").predict_device(img)
+    assert (lo - hi).abs().max().item() <= 2e-2
