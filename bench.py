@@ -145,6 +145,64 @@ class ClockSampler:
                            "samples": len(sm), "power_w_max": max(watts), "source": "nvidia-smi"}
 
 
+def layer_group_rooflines(net, x, torch, ops):
+    """One CUDA-event pair around every conv launch of EDSRNet.forward_device (5 forwards, medians), grouped by layer role."""
+    records, orig = [], ops.conv2d
+
+    def timed(xx, w, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig(xx, w, **kw)
+        e1.record()
+        records.append((w, xx.shape[0] * xx.shape[1] * xx.shape[2], kw, e0, e1))
+        return out
+    hook, net.event_hook = net.event_hook, None
+    ops.conv2d = timed
+    try:
+        per_rep = []
+        for _ in range(5):
+            records.clear()
+            net.forward_device(x)
+            torch.cuda.synchronize()
+            per_rep.append([(w, npx, kw, e0.elapsed_time(e1)) for (w, npx, kw, e0, e1) in records])
+    finally:
+        ops.conv2d = orig
+        net.event_hook = hook
+    groups = {}
+    for i, (w, npx, kw, _) in enumerate(per_rep[0]):
+        ms = statistics.median(rep[i][3] for rep in per_rep)
+        esz = lambda tns: tns.element_size()                                   # noqa: E731
+        in_b = npx * w.cin * (4 if w.cin == 3 else 2)
+        out_dt = kw.get("out_dtype")
+        out_b = npx * w.cout * (4 if out_dt == torch.float32 else 2)
+        if kw.get("out2_dtype") is not None:
+            out_b += npx * w.cout * torch.empty((), dtype=kw["out2_dtype"]).element_size()
+        for rk in ("res1", "res2"):
+            if kw.get(rk) is not None:
+                in_b += npx * w.cout * esz(kw[rk])
+        if w.cin == 3:
+            name = "head 3x3 3->64 (im2col GEMM)"
+        elif w.cout <= 4:
+            name = "RGB tail 3x3 64->3 (wide-tile fold)"
+        elif w.cout == 256:
+            name = "up-sampling 3x3 64->256 + depth_to_space (CTA pairs)"
+        elif kw.get("res1") is not None:
+            name = "res-block 2nd conv / body end 3x3 64->64 + residual (pair8 trunk)"
+        else:
+            name = "res-block 1st conv 3x3 64->64 + ReLU (wide-tile fold)"
+        g = groups.setdefault(name, {"layer_group": name, "launches": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
+        g["launches"] += 1
+        g["ms"] += ms
+        g["flop"] += 2.0 * npx * w.kh * w.kw * w.cin * w.cout
+        g["bytes"] += in_b + out_b
+    total = sum(g["ms"] for g in groups.values()) or 1.0
+    out = []
+    for g in sorted(groups.values(), key=lambda v: -v["ms"]):
+        out.append({"layer_group": g["layer_group"], "launches": g["launches"], "ms_per_forward": round(g["ms"], 4),
+                    "share": round(g["ms"] / total, 4), "tflops": g["flop"] / g["ms"] / 1e9, "gbs_min": g["bytes"] / g["ms"] / 1e6})
+    return out
+
+
 def lr_tiles(lo, hi, size):
     from srb200 import synth
     return np.stack([synth.hr_image(size, size, i) for i in range(lo, hi)]) if hi > lo else \
@@ -296,6 +354,9 @@ def run_gpu(args):
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
 
+    # per-launch CUDA-event times of one forward (separate, untimed pass on rank 0): which bound each layer group sits at
+    layer_groups = layer_group_rooflines(net, x_dev[:mb], torch, ops) if (rank == 0 and n_local) else None
+
     t = torch.tensor([ms, e2e_ms, tc_ms], dtype=torch.float64, device=dev)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
@@ -331,6 +392,16 @@ def run_gpu(args):
                          "avg_launch_ms": tc_ms / max(n_tc_launches, 1), "launches": n_tc_launches,
                          "whole_net_tflops": EDSR_FLOP_PER_LR_PX * tile * tile * args.batch * args.steps / (ms / 1e3) / 1e12},
         }
+        if layer_groups:
+            for g in layer_groups:
+                g["tensor_frac"] = g["tflops"] / peaks["tflops"]           # (sustained peak: the pass runs at the power cap)
+                g["hbm_frac"] = g["gbs_min"] / peaks["hbm_gbs"]
+                g["bound"] = "hbm" if g["hbm_frac"] > g["tensor_frac"] else "tensor"
+            line["roofline"]["by_layer_group"] = layer_groups
+            line["roofline"]["by_layer_group_note"] = ("median CUDA-event time per launch over 5 forwards of one micro-batch, right after the "
+                                                        "timed loop (same power-capped clocks, outside the timed region); gbs_min = algorithmic "
+                                                        "bytes (16-bit activations, pair8 trunk = 3 B per channel, fp32 RGB in / out) / time; "
+                                                        "fractions against the sustained bf16 peak and the copy peak")
         if args.gpus == 1 and not args.no_cpu:
             n_cpu = 24
             mp_s, cores, secs = cpu_edsr_mp_per_s(n_cpu, tile)
