@@ -107,17 +107,34 @@ class DeviceModel:
         mb = self.max_device_batch or 64
         comp = torch.cuda.current_stream()
         cin, cout = self._copy_streams()
-        for i in range(0, n, mb):
+        for i, m in self._chunks(n, mb):
             with torch.cuda.stream(cin):
-                xd = xt[i:i + mb].to("cuda", non_blocking=True)
+                xd = xt[i:i + m].to("cuda", non_blocking=True)
             comp.wait_stream(cin)
             xd.record_stream(comp)
             y = self.forward_device(xd)
             cout.wait_stream(comp)
             with torch.cuda.stream(cout):
-                ot[i:i + mb].copy_(y, non_blocking=True)
+                ot[i:i + m].copy_(y, non_blocking=True)
             y.record_stream(cout)
         cout.synchronize()
+        return out
+
+    @staticmethod
+    def _chunks(n, mb):
+        """(start, size) pieces of n images: micro-batches of ``mb``, with the last one cut into a half and two quarters -
+        only the final piece's device->host copy cannot hide behind later kernels, so it is kept small."""
+        sizes = [mb] * (n // mb) + ([n % mb] if n % mb else [])
+        last = sizes.pop()
+        if last >= 16 and sizes:
+            h, q = last // 2, last // 4
+            sizes += [h, q, last - h - q]
+        else:
+            sizes.append(last)
+        out, i = [], 0
+        for m in sizes:
+            out.append((i, m))
+            i += m
         return out
 
     def output_shape(self, in_shape):

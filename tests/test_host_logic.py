@@ -90,3 +90,15 @@ def test_constants_keep_the_reference_names():
     assert (c.ESRGAN_PATCH_SIZE, c.ESRGAN_STRIDE, c.ESRGAN_SCALE_FACTOR) == (24, 12, 2)
     assert (c.VGG_PATCH_SIZE, c.VGG_STRIDE, c.RANDOM_SEED) == (96, 48, 42)
     assert not hasattr(c, "SRCNN_SCALE_FACTOR") and not hasattr(c, "VGG_SCALE_FACTOR")
+
+
+def test_predict_chunk_schedule():
+    """engine.DeviceModel._chunks: contiguous cover of the batch, last micro-batch cut into 1/2 + 1/4 + 1/4."""
+    from srb200.engine import DeviceModel
+    for n, mb in [(512, 32), (64, 16), (70, 32), (5, 32), (32, 32), (33, 32), (16, 64)]:
+        ch = DeviceModel._chunks(n, mb)
+        assert ch[0][0] == 0 and sum(m for _, m in ch) == n and all(m > 0 for _, m in ch)
+        assert all(ch[k][0] + ch[k][1] == ch[k + 1][0] for k in range(len(ch) - 1))
+        assert max(m for _, m in ch) <= mb
+    assert [m for _, m in DeviceModel._chunks(512, 32)][-3:] == [16, 8, 8]
+    assert DeviceModel._chunks(32, 32) == [(0, 32)]
