@@ -107,16 +107,36 @@ class DeviceModel:
         mb = self.max_device_batch or 64
         comp = torch.cuda.current_stream()
         cin, cout = self._copy_streams()
-        for i, m in self._chunks(n, mb):
+        # two persistent device input buffers and explicit events instead of per-chunk allocations on the copy streams
+        # (record_stream defers the reuse of those blocks by the caching allocator, which showed up as occasional
+        # cudaMalloc stalls in the middle of a run)
+        key = (mb,) + tuple(x.shape[1:])
+        if getattr(self, "_in_key", None) != key:
+            self._in_bufs = [torch.empty(key, dtype=torch.float32, device="cuda") for _ in range(2)]
+            self._in_key = key
+        in_ready = [torch.cuda.Event(), torch.cuda.Event()]
+        in_free = [None, None]
+        prev = None                                       # (output of the previous chunk, event: its read-back has finished)
+        for k, (i, m) in enumerate(self._chunks(n, mb)):
+            b = k & 1
+            xd = self._in_bufs[b][:m]
             with torch.cuda.stream(cin):
-                xd = xt[i:i + m].to("cuda", non_blocking=True)
-            comp.wait_stream(cin)
-            xd.record_stream(comp)
+                if in_free[b] is not None:
+                    cin.wait_event(in_free[b])            # the kernels that read this buffer two chunks ago are done
+                xd.copy_(xt[i:i + m], non_blocking=True)
+                in_ready[b].record(cin)
+            comp.wait_event(in_ready[b])
             y = self.forward_device(xd)
+            in_free[b] = torch.cuda.Event()
+            in_free[b].record(comp)
             cout.wait_stream(comp)
             with torch.cuda.stream(cout):
                 ot[i:i + m].copy_(y, non_blocking=True)
-            y.record_stream(cout)
+                copied = torch.cuda.Event()
+                copied.record(cout)
+            if prev is not None:
+                comp.wait_event(prev[1])                  # later kernels may reuse the previous output's memory: order them
+            prev = (y, copied)                            # after its read-back (long finished by now), then drop it
         cout.synchronize()
         return out
 
