@@ -10,6 +10,8 @@ package never does, and it has no CPU fallback.
 Pinning status:
 * bicubic   - PINNED: checked against the reference's actual dependency call,
               ``cv2.resize`` (OpenCV 4.13.0 in this image), float32 and uint8.
+* Lanczos-4 / bilinear / area - PINNED: ``cv2.resize`` outputs in tests/golden/resize_cv2.npz (the bilinear and area
+              modes are checked on the device only; Lanczos-4 has a numpy restatement in bicubic.py).
 * tiling    - PINNED: checked against ``SRModels/loading_methods.py::add_padding`` imported
               from /root/reference when generating ``tests/golden``, and against the dataset
               shape print-outs of the reference notebooks.
@@ -20,4 +22,7 @@ Pinning status:
               known-answers listed in SURVEY.md section 8c and cross-checked against an
               independent scipy.ndimage evaluation of the same published definition
               (tests/test_oracle_metrics.py).
+* skimage-style PSNR/SSIM (the classical benchmark notebook's metric definitions) - parity unpinned (scikit-image is
+              absent): restated on the scipy.ndimage.uniform_filter primitive skimage itself calls, and checked
+              against a direct evaluation of every valid window with numpy's sample (co)variance.
 """
