@@ -82,6 +82,11 @@ int srb_resize_f32(const float* src, int batch, int src_h, int src_w, int channe
                    float* dst, int dst_h, int dst_w, int interpolation, int clip01, srb_stream_t stream);
 int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,
                    uint8_t* dst, int dst_h, int dst_w, int fixed_point, srb_stream_t stream);
+/* cv2.resize on uint8 images for the same four codes (super_resolucion_clasica.ipynb cell 7 calls interpolate_bilinear /
+ * _area / _lanczos on uint8 arrays): OpenCV's 11-bit fixed-point linear, area (up-scaling) and Lanczos-4 paths, bit-exact
+ * against cv2 4.13 golden outputs; SRB_INTER_CUBIC == srb_bicubic_u8(..., fixed_point = 0). */
+int srb_resize_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                  uint8_t* dst, int dst_h, int dst_w, int interpolation, srb_stream_t stream);
 
 /* ---- tiling (loading_methods.py:6-26; EDSR_model.py:201-256) -----------------------------------
  * pad_extract: reflect-pad bottom/right by the reference's rule and cut [ny*nx, P, P, C] patches at
@@ -101,7 +106,9 @@ int srb_overlap_add_f32(const float* patches, int ny, int nx, int patch_out, int
  * [B, H*r, W*r, cout/(r*r)] and PReLU slopes are indexed by the post-shuffle channel. */
 typedef struct srb_conv_args {
   const void* x;        int x_dtype;   int x_cstride;  int x_coffset;   /* input  NHWC, C-slice allowed */
-  void*       y;        int y_dtype;   int y_cstride;  int y_coffset;   /* output NHWC, C-slice allowed */
+  void*       y;        int y_dtype;   int y_cstride;  int y_coffset;   /* output NHWC, C-slice allowed; SRB_U8 (without
+                                                                           y2) stores saturate(rint(255 v)): the [0, 1]
+                                                                           image quantised for a 4x smaller read-back */
   void*       y2;       int y2_dtype;  int y2_cstride;  int y2_mode;    /* optional second output, same geometry:
                                                                            mode 0 = the same values in another dtype
                                                                            (fp32 trunk next to the 16-bit operand);

@@ -208,6 +208,69 @@ def resize_lanczos4_f32(src, dsize):
     return out[:, :, 0] if squeeze else out
 
 
+# ---- uint8 INTER_LINEAR / INTER_AREA (up-scaling) / INTER_LANCZOS4: OpenCV's 11-bit fixed-point paths ----------------
+# (classic_algorithms.py:7-9, 15-21 called on uint8 images by super_resolucion_clasica.ipynb cell 7)
+def linear_axis_table_u8(n_src, n_dst, area=False, clamp_t=True):
+    """-> (idx [n_dst, 2], icoef [n_dst, 2] = rint(c * 2048) as int).  OpenCV builds the x table with the fraction forced
+    to 0 where the tap pair leaves the image (``clamp_t``); the y table keeps the fraction and clamps the ROW INDEX in the
+    row loop instead, so a border row is blended with itself through both (separately truncated) products."""
+    scale = 1.0 / (float(n_dst) / float(n_src))
+    inv = float(n_dst) / float(n_src)
+    d = np.arange(n_dst, dtype=_f64)
+    if not area:
+        f = ((d + 0.5) * scale - 0.5).astype(_f32)
+        s = np.floor(f).astype(np.int64)
+        t = (f - s.astype(_f32)).astype(_f32)
+    else:
+        s = np.floor(d * scale).astype(np.int64)
+        t = ((d + 1) - (s + 1) * inv).astype(_f32)
+        t = np.where(t <= 0, _f32(0), (t - np.floor(t)).astype(_f32)).astype(_f32)
+    if clamp_t:
+        lo = s < 0
+        t, s = np.where(lo, _f32(0), t), np.where(lo, 0, s)
+        hi = s >= n_src - 1
+        t, s = np.where(hi, _f32(0), t), np.where(hi, n_src - 1, s)
+    c = np.stack([(_f32(1) - t).astype(_f32), t.astype(_f32)], -1)
+    idx = np.clip(np.stack([s, s + 1], -1), 0, n_src - 1)
+    return idx, _fix_coeffs(c).astype(np.int64)
+
+
+def resize_linear_u8(src, dsize, area=False):
+    """cv2.resize(uint8, INTER_LINEAR) and - when the image grows - INTER_AREA, bit-exact (HResizeLinear int32 pass, then
+    VResizeLinear<uchar>: ((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2)."""
+    src, squeeze = _as_hwc(np.asarray(src, dtype=np.uint8))
+    dw, dh = int(dsize[0]), int(dsize[1])
+    h, w, c = src.shape
+    xi, xa = linear_axis_table_u8(w, dw, area, clamp_t=True)
+    yi, yb = linear_axis_table_u8(h, dh, area, clamp_t=False)
+    s = src.astype(np.int64)
+    rows = s[:, xi[:, 0], :] * xa[None, :, 0, None] + s[:, xi[:, 1], :] * xa[None, :, 1, None]
+    s0, s1 = rows[yi[:, 0]], rows[yi[:, 1]]
+    b0, b1 = yb[:, 0, None, None], yb[:, 1, None, None]
+    out = np.clip((((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2, 0, 255).astype(np.uint8)
+    return out[:, :, 0] if squeeze else out
+
+
+def resize_lanczos4_u8(src, dsize):
+    """cv2.resize(uint8, INTER_LANCZOS4): coefficients rint(c * 2048) as int16, int32 horizontal pass, integer vertical pass
+    (sum + 2^21) >> 22, saturate."""
+    src, squeeze = _as_hwc(np.asarray(src, dtype=np.uint8))
+    dw, dh = int(dsize[0]), int(dsize[1])
+    h, w, c = src.shape
+    xi, xa = lanczos4_axis_table(w, dw)
+    yi, yb = lanczos4_axis_table(h, dh)
+    ia, ib = _fix_coeffs(xa).astype(np.int64), _fix_coeffs(yb).astype(np.int64)
+    s = src.astype(np.int64)
+    rows = np.zeros((h, dw, c), np.int64)
+    for k in range(8):
+        rows += s[:, xi[:, k], :] * ia[None, :, k, None]
+    acc = np.zeros((dh, dw, c), np.int64)
+    for k in range(8):
+        acc += rows[yi[:, k]] * ib[:, k, None, None]
+    out = np.clip((acc + (1 << 21)) >> 22, 0, 255).astype(np.uint8)
+    return out[:, :, 0] if squeeze else out
+
+
 def cv2_resize(src, dsize, optimized=True):
     """The reference's actual implementation of this step (classic_algorithms.py:13)."""
     import cv2

@@ -20,7 +20,9 @@ struct AxisTap { int idx[4]; float coef[4]; };   // 32 bytes
 
 // mode: 0 cubic (float path), 1 cubic (OpenCV 11-bit fixed-point coefficients), 2 bilinear, 3 bilinear with INTER_AREA's
 // up-scaling coefficients (cv2.resize treats INTER_AREA as that when the image grows).  The bilinear modes fill the same
-// four-tap table with (0, 1 - t, t, 0), so every kernel below serves them unchanged.
+// four-tap table with (0, 1 - t, t, 0), so every kernel below serves them unchanged.  Modes 4 / 5 are 2 / 3 without the
+// fraction clamp at the image ends: OpenCV builds its y tables that way and clamps the row index in the row loop, which
+// the uint8 fixed-point path can tell apart (a border row is blended with itself through two truncated products).
 __global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base_out, int n_src, int n_dst, int mode) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= n_dst) return;
@@ -33,7 +35,8 @@ __global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base
     // OpenCV resize.cpp, linear branch: fx in float, taps sx and sx + 1, both ends clamp to a pure copy
     float t;
     int sx;
-    if (mode == 2) {
+    const bool clamp_t = mode < 4;
+    if (mode == 2 || mode == 4) {
       const float f = (float)fd;
       sx = (int)floorf(f);
       t = __fsub_rn(f, (float)sx);
@@ -43,8 +46,10 @@ __global__ void bicubic_tables(AxisTap* __restrict__ tab, int* __restrict__ base
       t = (float)((double)(d + 1) - (double)(sx + 1) * inv_scale);
       t = t <= 0.f ? 0.f : __fsub_rn(t, floorf(t));
     }
-    if (sx < 0) { t = 0.f; sx = 0; }
-    if (sx >= n_src - 1) { t = 0.f; sx = n_src - 1; }
+    if (clamp_t) {
+      if (sx < 0) { t = 0.f; sx = 0; }
+      if (sx >= n_src - 1) { t = 0.f; sx = n_src - 1; }
+    }
     s = sx;
     c0 = 0.f; c1 = __fsub_rn(1.f, t); c2 = t; c3 = 0.f;
   } else if (mode == 1) {
@@ -500,6 +505,104 @@ static int run_lanczos4(const float* src, int batch, int sh, int sw, int C, floa
   return rc;
 }
 
+// ---- uint8 INTER_LINEAR / INTER_AREA (up-scaling) / INTER_LANCZOS4: OpenCV's 11-bit fixed-point paths, bit-exact --------
+// (classic_algorithms.py:7-9, 15-21 as super_resolucion_clasica.ipynb cell 7 calls them on uint8 images).  Coefficients are
+// saturate_cast<short>(rint(c * 2048)); the horizontal pass is an int32 sum; the vertical pass is
+//   linear / area : (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2      (VResizeLinear<uchar, int, short, ...>)
+//   Lanczos-4     : (sum_k S_k * b_k + 2^21) >> 22                                       (FixedPtCast<int, uchar, 22>)
+// One interleaved output column per thread; not a tuned path (the benchmark notebook resizes single images).
+__device__ __forceinline__ int fix11(float c) { return (int)fminf(fmaxf(rintf(__fmul_rn(c, 2048.f)), -32768.f), 32767.f); }
+
+__global__ void __launch_bounds__(kTE)
+linear_u8_fixed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const AxisTap* __restrict__ xtab,
+                       const AxisTap* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w, int rows_per_block) {
+  const int DE = dst_w * C, SE = src_w * C;
+  const int e = blockIdx.x * kTE + threadIdx.x;
+  if (e >= DE) return;
+  const int x = e / C, c = e - x * C;
+  const AxisTap xt = xtab[x];
+  const int o1 = xt.idx[1] * C + c, o2 = xt.idx[2] * C + c;
+  const int a1 = fix11(xt.coef[1]), a2 = fix11(xt.coef[2]);
+  const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, dst_h);
+  const uint8_t* simg = src + (size_t)blockIdx.z * src_h * SE;
+  uint8_t* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
+  for (int y = y0; y < y1; ++y, out += DE) {
+    const AxisTap yt = ytab[y];
+    const uint8_t* r0 = simg + (size_t)yt.idx[1] * SE;
+    const uint8_t* r1 = simg + (size_t)yt.idx[2] * SE;
+    const int s0 = (int)r0[o1] * a1 + (int)r0[o2] * a2, s1 = (int)r1[o1] * a1 + (int)r1[o2] * a2;
+    const int b0 = fix11(yt.coef[1]), b1 = fix11(yt.coef[2]);
+    const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
+    *out = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+__global__ void __launch_bounds__(kTE)
+lanczos4_u8_fixed_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, const AxisTap8* __restrict__ xtab,
+                         const AxisTap8* __restrict__ ytab, int src_h, int src_w, int C, int dst_h, int dst_w, int rows_per_block) {
+  const int DE = dst_w * C, SE = src_w * C;
+  const int e = blockIdx.x * kTE + threadIdx.x;
+  if (e >= DE) return;
+  const int x = e / C, c = e - x * C;
+  int o[8], a[8];
+  {
+    const AxisTap8 xt = xtab[x];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { o[k] = xt.idx[k] * C + c; a[k] = fix11(xt.coef[k]); }
+  }
+  const int y0 = blockIdx.y * rows_per_block, y1 = min(y0 + rows_per_block, dst_h);
+  const uint8_t* simg = src + (size_t)blockIdx.z * src_h * SE;
+  uint8_t* out = dst + (size_t)blockIdx.z * dst_h * DE + (size_t)y0 * DE + e;
+  for (int y = y0; y < y1; ++y, out += DE) {
+    const AxisTap8 yt = ytab[y];
+    long long acc = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint8_t* row = simg + (size_t)yt.idx[k] * SE;
+      int h = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h += (int)row[o[j]] * a[j];
+      acc += (long long)h * (long long)fix11(yt.coef[k]);
+    }
+    // (OpenCV accumulates in int32; |sum| < 2^31 for these coefficient magnitudes, so the wider accumulator agrees)
+    const int v = (int)((acc + (1ll << 21)) >> 22);
+    *out = (uint8_t)min(max(v, 0), 255);
+  }
+}
+
+static int run_resize_u8_fixed(const uint8_t* src, int batch, int sh, int sw, int C, uint8_t* dst, int dh, int dw,
+                               int interpolation, cudaStream_t stream) {
+  SRB_REQUIRE(src && dst, "resize_u8: null pointer");
+  SRB_REQUIRE(batch >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && C > 0, "resize_u8: bad geometry");
+  if (batch == 0) return SRB_OK;
+  int rows = 64;
+  const long target = 4L * sm_count();
+  while (rows > 8 && (long)((dw * C + kTE - 1) / kTE) * ((dh + rows - 1) / rows) * batch < target) rows >>= 1;
+  dim3 grid((dw * C + kTE - 1) / kTE, (dh + rows - 1) / rows, batch);
+  SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "resize_u8: grid too large");
+  int rc;
+  if (interpolation == SRB_INTER_LANCZOS4) {
+    AxisTap8* tabs = nullptr;
+    SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap8) * ((size_t)dw + dh) + sizeof(int) * ((size_t)dh + dw), stream));
+    int* base = reinterpret_cast<int*>(tabs + (size_t)dw + dh);
+    lanczos4_tables<<<(dw + 127) / 128, 128, 0, stream>>>(tabs, base + dh, sw, dw);
+    lanczos4_tables<<<(dh + 127) / 128, 128, 0, stream>>>(tabs + dw, base, sh, dh);
+    lanczos4_u8_fixed_kernel<<<grid, kTE, 0, stream>>>(src, dst, tabs, tabs + dw, sh, sw, C, dh, dw, rows);
+    rc = launch_check("lanczos4_u8_fixed_kernel");
+    SRB_CUDA(cudaFreeAsync(tabs, stream));
+  } else {
+    const int area = interpolation == SRB_INTER_AREA;
+    AxisTap* tabs = nullptr;
+    SRB_CUDA(cudaMallocAsync(&tabs, sizeof(AxisTap) * ((size_t)dw + dh), stream));
+    bicubic_tables<<<(dw + 127) / 128, 128, 0, stream>>>(tabs, nullptr, sw, dw, area ? 3 : 2);          // x: fraction clamped
+    bicubic_tables<<<(dh + 127) / 128, 128, 0, stream>>>(tabs + dw, nullptr, sh, dh, area ? 5 : 4);     // y: row index clamped
+    linear_u8_fixed_kernel<<<grid, kTE, 0, stream>>>(src, dst, tabs, tabs + dw, sh, sw, C, dh, dw, rows);
+    rc = launch_check("linear_u8_fixed_kernel");
+    SRB_CUDA(cudaFreeAsync(tabs, stream));
+  }
+  return rc;
+}
+
 template <typename T, bool FIXED>
 static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, int dh, int dw, int clip01,
                        cudaStream_t stream, int table_mode = FIXED ? 1 : 0) {
@@ -608,4 +711,17 @@ extern "C" int srb_bicubic_u8(const uint8_t* src, int batch, int src_h, int src_
   if (fixed_point)
     return run_bicubic<uint8_t, true>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, 0, (cudaStream_t)stream);
   return run_bicubic<uint8_t, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, 0, (cudaStream_t)stream);
+}
+
+extern "C" int srb_resize_u8(const uint8_t* src, int batch, int src_h, int src_w, int channels,
+                             uint8_t* dst, int dst_h, int dst_w, int interpolation, srb_stream_t stream) {
+  if (interpolation == SRB_INTER_CUBIC)
+    return run_bicubic<uint8_t, false>(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, 0, (cudaStream_t)stream);
+  if (interpolation == SRB_INTER_AREA)
+    SRB_REQUIRE(dst_h >= src_h && dst_w >= src_w, "resize_u8: INTER_AREA is built for up-scaling only (the reference's use); got %dx%d -> %dx%d",
+                src_w, src_h, dst_w, dst_h);
+  if (interpolation == SRB_INTER_LINEAR || interpolation == SRB_INTER_AREA || interpolation == SRB_INTER_LANCZOS4)
+    return run_resize_u8_fixed(src, batch, src_h, src_w, channels, dst, dst_h, dst_w, interpolation, (cudaStream_t)stream);
+  set_error("resize_u8: unsupported interpolation code %d (linear = 1, cubic = 2, area = 3, lanczos4 = 4)", interpolation);
+  return SRB_E_UNSUPPORTED;
 }

@@ -46,6 +46,10 @@ template <> __device__ __forceinline__ void store_from_float<float>(float* p, fl
 template <> __device__ __forceinline__ void store_from_float<__nv_bfloat16>(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16_rn(v);
 }
+template <> __device__ __forceinline__ void store_from_float<uint8_t>(uint8_t* p, float v) {   // saturate(rint(v))
+  *p = (uint8_t)__float2int_rn(fminf(fmaxf(v, 0.f), 255.f));
+}
+template <> __device__ __forceinline__ float load_as_float<uint8_t>(const uint8_t* p) { return (float)*p; }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -144,7 +144,8 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   auto float_dt = [](int d) { return d == SRB_F32 || d == SRB_BF16 || d == SRB_F16; };
   auto float_or_f8 = [&](int d) { return float_dt(d) || d == SRB_F8E5M2; };   // e5m2: second output / residuals only
   SRB_REQUIRE(float_dt(a->x_dtype), "conv2d: x dtype must be f32, bf16 or f16");
-  SRB_REQUIRE(float_dt(a->y_dtype), "conv2d: y dtype must be f32, bf16 or f16");
+  // (u8 output: the [0, 1] image quantised as saturate(rint(255 v)) - the read-back format of the RGB tail layers)
+  SRB_REQUIRE(float_dt(a->y_dtype) || (a->y_dtype == SRB_U8 && !a->y2), "conv2d: y dtype must be f32, bf16, f16 or (without y2) u8");
   SRB_REQUIRE(!a->y2 || float_or_f8(a->y2_dtype), "conv2d: y2 dtype must be f32, bf16, f16 or e5m2");
   SRB_REQUIRE(!a->res1 || float_or_f8(a->res1_dtype), "conv2d: res1 dtype must be f32, bf16, f16 or e5m2");
   SRB_REQUIRE(!a->res2 || float_or_f8(a->res2_dtype), "conv2d: res2 dtype must be f32, bf16, f16 or e5m2");

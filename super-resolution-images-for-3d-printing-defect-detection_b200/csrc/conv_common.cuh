@@ -47,6 +47,7 @@ __device__ __forceinline__ void store_elem(void* base, int dtype, size_t idx, fl
   if (dtype == SRB_BF16) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
   else if (dtype == SRB_F16) reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
   else if (dtype == SRB_F8E5M2) store_e5m2(base, idx, v);
+  else if (dtype == SRB_U8) reinterpret_cast<uint8_t*>(base)[idx] = (uint8_t)__float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
   else reinterpret_cast<float*>(base)[idx] = v;
 }
 

@@ -161,7 +161,7 @@ static bool head_aligned(const void* ptr, int dtype, int cstride, int coffset) {
 bool conv_head_eligible(const ConvParams& p) {
   if (p.kh != 3 || p.kw != 3 || p.cin != 3 || p.x_dtype != SRB_F32) return false;
   if (p.cout % 4 || p.cout > 128 || (32 % (p.cout / 4)) != 0) return false;
-  if (p.d2s != 1 || p.res1 || p.res2 || p.y_dtype == SRB_F8E5M2) return false;
+  if (p.d2s != 1 || p.res1 || p.res2 || p.y_dtype == SRB_F8E5M2 || p.y_dtype == SRB_U8) return false;
   if (!head_aligned(p.y, p.y_dtype, p.y_cstride, p.y_coffset)) return false;
   if (p.y2 && !head_aligned(p.y2, p.y2_dtype, p.y2_cstride, 0)) return false;
   return true;

@@ -1646,6 +1646,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     const bool any_f8 = p.y_dtype == SRB_F8E5M2 || (p.y2 && p.y2_dtype == SRB_F8E5M2) || (p.res1 && p.res1_dtype == SRB_F8E5M2) ||
                         (p.res2 && p.res2_dtype == SRB_F8E5M2);
     if (any_f8 && !pair8) vec = false;                 // (the generic scalar epilogue handles e5m2 element by element)
+    if (p.y_dtype == SRB_U8) vec = false;              // (quantised output: element-wise stores)
     if (p.y2 && !pair && !pair8 && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;

@@ -215,10 +215,12 @@ static int cast_impl(const void* src, int sdt, void* dst, int ddt, size_t n, flo
   if (ddt == SRB_F32) SRB_CAST(S, float);                                                      \
   else if (ddt == SRB_BF16) SRB_CAST(S, __nv_bfloat16);                                        \
   else if (ddt == SRB_F16) SRB_CAST(S, __half);                                                \
+  else if (ddt == SRB_U8) SRB_CAST(S, uint8_t);                                                \
   else { set_error("cast: unsupported destination dtype %d", ddt); return SRB_E_UNSUPPORTED; }
   if (sdt == SRB_F32) { SRB_CAST_FROM(float) }
   else if (sdt == SRB_BF16) { SRB_CAST_FROM(__nv_bfloat16) }
   else if (sdt == SRB_F16) { SRB_CAST_FROM(__half) }
+  else if (sdt == SRB_U8) { SRB_CAST_FROM(uint8_t) }
   else { set_error("cast: unsupported source dtype %d", sdt); return SRB_E_UNSUPPORTED; }
 #undef SRB_CAST_FROM
 #undef SRB_CAST

@@ -59,6 +59,8 @@ _SIGNATURES = {
                                  C.c_int, C.c_int, C.c_void_p]),
     "srb_bicubic_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_void_p]),
+    "srb_resize_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                C.c_int, C.c_void_p]),
     "srb_tiling_geometry": (C.c_int, [C.c_int] * 4 + [C.POINTER(C.c_int)] * 4),
     "srb_pad_extract_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                       C.c_void_p]),

@@ -2,7 +2,8 @@
 signatures (SRModels/classic_super_resolution_algorithms/classic_algorithms.py:7-21), computed on the GPU.
 
 ``target_shape`` is ``(width, height)`` exactly as for ``cv2.resize``; dtype is preserved (uint8 or
-float32); float results are not clipped.  Accepts ``[H, W, C]`` / ``[H, W]`` images or an
+float32); float results are not clipped.  uint8 images take OpenCV's fixed-point paths (linear, area and Lanczos-4
+bit-exact; bicubic as OpenCV's default dispatch, <= 1 LSB).  Accepts ``[H, W, C]`` / ``[H, W]`` images or an
 ``[B, H, W, C]`` batch; numpy in -> numpy out, CUDA tensor in -> CUDA tensor out.
 """
 from __future__ import annotations
@@ -58,13 +59,26 @@ def _not_on_path(name):
     return f
 
 
+# the reference's other classical upscalers (classic_algorithms.py:23-110) are outside the hot path; the names stay
+# importable so that ``from ...classic_algorithms import *`` style notebooks fail at the call, with a reason
+back_projection = _not_on_path("back_projection")
+non_local_means = _not_on_path("non_local_means")
+edge_guided_interpolation = _not_on_path("edge_guided_interpolation")
+frequency_extrapolation = _not_on_path("frequency_extrapolation")
+
+
 def _resize_float(img, target_shape, code):
     torch = capi.require_cuda()
     was_numpy = not isinstance(img, torch.Tensor)
-    t = torch.from_numpy(np.ascontiguousarray(img)).cuda() if was_numpy else (img if img.is_cuda else img.cuda())
-    if t.dtype != torch.float32:
-        raise NotImplementedError("bilinear / area / Lanczos resizing is built for float32 images (the reference's [0, 1] data); "
-                                  "uint8 uses OpenCV's fixed-point filter, which only the bicubic kernel reproduces")
+    if was_numpy:
+        arr = np.ascontiguousarray(img)
+        if arr.dtype not in (np.uint8, np.float32):
+            arr = arr.astype(np.float32)
+        t = torch.from_numpy(arr).cuda()
+    else:
+        t = img if img.is_cuda else img.cuda()
+    if t.dtype not in (torch.float32, torch.uint8):
+        raise TypeError(f"resize supports float32 and uint8 images, got {t.dtype}")
     nd = t.dim()
     t4 = t[None, :, :, None] if nd == 2 else t[None] if nd == 3 else t
     w, h = int(target_shape[0]), int(target_shape[1])

@@ -28,7 +28,17 @@ class EDSR:
         self._arch = dict(scale_factor=scale_factor, num_res_blocks=num_res_blocks, res_scaling=res_scaling)
         if from_pretrained:
             w = common.load_weight_file(pretrained_path)
-            self._arch["num_res_blocks"] = sum(1 for k in w if k.endswith("_c1/kernel"))
+            n_named = sum(1 for k in w if k.endswith("_c1/kernel"))
+            if n_named:
+                self._arch["num_res_blocks"] = n_named
+            else:
+                # a file exported from the reference's Keras model (auto-named conv2d, conv2d_1, ...): head + 2 per block +
+                # body end + one up-sampling conv per x2 stage (two for x4) + tail (EDSR_model.py:96-125)
+                n_conv = len(W.keras_conv_layers(W.normalize_keras_names(w)))
+                n_fixed = 3 + (2 if scale_factor == 4 else 1)
+                if n_conv < n_fixed or (n_conv - n_fixed) % 2:
+                    raise ValueError(f"{pretrained_path}: {n_conv} Conv2D layers do not form an EDSR x{scale_factor} graph")
+                self._arch["num_res_blocks"] = (n_conv - n_fixed) // 2
             self.model = engine.EDSRNet(w, precision=precision, **self._arch)
             self.trained = True
             print(f"Loaded pretrained model from {pretrained_path}")

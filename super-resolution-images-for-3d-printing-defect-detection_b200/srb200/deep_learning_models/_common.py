@@ -15,7 +15,9 @@ from .. import engine, ops
 
 
 def load_weight_file(path):
-    """``.npz`` with Keras-layout arrays (``<layer>/kernel`` HWIO, ``<layer>/bias``).  The reference
+    """``.npz`` with Keras-layout arrays (``<layer>/kernel`` HWIO, ``<layer>/bias``).  Keys may be the internal layer
+    names or the reference model's own variable names (``conv2d_3/kernel:0`` ...: ``weights.adopt`` maps the auto-named
+    layers in creation order and validates every shape when the network is constructed).  The reference
     stores ``.h5`` (SRCNN_model.py:258); reading those needs h5py, which this image lacks."""
     if path is None or not os.path.isfile(path):
         raise FileNotFoundError(f"Pretrained model file not found at {path}")

@@ -21,6 +21,7 @@ import numpy as np
 
 from . import _capi as capi
 from . import ops
+from . import weights as W
 
 
 def _torch():
@@ -57,6 +58,38 @@ class DeviceModel:
         self.max_device_batch = None   # images per launch sequence (None = whole input)
         self.event_hook = None         # bench.py: called with a tag at kernel-span boundaries
 
+    @staticmethod
+    def _first_conv(weights, name):
+        """Kernel of the network's first Conv2D: ``<name>/kernel`` or, for a file exported from the reference's
+        auto-named Keras layers, the first ``conv2d*`` layer in creation order."""
+        w = W.normalize_keras_names(weights)
+        if name + "/kernel" in w:
+            return w[name + "/kernel"]
+        auto = W.keras_conv_layers(w)
+        if not auto:
+            raise ValueError(f"weight dict has neither {name + '/kernel'!r} nor Keras auto-named conv2d layers")
+        return w[auto[0] + "/kernel"]
+
+    @staticmethod
+    def _chain_spec(weights, names):
+        """Shape spec of a plain conv chain taken from the file's own kernels (internal names or Keras creation order),
+        after checking that every layer's input channels are the previous layer's outputs."""
+        w = W.normalize_keras_names(weights)
+        src = names if all(n + "/kernel" in w for n in names) else W.keras_conv_layers(w)
+        if len(src) != len(names):
+            raise ValueError(f"expected {len(names)} Conv2D layers ({', '.join(names)}), found {len(src)}")
+        spec, prev = {}, None
+        for n, sname in zip(names, src):
+            k = np.asarray(w[sname + "/kernel"])
+            if k.ndim != 4:
+                raise ValueError(f"weight {sname + '/kernel'!r} must be HWIO [kh, kw, cin, cout], got shape {k.shape}")
+            if prev is not None and k.shape[2] != prev:
+                raise ValueError(f"layer {n!r} takes {k.shape[2]} input channels but the previous layer produces {prev}")
+            prev = k.shape[3]
+            spec[n + "/kernel"] = np.broadcast_to(np.float32(0), k.shape)
+            spec[n + "/bias"] = np.broadcast_to(np.float32(0), (k.shape[3],))
+        return spec
+
     # -- Keras-like surface ---------------------------------------------------------------
     def count_params(self):
         return int(sum(v.size for v in self.weights.values()))
@@ -76,43 +109,92 @@ class DeviceModel:
     def forward_device(self, x):
         raise NotImplementedError
 
-    def predict_device(self, x, micro_batch=None):
-        """x: [B,H,W,C] float32 CUDA tensor -> float32 CUDA tensor.  No host synchronisation."""
-        torch = _torch()
-        mb = micro_batch or self.max_device_batch
-        if not mb or x.shape[0] <= mb:
-            return self.forward_device(x)
-        outs = [self.forward_device(x[i:i + mb]) for i in range(0, x.shape[0], mb)]
-        return torch.cat(outs, 0)
+    # bytes of live activations per INPUT pixel of one image (the widest point of the graph, all buffers the caching
+    # allocator holds at once); subclasses refine it.  Only used to pick a default micro-batch.
+    def _activation_bytes_per_input_pixel(self):
+        s = self.output_scale()
+        return 3 * 64 * 4 * s * s
 
-    def predict(self, x, batch_size=32, verbose=0, out=None):
+    def default_micro_batch(self, h, w, budget_bytes=6 << 30):
+        """Images per launch sequence when ``max_device_batch`` is not set: as many as keep the live activations under
+        ``budget_bytes`` (the reference predicts 16 patches at a time, EDSR_model.py:274; one launch sequence over the
+        whole input would need ~9 GB for the 1,849 patches of a 1024 x 1024 LR image and overflow 32-bit tile counts at 4K)."""
+        per_image = max(1, int(h) * int(w) * self._activation_bytes_per_input_pixel())
+        return int(max(1, min(256, budget_bytes // per_image)))
+
+    def forward_device_as(self, x, out_dtype=None):
+        """forward_device with the result in ``out_dtype`` (None = float32).  uint8 = saturate(rint(255 v)) of the [0, 1]
+        image.  The default converts after the fact; networks whose last layer can store the type directly override it."""
+        torch = _torch()
+        y = self.forward_device(x)
+        if out_dtype is None or out_dtype == torch.float32:
+            return y
+        if out_dtype == torch.uint8:
+            return ops.cast(y.clamp_(0.0, 1.0), torch.uint8, scale=255.0)
+        return ops.cast(y, out_dtype)
+
+    def predict_device(self, x, micro_batch=None):
+        """x: [B,H,W,C] float32 CUDA tensor -> float32 CUDA tensor.  No host synchronisation.  Works through the batch in
+        micro-batches (``micro_batch`` / ``max_device_batch`` / ``default_micro_batch``), each written into its slice of
+        one preallocated output."""
+        torch = _torch()
+        mb = micro_batch or self.max_device_batch or self.default_micro_batch(x.shape[1], x.shape[2])
+        if x.shape[0] <= mb:
+            return self.forward_device(x)
+        out = None
+        for i in range(0, x.shape[0], mb):
+            y = self.forward_device(x[i:i + mb])
+            if out is None:
+                out = torch.empty((x.shape[0],) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
+            out[i:i + y.shape[0]].copy_(y)
+        return out
+
+    _NP_OUT = {"float32": "float32", "float16": "float16", "uint8": "uint8"}
+
+    def predict(self, x, batch_size=32, verbose=0, out=None, out_dtype=None):
         """numpy in, numpy out (``self.model.predict(patches, batch_size=16, verbose=0)``,
         SRCNN_model.py:210, EDSR_model.py:274).  ``batch_size`` is accepted for signature parity; the
         device works in micro-batches of ``max_device_batch`` images, with the host->device copy of
         micro-batch i+1 and the device->host copy of micro-batch i-1 overlapping the kernels of
-        micro-batch i on separate copy streams.  ``out`` may be a preallocated (ideally pinned) host array."""
+        micro-batch i on separate copy streams.
+
+        The stock call ``predict(x)`` returns a fresh float32 array whose storage is page-locked (it comes from torch's
+        caching host allocator, so a repeated call gets the previous result's block back without a new cudaHostAlloc once
+        the caller has dropped it): the read-back runs at the PCIe rate without an ``out=`` argument.  ``out`` may be a
+        preallocated (ideally pinned) host array.  ``out_dtype`` (np.float16 / np.uint8; extension) makes the last layer
+        store that type - uint8 is saturate(rint(255 v)) - which cuts the read-back bytes by 2x / 4x."""
         torch = _torch()
         x = np.ascontiguousarray(x, dtype=np.float32)
         if x.ndim != 4:
             raise ValueError(f"expected a 4-D NHWC array, got shape {x.shape}")
-        n, s = x.shape[0], self.output_scale()
+        np_dt = np.dtype(np.float32 if out_dtype is None else out_dtype)
+        if np_dt.name not in self._NP_OUT:
+            raise ValueError("out_dtype must be float32, float16 or uint8")
+        t_dt = {"float32": torch.float32, "float16": torch.float16, "uint8": torch.uint8}[np_dt.name]
+        n = x.shape[0]
         out_shape = self.output_shape(x.shape)
         if out is None:
-            out = np.empty(out_shape, dtype=np.float32)
-        elif tuple(out.shape) != tuple(out_shape) or out.dtype != np.float32:
-            raise ValueError(f"out must be float32 of shape {out_shape}")
+            ot = torch.empty(out_shape, dtype=t_dt, pin_memory=True)
+            out = ot.numpy()                              # (keeps the pinned block alive for as long as the caller holds it)
+        elif tuple(out.shape) != tuple(out_shape) or out.dtype != np_dt:
+            raise ValueError(f"out must be {np_dt.name} of shape {out_shape}")
+        else:
+            ot = torch.from_numpy(out)
         if n == 0:
             return out
-        xt, ot = torch.from_numpy(x), torch.from_numpy(out)
-        mb = self.max_device_batch or 64
+        xt = torch.from_numpy(x)
+        mb = self.max_device_batch or min(64, self.default_micro_batch(x.shape[1], x.shape[2]))
         comp = torch.cuda.current_stream()
         cin, cout = self._copy_streams()
+        # earlier work of the compute stream may still be using the memory the input buffers are carved from (or, when the
+        # buffers are reused from a previous call, reading them): the copy stream starts after it
+        cin.wait_stream(comp)
         # two persistent device input buffers and explicit events instead of per-chunk allocations on the copy streams
         # (record_stream defers the reuse of those blocks by the caching allocator, which showed up as occasional
         # cudaMalloc stalls in the middle of a run)
-        key = (mb,) + tuple(x.shape[1:])
+        key = (torch.cuda.current_device(), mb) + tuple(x.shape[1:])
         if getattr(self, "_in_key", None) != key:
-            self._in_bufs = [torch.empty(key, dtype=torch.float32, device="cuda") for _ in range(2)]
+            self._in_bufs = [torch.empty(key[1:], dtype=torch.float32, device="cuda") for _ in range(2)]
             self._in_key = key
         in_ready = [torch.cuda.Event(), torch.cuda.Event()]
         in_free = [None, None]
@@ -126,7 +208,7 @@ class DeviceModel:
                 xd.copy_(xt[i:i + m], non_blocking=True)
                 in_ready[b].record(cin)
             comp.wait_event(in_ready[b])
-            y = self.forward_device(xd)
+            y = self.forward_device_as(xd, t_dt)
             in_free[b] = torch.cuda.Event()
             in_free[b].record(comp)
             cout.wait_stream(comp)
@@ -181,6 +263,7 @@ class SRCNNNet(DeviceModel):
     arch = "SRCNN"
 
     def __init__(self, weights, precision="fp32"):
+        weights = W.adopt(weights, self._chain_spec(weights, ["conv1", "conv2", "conv3"]), "SRCNN")
         super().__init__(weights, precision)
         self._tc = None
         k1, k2, k3 = (self.weights[f"conv{i}/kernel"] for i in (1, 2, 3))
@@ -228,6 +311,9 @@ class EDSRNet(DeviceModel):
     def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16", trunk=None):
         if scale_factor not in (2, 3, 4):
             raise ValueError(f"Scale factor {scale_factor} not supported. Use 2, 3, or 4.")
+        head = self._first_conv(weights, "head")
+        weights = W.adopt(weights, W.edsr_weights(scale_factor, head.shape[2], num_res_blocks, head.shape[3], shapes_only=True),
+                          f"EDSR x{scale_factor} ({num_res_blocks} res-blocks)")
         super().__init__(weights, precision)
         if trunk is not None and precision != "fp32":
             if trunk not in ("pair", "pair8", "fp32", "half"):
@@ -238,9 +324,18 @@ class EDSRNet(DeviceModel):
     def output_scale(self):
         return self.scale_factor
 
+    def _activation_bytes_per_input_pixel(self):
+        s = self.scale_factor
+        # widest point: the last up-sampling conv's 64-channel input and output at full resolution + the fp32 RGB result
+        return (2 * 64 * 2 + 12) * s * s + 4 * 64 * 4
+
     def forward_device(self, x):
+        return self.forward_device_as(x, None)
+
+    def forward_device_as(self, x, out_dtype=None):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
+        out_dtype = out_dtype or torch.float32
         if self.trunk in ("pair", "pair8"):
             # compensated 16-bit trunk: (h, e) with h the tensor-core operand of the next conv and h + e the trunk value
             et = torch.float8_e5m2 if self.trunk == "pair8" else dt
@@ -278,7 +373,7 @@ class EDSRNet(DeviceModel):
         else:
             h = ops.conv2d(h, L["up0"], d2s=2, out_dtype=dt)
             h = ops.conv2d(h, L["up1"], d2s=2, out_dtype=dt)
-        y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=torch.float32)
+        y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=out_dtype)   # (uint8: the epilogue quantises the clipped value)
         if self.event_hook:
             self.event_hook("tc_end")
         return y
@@ -289,6 +384,10 @@ class ESPCNNet(DeviceModel):
     arch = "ESPCN"
 
     def __init__(self, weights, scale_factor=4, activation="relu", precision="fp16"):
+        weights = W.adopt(weights, self._chain_spec(weights, ["conv1", "conv2", "conv3"]), "ESPCN")
+        if weights["conv3/kernel"].shape[3] % (scale_factor * scale_factor):
+            raise ValueError(f"ESPCN: the last layer's {weights['conv3/kernel'].shape[3]} filters are not a multiple of "
+                             f"scale_factor^2 = {scale_factor * scale_factor}")
         super().__init__(weights, precision)
         self.scale_factor, self.activation = scale_factor, activation
         # 16-bit modes: the tensor-core engine needs Cin = 64, so conv3's 32 input channels are zero-padded to 64
@@ -329,6 +428,14 @@ class SRResNetNet(DeviceModel):
     def __init__(self, weights, scale_factor=4, num_res_blocks=16, precision="fp16"):
         if scale_factor not in (2, 4):
             raise ValueError("SRResNet scale factor must be 2 or 4")
+        head = self._first_conv(weights, "head")
+        spec = W.srresnet_weights(scale_factor, head.shape[2], num_res_blocks, head.shape[3], shapes_only=True)
+        prelu = {k: np.asarray(v, np.float32) for k, v in W.normalize_keras_names(weights).items() if k.endswith("/prelu")}
+        missing = [k for k in spec if k.endswith("/prelu") and k not in prelu]
+        if missing:
+            raise ValueError(f"SRResNet: PReLU slope vector {missing[0]!r} is missing")
+        weights = dict(W.adopt(weights, {k: v for k, v in spec.items() if not k.endswith("/prelu")},
+                               f"SRResNet x{scale_factor} ({num_res_blocks} res-blocks)"), **prelu)
         super().__init__(weights, precision)
         self.scale_factor, self.num_res_blocks = scale_factor, num_res_blocks
 
@@ -366,6 +473,10 @@ class ESRGANGeneratorNet(DeviceModel):
     arch = "ESRGAN-generator"
 
     def __init__(self, weights, scale_factor=2, growth_channels=32, num_rrdb_blocks=23, precision="fp32"):
+        first = self._first_conv(weights, "initial_conv")
+        weights = W.adopt(weights, W.esrgan_generator_weights(scale_factor, growth_channels, num_rrdb_blocks, first.shape[2],
+                                                              shapes_only=True),
+                          f"ESRGAN generator x{scale_factor} ({num_rrdb_blocks} RRDB, growth {growth_channels})")
         super().__init__(weights, precision)
         self.scale_factor, self.growth, self.num_rrdb = scale_factor, growth_channels, num_rrdb_blocks
 
@@ -423,6 +534,11 @@ class VGG16ClassifierNet(DeviceModel):
     CFG = [(1, 2), (2, 2), (3, 3), (4, 3), (5, 3)]
 
     def __init__(self, weights, precision="fp32"):
+        w = W.normalize_keras_names(weights)
+        if "predictions/kernel" not in w:
+            raise ValueError("VGG16 classifier: weight 'predictions/kernel' is missing")
+        weights = W.adopt(weights, W.vgg16_classifier_weights(int(np.asarray(w["predictions/kernel"]).shape[-1]), shapes_only=True),
+                          "VGG16 classifier")
         super().__init__(weights, precision)
         torch = _torch()
         self.dense = {k: torch.from_numpy(self.weights[k]).cuda() for k in

@@ -69,7 +69,7 @@ def ssim(y_true, y_pred):
 # (super_resolucion_clasica.ipynb cell 7: psnr(hr_f, sr_f, data_range=1.0), ssim(hr_f, sr_f, channel_axis=2,
 #  data_range=1.0), grayscale: ssim(hr_g, sr_g, data_range=dr); EDA.ipynb: data_range=255 on uint8)
 # ---------------------------------------------------------------------------------------------
-def _skimage_pair(im1, im2, data_range, channel_axis):
+def _skimage_pair(im1, im2, data_range, channel_axis, metric="ssim"):
     torch = capi.require_cuda()
     tensors = []
     for im in (im1, im2):
@@ -87,9 +87,23 @@ def _skimage_pair(im1, im2, data_range, channel_axis):
     if a.shape != b.shape:
         raise ValueError("Input images must have the same dimensions.")
     if data_range is None:
-        if a.dtype.is_floating_point:
-            raise ValueError("data_range must be given for floating-point images (skimage >= 0.19 requires it for SSIM)")
-        data_range = 255.0
+        if metric == "ssim":
+            if a.dtype.is_floating_point:
+                raise ValueError("Since image dtype is floating point, you must specify the data_range parameter. Please read "
+                                 "the documentation carefully (including the note). It is recommended that you always "
+                                 "specify the data_range anyway.")
+            data_range = 255.0
+        else:
+            # skimage.metrics.peak_signal_noise_ratio: the dtype's range - (-1, 1) for floats, so 1 for non-negative float
+            # images and 2 otherwise; integer images 0 .. dtype max
+            if a.dtype.is_floating_point:
+                lo, hi = float(a.min().item()), float(a.max().item())
+                if hi > 1.0 or lo < -1.0:
+                    raise ValueError("image_true has intensity values outside the range expected for its data type. Please "
+                                     "manually specify the data_range.")
+                data_range = 1.0 if lo >= 0.0 else 2.0
+            else:
+                data_range = float(torch.iinfo(a.dtype).max) if a.dtype != torch.bool else 1.0
     # both metrics are invariant under a common scale when data_range scales with it: evaluate on [0, 1]
     scale = 1.0 / float(data_range)
     a = (a.to(torch.float32) * scale).contiguous()[None]
@@ -98,8 +112,10 @@ def _skimage_pair(im1, im2, data_range, channel_axis):
 
 
 def peak_signal_noise_ratio(image_true, image_test, *, data_range=None):
-    """skimage.metrics.peak_signal_noise_ratio: 10 log10(data_range^2 / mse) over the whole array -> float."""
-    a, b = _skimage_pair(image_true, image_test, data_range, None if np.ndim(image_true) == 2 else -1)
+    """skimage.metrics.peak_signal_noise_ratio: 10 log10(data_range^2 / mse) over the whole array -> float.
+    ``data_range=None`` falls back to the dtype's range as skimage does.  The squared error is summed in float64 from
+    float32 differences of the [0, 1]-scaled images (skimage subtracts in float64: relative difference ~1e-7)."""
+    a, b = _skimage_pair(image_true, image_test, data_range, None if np.ndim(image_true) == 2 else -1, metric="psnr")
     return float(ops.psnr(a, b, 1.0, window=capi.SSIM_SKIMAGE)[0].item())
 
 

@@ -113,17 +113,21 @@ def bicubic(src, dst_h, dst_w, clip01=False, fixed_point=False):
 
 
 def resize(src, dst_h, dst_w, interpolation=capi.INTER_CUBIC, clip01=False):
-    """cv2.resize(src, (dst_w, dst_h), interpolation) for float32 NHWC CUDA tensors; INTER_CUBIC, INTER_LINEAR and
+    """cv2.resize(src, (dst_w, dst_h), interpolation) for float32 or uint8 NHWC CUDA tensors; INTER_CUBIC, INTER_LINEAR and
     (up-scaling) INTER_AREA share the bicubic kernels through the four-tap table; INTER_LANCZOS4 has an eight-tap one."""
     torch = _torch()
     _check_nhwc(src, "src")
-    if src.dtype != torch.float32:
-        raise TypeError(f"resize supports float32, got {src.dtype}")
+    if src.dtype not in (torch.float32, torch.uint8):
+        raise TypeError(f"resize supports float32 and uint8, got {src.dtype}")
     B, H, W, Cc = src.shape
     dst = torch.empty((B, int(dst_h), int(dst_w), Cc), dtype=src.dtype, device=src.device)
     with torch.cuda.device(src.device):
-        capi.check(capi.lib().srb_resize_f32(capi.ptr(src), B, H, W, Cc, capi.ptr(dst), int(dst_h), int(dst_w),
-                                             int(interpolation), int(bool(clip01)), capi.stream_ptr()))
+        if src.dtype == torch.uint8:            # OpenCV's fixed-point uint8 paths (bit-exact)
+            capi.check(capi.lib().srb_resize_u8(capi.ptr(src), B, H, W, Cc, capi.ptr(dst), int(dst_h), int(dst_w),
+                                                int(interpolation), capi.stream_ptr()))
+        else:
+            capi.check(capi.lib().srb_resize_f32(capi.ptr(src), B, H, W, Cc, capi.ptr(dst), int(dst_h), int(dst_w),
+                                                 int(interpolation), int(bool(clip01)), capi.stream_ptr()))
     _LAUNCHES[0] += 3
     return dst
 

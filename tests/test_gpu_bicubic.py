@@ -100,8 +100,6 @@ def test_bilinear_and_area_vs_cv2_golden(golden_dir):
         assert lin.dtype == np.float32 and lin.shape == (dh, dw, 3)
         assert np.abs(lin - g[f"c{n}_linear"]).max() <= 1e-6, n
         assert np.abs(interpolate_area(src, (dw, dh)) - g[f"c{n}_area"]).max() <= 1e-6, n
-    with pytest.raises(NotImplementedError):
-        interpolate_bilinear(np.zeros((8, 8, 3), np.uint8), (16, 16))
     with pytest.raises(ValueError):
         interpolate_area(np.zeros((16, 16, 3), np.float32), (8, 8))          # down-scaling area resampling is not built
 
@@ -128,5 +126,28 @@ def test_lanczos4_vs_cv2_golden_and_oracle(golden_dir):
     t = torch.from_numpy(f).cuda()
     clipped = ops.resize(t, 82, 58, interpolation=_capi.INTER_LANCZOS4, clip01=True).cpu().numpy()
     assert np.abs(clipped - np.clip(np.stack([ob.resize_lanczos4_f32(x, (58, 82)) for x in f]), 0, 1)).max() <= 2e-6
-    with pytest.raises(NotImplementedError):
-        interpolate_lanczos(np.zeros((8, 8, 3), np.uint8), (16, 16))
+
+
+def test_uint8_linear_area_lanczos_bit_exact_vs_cv2_golden(golden_dir):
+    """The classical benchmark (super_resolucion_clasica.ipynb cell 7) calls all four interpolators on uint8 images:
+    OpenCV's fixed-point linear / area / Lanczos-4 paths, bit-exact against cv2.resize outputs and the restatement."""
+    from srb200.classic_super_resolution_algorithms.classic_algorithms import (interpolate_area, interpolate_bilinear,
+                                                                               interpolate_lanczos)
+    g = np.load(os.path.join(golden_dir, "resize_u8_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw, c = (int(v) for v in g[f"c{n}_shape"])
+        src = g[f"c{n}_in"]
+        for fn, key in ((interpolate_bilinear, "linear"), (interpolate_area, "area"), (interpolate_lanczos, "lanczos4")):
+            got = fn(src, (dw, dh))
+            assert got.dtype == np.uint8 and got.shape == g[f"c{n}_{key}"].shape
+            assert np.array_equal(got, g[f"c{n}_{key}"]), (n, key)
+    rng = np.random.default_rng(5)
+    u = rng.integers(0, 256, (2, 90, 70, 3), dtype=np.uint8)                 # batch, several row strips
+    for fn, ref in ((interpolate_bilinear, lambda x, d: ob.resize_linear_u8(x, d)),
+                    (interpolate_area, lambda x, d: ob.resize_linear_u8(x, d, area=True)),
+                    (interpolate_lanczos, ob.resize_lanczos4_u8)):
+        got = fn(u, (211, 300))
+        for i in range(2):
+            assert np.array_equal(got[i], ref(u[i], (211, 300)))
+    with pytest.raises(ValueError):
+        interpolate_area(np.zeros((16, 16, 3), np.uint8), (8, 8))

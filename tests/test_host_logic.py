@@ -102,3 +102,51 @@ def test_predict_chunk_schedule():
         assert max(m for _, m in ch) <= mb
     assert [m for _, m in DeviceModel._chunks(512, 32)][-3:] == [16, 8, 8]
     assert DeviceModel._chunks(32, 32) == [(0, 32)]
+
+
+def test_adopt_maps_keras_auto_names_in_creation_order_and_validates_shapes():
+    """weights.adopt: files exported from the reference's Keras models ({v.name: v.numpy() for v in model.weights}) carry
+    conv2d, conv2d_7, ... (SRCNN_model.py:50-52, EDSR_model.py:61-121 leave the layers unnamed): matched by creation order;
+    explicit names (ESRGAN, VGG16) are the internal ones, with the SelfAttention sub-layer path stripped; wrong depth, wrong
+    shape and missing layers fail at load time."""
+    import numpy as np
+    from srb200 import weights as W
+    w = W.edsr_weights(4, num_res_blocks=2, bias_scale=0.05)
+    spec = W.edsr_weights(4, num_res_blocks=2, shapes_only=True)
+    assert list(spec) == list(w) and all(spec[k].shape == w[k].shape for k in w)
+    layers = [k[:-len("/kernel")] for k in w if k.endswith("/kernel")]
+    raw = {}
+    for i, name in enumerate(layers):
+        kname = f"conv2d_{i + 40}"                         # a session that built other models before
+        raw[f"{kname}/kernel:0"], raw[f"{kname}/bias:0"] = w[name + "/kernel"], w[name + "/bias"]
+    got = W.adopt(raw, spec, "EDSR")
+    assert list(got) == list(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    assert all(np.array_equal(W.adopt(w, spec)[k], w[k]) for k in w)          # internal names pass through
+    with pytest.raises(ValueError, match="auto-named Keras Conv2D"):
+        W.adopt({k: v for k, v in raw.items() if not k.startswith("conv2d_41/")}, spec, "EDSR")
+    bad = dict(w)
+    bad["rb1_c2/kernel"] = np.zeros((3, 3, 64, 32), np.float32)
+    with pytest.raises(ValueError, match="rb1_c2/kernel.*expected \\(3, 3, 64, 64\\)"):
+        W.adopt(bad, spec, "EDSR")
+    g = W.esrgan_generator_weights(2, 8, 1)
+    named = {}
+    for k, v in g.items():
+        layer, var = k.split("/")
+        prefix = layer.rsplit("_", 1)[0] + "/" if layer.startswith("self_attention") else ""
+        named[f"{prefix}{layer}/{var}:0"] = v
+    got = W.adopt(named, W.esrgan_generator_weights(2, 8, 1, shapes_only=True), "ESRGAN")
+    assert all(np.array_equal(got[k], g[k]) for k in g)
+    no_bias = {k: v for k, v in w.items() if k != "tail/bias"}
+    assert np.array_equal(W.adopt(no_bias, spec)["tail/bias"], np.zeros(3, np.float32))   # use_bias=False layers
+    assert W.count_params(W.vgg16_classifier_weights(2, shapes_only=True)) == 14_846_530
+    assert W.count_params(W.esrgan_generator_weights(2, 8, 4, shapes_only=True)) == 1_162_915
+
+
+def test_classical_upscalers_outside_the_path_fail_at_the_call_with_a_reason():
+    """classic_algorithms.py:23-110: the four non-cv2.resize upscalers keep their names (imports work) and raise
+    NotImplementedError when called."""
+    from srb200.classic_super_resolution_algorithms import classic_algorithms as ca
+    for name in ("back_projection", "non_local_means", "edge_guided_interpolation", "frequency_extrapolation"):
+        with pytest.raises(NotImplementedError, match="outside the B200 hot path"):
+            getattr(ca, name)(None, None)
+    assert {"interpolate_bilinear", "interpolate_bicubic", "interpolate_area", "interpolate_lanczos"} <= set(dir(ca))

@@ -84,3 +84,20 @@ def test_lanczos4_restatement_against_cv2_golden(golden_dir):
     assert np.allclose(c[1], c[1][::-1], atol=1e-7) and abs(float(c[1].sum()) - 1.0) <= 1e-6
     idx, _ = ob.lanczos4_axis_table(10, 20)
     assert idx.min() == 0 and idx.max() == 9 and idx.shape == (20, 8)
+
+
+def test_uint8_linear_area_lanczos_restatements_against_cv2_golden(golden_dir):
+    """OpenCV's fixed-point uint8 paths for INTER_LINEAR, up-scaling INTER_AREA and INTER_LANCZOS4 (what
+    classic_algorithms.py:7-21 return on the uint8 images of the classical benchmark), bit-exact against cv2 outputs."""
+    g = np.load(os.path.join(golden_dir, "resize_u8_cv2.npz"))
+    for n in range(int(g["n_cases"])):
+        h, w, dh, dw, c = (int(v) for v in g[f"c{n}_shape"])
+        src = g[f"c{n}_in"]
+        assert np.array_equal(ob.resize_linear_u8(src, (dw, dh)), g[f"c{n}_linear"]), n
+        assert np.array_equal(ob.resize_linear_u8(src, (dw, dh), area=True), g[f"c{n}_area"]), n
+        assert np.array_equal(ob.resize_lanczos4_u8(src, (dw, dh)), g[f"c{n}_lanczos4"]), n
+    # the y table keeps the fraction at the image ends (row index clamped instead): a x2 border row is a 1/4 : 3/4 blend
+    idx, co = ob.linear_axis_table_u8(8, 16, clamp_t=False)
+    assert idx[0].tolist() == [0, 0] and co[0].tolist() == [512, 1536]
+    idx, co = ob.linear_axis_table_u8(8, 16, clamp_t=True)
+    assert idx[0].tolist() == [0, 1] and co[0].tolist() == [2048, 0]

@@ -1,6 +1,7 @@
 """Sharded evaluation check: every rank evaluates its contiguous shard of a synthetic test set with the same
 seeded EDSR, the four metric sums are all-reduced once (NCCL), and rank 0 compares the means with a
-single-process evaluation of the whole set.
+single-process evaluation of the whole set AND with the CPU oracle's evaluation of it (oracle network + oracle
+tf.image.psnr/ssim restatement, fp64 means).
 
     python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tools/eval_sharded.py
 """
@@ -25,7 +26,8 @@ def main():
     n = 37                                              # deliberately not divisible by the world size
     hr = synth.hr_batch(n, 48, 48)
     lr = synth.area_downsample(hr, 2)
-    net = engine.EDSRNet(weights.edsr_weights(2, num_res_blocks=2, bias_scale=0.05), 2, 2, precision="fp16")
+    w = weights.edsr_weights(2, num_res_blocks=2, bias_scale=0.05)
+    net = engine.EDSRNet(w, 2, 2, precision="fp16")
     lo, hi = D.shard_bounds(n, rank, world)
     sums = common.evaluate_arrays(net, lr[lo:hi], hr[lo:hi], micro_batch=8)
     means = common.finish_evaluation(sums)
@@ -34,7 +36,12 @@ def main():
         ref = D.means_from_sums(full)
         err = [abs(a - b) for a, b in zip(means, ref)]
         ok = err[0] <= 1e-7 and err[1] <= 1e-4 and err[2] <= 1e-6 and full[2] == n
-        print("SHARDED_EVAL", "OK" if ok else "MISMATCH", "world", world, "means", means, "ref", ref)
+        from oracle import convnets as oc, metrics as om
+        want = om.evaluate_means(hr, oc.edsr_forward(w, lr, 2, 2))            # [mse, psnr, ssim] of the oracle chain
+        oerr = [abs(a - b) for a, b in zip(means, want)]
+        ok = ok and oerr[1] <= 0.05 and oerr[2] <= 1e-3                       # 16-bit operands on random-init weights
+        print("SHARDED_EVAL", "OK" if ok else "MISMATCH", "world", world, "means", means, "ref", ref, "oracle", want,
+              "abs diff vs oracle", oerr)
         if not ok:
             sys.exit(1)
     if world > 1:
