@@ -177,8 +177,8 @@ def test_large_image_super_resolve_uses_bounded_micro_batches():
     assert sr.shape == (1200, 1200, 3) and np.array_equal(sr, sr2)
     padded = ot.add_padding(lr, 24, 12)
     patches, pos = ot.extract_patches(padded, 24, 12)
-    want0 = oc.edsr_forward(w, patches[:50], 2, 2)                 # the first row of patches against the oracle
-    got0 = m.model.predict_device(torch.from_numpy(patches[:50]).cuda()).cpu().numpy()
+    want0 = oc.edsr_forward(w, np.ascontiguousarray(patches[:50]), 2, 2)                 # the first row of patches against the oracle
+    got0 = m.model.predict_device(torch.from_numpy(np.ascontiguousarray(patches[:50])).cuda()).cpu().numpy()
     assert np.abs(got0 - want0).max() <= 2e-2
 
 
