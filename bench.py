@@ -488,6 +488,21 @@ def config_c4(torch, peaks, batch=1024):
             "pipeline_out_MPps": out_px / (ms_sr + ms_vgg) / 1e3, "votes_class1": int(sum(votes)), "bound": "tensor"}
 
 
+def config_esrgan(torch, peaks):
+    """The reference's own GAN generator at its trained configuration (ESRGAN.ipynb cell 6: 4 RRDB, growth 8, x2, 24x24 LR
+    patches): the 1,521 patches of one 478x478 image (stride 12), fp16 operands on the tcgen05 engine (dense-block growth convs
+    in 64-channel K chunks), SelfAttention on 576 and 2,304 positions per patch on the CUDA cores."""
+    from srb200 import engine, weights
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand((1521, 24, 24, 3), device="cuda", generator=g) * 2 - 1
+    out = {"workload": "ESRGAN generator x2 (4 RRDB, growth 8, 2 SelfAttention), 1,521 LR patches 24x24 -> 48x48"}
+    for prec in ("fp16", "fp32"):
+        net = engine.ESRGANGeneratorNet(weights.esrgan_generator_weights(2, 8, 4), 2, 8, 4, precision=prec)
+        ms = cuda_timed(torch, lambda: net.predict_device(x, micro_batch=512), 2, warm=1)
+        out[prec] = {"ms": ms, "out_MPps": 1521 * 48 * 48 / ms / 1e3, "patches_per_s": 1521 / ms * 1e3}
+    return out
+
+
 def config_c5(torch, peaks, reps=5):
     """C5: bicubic x2/x3/x4 (fp32 + uint8), PSNR and fused PSNR+SSIM at 1K / 2K / 4K outputs, >= ~2 GB per launch, against the
     measured HBM copy peak.  Algorithmic bytes: bicubic fp32 (12 + 12/s^2) B per RGB output pixel, uint8
@@ -685,6 +700,7 @@ def run_gpu(args):
                 configs["c1"] = config_c1(torch, peaks)
                 configs["c2"] = config_c2(torch, peaks)
                 configs["c4"] = config_c4(torch, peaks, args.c4_batch)
+                configs["esrgan"] = config_esrgan(torch, peaks)
             configs["clocks"] = clk2.result
         barrier()
 

@@ -77,9 +77,10 @@ struct srb_conv_weights {
   float* hwio;            // [kh*kw][cin][cout_pad4] float32 (direct engine), cout padded to a multiple of 4
   int cout_pad4;
   float* bias;            // [cout] float32 (zeros when the layer has none)
-  __nv_bfloat16* tc;      // [kh*kw][cout_pad][cin] bf16, K-major rows (tcgen05 engine) or nullptr
+  __nv_bfloat16* tc;      // [kh*kw][cout_pad][cin_pad] bf16, K-major rows (tcgen05 engine) or nullptr
   __half* tc_f16;         // same, IEEE half
   int tc_cout_pad;        // rows per tap in `tc` (multiple of 16)
+  int tc_cin_pad;         // K extent of a row of `tc`: cin rounded up to a multiple of 64 (zero columns past cin)
   __nv_bfloat16* tc_fold; // cout <= 4 only: [dy][16 rows = dx*5+co][cin] (horizontal taps folded into N) or nullptr
   __half* tc_fold_f16;
   __nv_bfloat16* tc_head; // cin == 3, cout == 64 only: im2col GEMM operand [n_kb][64 cout rows][64 k], k = (dy*kw + dx)*3 + c, or nullptr

@@ -54,18 +54,22 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
       return cuda_fail(e, "conv_weights_create(tc head)");
     }
   }
-  // tensor-core copies: [tap][cout_pad16][cin] K(cin)-major rows in bf16 and fp16, for cin == 64
-  if (cin == 64) {
+  // tensor-core copies: [tap][cout_pad16][cin_pad64] K(cin)-major rows in bf16 and fp16.  cin = 64 is the native shape of
+  // the tcgen05 engine; wider inputs (VGG16 blocks 2-5: 128 .. 512 channels, the ESRGAN dense blocks' growing concatenation:
+  // 64 + j * growth) are walked in 64-channel K chunks with zero columns past cin.
+  if (cin >= 32 && cin % 8 == 0 && cin <= 1024 && kh <= 9 && kw <= 9) {
     const int rows = (cout + 15) & ~15;
+    const int kp = (cin + 63) & ~63;
     w->tc_cout_pad = rows;
-    std::vector<__nv_bfloat16> tb((size_t)taps * rows * cin, __float2bfloat16_rn(0.f));
-    std::vector<__half> th((size_t)taps * rows * cin, __float2half_rn(0.f));
+    w->tc_cin_pad = kp;
+    std::vector<__nv_bfloat16> tb((size_t)taps * rows * kp, __float2bfloat16_rn(0.f));
+    std::vector<__half> th((size_t)taps * rows * kp, __float2half_rn(0.f));
     for (int t = 0; t < taps; ++t)
       for (int o = 0; o < cout; ++o)
         for (int c = 0; c < cin; ++c) {
           const float v = hwio[((size_t)t * cin + c) * cout + o];
-          tb[((size_t)t * rows + o) * cin + c] = __float2bfloat16_rn(v);
-          th[((size_t)t * rows + o) * cin + c] = __float2half_rn(v);
+          tb[((size_t)t * rows + o) * kp + c] = __float2bfloat16_rn(v);
+          th[((size_t)t * rows + o) * kp + c] = __float2half_rn(v);
         }
     if ((e = cudaMalloc(&w->tc, tb.size() * 2)) != cudaSuccess ||
         (e = cudaMemcpy(w->tc, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -74,6 +78,8 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
       srb_conv_weights_destroy(w);
       return cuda_fail(e, "conv_weights_create(tc)");
     }
+  }
+  if (cin == 64) {
     if (kh == 3 && kw == 3 && cout % 16 == 0 && cout >= 16 && cout <= 64) {
       // 64 -> 16 / 32 / 48 / 64 layers: horizontal taps folded into N = 3 * cout rows per vertical tap, row = dx * cout + co
       // (wide-tile kernel)
@@ -166,6 +172,7 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.kh = w->kh; p.kw = w->kw; p.cin = w->cin; p.cout = w->cout;
   p.w_hwio = w->hwio; p.w_cout_pad = w->cout_pad4;
   p.w_tc = a->x_dtype == SRB_F16 ? (const void*)w->tc_f16 : (const void*)w->tc; p.w_tc_rows = w->tc_cout_pad;
+  p.w_tc_cin = w->tc_cin_pad;
   p.w_tc_fold = a->x_dtype == SRB_F16 ? (const void*)w->tc_fold_f16 : (const void*)w->tc_fold;
   p.w_tc_head = a->y_dtype == SRB_F16 ? (const void*)w->tc_head_f16 : (const void*)w->tc_head; p.w_tc_head_kb = w->tc_head_kb;
   p.bias = w->bias;
@@ -199,7 +206,8 @@ extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
     if (rc != SRB_E_UNSUPPORTED || a->engine == SRB_ENGINE_TCGEN05) return rc;
   }
   if (a->engine == SRB_ENGINE_TCGEN05 && !tc_ok) {
-    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, cin == 64, odd filter up to 9x9)");
+    set_error("conv2d: shape not eligible for the tcgen05 engine (needs bf16/fp16 NHWC input with 16-byte aligned pixels, 32 <= cin <= 1024 "
+              "in multiples of 8, odd filter up to 9x9)");
     return SRB_E_UNSUPPORTED;
   }
   if (a->engine == SRB_ENGINE_TCGEN05) return conv_tc_launch(p, (cudaStream_t)stream);

@@ -11,7 +11,8 @@ struct ConvParams {
   int B, H, W;
   int kh, kw, cin, cout;
   const float* w_hwio; int w_cout_pad;      // direct engine weights
-  const void* w_tc; int w_tc_rows;          // tcgen05 engine weights [tap][rows][cin] in the dtype of x
+  const void* w_tc; int w_tc_rows;          // tcgen05 engine weights [tap][rows][w_tc_cin] in the dtype of x
+  int w_tc_cin;                             // cin rounded up to a multiple of 64 (the kernel walks it in 64-channel chunks)
   const void* w_tc_fold;                    // dx-folded weights ([dy][16][cin] for cout <= 4, [dy][192][cin] for cout == 64), or nullptr
   const void* w_tc_head; int w_tc_head_kb;  // cin == 3 im2col weights in the 16-bit dtype of y, or nullptr
   const float* bias;                        // [cout], never null

@@ -57,6 +57,7 @@ struct TcParams {
   int fold;              // horizontal taps folded into N (cout <= 4): 3 MMA taps (dy), 8 input columns -> 6 output columns
   int tile_cols_out;     // 8, or 6 when folded
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
+  int n_kc;              // 64-channel K chunks of the input (cin_pad / 64): one halo load and one set of tap MMAs per chunk
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
   uint32_t magic_tpi, magic_tx;   // ceil(2^32 / tiles_per_img), ceil(2^32 / tiles_x) for multiply-high division, or 0
@@ -146,7 +147,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const int n_taps = q.fold ? 3 : q.kh * q.kw;
   const uint32_t rank = k2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   const uint32_t n_local = k2 ? (uint32_t)q.n_tile / 2u : (uint32_t)q.n_tile;   // weight rows held by this CTA
-  const uint32_t w_bytes = (uint32_t)n_taps * n_local * 128u;
+  const int n_kc = q.n_kc;
+  const uint32_t w_kc_bytes = (uint32_t)n_taps * n_local * 128u;      // one K chunk of this CTA's weight rows, all taps
+  const uint32_t w_bytes = w_kc_bytes * (uint32_t)n_kc;
   const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
   const uint32_t w_smem = base;
   const uint32_t a_smem = base + w_span;
@@ -217,11 +220,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       // k2: both CTAs' weight halves and A tiles report to the LEADER's barriers (it issues the MMAs for the pair)
       if (!k2) mbar_expect_tx(wfull_bar, w_bytes);
       else if (rank == 0) mbar_expect_tx(wfull_bar, 2u * w_bytes);
-      for (int t = 0; t < n_taps; ++t) {
-        const uint32_t dstw = w_smem + (uint32_t)t * n_local * 128u;
-        const int row = t * q.w_rows + co_base + (int)(rank * n_local);
-        if (k2) tma_load_2d_2sm(dstw, &tmap_w, wfull_bar, 0, row); else tma_load_2d(dstw, &tmap_w, wfull_bar, 0, row);
-      }
+      for (int kc = 0; kc < n_kc; ++kc)
+        for (int t = 0; t < n_taps; ++t) {
+          const uint32_t dstw = w_smem + (uint32_t)kc * w_kc_bytes + (uint32_t)t * n_local * 128u;
+          const int row = t * q.w_rows + co_base + (int)(rank * n_local);
+          if (k2) tma_load_2d_2sm(dstw, &tmap_w, wfull_bar, kc * 64, row); else tma_load_2d(dstw, &tmap_w, wfull_bar, kc * 64, row);
+        }
     }
     __syncwarp();
     pdl_wait();
@@ -231,19 +235,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int b = fast_div(tl, tiles_per_img, q.magic_tpi), r = tl - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
       const int ty_ = fast_div(r, q.tiles_x, q.magic_tx);
       const int y0 = ty_ * kTileH, x0 = (r - ty_ * q.tiles_x) * q.tile_cols_out;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
-      if (elect_one()) {
-        const uint32_t bytes = q.load_bytes * (uint32_t)q.n_loads;
-        if (!k2) mbar_expect_tx(full_bar(s), bytes);
-        else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes);
-        for (int l = 0; l < q.n_loads; ++l) {
-          if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
-          else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), 0, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
+      for (int kc = 0; kc < n_kc; ++kc) {              // one halo tile per 64-channel K chunk
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
+        if (elect_one()) {
+          const uint32_t bytes = q.load_bytes * (uint32_t)q.n_loads;
+          if (!k2) mbar_expect_tx(full_bar(s), bytes);
+          else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes);
+          for (int l = 0; l < q.n_loads; ++l) {
+            if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
+            else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
+          }
         }
+        __syncwarp();
+        if (++s == q.stages) { s = 0; ph ^= 1u; }
       }
-      __syncwarp();
-      if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -269,7 +275,29 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tc_fence_after();
       const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
-      if (q.fold) {
+      if (n_kc > 1) {
+        // wide inputs: the accumulator collects every (K chunk, tap) product; each chunk has its own halo stage and its own
+        // block of resident weight rows
+        for (int kc = 0; kc < n_kc; ++kc) {
+          if (kc) { mbar_wait(full_bar(s), ph); tc_fence_after(); }
+          const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo, 0);
+          const uint64_t b_kc = b_desc0 + (uint64_t)((uint32_t)kc * (w_kc_bytes >> 4));
+          if (elect_one()) {
+            int tap = 0;
+            for (int ty_ = 0; ty_ < q.kh; ++ty_)
+              for (int tx_ = 0; tx_ < q.kw; ++tx_, ++tap) {
+                const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ty_ * a_dy + (uint32_t)tx_ * 8u);
+                const uint64_t bd = b_kc + (uint64_t)tap * b_tap_step;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((kc | tap | k) != 0));
+              }
+            commit(empty_bar(s));
+            if (kc == n_kc - 1) commit(tfull_bar(acc));
+          }
+          __syncwarp();
+          if (kc < n_kc - 1 && ++s == q.stages) { s = 0; ph ^= 1u; }
+        }
+      } else if (q.fold) {
         // dx folded into N: D[input pixel, (dx, co)] += sum over dy of A shifted by dy halo rows (1,024-B aligned)
         const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
         if (q.debug == 2) {
@@ -1421,10 +1449,13 @@ EncodeTiledFn tc_encode_fn() {
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 bool conv_tc_eligible(const ConvParams& p) {
-  if (p.cin != 64 || !p.w_tc || p.kh > 9 || p.kw > 9) return false;
-  if ((p.kh != 3 || p.kw != 3) && g_variant != 0) return false;   // the staging experiments are 3x3 only
-  // 16-row weight chunk for every tap + one halo stage must fit next to barriers and staging (9x9: 166 KB + 48 KB)
-  if ((size_t)p.kh * p.kw * 16 * 128 + (size_t)(kTileH + p.kh - 1) * (kTileW + p.kw - 1) * 128 > 216 * 1024) return false;
+  if (!p.w_tc || p.w_tc_cin < 64 || p.kh > 9 || p.kw > 9) return false;
+  const int n_kc = p.w_tc_cin / 64;
+  if ((p.kh != 3 || p.kw != 3 || n_kc != 1) && g_variant != 0) return false;   // the staging experiments are 3x3, cin = 64 only
+  // the smallest weight chunk (16 rows; 32 rows as 16 per CTA of a pair when the input is wider than 64 channels) for every tap
+  // and K chunk + two halo stages must fit next to barriers and staging (9x9, cin = 64: 166 KB + 48 KB)
+  if ((size_t)p.kh * p.kw * 16 * 128 * n_kc + (size_t)(n_kc > 1 ? 2 : 1) * (kTileH + p.kh - 1) * (kTileW + p.kw - 1) * 128 > 216 * 1024)
+    return false;
   if (p.x_dtype != SRB_BF16 && p.x_dtype != SRB_F16) return false;
   if ((p.x_cstride % 8) || (p.x_coffset % 8) || !aligned16(p.x)) return false;
   if (p.W < 1 || p.H < 1) return false;
@@ -1588,8 +1619,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   if (g_two_cta < 0) { const char* e = getenv("SRB_TC_2CTA"); g_two_cta = e ? atoi(e) : 0; }
   const int two_cta = g_two_cta;
 
-  // channel-chunk width per CTA: the widest of {128, 64, rows, 16} that divides the padded cout and whose weights,
-  // >= 2 A stages and epilogue staging fit shared memory (N = 128 halves the A-operand smem traffic per FLOP)
+  // channel-chunk width per CTA: the widest of {256 (pairs), 128, 64, 32 (wide inputs), rows, 16} that divides the padded cout
+  // and whose weights (all K chunks), >= 2 A stages and epilogue staging fit shared memory
   TcParams q{};
   size_t smem = 0;
   // 256-channel chunks exist only as CTA pairs (each CTA holds 128 weight rows) with the TMA epilogue, for plain 16-bit
@@ -1598,13 +1629,24 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   static const bool pairs256 = !(getenv("SRB_TC_PAIRS256") && atoi(getenv("SRB_TC_PAIRS256")) == 0);
   const bool plain_layer = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && dt16(p.y_dtype) &&
                            (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu));
-  const int cand[5] = {256, 128, 64, rows < 64 ? rows : 16, 16};
+  const int n_kc = p.w_tc_cin / 64;                   // 64-channel K chunks (weights of every chunk stay resident)
+  // candidates, widest first.  Wide inputs (n_kc > 1) also try every width as a CTA pair: each CTA then keeps half of the
+  // weight rows, so the pair's MMA is twice as wide for the same resident bytes (N is what pays for the A-operand fetch)
+  const int cand[6] = {256, 128, 64, 32, rows < 64 ? rows : 16, 16};
   bool found = false;
-  for (int ci = 0; ci < 5 && !found; ++ci) {
-    const int nt = fold ? 16 : cand[ci];
+  for (int ci = 0; ci < 12 && !found; ++ci) {
+    const int nt = fold ? 16 : cand[ci >> 1];
+    const bool try_pair = (ci & 1) == 0;               // even: as a CTA pair, odd: single CTAs
     if (!fold && ((nt > ntile_max && nt != 256) || rows % nt)) continue;
-    if (nt == 256 && !(pairs256 && plain_layer && variant == 0 && p.kh == 3 && p.kw == 3 && !g_debug_env())) continue;
+    if (nt == 32 && n_kc == 1) continue;               // (cin = 64 keeps its round-1 choices: 128 / 64 / rows / 16)
+    if (nt == 256 && !try_pair) continue;
+    if (nt == 256 && n_kc == 1 && !(pairs256 && plain_layer && variant == 0 && p.kh == 3 && p.kw == 3 && !g_debug_env())) continue;
+    if (nt == 256 && n_kc > 1 && !plain_layer) continue;
+    if (try_pair && nt != 256 && !(two_cta || n_kc > 1)) continue;
+    if (!try_pair && nt != 256 && two_cta && n_kc == 1 && nt >= 32 && variant == 0) continue;   // (SRB_TC_2CTA=1: pairs wherever possible)
+    if (try_pair && (nt < 32 || variant != 0)) continue;
     q = TcParams{};
+    q.n_kc = n_kc;
     q.fold = fold ? 1 : 0;
     q.kh = p.kh; q.kw = p.kw;
     q.halo_rows = kTileH + p.kh - 1;
@@ -1625,7 +1667,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.tmem_cols = 32;
     while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
     const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
-    const bool k2c = (two_cta || nt == 256) && !fold && variant == 0 && nt >= 32;
+    const bool k2c = try_pair && !fold;
     q.two_cta = k2c ? 1 : 0;
     q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)((k2c ? 2 * kTileM : kTileM) >> 4) << 24);
     // staged vector epilogue: one fp32 and/or one 16-bit destination; a warp's columns map to one d2s sub-pixel
@@ -1679,7 +1721,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       }
     }
     if (nt == 256 && !q.tma_epi) continue;                    // (256-channel chunks only exist with the TMA epilogue)
-    const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 + 1023) & ~(size_t)1023;
+    const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 * n_kc + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
     static int stage_cap = 0;
@@ -1688,7 +1730,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     q.stages = stage_cap;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);
-    found = smem <= (size_t)max_smem && (q.stages >= 2 || nt == 16 || ci == 4);
+    found = smem <= (size_t)max_smem && (q.stages >= 2 || (n_kc == 1 && nt == 16));
   }
   if (!found) { set_error("conv(tcgen05): weights + one pipeline stage + epilogue staging do not fit shared memory"); return SRB_E_UNSUPPORTED; }
 
@@ -1696,7 +1738,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmx, tmw;
   {
-    const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+    // channel extent: the K chunks the weights cover, but never past the end of the pixel (the buffer may be narrower than
+    // the padded cin: TMA zero-fills what lies beyond it; channels between cin and the extent meet zero weight columns)
+    const int c_avail = p.x_cstride - p.x_coffset;
+    const cuuint64_t c_ext = (cuuint64_t)(p.w_tc_cin < c_avail ? p.w_tc_cin : c_avail);
+    const cuuint64_t dims[4] = {c_ext, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
     const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2,
                                    (cuuint64_t)p.H * p.W * p.x_cstride * 2};
     const cuuint32_t box[4] = {64, (cuuint32_t)q.pitch, (cuuint32_t)q.halo_rows, 1};
@@ -1707,8 +1753,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, q.fold ? (cuuint64_t)48 : (cuuint64_t)(p.kh * p.kw) * rows};
-    const cuuint64_t strides[1] = {128};
+    const cuuint64_t dims[2] = {(cuuint64_t)(q.fold ? 64 : p.w_tc_cin), q.fold ? (cuuint64_t)48 : (cuuint64_t)(p.kh * p.kw) * rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)(q.fold ? 64 : p.w_tc_cin) * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)(q.two_cta ? q.n_tile / 2 : q.n_tile)};
     const cuuint32_t es[2] = {1, 1};
     CUresult r = encode(&tmw, tdt, 2, (void*)(q.fold ? p.w_tc_fold : p.w_tc), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,

@@ -489,7 +489,9 @@ class ESRGANGeneratorNet(DeviceModel):
         torch = _torch()
         L, g = self.layers, self.growth
         B, H, W, Cc = x.shape
-        buf = torch.empty((B, H, W, 64 + 4 * g), dtype=x.dtype, device=x.device)
+        # (zeros, not empty: the tcgen05 engine reads the input in 64-channel chunks, so a growth conv also reads the slices
+        #  that later convs of the block will write - against zero weight columns, which only cancel finite values)
+        buf = torch.zeros((B, H, W, 64 + 4 * g), dtype=x.dtype, device=x.device)
         buf[..., :64].copy_(x)
         for j in range(4):
             # reads channels [0, 64 + j*g) of the wide buffer via cstride; writes slice j
@@ -543,20 +545,26 @@ class VGG16ClassifierNet(DeviceModel):
         torch = _torch()
         self.dense = {k: torch.from_numpy(self.weights[k]).cuda() for k in
                       ("dense/kernel", "dense/bias", "predictions/kernel", "predictions/bias")}
-        # 16-bit modes: the tcgen05 engine takes 64 input channels per launch, so a layer with Cin = 64 s is run as s
-        # passes over 64-channel slices of its input (x_coffset), partial sums accumulated in one fp32 tensor through the
-        # residual input, followed by one ReLU + cast (the direct engine would run these layers at ~30 TFLOP/s)
+        # 16-bit modes: layers with Cin = 64 s run on the tcgen05 engine in one launch (the kernel walks the input in
+        # 64-channel K chunks with every chunk's weights resident).  ``slice_passes = True`` selects the round-1 scheme
+        # instead - s launches over 64-channel slices of the input (x_coffset), partial sums accumulated in one fp32 tensor
+        # through the residual input, then one ReLU + cast - kept for comparison.
+        self.slice_passes = False
         self.slices = {}
-        if precision != "fp32":
-            for name, w in self.layers.items():
-                if w.cin > 64 and w.cin % 64 == 0 and w.kh == 3:
-                    k, b = self.weights[name + "/kernel"], self.weights.get(name + "/bias")
-                    self.slices[name] = [ops.ConvWeights(k[:, :, 64 * i:64 * (i + 1), :], b if i == 0 else None)
-                                         for i in range(w.cin // 64)]
+
+    def _slices_of(self, name):
+        if name not in self.slices:
+            w = self.layers[name]
+            self.slices[name] = None
+            if self.precision != "fp32" and w.cin > 64 and w.cin % 64 == 0 and w.kh == 3:
+                k, b = self.weights[name + "/kernel"], self.weights.get(name + "/bias")
+                self.slices[name] = [ops.ConvWeights(k[:, :, 64 * i:64 * (i + 1), :], b if i == 0 else None)
+                                     for i in range(w.cin // 64)]
+        return self.slices[name]
 
     def _conv_relu(self, h, name):
         torch = _torch()
-        sl = self.slices.get(name)
+        sl = self._slices_of(name) if self.slice_passes else None
         if sl is None:
             return ops.conv2d(h, self.layers[name], act="relu", out_dtype=self.act_dtype)
         acc = ops.conv2d(h, sl[0], x_coffset=0, out_dtype=torch.float32)

@@ -156,18 +156,24 @@ def test_vgg16_classifier_vs_oracle():
     assert np.abs(got - want).max() <= 2e-3 and np.array_equal(got.argmax(1), want.argmax(1))
 
 
-def test_vgg16_classifier_16bit_sliced_layers():
-    """16-bit VGG16: layers with Cin = 128/256/512 run as passes over 64-channel input slices on the tcgen05 engine with
-    fp32 partial sums (srb_conv2d_nhwc x_coffset + res1, then srb_cast_relu).  SURVEY C4: softmax probabilities within
-    2e-2 of the oracle and the same argmax."""
-    from srb200 import engine, weights
+def test_vgg16_classifier_16bit_wide_layers():
+    """16-bit VGG16: layers with Cin = 128/256/512 run on the tcgen05 engine in one launch each (64-channel K chunks with
+    resident weights); ``slice_passes`` selects the round-1 scheme (passes over 64-channel input slices with fp32 partial
+    sums through res1, then srb_cast_relu) for comparison.  SURVEY C4: softmax probabilities within 2e-2 of the oracle and
+    the same argmax."""
+    from srb200 import engine, ops, weights, _capi
     w = weights.vgg16_classifier_weights(2, bias_scale=0.05)
     x = np.random.default_rng(1).random((5, 32, 32, 3), dtype=np.float32)
     want = oc.vgg16_classifier_forward(w, x)
     net = engine.VGG16ClassifierNet(w, precision="fp16")
-    assert len(net.slices) == 10 and len(net.slices["block5_conv3"]) == 8
+    probe = torch.zeros((1, 8, 8, 512), dtype=torch.float16, device="cuda")
+    assert ops.conv2d_engine(probe, net.layers["block5_conv3"]) == _capi.ENGINE_TCGEN05
     got = net.predict(x)
     assert np.abs(got - want).max() <= 2e-2 and np.array_equal(got.argmax(1), want.argmax(1))
+    net.slice_passes = True
+    got2 = net.predict(x)
+    assert len(net.slices["block5_conv3"]) == 8
+    assert np.abs(got2 - want).max() <= 2e-2 and np.abs(got2 - got).max() <= 1e-2
 
 
 def test_edsr_full_depth_vs_oracle():

@@ -23,10 +23,13 @@ def _rand(shape, seed, lo=-1.0, hi=1.0):
     return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
 
 
-def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, **kw):
+def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, cin=64, x_width=None, **kw):
+    """``cin``: input channels of the layer; ``x_width``: channels of the buffer the layer reads a prefix of (>= cin)."""
     from srb200 import ops, _capi
-    x = _round(_rand((B, H, W, 64), 1), kind)
-    kern = _round(_rand((ksize, ksize, 64, cout), 2, -0.1, 0.1), kind)
+    xw = x_width or cin
+    x_full = _round(_rand((B, H, W, xw), 1), kind)
+    x = np.ascontiguousarray(x_full[..., :cin])
+    kern = _round(_rand((ksize, ksize, cin, cout), 2, -0.1, 0.1), kind)
     bias = _rand((cout,), 3, -0.1, 0.1)
     r = kw.get("d2s", 1)
     c_post = cout // (r * r)
@@ -42,7 +45,7 @@ def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, **
     if kw.get("clip01"):
         want = np.clip(want, 0, 1)
     w = ops.ConvWeights(kern, bias)
-    xd = torch.from_numpy(x).cuda().to(DT[kind])
+    xd = torch.from_numpy(x_full).cuda().to(DT[kind])
     prev = _capi.lib().srb_conv_tc_set_variant(-1 if variant is None else variant)
     try:
         assert ops.conv2d_engine(xd, w, r) == _capi.ENGINE_TCGEN05
@@ -338,3 +341,39 @@ def test_espcn_layers_at_benchmark_tile_size():
     lo = engine.ESPCNNet(w, 4, precision="fp16").predict_device(img)
     hi = engine.ESPCNNet(w, 4, precision="fp32").predict_device(img)
     assert (lo - hi).abs().max().item() <= 2e-2
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", [
+    # (B, H, W, cin, cout): VGG16 blocks 2-5 (VGG16_model.py:69-83) - resident weights of every 64-channel K chunk, CTA pairs
+    (2, 32, 32, 128, 128), (1, 24, 16, 128, 256), (2, 16, 16, 256, 256), (1, 16, 16, 256, 512), (3, 8, 8, 512, 512),
+    (1, 19, 13, 128, 64), (1, 40, 9, 192, 64),
+    # ESRGAN dense blocks (ESRGAN_model.py:230-246): cin = 64 + j * growth is padded to whole chunks; growth 32 and 8
+    (1, 24, 24, 96, 32), (1, 24, 24, 160, 32), (2, 24, 24, 72, 8), (1, 24, 24, 88, 8), (1, 12, 20, 32, 48)])
+def test_wide_input_layers_k_chunks(kind, case):
+    """Cin != 64 on the tcgen05 engine: ReLU layers with 16-bit and fp32 outputs against the float64 im2col oracle."""
+    B, H, W, cin, cout = case
+    tol16 = 4e-2 if kind == "bf16" else 8e-3                 # output rounding of sums over up to 4,608 products
+    got, want = _run(kind, B, H, W, cout, cin=cin, act="relu", out_dtype=DT[kind])
+    assert got.shape == want.shape and np.abs(got - want).max() <= tol16 * max(1.0, np.abs(want).max() / 4)
+    got, want = _run(kind, B, H, W, cout, cin=cin)
+    assert np.abs(got - want).max() <= 4e-3
+
+
+def test_wide_input_prefix_of_a_wider_buffer_and_fused_epilogue():
+    """The ESRGAN dense-block pattern: a growth conv reads channels [0, cin) of the block's wide NHWC buffer (cstride >
+    cin; the chunk padding reads further channels of the buffer against zero weight columns, or past its end where TMA
+    zero-fills), writes a 16-bit slice of it, and the block's last conv adds two scaled residuals."""
+    from srb200 import ops
+    kind = "fp16"
+    got, want = _run(kind, 1, 24, 24, 32, cin=96, x_width=192, act="relu", out_dtype=DT[kind])
+    assert np.abs(got - want).max() <= 8e-3
+    got, want = _run(kind, 2, 16, 24, 8, cin=72, x_width=96, act="relu")
+    assert np.abs(got - want).max() <= 4e-3
+    got, want = _run(kind, 1, 20, 20, 64, cin=192, alpha=0.2, res1=True)
+    assert np.abs(got - want).max() <= 4e-3
+    # 5x5 and 1x1 filters with a wide input
+    got, want = _run(kind, 1, 18, 14, 64, cin=128, ksize=5)
+    assert np.abs(got - want).max() <= 6e-3
+    got, want = _run(kind, 1, 18, 14, 32, cin=128, ksize=1, act="relu")
+    assert np.abs(got - want).max() <= 4e-3
