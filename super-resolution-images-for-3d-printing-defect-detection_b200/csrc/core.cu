@@ -97,72 +97,92 @@ gap_dense_softmax_kernel(const T* __restrict__ x, int HW, int C, const float* __
   }
 }
 
-// SelfAttention core (ESRGAN_model.py:58-66): o[q] = sum_k softmax_k(g[q] . f[k]) h[k].
-// One warp per query row, online softmax over keys staged through shared memory in tiles of 64.
+// SelfAttention core (ESRGAN_model.py:58-66): o[q] = sum_k softmax_k(g[q] . f[k]) h[k], exact fp32 on the CUDA cores.
+// One THREAD per query (a block = 128 consecutive queries of one image): the query vector, the running maximum / sum of the
+// online softmax and the DV output accumulators live in registers, so the key loop needs no cross-lane reduction at all.
+// Keys and values are staged through shared memory in tiles of 64 and read back as broadcasts (every lane of a warp reads
+// the same key: one wavefront per 16-byte load).  Per (query, key) pair: DK + DV FMAs - the value update as packed fp32x2 -
+// plus one exp; keys are scored in groups of eight so that the accumulators are rescaled at most once per group.
 template <int DK, int DV>
 __global__ void __launch_bounds__(128)
 self_attention_kernel(const float* __restrict__ f, const float* __restrict__ g, const float* __restrict__ h,
                       int HW, float* __restrict__ o) {
-  constexpr int KT = 64;
-  __shared__ float sf[KT][DK + 1];
-  __shared__ float sh[KT][DV + 1];
+  constexpr int KT = 64, KG = 8;
+  __shared__ __align__(16) float sf[KT * DK];
+  __shared__ __align__(16) float sh[KT * DV];
   const int b = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = blockIdx.x * 4 + warp;
+  const int q = blockIdx.x * 128 + threadIdx.x;
   const float* fb = f + (size_t)b * HW * DK;
   const float* hb = h + (size_t)b * HW * DV;
   float gq[DK];
+  {
+    const float* gp = g + ((size_t)b * HW + (q < HW ? q : HW - 1)) * DK;
 #pragma unroll
-  for (int d = 0; d < DK; ++d) gq[d] = q < HW ? __ldg(g + ((size_t)b * HW + q) * DK + d) : 0.f;
+    for (int d = 0; d < DK; d += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(gp + d));
+      gq[d] = v.x; gq[d + 1] = v.y; gq[d + 2] = v.z; gq[d + 3] = v.w;
+    }
+  }
   float m = -INFINITY, z = 0.f;
-  float acc[(DV + 31) / 32];
+  float2 acc[DV / 2];
 #pragma unroll
-  for (int i = 0; i < (DV + 31) / 32; ++i) acc[i] = 0.f;
+  for (int i = 0; i < DV / 2; ++i) acc[i] = make_float2(0.f, 0.f);
   for (int k0 = 0; k0 < HW; k0 += KT) {
+    const int nk = min(KT, HW - k0);
     __syncthreads();
-    for (int i = threadIdx.x; i < KT * DK; i += 128) {
-      const int kk = i / DK, d = i % DK;
-      sf[kk][d] = (k0 + kk < HW) ? __ldg(fb + (size_t)(k0 + kk) * DK + d) : 0.f;
-    }
-    for (int i = threadIdx.x; i < KT * DV; i += 128) {
-      const int kk = i / DV, d = i % DV;
-      sh[kk][d] = (k0 + kk < HW) ? __ldg(hb + (size_t)(k0 + kk) * DV + d) : 0.f;
-    }
+    // the tile's keys and values are contiguous in global memory: 16-byte coalesced copies (rows past HW: zeros)
+    for (int i = threadIdx.x; i < KT * DK / 4; i += 128)
+      reinterpret_cast<float4*>(sf)[i] = (4 * i < nk * DK) ? __ldg(reinterpret_cast<const float4*>(fb + (size_t)k0 * DK) + i)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = threadIdx.x; i < KT * DV / 4; i += 128)
+      reinterpret_cast<float4*>(sh)[i] = (4 * i < nk * DV) ? __ldg(reinterpret_cast<const float4*>(hb + (size_t)k0 * DV) + i)
+                                                            : make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    // each lane scores keys lane and lane+32 of the tile
-    float s0 = -INFINITY, s1 = -INFINITY;
-    if (k0 + lane < HW) { s0 = 0.f;
+#pragma unroll 1
+    for (int kg = 0; kg < nk; kg += KG) {
+      float sc[KG];
+      float gm = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) s0 = fmaf(gq[d], sf[lane][d], s0); }
-    if (k0 + lane + 32 < HW) { s1 = 0.f;
+      for (int j = 0; j < KG; ++j) {
+        const float4* kp = reinterpret_cast<const float4*>(sf + (kg + j) * DK);
+        float a = 0.f;
 #pragma unroll
-      for (int d = 0; d < DK; ++d) s1 = fmaf(gq[d], sf[lane + 32][d], s1); }
-    float tm = fmaxf(s0, s1);
+        for (int d = 0; d < DK; d += 4) {
+          const float4 v = kp[d / 4];
+          a = fmaf(gq[d], v.x, a); a = fmaf(gq[d + 1], v.y, a); a = fmaf(gq[d + 2], v.z, a); a = fmaf(gq[d + 3], v.w, a);
+        }
+        sc[j] = (kg + j < nk) ? a : -INFINITY;
+        gm = fmaxf(gm, sc[j]);
+      }
+      if (gm > m) {                                     // new running maximum: rescale what has been accumulated so far
+        const float corr = __expf(m - gm);              // (m = -inf on the first group: corr = 0, and z, acc are 0 anyway)
+        z *= corr;
+        const float2 c2 = make_float2(corr, corr);
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, off));
-    const float nm = fmaxf(m, tm);
-    const float corr = (m == -INFINITY) ? 0.f : expf(m - nm);
-    const float p0 = (s0 == -INFINITY) ? 0.f : expf(s0 - nm);
-    const float p1 = (s1 == -INFINITY) ? 0.f : expf(s1 - nm);
-    z = z * corr + warp_sum(p0 + p1);
+        for (int i = 0; i < DV / 2; ++i) acc[i] = __fmul2_rn(acc[i], c2);
+        m = gm;
+      }
 #pragma unroll
-    for (int i = 0; i < (DV + 31) / 32; ++i) acc[i] *= corr;
-    for (int kk = 0; kk < KT; ++kk) {
-      const float p = __shfl_sync(0xffffffffu, kk < 32 ? p0 : p1, kk & 31);
+      for (int j = 0; j < KG; ++j) {
+        const float p = __expf(sc[j] - m);              // (exp(-inf) = 0 for the keys past HW)
+        z += p;
+        const float2 p2 = make_float2(p, p);
+        const float4* vp = reinterpret_cast<const float4*>(sh + (kg + j) * DV);
 #pragma unroll
-      for (int i = 0; i < (DV + 31) / 32; ++i) {
-        const int d = lane + 32 * i;
-        if (d < DV) acc[i] = fmaf(p, sh[kk][d], acc[i]);
+        for (int i = 0; i < DV / 4; ++i) {
+          const float4 v = vp[i];
+          acc[2 * i] = __ffma2_rn(p2, make_float2(v.x, v.y), acc[2 * i]);
+          acc[2 * i + 1] = __ffma2_rn(p2, make_float2(v.z, v.w), acc[2 * i + 1]);
+        }
       }
     }
-    m = nm;
   }
   if (q < HW) {
+    const float inv = 1.f / z;
+    float4* op = reinterpret_cast<float4*>(o + ((size_t)b * HW + q) * DV);
 #pragma unroll
-    for (int i = 0; i < (DV + 31) / 32; ++i) {
-      const int d = lane + 32 * i;
-      if (d < DV) o[((size_t)b * HW + q) * DV + d] = acc[i] / z;
-    }
+    for (int i = 0; i < DV / 4; ++i)
+      op[i] = make_float4(acc[2 * i].x * inv, acc[2 * i].y * inv, acc[2 * i + 1].x * inv, acc[2 * i + 1].y * inv);
   }
 }
 
@@ -268,7 +288,9 @@ extern "C" int srb_self_attention_f32(const float* f, const float* g, const floa
   SRB_REQUIRE(batch >= 0 && hw > 0, "self_attention: bad geometry");
   if (batch == 0) return SRB_OK;
   SRB_REQUIRE(batch <= 65535, "self_attention: batch too large for one launch");
-  dim3 grid((hw + 3) / 4, batch);
+  SRB_REQUIRE(((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h) |
+                reinterpret_cast<uintptr_t>(o)) & 15) == 0, "self_attention: tensors must be 16-byte aligned");
+  dim3 grid((hw + 127) / 128, batch);
   if (dk == 8 && dv == 32) self_attention_kernel<8, 32><<<grid, 128, 0, stream>>>(f, g, h, hw, o);
   else if (dk == 4 && dv == 16) self_attention_kernel<4, 16><<<grid, 128, 0, stream>>>(f, g, h, hw, o);
   else if (dk == 16 && dv == 64) self_attention_kernel<16, 64><<<grid, 128, 0, stream>>>(f, g, h, hw, o);

@@ -155,6 +155,10 @@ constexpr int kPairPx = 64;                        // map pixels per warp row (2
 constexpr int kPairLW = kPairPx + 10;              // line width in pixels (even: 16-byte aligned planes)
 constexpr int kPairAhead = 8;                      // rows in flight = line buffers (refilled after the row is retired)
 
+// (Three resident blocks per SM, 157 registers.  Holding the allocation to five blocks (128 registers, no spills) or six
+//  (96, spills) makes it SLOWER - 60 -> 49 -> 39 GP/s at 1K / 2K / 4K, profiles/r02_ssim_occupancy.txt: the kernel is bound
+//  by shared-memory wavefronts (48 tap-load + 12 product + 6 fill wavefronts per 64 outputs against 44 FFMA2 issue cycles),
+//  not by latency, so more warps only add instructions.)
 template <int C>
 __global__ void __launch_bounds__((C == 3 ? 3 : 4) * 32, 3)
 psnr_ssim_pair_kernel(const float* __restrict__ a, const float* __restrict__ b, int H, int W, int rows_per_strip,

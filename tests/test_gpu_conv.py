@@ -212,3 +212,21 @@ def test_srcnn_16bit_runs_on_the_tensor_core_kernels():
     w2["conv2/kernel"] = w["conv2/kernel"][:, :, :64, :]
     assert engine.SRCNNNet(w2, precision="fp16")._tc is None
     assert np.abs(engine.SRCNNNet(w2, precision="fp16").predict(x) - oc.srcnn_forward(w2, x)).max() <= HALF_TOL
+
+
+@pytest.mark.parametrize("hw,dk,dv,batch", [(576, 8, 32, 3), (2304, 8, 32, 1), (130, 8, 32, 2), (61, 4, 16, 2), (200, 16, 64, 1)])
+def test_self_attention_core_vs_float64(hw, dk, dv, batch):
+    """srb_self_attention_f32 (ESRGAN_model.py:58-66: beta = softmax(g f^T), o = beta h) against a float64 evaluation:
+    the two sizes of the trained ESRGAN configuration (24x24 and 48x48 positions), ragged lengths (not a multiple of the
+    128-query block or the 64-key tile), the other head sizes, and large logits (running-maximum rescaling)."""
+    from srb200 import ops
+    rng = np.random.default_rng(hw)
+    for scale in (1.0, 6.0):
+        f = (rng.standard_normal((batch, hw, dk)) * scale).astype(np.float32)
+        g = (rng.standard_normal((batch, hw, dk)) * scale).astype(np.float32)
+        h = rng.standard_normal((batch, hw, dv)).astype(np.float32)
+        s = np.einsum("bqd,bkd->bqk", g.astype(np.float64), f.astype(np.float64))
+        p = np.exp(s - s.max(-1, keepdims=True))
+        want = (p / p.sum(-1, keepdims=True)) @ h.astype(np.float64)
+        got = ops.self_attention_core(torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda(), torch.from_numpy(h).cuda()).cpu().numpy()
+        assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5 * max(1.0, scale * scale)
