@@ -136,15 +136,11 @@ void srb_conv_weights_destroy(srb_conv_weights* w);
 int srb_conv2d_nhwc(const srb_conv_args* args, srb_stream_t stream);
 /* which engine AUTO would pick for these args: SRB_ENGINE_DIRECT or SRB_ENGINE_TCGEN05 */
 int srb_conv2d_engine(const srb_conv_args* args);
-/* tcgen05 engine A-operand staging variant (process-wide; returns the previous value, or the current
- * one for variant < 0).  0 = one TMA halo tile per pixel tile, taps addressed by shifted UMMA
- * descriptors; 1 = as 0 with the descriptor base-offset field set from the shifted address;
- * 2 = three dx-shifted TMA tiles so that every tap starts on a 1024-byte swizzle boundary. */
-int srb_conv_tc_set_variant(int variant);
-/* tcgen05 engine: launch eligible layers (>= 32-channel chunks) as CTA pairs - clusters of two CTAs issuing
+/* tcgen05 engine: launch every eligible Cin = 64 layer (>= 32-channel chunks) as CTA pairs - clusters of two CTAs issuing
  * cta_group::2 MMAs (M = 256) from the leader, each CTA keeping half of the weight rows.  Returns the previous
- * setting (on < 0 only queries).  Default off (environment SRB_TC_2CTA=1 turns it on): measured equal to the
- * single-CTA kernel on B200 for these N <= 128 tiles. */
+ * setting (on < 0 only queries).  Default off: pairs are then used only where they pay - 256-channel chunks (the
+ * up-sampling convs) and inputs wider than 64 channels, where they double the MMA width per resident weight byte;
+ * for Cin = 64 and N <= 128 they measured equal to single CTAs on B200. */
 int srb_conv_tc_set_cta_pairs(int on);
 
 /* ---- small layout / elementwise helpers used between layers -------------------------------------- */

@@ -87,8 +87,6 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  if (warp != kHProd) pdl_wait();                     // producers read the image, epilogue warps write the outputs (the MMA warp touches neither)
   const int tiles_per_img = q.tiles_x * q.tiles_y;
   const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
   auto coords = [&](int tile, int& b, int& y0, int& x0) {
@@ -196,7 +194,7 @@ conv_headtc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_cons
       if (elect_one()) {
         for (int k = 0; k < n_k; ++k) {
           const uint32_t kb = (uint32_t)k >> 2, ks = (uint32_t)k & 3u;
-          umma_f16(d_tmem, make_desc(a_stage + kb * 16384u + ks * 32u, 1024u, 0), make_desc(w_smem + kb * 8192u + ks * 32u, 1024u, 0),
+          umma_f16(d_tmem, make_desc(a_stage + kb * 16384u + ks * 32u, 1024u), make_desc(w_smem + kb * 8192u + ks * 32u, 1024u),
                    q.idesc, (uint32_t)(k != 0));
         }
         umma_commit(empty_bar(s));

@@ -1,5 +1,7 @@
-// tcgen05 / TMEM implicit-GEMM engine for 3x3, Cin = 64 convolutions on NHWC bf16 / fp16 activations
-// (the EDSR / SRResNet / ESRGAN body, up-sampling and tail layers: EDSR_model.py:61,65,80-89,112,121).
+// tcgen05 / TMEM implicit-GEMM engine for odd K x K convolutions on NHWC bf16 / fp16 activations with Cin = 64 (the EDSR /
+// SRResNet / ESRGAN body, up-sampling and tail layers: EDSR_model.py:61,65,80-89,112,121) or wider (VGG16 blocks 2-5,
+// VGG16_model.py:69-83; the ESRGAN dense blocks' growing concatenation, ESRGAN_model.py:230-246): 64-channel K chunks.
+// The wide-tile, dx-folded sibling for layers with few output channels per MMA lives in conv_fold.cu.
 //
 // GEMM view per CTA tile:  D[128 pixels x N] += sum over 9 taps  A_tap[128 x 64] * W_tap[64 x N]
 //   * a tile is 16 rows x 8 columns of output pixels of one image; pixel (ty, tx) is GEMM row ty*8+tx, so
@@ -29,11 +31,6 @@ constexpr int kTileH = 16, kTileW = 8, kTileM = kTileH * kTileW;   // 128 GEMM r
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 
-// n / d by multiply-high with magic = ceil(2^32 / d) (exact while n * d < 2^32: checked on the host, which passes 0 otherwise)
-__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
-  return magic ? (int)__umulhi((uint32_t)n, magic) : n / d;
-}
-
 struct TcParams {
   int n_tile;            // output channels per CTA (multiple of 16, <= 128)
   int n_chunks;          // ceil(cout_pad / n_tile); CTA c owns chunk c % n_chunks
@@ -42,20 +39,17 @@ struct TcParams {
   int stages;
   uint32_t stage_bytes;  // multiple of 1024
   int pitch;             // halo row pitch in pixels (= TMA box width)
-  int n_loads;           // 1 (one halo tile) or 3 (one tile per dx)
-  uint32_t load_bytes;   // bytes per TMA load
-  int base_off_mode;     // 0: descriptor base_offset = 0; 1: (start_address >> 7) & 7
+  uint32_t load_bytes;   // bytes of the one halo tile a stage holds
   uint32_t tmem_cols;
   uint32_t idesc;
   int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses);
-                         // 2: few-channel epilogue (cout <= 4, e.g. the RGB tail); 3: dx-folded few-channel epilogue;
+                         // 2: few-channel epilogue (cout <= 4, e.g. an RGB tail with a filter the fold kernel does not take);
                          // 4: depth_to_space to few channels (ESPCN): r*c_post contiguous floats per output row
   int f_bufs;            // per-warp fp32 staging buffers (0, 1, or 2 when the residual is prefetched)
   int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
-  int res_prefetch;      // res1 is fp32 and is prefetched into the F buffers with cp.async
+  int res_prefetch;      // 1: res1 is fp32 and is prefetched into the F buffers with cp.async; 2: 16-bit (res1, res2) pair
+                         // prefetched the same way; 3: pair8 trunk (TMA epilogue)
   uint32_t epi_warp_bytes;
-  int fold;              // horizontal taps folded into N (cout <= 4): 3 MMA taps (dy), 8 input columns -> 6 output columns
-  int tile_cols_out;     // 8, or 6 when folded
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int n_kc;              // 64-channel K chunks of the input (cin_pad / 64): one halo load and one set of tap MMAs per chunk
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
@@ -64,8 +58,6 @@ struct TcParams {
   int reverse;           // walk the tiles from the last to the first (alternate launches: the next layer starts on the
                          // rows the previous one wrote last, which are still in L2)
   int tma_epi;           // staged epilogue moves its rows with TMA (residual loads, output stores) instead of per-lane copies
-  int debug;             // diagnostics (SRB_TC_DEBUG): 1 = epilogue only releases TMEM (no math / stores: wrong results),
-                         // 2 = the MMA warp issues no MMAs (commits only: wrong results)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -144,7 +136,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
 
-  const int n_taps = q.fold ? 3 : q.kh * q.kw;
+  const int n_taps = q.kh * q.kw;
   const uint32_t rank = k2 ? cluster_ctarank() : 0u;          // 0 = leader of the pair
   const uint32_t n_local = k2 ? (uint32_t)q.n_tile / 2u : (uint32_t)q.n_tile;   // weight rows held by this CTA
   const int n_kc = q.n_kc;
@@ -205,12 +197,8 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (k2) cluster_sync_all(); else __syncthreads();   // barrier inits must be visible to the peer before it signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();                            // the next layer may begin its prologue as SMs free up
 
   const int tiles_per_img = q.tiles_x * q.tiles_y;
-  // (the weights do not depend on the previous launch; everything else read or written below does: the producer waits
-  //  after queueing the weight loads, the epilogue warps before their first global access)
-  if (warp >= 2) pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -228,24 +216,20 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
     }
     __syncwarp();
-    pdl_wait();
     int s = 0; uint32_t ph = 0;
     for (int tile = first_tile; tile < tile_end; tile += tile_step) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
       const int b = fast_div(tl, tiles_per_img, q.magic_tpi), r = tl - b * tiles_per_img;   // (dummy tile: b == B, zero-filled by TMA)
       const int ty_ = fast_div(r, q.tiles_x, q.magic_tx);
-      const int y0 = ty_ * kTileH, x0 = (r - ty_ * q.tiles_x) * q.tile_cols_out;
+      const int y0 = ty_ * kTileH, x0 = (r - ty_ * q.tiles_x) * kTileW;
       for (int kc = 0; kc < n_kc; ++kc) {              // one halo tile per 64-channel K chunk
         mbar_wait(empty_bar(s), ph ^ 1u);
         const uint32_t dst = a_smem + (uint32_t)s * q.stage_bytes;
         if (elect_one()) {
-          const uint32_t bytes = q.load_bytes * (uint32_t)q.n_loads;
-          if (!k2) mbar_expect_tx(full_bar(s), bytes);
-          else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * bytes);
-          for (int l = 0; l < q.n_loads; ++l) {
-            if (k2) tma_load_4d_2sm(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
-            else tma_load_4d(dst + (uint32_t)l * q.load_bytes, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1) + l, y0 - (q.kh >> 1), b);
-          }
+          if (!k2) mbar_expect_tx(full_bar(s), q.load_bytes);
+          else if (rank == 0) mbar_expect_tx(full_bar(s), 2u * q.load_bytes);
+          if (k2) tma_load_4d_2sm(dst, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1), y0 - (q.kh >> 1), b);
+          else tma_load_4d(dst, &tmap_x, full_bar(s), kc * 64, x0 - (q.kw >> 1), y0 - (q.kh >> 1), b);
         }
         __syncwarp();
         if (++s == q.stages) { s = 0; ph ^= 1u; }
@@ -263,24 +247,40 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     mbar_wait(wfull_bar, 0);
     int s = 0; uint32_t ph = 0; int it = 0;
     const uint32_t sbo = (uint32_t)q.pitch * 128u;
-    const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
+    const uint64_t b_desc0 = make_desc(w_smem, 1024u);
     const uint32_t b_tap_step = (n_local * 128u) >> 4;                  // descriptor address units (16 B)
-    const uint32_t a_dy = (uint32_t)q.pitch * 8u;                       // one halo row, in 16-B units
-    const uint32_t a_dx = (q.n_loads == 1) ? 8u : (q.load_bytes >> 4);  // one pixel / one dx sub-tile
+    const uint32_t a_dy = (uint32_t)q.pitch * 8u;                       // one halo row, in 16-B units (one pixel = 8 units)
+    const bool unrolled = n_kc == 1 && q.kh == 3 && q.kw == 3;          // the hot case: nine taps from uniform registers
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint32_t a_stage = a_smem + (uint32_t)s * q.stage_bytes;
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
-      if (n_kc > 1) {
-        // wide inputs: the accumulator collects every (K chunk, tap) product; each chunk has its own halo stage and its own
-        // block of resident weight rows
+      if (unrolled) {
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
+        const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo);
+        if (elect_one()) {
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap) {
+            const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * 8u);
+            const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
+          }
+          commit(empty_bar(s));            // smem stage reusable once these MMAs have read it (both CTAs in k2)
+          commit(tfull_bar(acc));          // accumulator complete
+        }
+        __syncwarp();
+        if (++s == q.stages) { s = 0; ph ^= 1u; }
+      } else {
+        // general odd filter and / or wide input: the accumulator collects every (K chunk, tap) product; each 64-channel
+        // chunk has its own halo stage and its own block of resident weight rows
         for (int kc = 0; kc < n_kc; ++kc) {
-          if (kc) { mbar_wait(full_bar(s), ph); tc_fence_after(); }
-          const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo, 0);
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo);
           const uint64_t b_kc = b_desc0 + (uint64_t)((uint32_t)kc * (w_kc_bytes >> 4));
           if (elect_one()) {
             int tap = 0;
@@ -295,82 +295,9 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
             if (kc == n_kc - 1) commit(tfull_bar(acc));
           }
           __syncwarp();
-          if (kc < n_kc - 1 && ++s == q.stages) { s = 0; ph ^= 1u; }
+          if (++s == q.stages) { s = 0; ph ^= 1u; }
         }
-      } else if (q.fold) {
-        // dx folded into N: D[input pixel, (dx, co)] += sum over dy of A shifted by dy halo rows (1,024-B aligned)
-        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
-        if (q.debug == 2) {
-          if (elect_one()) { commit(empty_bar(s)); commit(tfull_bar(acc)); }
-        } else if (elect_one()) {
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t ad = a_desc0 + (uint64_t)(dy * a_dy), bd = b_desc0 + (uint64_t)dy * b_tap_step;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((dy | k) != 0));
-          }
-          commit(empty_bar(s));
-          commit(tfull_bar(acc));
-        }
-      } else if (q.kh != 3 || q.kw != 3) {
-        // general odd filter (5x5, 9x9 ...): same shifted-descriptor scheme, rolled tap loops
-        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
-        if (elect_one()) {
-          int tap = 0;
-          for (int ty_ = 0; ty_ < q.kh; ++ty_)
-            for (int tx_ = 0; tx_ < q.kw; ++tx_, ++tap) {
-              const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ty_ * a_dy + (uint32_t)tx_ * 8u);
-              const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
-            }
-          commit(empty_bar(s));
-          commit(tfull_bar(acc));
-        }
-      } else if (q.base_off_mode == 0) {
-        // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
-        const uint64_t a_desc0 = make_desc(a_stage, sbo, 0);
-        if (q.debug == 2) {
-          if (elect_one()) { commit(empty_bar(s)); commit(tfull_bar(acc)); }
-        } else if (q.debug == 3) {          // timing probe: consecutive MMAs alternate between the two accumulators
-          const uint32_t d_alt = tmem_base + (uint32_t)((acc ^ 1) * q.n_tile);
-          if (elect_one()) {
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
-              const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) mma((k & 1) ? d_alt : d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
-            }
-            commit(empty_bar(s));
-            commit(tfull_bar(acc));
-          }
-        } else if (elect_one()) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * a_dx);
-            const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
-          }
-          commit(empty_bar(s));            // smem stage reusable once these MMAs have read it (both CTAs in k2)
-          commit(tfull_bar(acc));          // accumulator complete
-        }
-      } else if (elect_one()) {            // diagnostic variants 1 / 3 (descriptor base-offset field set)
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int dy = tap / 3, dx = tap - dy * 3;
-          const uint32_t a_tap = a_stage + (uint32_t)(dy * q.pitch + dx) * 128u;
-          const uint32_t b_tap = w_smem + (uint32_t)tap * (uint32_t)q.n_tile * 128u;
-          for (int k = 0; k < 4; ++k)
-            umma_f16(d_tmem, make_desc(a_tap + (uint32_t)k * 32u, sbo, 1), make_desc(b_tap + (uint32_t)k * 32u, 1024u, 0),
-                     q.idesc, (uint32_t)((tap | k) != 0));
-        }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(acc));
       }
-      __syncwarp();
-      if (++s == q.stages) { s = 0; ph ^= 1u; }
     }
     }
   } else if ((kSpec == 1 || kSpec == 2 || kSpec == 6 || kSpec == 7) && !(k2 && kSpec == 6) && q.tma_epi) {
@@ -570,49 +497,15 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const bool do_clip = G && p.clip01;
     const bool f_on = G ? f_dst != 0 : kSpec == 3;
     const bool h_on = G ? h_dst != 0 : (kSpec != 5 && kSpec != 6);
-    constexpr bool P8 = kSpec == 6;
-    // pair8 staging geometry (per prefetch buffer): 32 rows of 16-bit hi (ncols * 2 B), then 32 rows of e5m2 lo (ncols B)
-    const uint32_t p8_hb = (uint32_t)ncols * 2u, p8_lb = (uint32_t)ncols;
-    const uint32_t p8_hc = p8_hb >> 4, p8_lc = p8_lb >> 4;        // 16-byte chunks per row: (4, 2) or (8, 4)
-    const uint32_t p8_hlg = 31u - (uint32_t)__clz((int)p8_hc), p8_llg = 31u - (uint32_t)__clz((int)p8_lc);
-    const uint32_t p8_buf_bytes = 32u * (p8_hb + p8_lb);
-    auto p8_hi = [&](uint32_t buf, uint32_t row, uint32_t chunk) { return buf + row * p8_hb + ((chunk ^ (row & (p8_hc - 1u))) << 4); };
-    auto p8_lo = [&](uint32_t buf, uint32_t row, uint32_t chunk) { return buf + 32u * p8_hb + row * p8_lb + ((chunk ^ (row & (p8_lc - 1u))) << 4); };
     const int epi_mode = G ? q.epi_mode : 1;
     // cooperative (coalesced) move of 32 staged rows: lane -> (row within a group of 32/cpr rows, 16-B chunk)
     auto prefetch_res = [&](int tile, int fb) {
       const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
       const int b = fast_div(tl, tiles_per_img, q.magic_tpi), rr_ = tl - b * tiles_per_img;
       const int ty_ = fast_div(rr_, q.tiles_x, q.magic_tx);
-      const int y0 = ty_ * kTileH, x0 = (rr_ - ty_ * q.tiles_x) * q.tile_cols_out;
+      const int y0 = ty_ * kTileH, x0 = (rr_ - ty_ * q.tiles_x) * kTileW;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const size_t tp = tile_pixel(b, y0, x0);
-      if (P8) {
-        const uint32_t buf = my_epi + (uint32_t)fb * p8_buf_bytes;
-        {
-          const uint32_t ch = (uint32_t)lane & (p8_hc - 1u), rsub = (uint32_t)lane >> p8_hlg;
-          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.res1) + (tp * (size_t)p.res1_cstride + c_out0) * 2u + ch * 16u;
-          const uint32_t pix_bytes = (uint32_t)p.res1_cstride * 2u;
-#pragma unroll 4
-          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_hlg) {
-            const int mm = quad * 32 + (int)row;
-            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
-              cp_async16(p8_hi(buf, row, ch), src0 + (size_t)pix_off(mm) * pix_bytes);
-          }
-        }
-        {
-          const uint32_t ch = (uint32_t)lane & (p8_lc - 1u), rsub = (uint32_t)lane >> p8_llg;
-          const uint8_t* src0 = reinterpret_cast<const uint8_t*>(p.res2) + (tp * (size_t)p.res2_cstride + c_out0) + ch * 16u;
-          const uint32_t pix_bytes = (uint32_t)p.res2_cstride;
-#pragma unroll 2
-          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_llg) {
-            const int mm = quad * 32 + (int)row;
-            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
-              cp_async16(p8_lo(buf, row, ch), src0 + (size_t)pix_off(mm) * pix_bytes);
-          }
-        }
-        return;
-      }
       const uint32_t buf = my_epi + (uint32_t)fb * 32u * f_rb;
       const uint32_t rows_per_it = 32u >> f_lg;
       const uint32_t ch = (uint32_t)lane & (f_cpr - 1u), rsub = (uint32_t)lane >> f_lg;
@@ -684,7 +577,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const int tl = !live ? 0 : q.reverse ? q.total_tiles - 1 - tile : tile;   // (never negative: multiply-high division)
       const int b = fast_div(tl, tiles_per_img, q.magic_tpi), rr_ = tl - b * tiles_per_img;
       const int ty_ = fast_div(rr_, q.tiles_x, q.magic_tx);
-      const int y0 = live ? ty_ * kTileH : p.H, x0 = (rr_ - ty_ * q.tiles_x) * q.tile_cols_out;
+      const int y0 = live ? ty_ * kTileH : p.H, x0 = (rr_ - ty_ * q.tiles_x) * kTileW;
       const bool full = (y0 + kTileH <= p.H) && (x0 + kTileW <= p.W);
       const bool valid = full || (y0 + (m >> 3) < p.H && x0 + (m & 7) < p.W);
       const int acc = it & 1;
@@ -696,11 +589,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         cp_async_commit();
         cp_async_wait1();                               // this tile's residual rows have landed
         __syncwarp();
-        f_buf = my_epi + (uint32_t)(it & 1) * (P8 ? p8_buf_bytes : 32u * f_rb);
+        f_buf = my_epi + (uint32_t)(it & 1) * 32u * f_rb;
       }
       mbar_wait(tfull_bar(acc), acc_ph);
       tc_fence_after();
-      if (!active || q.debug == 1 || q.debug == 3) {                    // chunk too narrow to split: this warp only keeps the protocol
+      if (!active) {                                    // chunk too narrow to split: this warp only keeps the protocol
         release_tmem(acc);
         continue;
       }
@@ -755,48 +648,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tmem_ld16(t_row + (uint32_t)c0, rr);
         tmem_ld_wait();
         if (c0 + 16 >= ncols) release_tmem(acc);        // last read of this accumulator: hand it back to the MMA warp
-        if (P8) {
-          // pair8 trunk: v = alpha * (acc + bias) + beta1 * hi + beta2 * lo;  y = round16(v), y2 = e5m2(v - y), in place
-          const uint32_t c16 = (uint32_t)c0 >> 4;
-          const uint32_t a_h0 = p8_hi(f_buf, my_row_sw, 2u * c16), a_h1 = p8_hi(f_buf, my_row_sw, 2u * c16 + 1u);
-          const uint32_t a_l = p8_lo(f_buf, my_row_sw, c16);
-          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
-          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
-          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
-          const float bb[16] = {bv[0].x, bv[0].y, bv[0].z, bv[0].w, bv[1].x, bv[1].y, bv[1].z, bv[1].w,
-                                bv[2].x, bv[2].y, bv[2].z, bv[2].w, bv[3].x, bv[3].y, bv[3].z, bv[3].w};
-          uint32_t oh[8], ol[4];
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {              // four channels at a time
-            float lo4[4], hi4[4], v4[4], er[4];
-            e5m2x4_to_float4(wl[i4], lo4);
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float2 fh;
-              if (p.y_dtype == SRB_BF16) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
-              else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
-              hi4[2 * hh] = fh.x; hi4[2 * hh + 1] = fh.y;
-            }
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float a = (__uint_as_float(rr[4 * i4 + e]) + bb[4 * i4 + e]) * p.alpha;
-              v4[e] = fmaf(p.beta2, lo4[e], fmaf(p.beta1, hi4[e], a));
-            }
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const uint32_t pk = pack2(v4[2 * hh], v4[2 * hh + 1], p.y_dtype);
-              oh[2 * i4 + hh] = pk;
-              float2 back;
-              if (p.y_dtype == SRB_BF16) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-              else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-              er[2 * hh] = v4[2 * hh] - back.x; er[2 * hh + 1] = v4[2 * hh + 1] - back.y;
-            }
-            ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
-          }
-          sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
-          sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
-          if (p.y2) sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
-        } else if (epi_mode == 1) {
+        if (epi_mode == 1) {
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             const int cc = c0 + g * 8;                  // channel offset inside this warp's column range
@@ -893,32 +745,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4), pk);
             }
           }
-        } else if (epi_mode == 3) {
-          // dx-folded few-channel layer: lane m holds D[input pixel (ty, xx), (dx, co)], xx = 0..7 <-> image column x0-1+xx.
-          // Output column xx (1..6) = D[xx-1][dx=0] + D[xx][dx=1] + D[xx+1][dx=2]: neighbours are adjacent lanes.
-          const int xx = m & 7;
-          float v[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(rr[0 * 5 + e]), 1);
-            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[2 * 5 + e]), 1);
-            v[e] = bias_s[e] + left + __uint_as_float(rr[1 * 5 + e]) + right;
-          }
-          const int oy = y0 + (m >> 3), ox = x0 + xx - 1;
-          if (xx >= 1 && xx <= 6 && oy < p.H && ox < p.W) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-              else if (p.act != SRB_ACT_NONE)
-                v[e] = act_generic(v[e], p.act, (p.act == SRB_ACT_PRELU && e < p.cout) ? __ldg(p.prelu + e) : p.act_slope);
-              v[e] *= p.alpha;
-              if (p.clip01) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
-            }
-            const size_t o = (my_pix - 1) * p.y_cstride + p.y_coffset;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (e < p.cout) store_elem(p.y, p.y_dtype, o + e, v[e]);
-          }
         } else if (epi_mode == 2) {
           // few output channels (the RGB tail layers): <= 4 channels per pixel, no residual, no shuffle
           if (valid && c0 == 0) {
@@ -946,32 +772,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           }
         }
       }
-      if (P8) {
-        __syncwarp();
-        {
-          const uint32_t ch = (uint32_t)lane & (p8_hc - 1u), rsub = (uint32_t)lane >> p8_hlg;
-          uint8_t* dst0 = reinterpret_cast<uint8_t*>(p.y) + (tpix * (size_t)p.y_cstride + (size_t)(p.y_coffset + c_out0)) * 2u + ch * 16u;
-          const uint32_t pix_bytes = (uint32_t)p.y_cstride * 2u;
-#pragma unroll 4
-          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_hlg) {
-            const int mm = quad * 32 + (int)row;
-            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
-              *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes) = lds128(p8_hi(f_buf, row, ch));
-          }
-        }
-        if (p.y2) {
-          const uint32_t ch = (uint32_t)lane & (p8_lc - 1u), rsub = (uint32_t)lane >> p8_llg;
-          uint8_t* dst0 = reinterpret_cast<uint8_t*>(p.y2) + (tpix * (size_t)p.y2_cstride + (size_t)c_out0) + ch * 16u;
-          const uint32_t pix_bytes = (uint32_t)p.y2_cstride;
-#pragma unroll 2
-          for (uint32_t row = rsub; row < 32u; row += 32u >> p8_llg) {
-            const int mm = quad * 32 + (int)row;
-            if (full || (y0 + (mm >> 3) < p.H && x0 + (mm & 7) < p.W))
-              *reinterpret_cast<uint4*>(dst0 + (size_t)pix_off(mm) * pix_bytes) = lds128(p8_lo(f_buf, row, ch));
-          }
-        }
-        __syncwarp();
-      } else if (epi_mode == 1 && pair) {
+      if (epi_mode == 1 && pair) {
         __syncwarp();
         // chunks [0, cpr/2) of every staged row -> y, chunks [cpr/2, cpr) -> y2 (both 16-bit)
         const uint32_t hcn = f_cpr >> 1;
@@ -1012,427 +813,14 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 }
 
 
-// ===================================================================================================================
-// Wide-tile, dx-folded kernel for 3x3 layers with few output channels per MMA (Cout = 64 and the RGB tails).
-//
-// A tcgen05.mma with M = 128 spends ~64 cycles fetching its 128 x 16 A block from shared memory whatever N is (measured:
-// N = 16, 64 and 128 all issue at ~60-64 cycles per instruction), so the 36-MMA, N = 64 formulation of a 64 -> 64 layer
-// cannot pass 50 % of the tensor peak.  Folding the three horizontal taps into N makes the instruction three times wider
-// and the tile three times shorter:
-//     D[input pixel p, (dx, co)] = sum over dy, ci of  X[p_y + dy - 1, p_x, ci] * W[dy, dx, ci, co]      (N = 3 * Cout, 12 MMAs)
-//     out[y, x, co] = D[(y, x - 1), (0, co)] + D[(y, x), (1, co)] + D[(y, x + 1), (2, co)]
-// The second line is a sum over neighbouring GEMM rows, i.e. neighbouring TMEM lanes: a tile is 4 image rows x 32
-// consecutive input columns (one row per lane quadrant), lane l of a quadrant holds input column x0 - 1 + l, and the
-// epilogue warp combines own / lane + 1 / lane + 2 with two shuffles per channel; lanes 0..29 hold the 30 output columns.
-// The halo is one TMA box of 64 c x 32 w x 6 h; the dy shift is 4,096 bytes (swizzle-atom aligned).  Output rows move with
-// TMA exactly as in the staged epilogue above (boxes of {32 channels, 30 pixels, 1 row}).
-// Modes: 0 plain 16-bit y, 1 ReLU 16-bit y, 4 PReLU / leaky 16-bit y, 2 pair8 trunk (16-bit hi + e5m2 lo residual in, y + rounding error out),
-//        5 depth_to_space straight to a few-channel fp32 image (ESPCN: 48 -> 4 x 4 x RGB), float4 stores,
-//        3 few channels (Cout <= 4, groups of 5 columns): bias / activation / alpha / clip, stored element-wise.
-// ===================================================================================================================
-constexpr int kFW = 32, kFH = 4, kFOut = 30;
-constexpr int kFoldEpiWarps = 16;
-constexpr int kFoldThreads = 64 + 32 * kFoldEpiWarps;
-
-struct FoldParams {
-  int n;                 // MMA N: 192 (3 x 64), or kw x 4 rounded up to 16 for the few-channel layers (16 / 32 / 48)
-  int gw;                // accumulator columns per dx group: 64 or 4
-  int kh, kw;            // filter size (3 x 3 for the 64-channel modes; odd, <= 9 for mode 3)
-  int out_cols;          // output columns per tile row: 32 - (kw - 1)
-  uint32_t stage_bytes;  // (kFH + kh - 1) halo rows x 32 columns x 128 B
-  int tiles_x, tiles_y, total_tiles;
-  int stages;
-  uint32_t tmem_cols, idesc, epi_warp_bytes;
-  int reverse;           // as TcParams::reverse
-  uint32_t magic_tpi, magic_tx;   // as TcParams
-};
-
-template <int kMode, bool kGen>   // kGen: filter size from q.kh / q.kw (mode 3 only); otherwise 3 x 3 with compile-time geometry
-__global__ void __launch_bounds__(kFoldThreads, 1)
-conv3x3_fold_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
-                    const __grid_constant__ EpiMaps em, const FoldParams q, const ConvParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* smem = smem_raw + (base - raw);
-  const int f_kh = kGen ? q.kh : 3, f_kw = kGen ? q.kw : 3;
-  const int f_out = kGen ? q.out_cols : kFOut;
-  const uint32_t f_stage = kGen ? q.stage_bytes : 6u * kFW * 128u;
-  const uint32_t w_bytes = (uint32_t)f_kh * (uint32_t)q.n * 128u;
-  const uint32_t w_span = (w_bytes + 1023u) & ~1023u;
-  const uint32_t w_smem = base, a_smem = base + w_span;
-  const uint32_t epi_smem = a_smem + (uint32_t)q.stages * f_stage;
-  uint8_t* tail = smem + w_span + (size_t)q.stages * f_stage + (uint32_t)kFoldEpiWarps * q.epi_warp_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  const uint32_t bar0 = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar0 + 8u * (uint32_t)s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (uint32_t)(kMaxStages + s); };
-  const uint32_t wfull_bar = bar0 + 8u * (2 * kMaxStages);
-  auto tfull_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 1 + a); };
-  auto tempty_bar = [&](int a) { return bar0 + 8u * (uint32_t)(2 * kMaxStages + 3 + a); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);     // [64]
-  const uint32_t rbar0 = smem_u32(bias_s) + 64u * 4u;                        // [kFoldEpiWarps][2]
-  float* slope_s = bias_s + 64 + 4 * kFoldEpiWarps;                          // [64] PReLU / leaky slopes (mode 4)
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < q.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(wfull_bar, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), kMode == 3 ? 4 : kFoldEpiWarps); }
-    for (int i = 0; i < 2 * kFoldEpiWarps; ++i) mbar_init(rbar0 + 8u * (uint32_t)i, 1);
-    fence_barrier_init();
-  }
-  for (int i = threadIdx.x; i < 64; i += kFoldThreads) {
-    bias_s[i] = i < p.cout ? p.bias[i] : 0.f;
-    if (kMode == 4) slope_s[i] = (p.act == SRB_ACT_PRELU && i < p.cout) ? p.prelu[i] : p.act_slope;
-  }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&tmap_x); prefetch_tmap(&tmap_w); }
-  if (warp == 2 && lane == 0 && kMode != 3 && kMode != 5) {
-    prefetch_tmap(&em.y);
-    if (kMode == 2) { prefetch_tmap(&em.r1); prefetch_tmap(&em.r2); if (p.y2) prefetch_tmap(&em.y2); }
-  }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), q.tmem_cols);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_launch_dependents();
-  if (warp >= 2) pdl_wait();                          // epilogue warps: before their first global access
-  const int tiles_per_img = q.tiles_x * q.tiles_y;
-  const int first_tile = (int)blockIdx.x, tile_step = (int)gridDim.x;
-  auto coords = [&](int tile, int& b, int& y0, int& x0) {
-    const int tl = q.reverse ? q.total_tiles - 1 - tile : tile;
-    b = fast_div(tl, tiles_per_img, q.magic_tpi);
-    const int rr_ = tl - b * tiles_per_img;
-    const int ty = fast_div(rr_, q.tiles_x, q.magic_tx);
-    y0 = ty * kFH;
-    x0 = (rr_ - ty * q.tiles_x) * f_out;
-  };
-
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (elect_one()) {
-      mbar_expect_tx(wfull_bar, w_bytes);
-      for (int dy = 0; dy < f_kh; ++dy) tma_load_2d(w_smem + (uint32_t)(dy * q.n) * 128u, &tmap_w, wfull_bar, 0, dy * q.n);
-    }
-    __syncwarp();
-    pdl_wait();                                       // (the weight loads above do not depend on the previous launch)
-    int s = 0; uint32_t ph = 0;
-    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step) {
-      int b, y0, x0;
-      coords(tile, b, y0, x0);
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      if (elect_one()) {
-        mbar_expect_tx(full_bar(s), f_stage);
-        tma_load_4d(a_smem + (uint32_t)s * f_stage, &tmap_x, full_bar(s), 0, x0 - (f_kw >> 1), y0 - (f_kh >> 1), b);
-      }
-      __syncwarp();
-      if (++s == q.stages) { s = 0; ph ^= 1u; }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: 3 vertical taps x 4 k-steps, N = 3 * group width =====================
-    mbar_wait(wfull_bar, 0);
-    int s = 0; uint32_t ph = 0; int it = 0;
-    const uint64_t b_desc0 = make_desc(w_smem, 1024u, 0);
-    const uint32_t b_dy = ((uint32_t)q.n * 128u) >> 4;
-    for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-      mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * f_stage, 1024u, 0);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n);
-      if (!kGen) {                                        // 3 x 3: twelve MMAs, fully unrolled (descriptors in uniform registers)
-        if (elect_one()) {
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
-          }
-          umma_commit(empty_bar(s));
-          umma_commit(tfull_bar(acc));
-        }
-      } else if (elect_one()) {                          // taller filters (5 x 5, 9 x 9 tails): rolled over the vertical taps
-        for (int dy = 0; dy < f_kh; ++dy) {
-          const uint64_t ad = a_desc0 + (uint64_t)(dy * ((kFW * 128) >> 4)), bd = b_desc0 + (uint64_t)dy * b_dy;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(d_tmem, ad + 2u * k, bd + 2u * k, q.idesc, (uint32_t)((dy | k) != 0));
-        }
-        umma_commit(empty_bar(s));
-        umma_commit(tfull_bar(acc));
-      }
-      __syncwarp();
-      if (++s == q.stages) { s = 0; ph ^= 1u; }
-    }
-  } else {
-    // ===================== epilogue =====================
-    const int ew = warp - 2, quad = warp & 3, cq = ew >> 2;   // cq: warp set (mode 3) / 16-channel quarter (modes 0-2)
-    auto release_tmem = [&](int acc) {
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    };
-    if (kMode == 3) {
-      // few channels: the two warp sets take alternate tiles; element-wise stores (lanes 0..29 = output columns x0 + lane)
-      int it = 0;
-      for (int tile = first_tile; tile < q.total_tiles && cq < 2; tile += tile_step, ++it) {
-        const int acc = it & 1;
-        if (acc != cq) continue;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        int b, y0, x0;
-        coords(tile, b, y0, x0);
-        mbar_wait(tfull_bar(acc), acc_ph);
-        tc_fence_after();
-        float v[4];
-        const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n);
-        if (!kGen) {                                      // the hot case (RGB tail of EDSR): one TMEM load, two shuffles per channel
-          uint32_t rr[16];                                // columns dx * 4 + co
-          __syncwarp();
-          tmem_ld16(t_acc, rr);
-          tmem_ld_wait();
-          release_tmem(acc);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float mid = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[4 + e]), 1);
-            const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(rr[8 + e]), 2);
-            v[e] = (bias_s[e] + __uint_as_float(rr[e])) + (mid + right);
-          }
-        } else {
-          uint32_t rr[48];
-          __syncwarp();
-          tmem_ld16(t_acc, *reinterpret_cast<uint32_t(*)[16]>(&rr[0]));
-          if (q.n > 16) tmem_ld16(t_acc + 16u, *reinterpret_cast<uint32_t(*)[16]>(&rr[16]));
-          if (q.n > 32) tmem_ld16(t_acc + 32u, *reinterpret_cast<uint32_t(*)[16]>(&rr[32]));
-          tmem_ld_wait();
-          release_tmem(acc);
-#pragma unroll
-          for (int e = 0; e < 4; ++e) v[e] = bias_s[e] + __uint_as_float(rr[e]);
-#pragma unroll
-          for (int dx = 1; dx < 9; ++dx) {
-            if (dx < f_kw) {                              // (uniform) tap dx of output column l sits in lane l + dx
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] += __shfl_down_sync(0xffffffffu, __uint_as_float(rr[dx * 4 + e]), dx);
-            }
-          }
-        }
-        const int oy = y0 + quad, ox = x0 + lane;
-        if (lane < f_out && oy < p.H && ox < p.W) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (p.act == SRB_ACT_RELU) v[e] = fmaxf(v[e], 0.f);
-            else if (p.act != SRB_ACT_NONE)
-              v[e] = act_generic(v[e], p.act, (p.act == SRB_ACT_PRELU && e < p.cout) ? __ldg(p.prelu + e) : p.act_slope);
-            v[e] *= p.alpha;
-            if (p.clip01) v[e] = fminf(fmaxf(v[e], 0.f), 1.f);
-          }
-          const size_t o = (((size_t)b * p.H + oy) * p.W + ox) * p.y_cstride + p.y_coffset;
-          if (p.y_dtype == SRB_F32) {
-            float* d = reinterpret_cast<float*>(p.y) + o;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (e < p.cout) d[e] = v[e];
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) if (e < p.cout) store_elem(p.y, p.y_dtype, o + e, v[e]);
-          }
-        }
-      }
-    } else {
-      // 16 .. 64 output channels, 16-bit y: warp (quadrant = tile row, cq = 16 of the channels); rows move with TMA.
-      // Sixteen epilogue warps (four per scheduler) hide the TMEM-load / shuffle latencies of this role.
-      constexpr bool P8 = kMode == 2;
-      const int col0 = cq * 16;                           // first output channel of this warp
-      constexpr uint32_t hb = 32u, lb = 16u;              // staged row bytes: 16 x 16-bit, 16 x e5m2
-      const uint32_t buf_bytes = 32u * hb + (P8 ? 32u * lb : 0u);
-      const uint32_t my_epi = epi_smem + (uint32_t)ew * q.epi_warp_bytes;
-      const uint32_t row = (uint32_t)lane;
-      const uint32_t h_row = row * hb, h_x = (row >> 2) & 1u;            // 32-byte swizzle
-      const uint32_t l_row = 32u * hb + row * lb;                        // 16-byte rows: no swizzle
-      const uint32_t my_rbar = rbar0 + 16u * (uint32_t)ew;
-      const float alpha = p.alpha, beta1 = p.beta1, beta2 = p.beta2;
-      const bool bf = p.y_dtype == SRB_BF16;
-      float bb[16];
-#pragma unroll
-      for (int e = 0; e < 16; ++e) bb[e] = bias_s[col0 + e];
-      uint32_t d2s_off[4] = {};                           // mode 5: float offset of each 4-channel group inside the r x r block
-      const bool d2s_plain = p.act == SRB_ACT_NONE && p.alpha == 1.f && !p.clip01;
-      if (kMode == 5) {
-        const int rg = p.d2s * p.c_post;                  // floats per output sub-row (a multiple of 4)
-        const uint32_t sub_row = (uint32_t)(p.W * p.d2s) * (uint32_t)p.c_post;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int cb = col0 + 4 * g, i = cb / rg;
-          d2s_off[g] = (uint32_t)i * sub_row + (uint32_t)(cb - i * rg);
-        }
-      }
-      __syncwarp();
-      auto load_res = [&](int tile, uint32_t nb) {
-        int b, y0, x0;
-        coords(tile, b, y0, x0);
-        const uint32_t buf = my_epi + nb * buf_bytes, bar = my_rbar + 8u * nb;
-        mbar_expect_tx(bar, (uint32_t)kFOut * (hb + lb));
-        tma_load_4d(buf, &em.r1, bar, col0, x0, y0 + quad, b);
-        tma_load_4d(buf + 32u * hb, &em.r2, bar, col0, x0, y0 + quad, b);
-      };
-      int it = 0;
-      if (P8 && lane == 0 && first_tile < q.total_tiles) load_res(first_tile, 0u);
-      for (int tile = first_tile; tile < q.total_tiles; tile += tile_step, ++it) {
-        int b, y0, x0;
-        coords(tile, b, y0, x0);
-        const int acc = it & 1;
-        const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
-        const uint32_t buf = my_epi + (P8 ? (uint32_t)(it & 1) * buf_bytes : 0u);
-        if (col0 >= p.cout) {                             // layers with fewer than 64 outputs: this channel quarter only keeps the protocol
-          mbar_wait(tfull_bar(acc), acc_ph);
-          release_tmem(acc);
-          continue;
-        }
-        if (lane == 0 && kMode != 5) {
-          bulk_wait_read0();
-          if (P8 && tile + tile_step < q.total_tiles) load_res(tile + tile_step, (uint32_t)((it + 1) & 1));
-        }
-        __syncwarp();
-        mbar_wait(tfull_bar(acc), acc_ph);
-        tc_fence_after();
-        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * q.n + col0);
-        uint32_t d0[16], d1[16], d2[16];
-        __syncwarp();
-        tmem_ld16(t_row, d0);
-        tmem_ld16(t_row + (uint32_t)q.gw, d1);
-        tmem_ld16(t_row + 2u * (uint32_t)q.gw, d2);
-        tmem_ld_wait();
-        release_tmem(acc);
-        float a[16];                                      // conv + bias of output column x0 + lane (packed fp32x2 adds)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float2 mid = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(d1[2 * i]), 1),
-                                         __shfl_down_sync(0xffffffffu, __uint_as_float(d1[2 * i + 1]), 1));
-          const float2 right = make_float2(__shfl_down_sync(0xffffffffu, __uint_as_float(d2[2 * i]), 2),
-                                           __shfl_down_sync(0xffffffffu, __uint_as_float(d2[2 * i + 1]), 2));
-          const float2 sum = __fadd2_rn(__fadd2_rn(make_float2(__uint_as_float(d0[2 * i]), __uint_as_float(d0[2 * i + 1])), mid),
-                                        __fadd2_rn(right, make_float2(bb[2 * i], bb[2 * i + 1])));
-          a[2 * i] = sum.x; a[2 * i + 1] = sum.y;
-        }
-        if (kMode == 5) {
-          // depth_to_space straight to the fp32 image: the 16 channels of this warp are four groups of four consecutive
-          // floats inside the pixel's r x r block (offsets precomputed per warp); lanes 0..29 are output columns
-          const int oy = y0 + quad, ox = x0 + lane;
-          if (lane < kFOut && oy < p.H && ox < p.W) {
-            const int r = p.d2s;
-            float* drow = reinterpret_cast<float*>(p.y) +
-                          (((size_t)b * p.H * r + (size_t)oy * r) * ((size_t)p.W * r) + (size_t)ox * r) * p.c_post;
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              float v[4] = {a[4 * g], a[4 * g + 1], a[4 * g + 2], a[4 * g + 3]};
-              if (!d2s_plain) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  float t = v[u];
-                  if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
-                  else if (p.act != SRB_ACT_NONE) t = act_generic(t, p.act, p.act_slope);
-                  t *= alpha;
-                  if (p.clip01) t = fminf(fmaxf(t, 0.f), 1.f);
-                  v[u] = t;
-                }
-              }
-              *reinterpret_cast<float4*>(drow + d2s_off[g]) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-          }
-          continue;
-        }
-        const uint32_t a_h0 = buf + h_row + ((0u ^ h_x) << 4), a_h1 = buf + h_row + ((1u ^ h_x) << 4);
-        uint32_t oh[8];
-        if (!P8) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float v0 = a[2 * i], v1 = a[2 * i + 1];
-            if (kMode == 4) {
-              const float2 sl = *reinterpret_cast<const float2*>(slope_s + col0 + 2 * i);
-              v0 = fmaf(sl.x, fminf(v0, 0.f), fmaxf(v0, 0.f)); v1 = fmaf(sl.y, fminf(v1, 0.f), fmaxf(v1, 0.f));
-            }
-            uint32_t pk = bf ? pack2(v0, v1, SRB_BF16) : pack2(v0, v1, SRB_F16);
-            if (kMode == 1) {                              // ReLU on the packed pair (rounding is monotonic and 0 is exact)
-              if (bf) { const __nv_bfloat162 r2 = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&pk), __float2bfloat162_rn(0.f)); pk = *reinterpret_cast<const uint32_t*>(&r2); }
-              else { const __half2 r2 = __hmax2(*reinterpret_cast<const __half2*>(&pk), __float2half2_rn(0.f)); pk = *reinterpret_cast<const uint32_t*>(&r2); }
-            }
-            oh[i] = pk;
-          }
-        } else {
-          mbar_wait(my_rbar + 8u * (uint32_t)(it & 1), acc_ph);
-          const uint32_t a_l = buf + l_row;
-          const uint4 uh0 = lds128(a_h0), uh1 = lds128(a_h1), ul = lds128(a_l);
-          const uint32_t wh[8] = {uh0.x, uh0.y, uh0.z, uh0.w, uh1.x, uh1.y, uh1.z, uh1.w};
-          const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
-          uint32_t ol[4];
-          auto half_block = [&](auto is_bf) {
-            constexpr bool kBf = decltype(is_bf)::value;
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              float lo4[4], er[4];
-              e5m2x4_to_float4(wl[i4], lo4);
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const int e0 = 4 * i4 + 2 * hh;
-                float2 fh;
-                if (kBf) fh = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wh[2 * i4 + hh]));
-                else fh = __half22float2(*reinterpret_cast<const __half2*>(&wh[2 * i4 + hh]));
-                const float v0 = fmaf(beta2, lo4[2 * hh], fmaf(beta1, fh.x, a[e0] * alpha));
-                const float v1 = fmaf(beta2, lo4[2 * hh + 1], fmaf(beta1, fh.y, a[e0 + 1] * alpha));
-                const uint32_t pk = pack2(v0, v1, kBf ? SRB_BF16 : SRB_F16);
-                oh[2 * i4 + hh] = pk;
-                float2 back;
-                if (kBf) back = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk));
-                else back = __half22float2(*reinterpret_cast<const __half2*>(&pk));
-                er[2 * hh] = v0 - back.x; er[2 * hh + 1] = v1 - back.y;
-              }
-              ol[i4] = float4_to_e5m2x4(er[0], er[1], er[2], er[3]);
-            }
-          };
-          if (bf) half_block(std::true_type{}); else half_block(std::false_type{});
-          sts128(a_l, make_uint4(ol[0], ol[1], ol[2], ol[3]));
-        }
-        sts128(a_h0, make_uint4(oh[0], oh[1], oh[2], oh[3]));
-        sts128(a_h1, make_uint4(oh[4], oh[5], oh[6], oh[7]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_4d(&em.y, buf, col0, x0, y0 + quad, b);               // rows 0..29 of the staging block
-          if (P8 && p.y2) tma_store_4d(&em.y2, buf + 32u * hb, col0, x0, y0 + quad, b);
-          bulk_commit();
-        }
-      }
-      if (lane == 0) bulk_wait0();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after();
-    tmem_dealloc(tmem_base, q.tmem_cols);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static bool g_debug_env() { static const bool on = getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")); return on; }
-static uint32_t div_magic(long max_n, int d) {      // 0: not representable / not exact -> the kernel divides
-  if (d <= 1 || max_n * (long)d >= (1L << 32)) return 0;
-  return (uint32_t)(((1UL << 32) + (unsigned long)d - 1) / (unsigned long)d);
-}
-static int g_variant = 0;
-static int g_snake = -1;        // -1: read SRB_TC_SNAKE on first use (default on); alternate the tile walk direction of successive
-                                // launches: +1.5 % on the EDSR bench, the next layer starts on what is still in L2
 static unsigned g_launch_parity = 0;
-static int next_reverse() {
-  if (g_snake < 0) { const char* e = getenv("SRB_TC_SNAKE"); g_snake = e ? atoi(e) : 1; }
-  return g_snake ? (int)(g_launch_parity++ & 1u) : 0;
-}
-static int g_two_cta = -1;      // -1: read SRB_TC_2CTA on first use
+int tc_next_reverse() { return (int)(g_launch_parity++ & 1u); }
+static int g_two_cta = 0;       // srb_conv_tc_set_cta_pairs: launch every eligible cin = 64 layer as CTA pairs (default: only
+                                // where pairs pay - 256-channel chunks and inputs wider than 64 channels)
 
 EncodeTiledFn tc_encode_fn() {
   static EncodeTiledFn fn = nullptr;
@@ -1446,12 +834,9 @@ EncodeTiledFn tc_encode_fn() {
   return fn;
 }
 
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
 bool conv_tc_eligible(const ConvParams& p) {
   if (!p.w_tc || p.w_tc_cin < 64 || p.kh > 9 || p.kw > 9) return false;
   const int n_kc = p.w_tc_cin / 64;
-  if ((p.kh != 3 || p.kw != 3 || n_kc != 1) && g_variant != 0) return false;   // the staging experiments are 3x3, cin = 64 only
   // the smallest weight chunk (16 rows; 32 rows as 16 per CTA of a pair when the input is wider than 64 channels) for every tap
   // and K chunk + two halo stages must fit next to barriers and staging (9x9, cin = 64: 166 KB + 48 KB)
   if ((size_t)p.kh * p.kw * 16 * 128 * n_kc + (size_t)(n_kc > 1 ? 2 : 1) * (kTileH + p.kh - 1) * (kTileW + p.kw - 1) * 128 > 216 * 1024)
@@ -1470,153 +855,21 @@ static bool vec_ok_for(const void* ptr, int dtype, int cstride, int coffset) {
 
 
 // ---- wide-tile fold kernel: eligibility and launch ----
-static int fold_mode(const ConvParams& p) {          // -1: not eligible
-  static const bool enabled = getenv("SRB_TC_NO_WIDE") == nullptr;
-  if (!enabled || g_variant != 0 || p.cin != 64 || !p.w_tc_fold || p.kh > 9 || p.kw > 9) return -1;
-  if (getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG"))) return -1;
-  auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
-  if (p.d2s != 1) {
-    // mode 5: depth_to_space straight to a few-channel fp32 image (ESPCN's last layer: 48 -> 4 x 4 x RGB)
-    const bool ok = p.kh == 3 && p.kw == 3 && p.cout % 16 == 0 && p.cout >= 16 && p.cout <= 64 && p.y_dtype == SRB_F32 &&
-                    !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU && p.y_cstride == p.c_post && p.y_coffset == 0 &&
-                    (p.d2s * p.c_post) % 4 == 0 && aligned16(p.y) &&
-                    (long)p.B * p.H * p.W * p.cout < (1L << 31);          // (32-bit element offsets inside the image batch)
-    return ok ? 5 : -1;
-  }
-  if (p.cout <= 4) return (!p.res1 && !p.res2 && !p.y2) ? 3 : -1;
-  if (p.kh != 3 || p.kw != 3) return -1;
-  if (p.cout % 16 || p.cout < 16 || p.cout > 64 || !dt16(p.y_dtype) || p.y_coffset % 8 || p.y_cstride % 8 || !aligned16(p.y)) return -1;
-  if (!p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f) {
-    if (p.act == SRB_ACT_NONE) return 0;
-    if (p.act == SRB_ACT_RELU) return 1;
-    if (p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu)) return 4;
-    return -1;
-  }
-  const bool pair8 = p.cout == 64 && p.res1 && p.res2 && p.res1_dtype == p.y_dtype && p.res2_dtype == SRB_F8E5M2 &&
-                     (!p.y2 || (p.y2_mode == 1 && p.y2_dtype == SRB_F8E5M2)) && p.act == SRB_ACT_NONE && !p.clip01 &&
-                     p.res1_cstride % 8 == 0 && p.res2_cstride % 16 == 0 && (!p.y2 || p.y2_cstride % 16 == 0) &&
-                     aligned16(p.res1) && aligned16(p.res2) && (!p.y2 || aligned16(p.y2));
-  // (the pair8 epilogue on wide tiles is issue-bound by its shuffles and conversions: 0.125 ms per 32 tiles against 0.111 ms for
-  //  the 16 x 8-tile kernel with the same TMA epilogue, so it is opt-in)
-  static const bool wide_p8 = getenv("SRB_TC_WIDE_P8") != nullptr;
-  return (pair8 && wide_p8) ? 2 : -1;
-}
-
-static int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream) {
-  EncodeTiledFn encode = tc_encode_fn();
-  if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
-  FoldParams q{};
-  q.gw = mode == 3 ? 4 : p.cout;                       // 16 / 32 / 48 / 64 output channels: N = 48 / 96 / 144 / 192
-  q.kh = p.kh; q.kw = p.kw;
-  q.n = mode == 3 ? ((p.kw * 4 + 15) & ~15) : 3 * p.cout;
-  q.out_cols = kFW - (p.kw - 1);
-  q.stage_bytes = (uint32_t)(kFH + p.kh - 1) * kFW * 128u;
-  q.tiles_x = (p.W + q.out_cols - 1) / q.out_cols;
-  q.tiles_y = (p.H + kFH - 1) / kFH;
-  const long total = (long)p.B * q.tiles_x * q.tiles_y;
-  SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
-  q.total_tiles = (int)total;
-  q.tmem_cols = 32;
-  while (q.tmem_cols < (uint32_t)(2 * q.n)) q.tmem_cols <<= 1;
-  const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;
-  q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(q.n >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-  q.epi_warp_bytes = (mode == 3 || mode == 5) ? 0u : (mode == 2 ? 2u * 1536u : 1024u);
-  q.reverse = next_reverse();
-  q.magic_tpi = div_magic(total + 1, q.tiles_x * q.tiles_y);
-  q.magic_tx = div_magic((long)q.tiles_x * q.tiles_y, q.tiles_x);
-  int dev = 0, max_smem = 0;
-  SRB_CUDA(cudaGetDevice(&dev));
-  SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const size_t w_bytes = ((size_t)p.kh * q.n * 128 + 1023) & ~(size_t)1023;
-  const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * 64 * sizeof(float) + 2 * kFoldEpiWarps * 8;
-  auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kFoldEpiWarps * q.epi_warp_bytes + tail_bytes; };
-  q.stages = 4;
-  while (q.stages > 2 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
-  const size_t smem = smem_need(q.stages);
-  if (smem > (size_t)max_smem) { set_error("conv(tcgen05, fold): staging does not fit shared memory"); return SRB_E_UNSUPPORTED; }
-
-  const CUtensorMapDataType tdt = p.x_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUtensorMap tmx, tmw;
-  {
-    const cuuint64_t dims[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-    const cuuint64_t strides[3] = {(cuuint64_t)p.x_cstride * 2, (cuuint64_t)p.W * p.x_cstride * 2, (cuuint64_t)p.H * p.W * p.x_cstride * 2};
-    const cuuint32_t box[4] = {64, (cuuint32_t)kFW, (cuuint32_t)(kFH + p.kh - 1), 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    void* gptr = (void*)((const uint16_t*)p.x + p.x_coffset);
-    CUresult r = encode(&tmx, tdt, 4, gptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
-  }
-  {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)p.kh * q.n};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, (cuuint32_t)q.n};
-    const cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tmw, tdt, 2, (void*)p.w_tc_fold, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
-  }
-  EpiMaps em;
-  memset(&em, 0, sizeof(em));
-  if (mode != 3 && mode != 5) {
-    auto encode_epi = [&](CUtensorMap* m, const void* ptr, int coffset, int cstride, bool f8) -> bool {
-      const size_t es = f8 ? 1 : 2;
-      const cuuint64_t dims[4] = {(cuuint64_t)p.cout, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
-      const cuuint64_t strides[3] = {(cuuint64_t)cstride * es, (cuuint64_t)p.W * cstride * es, (cuuint64_t)p.H * p.W * cstride * es};
-      const cuuint32_t box[4] = {16, (cuuint32_t)kFOut, 1, 1};
-      const cuuint32_t es1[4] = {1, 1, 1, 1};
-      const CUtensorMapDataType dt = f8 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                                        : (p.y_dtype == SRB_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
-      void* g = (void*)((const uint8_t*)ptr + (size_t)coffset * es);
-      return encode(m, dt, 4, g, dims, strides, box, es1, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    f8 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-    };
-    bool ok = encode_epi(&em.y, p.y, p.y_coffset, p.y_cstride, false);
-    if (mode == 2) {
-      ok = ok && encode_epi(&em.r1, p.res1, 0, p.res1_cstride, false) && encode_epi(&em.r2, p.res2, 0, p.res2_cstride, true);
-      if (p.y2) ok = ok && encode_epi(&em.y2, p.y2, 0, p.y2_cstride, true);
-    }
-    if (!ok) { set_error("conv(tcgen05, fold): cuTensorMapEncodeTiled(epilogue) failed"); return SRB_E_CUDA; }
-  }
-  typedef void (*FoldFn)(const CUtensorMap, const CUtensorMap, const EpiMaps, const FoldParams, const ConvParams);
-  static const FoldFn kernels[7] = {conv3x3_fold_kernel<0, false>, conv3x3_fold_kernel<1, false>, conv3x3_fold_kernel<2, false>,
-                                    conv3x3_fold_kernel<3, false>, conv3x3_fold_kernel<4, false>, conv3x3_fold_kernel<3, true>,
-                                    conv3x3_fold_kernel<5, false>};
-  static size_t configured[7] = {0, 0, 0, 0, 0, 0, 0};
-  const int ki = (mode == 3 && (p.kh != 3 || p.kw != 3)) ? 5 : mode == 5 ? 6 : mode;
-  if (smem > configured[ki]) {
-    SRB_CUDA(cudaFuncSetAttribute(kernels[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[ki] = smem;
-  }
-  int grid = sm_count();
-  if ((long)grid > total) grid = (int)total;
-  SRB_CUDA(tc_launch(kernels[ki], grid, kFoldThreads, smem, stream, false, tmx, tmw, em, q, p));
-  return launch_check("conv3x3_fold_kernel");
-}
+int conv_fold_mode(const ConvParams& p);
+int conv_fold_launch(const ConvParams& p, int mode, cudaStream_t stream);
 
 int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
-  { const int fm = fold_mode(p); if (fm >= 0) return conv_fold_launch(p, fm, stream); }
+  { const int fm = conv_fold_mode(p); if (fm >= 0) return conv_fold_launch(p, fm, stream); }
   EncodeTiledFn encode = tc_encode_fn();
   if (!encode) { set_error("conv(tcgen05): cuTensorMapEncodeTiled is not available from the driver"); return SRB_E_CUDA; }
 
   const int rows = p.w_tc_rows;                       // cout padded to 16
-  static int ntile_max = 0;
-  if (!ntile_max) { const char* e = getenv("SRB_TC_NTILE"); ntile_max = e ? atoi(e) : 128; if (ntile_max < 16) ntile_max = 128; }
   int dev = 0, max_smem = 0;
   SRB_CUDA(cudaGetDevice(&dev));
   SRB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  const int variant = g_variant;
-  static const bool fold_enabled = getenv("SRB_TC_NOFOLD") == nullptr;
-  (void)fold_enabled;
-  const bool fold = false;      // (the 16 x 6 dx-folded tile of this kernel is superseded by conv3x3_fold_kernel's wide tiles)
-  const int cols_out = fold ? kTileW - 2 : kTileW;
-  const long total = (long)p.B * ((p.W + cols_out - 1) / cols_out) * ((p.H + kTileH - 1) / kTileH);
+  const long total = (long)p.B * ((p.W + kTileW - 1) / kTileW) * ((p.H + kTileH - 1) / kTileH);
   SRB_REQUIRE(total < (1L << 30), "conv(tcgen05): too many tiles");
   auto dt16 = [](int d) { return d == SRB_BF16 || d == SRB_F16; };
-
-  // cta_group::2 (CTA pairs): 0 = off, 1 = on for every eligible layer
-  if (g_two_cta < 0) { const char* e = getenv("SRB_TC_2CTA"); g_two_cta = e ? atoi(e) : 0; }
   const int two_cta = g_two_cta;
 
   // channel-chunk width per CTA: the widest of {256 (pairs), 128, 64, 32 (wide inputs), rows, 16} that divides the padded cout
@@ -1625,8 +878,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   size_t smem = 0;
   // 256-channel chunks exist only as CTA pairs (each CTA holds 128 weight rows) with the TMA epilogue, for plain 16-bit
   // layers with >= 256 output channels (the up-sampling convs): halves the B-operand shared-memory traffic per CTA that
-  // the epilogue competes with.  SRB_TC_PAIRS256=0 turns the choice off.
-  static const bool pairs256 = !(getenv("SRB_TC_PAIRS256") && atoi(getenv("SRB_TC_PAIRS256")) == 0);
+  // the epilogue competes with.
   const bool plain_layer = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && dt16(p.y_dtype) &&
                            (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu));
   const int n_kc = p.w_tc_cin / 64;                   // 64-channel K chunks (weights of every chunk stay resident)
@@ -1635,39 +887,32 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
   const int cand[6] = {256, 128, 64, 32, rows < 64 ? rows : 16, 16};
   bool found = false;
   for (int ci = 0; ci < 12 && !found; ++ci) {
-    const int nt = fold ? 16 : cand[ci >> 1];
+    const int nt = cand[ci >> 1];
     const bool try_pair = (ci & 1) == 0;               // even: as a CTA pair, odd: single CTAs
-    if (!fold && ((nt > ntile_max && nt != 256) || rows % nt)) continue;
+    if (nt > 256 || rows % nt) continue;
     if (nt == 32 && n_kc == 1) continue;               // (cin = 64 keeps its round-1 choices: 128 / 64 / rows / 16)
     if (nt == 256 && !try_pair) continue;
-    if (nt == 256 && n_kc == 1 && !(pairs256 && plain_layer && variant == 0 && p.kh == 3 && p.kw == 3 && !g_debug_env())) continue;
-    if (nt == 256 && n_kc > 1 && !plain_layer) continue;
+    if (nt == 256 && !(plain_layer && (n_kc > 1 || (p.kh == 3 && p.kw == 3)))) continue;
     if (try_pair && nt != 256 && !(two_cta || n_kc > 1)) continue;
-    if (!try_pair && nt != 256 && two_cta && n_kc == 1 && nt >= 32 && variant == 0) continue;   // (SRB_TC_2CTA=1: pairs wherever possible)
-    if (try_pair && (nt < 32 || variant != 0)) continue;
+    if (!try_pair && nt != 256 && two_cta && n_kc == 1 && nt >= 32) continue;   // (set_cta_pairs(1): pairs wherever possible)
+    if (try_pair && nt < 32) continue;
     q = TcParams{};
     q.n_kc = n_kc;
-    q.fold = fold ? 1 : 0;
     q.kh = p.kh; q.kw = p.kw;
     q.halo_rows = kTileH + p.kh - 1;
-    q.tile_cols_out = cols_out;
     q.n_tile = nt;
-    q.n_chunks = fold ? 1 : rows / nt;
-    q.w_rows = fold ? 16 : rows;
-    q.tiles_x = (p.W + cols_out - 1) / cols_out;
+    q.n_chunks = rows / nt;
+    q.w_rows = rows;
+    q.tiles_x = (p.W + kTileW - 1) / kTileW;
     q.tiles_y = (p.H + kTileH - 1) / kTileH;
     q.total_tiles = (int)total;
-    if (fold) { q.pitch = kTileW; q.n_loads = 1; }       // 8 input columns: every dy shift is 1,024-B aligned
-    else if (variant == 2) { q.pitch = kTileW; q.n_loads = 3; }
-    else if (variant == 3) { q.pitch = 16; q.n_loads = 1; }
-    else { q.pitch = kTileW + p.kw - 1; q.n_loads = 1; }
-    q.base_off_mode = (variant == 1 || variant == 3) ? 1 : 0;
+    q.pitch = kTileW + p.kw - 1;
     q.load_bytes = (uint32_t)(q.halo_rows * q.pitch * 128);
-    q.stage_bytes = ((q.load_bytes * (uint32_t)q.n_loads) + 1023u) & ~1023u;
+    q.stage_bytes = (q.load_bytes + 1023u) & ~1023u;
     q.tmem_cols = 32;
     while (q.tmem_cols < (uint32_t)(2 * nt)) q.tmem_cols <<= 1;
     const uint32_t fmt = p.x_dtype == SRB_BF16 ? 1u : 0u;   // F16F32Format: 0 = F16, 1 = BF16
-    const bool k2c = try_pair && !fold;
+    const bool k2c = try_pair;
     q.two_cta = k2c ? 1 : 0;
     q.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(nt >> 3) << 17) | ((uint32_t)((k2c ? 2 * kTileM : kTileM) >> 4) << 24);
     // staged vector epilogue: one fp32 and/or one 16-bit destination; a warp's columns map to one d2s sub-pixel
@@ -1692,9 +937,8 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (p.y2 && !pair && !pair8 && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
-    if (fold) { vec = false; q.epi_mode = 3; }
     // depth_to_space onto a few-channel fp32 image: every warp's column range is whole sub-rows of r*c_post floats
-    if (!vec && !fold && p.d2s > 1 && p.y_dtype == SRB_F32 && !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU &&
+    if (!vec && p.d2s > 1 && p.y_dtype == SRB_F32 && !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU &&
         p.y_cstride == p.c_post && p.y_coffset == 0 && (p.d2s * p.c_post) % 4 == 0 && aligned16(p.y) &&
         nt <= 64 && p.cout == nt && warp_cols % (p.d2s * p.c_post) == 0)
       q.epi_mode = 4;
@@ -1707,27 +951,25 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
       q.f_bufs = q.res_prefetch ? 2 : (q.f_dst ? 1 : 0);
       q.epi_warp_bytes = (uint32_t)(q.f_bufs * 32 * warp_cols * 4 + (q.h_dst ? 32 * warp_cols * 2 : 0));
       if (pair8) q.epi_warp_bytes = (uint32_t)(2 * 32 * warp_cols * 3);
-      // TMA epilogue: 16-bit y without depth_to_space, 64- or 128-channel chunks, the plain / ReLU / pair8 layer types
-      static const bool tma_enabled = getenv("SRB_TC_NO_TMA_EPI") == nullptr && !(getenv("SRB_TC_DEBUG") && atoi(getenv("SRB_TC_DEBUG")));
+      // TMA epilogue: 16-bit y, 64- / 128- / 256-channel chunks, the plain / ReLU / PReLU / pair8 layer types
       const bool slope_act = p.act == SRB_ACT_LEAKY || (p.act == SRB_ACT_PRELU && p.prelu);
       const bool plain16 = !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f && q.h_dst == 1 && q.f_dst == 0 &&
                            (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || slope_act);
       // (depth_to_space: plain layers whose warp columns are whole sub-pixels, images made of whole 16-row tiles because
       //  the 5-D output map merges the image and row dimensions)
       const bool d2s_ok = p.d2s == 1 || (plain16 && p.c_post % sb_cols == 0 && p.H % kTileH == 0 && p.y_coffset == 0 && p.y_cstride == p.c_post);
-      if (tma_enabled && d2s_ok && (nt == 64 || nt == 128 || nt == 256) && dt16(p.y_dtype) && ((plain16) || (pair8 && !k2c))) {
+      if (d2s_ok && (nt == 64 || nt == 128 || nt == 256) && dt16(p.y_dtype) && ((plain16) || (pair8 && !k2c))) {
         q.tma_epi = 1;
         q.epi_warp_bytes = (uint32_t)(pair8 ? 2 * 32 * warp_cols * 3 : 32 * sb_cols * 2);   // multiples of 1,024 bytes
       }
+      // (the pair8 trunk epilogue only exists in its TMA form; any other chunk width takes the generic scalar epilogue)
+      if (pair8 && !q.tma_epi) { q.epi_mode = 0; q.res_prefetch = 0; q.f_bufs = 0; q.epi_warp_bytes = 0; }
     }
     if (nt == 256 && !q.tma_epi) continue;                    // (256-channel chunks only exist with the TMA epilogue)
-    const size_t w_bytes = ((size_t)(fold ? 3 : p.kh * p.kw) * (q.two_cta ? nt / 2 : nt) * 128 * n_kc + 1023) & ~(size_t)1023;
+    const size_t w_bytes = ((size_t)p.kh * p.kw * (q.two_cta ? nt / 2 : nt) * 128 * n_kc + 1023) & ~(size_t)1023;
     const size_t tail_bytes = (2 * kMaxStages + 6) * 8 + 2 * (size_t)nt * sizeof(float) + 2 * kEpiWarps * 8;
     auto smem_need = [&](int st) { return 1024 + w_bytes + (size_t)st * q.stage_bytes + (size_t)kEpiWarps * q.epi_warp_bytes + tail_bytes; };
-    static int stage_cap = 0;
-    if (!stage_cap) { const char* e = getenv("SRB_TC_STAGES"); stage_cap = e ? atoi(e) : kMaxStages; if (stage_cap < 1 || stage_cap > kMaxStages) stage_cap = kMaxStages; }
-    { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SRB_TC_DEBUG"); dbg = e ? atoi(e) : 0; } q.debug = dbg; }
-    q.stages = stage_cap;
+    q.stages = kMaxStages;
     while (q.stages > 1 && smem_need(q.stages) > (size_t)max_smem) --q.stages;
     smem = smem_need(q.stages);
     found = smem <= (size_t)max_smem && (q.stages >= 2 || (n_kc == 1 && nt == 16));
@@ -1753,11 +995,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(x) failed with %d", (int)r); return SRB_E_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)(q.fold ? 64 : p.w_tc_cin), q.fold ? (cuuint64_t)48 : (cuuint64_t)(p.kh * p.kw) * rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)(q.fold ? 64 : p.w_tc_cin) * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)p.w_tc_cin, (cuuint64_t)(p.kh * p.kw) * rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.w_tc_cin * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)(q.two_cta ? q.n_tile / 2 : q.n_tile)};
     const cuuint32_t es[2] = {1, 1};
-    CUresult r = encode(&tmw, tdt, 2, (void*)(q.fold ? p.w_tc_fold : p.w_tc), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = encode(&tmw, tdt, 2, (void*)p.w_tc, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv(tcgen05): cuTensorMapEncodeTiled(w) failed with %d", (int)r); return SRB_E_CUDA; }
   }
@@ -1825,7 +1067,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
        conv3x3_tc_kernel<4, true>, conv3x3_tc_kernel<5, true>, conv3x3_tc_kernel<6, true>, conv3x3_tc_kernel<7, true>}};
   static size_t configured[2][8] = {{0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0}};
   const int k2 = q.two_cta;
-  q.reverse = k2 ? 0 : next_reverse();
+  q.reverse = k2 ? 0 : tc_next_reverse();
   q.magic_tpi = div_magic((long)q.total_tiles + 2, q.tiles_x * q.tiles_y);
   q.magic_tx = div_magic((long)q.tiles_x * q.tiles_y, q.tiles_x);
   if (smem > configured[k2][spec]) {
@@ -1845,13 +1087,7 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
 }  // namespace srb
 
 extern "C" int srb_conv_tc_set_cta_pairs(int on) {
-  const int prev = srb::g_two_cta > 0 ? 1 : 0;
+  const int prev = srb::g_two_cta ? 1 : 0;
   if (on >= 0) srb::g_two_cta = on ? 1 : 0;
-  return prev;
-}
-
-extern "C" int srb_conv_tc_set_variant(int variant) {
-  const int prev = srb::g_variant;
-  if (variant >= 0 && variant <= 3) srb::g_variant = variant;
   return prev;
 }

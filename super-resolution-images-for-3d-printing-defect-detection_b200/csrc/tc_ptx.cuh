@@ -38,10 +38,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "DONE_%=:\n"
       "}\n" ::"r"(bar), "r"(parity) : "memory");
 }
-// Programmatic dependent launch: the next kernel of the stream may start its prologue (barrier init, TMEM allocation,
-// weight loads) while this one drains; it blocks in pdl_wait() before touching anything the previous kernel wrote.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -158,14 +154,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start address >> 4, [16,30) leading byte offset >> 4 (unused for one swizzle row of K),
 //   [32,46) stride byte offset >> 4 (distance between 8-row groups), [46,48) version = 1,
-//   [49,52) base offset, [61,64) layout type = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, int base_off_mode) {
+//   [49,52) base offset = 0 (the 128-byte swizzle is a function of the absolute shared-memory address, so a start address
+//   shifted by whole pixels inside a TMA-written tile needs no correction: verified on silicon in round 1),
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
   d |= (uint64_t)1 << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  if (base_off_mode) d |= (uint64_t)((addr >> 7) & 7u) << 49;
   d |= (uint64_t)2 << 61;
   return d;
 }
@@ -203,18 +200,29 @@ __device__ __forceinline__ uint32_t float4_to_e5m2x4(float a, float b, float c, 
 }
 
 
+// n / d by multiply-high with magic = ceil(2^32 / d) (exact while n * d < 2^32: checked on the host, which passes 0 otherwise)
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t magic) {
+  return magic ? (int)__umulhi((uint32_t)n, magic) : n / d;
+}
+inline uint32_t div_magic(long max_n, int d) {      // 0: not representable / not exact -> the kernel divides
+  if (d <= 1 || max_n * (long)d >= (1L << 32)) return 0;
+  return (uint32_t)(((1UL << 32) + (unsigned long)d - 1) / (unsigned long)d);
+}
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// Successive tcgen05 launches walk their tiles in alternating directions, so that a layer starts on the rows its predecessor
+// wrote last and finds them in L2 (+1.5 % on the EDSR bench, round 1).
+int tc_next_reverse();
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn tc_encode_fn();     // cuTensorMapEncodeTiled through the runtime's driver entry point (conv_tc.cu)
 
-// Launch, optionally as a cluster of two CTAs and (SRB_PDL=1) with the programmatic-stream-serialization attribute, which
-// lets the next layer's prologue overlap this layer's drain.  Off by default: the EDSR bench runs at the power cap, where
-// closing the ~5 us gaps between launches does not change the throughput (3,265 vs 3,287 MP/s measured).
+// Launch, optionally as a cluster of two CTAs.  (Programmatic dependent launch was tried in round 1: the EDSR bench runs at
+// the power cap, where closing the ~5 us gaps between launches did not change the throughput - 3,265 vs 3,287 MP/s.)
 template <typename... KArgs, typename... Args>
 static inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pair,
                                     Args&&... args) {
-  static const bool pdl = getenv("SRB_PDL") != nullptr && atoi(getenv("SRB_PDL")) != 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(block);
@@ -223,7 +231,6 @@ static inline cudaError_t tc_launch(void (*kernel)(KArgs...), int grid, int bloc
   cudaLaunchAttribute attr[2];
   int n = 0;
   if (pair) { attr[n].id = cudaLaunchAttributeClusterDimension; attr[n].val.clusterDim.x = 2; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1; ++n; }
-  if (pdl) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
   cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }

@@ -79,7 +79,6 @@ _SIGNATURES = {
                                         C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "srb_self_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p]),
-    "srb_conv_tc_set_variant": (C.c_int, [C.c_int]),
     "srb_conv_tc_set_cta_pairs": (C.c_int, [C.c_int]),
 }
 

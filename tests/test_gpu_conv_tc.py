@@ -23,7 +23,7 @@ def _rand(shape, seed, lo=-1.0, hi=1.0):
     return np.random.default_rng(seed).uniform(lo, hi, shape).astype(np.float32)
 
 
-def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, cin=64, x_width=None, **kw):
+def _run(kind, B, H, W, cout, out_dtype=torch.float32, ksize=3, cin=64, x_width=None, **kw):
     """``cin``: input channels of the layer; ``x_width``: channels of the buffer the layer reads a prefix of (>= cin)."""
     from srb200 import ops, _capi
     xw = x_width or cin
@@ -46,30 +46,12 @@ def _run(kind, B, H, W, cout, variant=None, out_dtype=torch.float32, ksize=3, ci
         want = np.clip(want, 0, 1)
     w = ops.ConvWeights(kern, bias)
     xd = torch.from_numpy(x_full).cuda().to(DT[kind])
-    prev = _capi.lib().srb_conv_tc_set_variant(-1 if variant is None else variant)
-    try:
-        assert ops.conv2d_engine(xd, w, r) == _capi.ENGINE_TCGEN05
-        got = ops.conv2d(xd, w, act=kw.get("act"), alpha=kw.get("alpha", 1.0), clip01=kw.get("clip01", False),
-                         res1=None if res1 is None else torch.from_numpy(res1).cuda(), d2s=r,
-                         out_dtype=out_dtype, engine=_capi.ENGINE_TCGEN05)
-        torch.cuda.synchronize()
-    finally:
-        _capi.lib().srb_conv_tc_set_variant(prev)
+    assert ops.conv2d_engine(xd, w, r) == _capi.ENGINE_TCGEN05
+    got = ops.conv2d(xd, w, act=kw.get("act"), alpha=kw.get("alpha", 1.0), clip01=kw.get("clip01", False),
+                     res1=None if res1 is None else torch.from_numpy(res1).cuda(), d2s=r,
+                     out_dtype=out_dtype, engine=_capi.ENGINE_TCGEN05)
+    torch.cuda.synchronize()
     return got.float().cpu().numpy(), want
-
-
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
-def test_operand_staging_variants(variant):
-    """Which A-operand staging schemes produce the right answer on this silicon (diagnostic: the
-    default variant must pass; the result table is recorded in DESIGN.md)."""
-    from srb200 import _capi
-    got, want = _run("fp16", 1, 32, 24, 64, variant=variant)
-    err = np.abs(got - want).max()
-    print(f"variant {variant}: max-abs {err:.3e}")
-    if variant == _capi.lib().srb_conv_tc_set_variant(-1):
-        assert err <= 2e-3
-    elif err > 2e-3:
-        pytest.xfail(f"variant {variant} is not a valid operand layout on this GPU (max-abs {err:.3e})")
 
 
 @pytest.mark.parametrize("kind", ["fp16", "bf16"])
