@@ -16,6 +16,10 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "sm__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "smsp__inst_executed.sum", "sm__cycles_active.avg", "launch__grid_size", "launch__shared_mem_per_block_dynamic"]
+if "Kernel Name" in hdr:
+    i = hdr.index("Kernel Name")
+    for k, r in enumerate(rows[2:]):
+        print(f"launch {k}: {r[i][:110]}")
 for w in want:
     if w in hdr:
         i = hdr.index(w)
