@@ -143,6 +143,24 @@ int srb_conv2d_engine(const srb_conv_args* args);
  * for Cin = 64 and N <= 128 they measured equal to single CTAs on B200. */
 int srb_conv_tc_set_cta_pairs(int on);
 
+/* ---- EDSR up-sampling tail as one composed 5 x 5 convolution (EDSR_model.py:76-95, 117-123) --------
+ * Conv2D(64 -> 64 r'^2, 3x3) -> depth_to_space(r') [twice for x4] -> Conv2D(64 -> C, 3x3) has no activation in between, so it
+ * is one linear map from the 64-channel low-resolution image to the r x r x C block of every low-resolution pixel with a
+ * 5 x 5 footprint.  w_host: [3][3][5][5][cin][r*r*C] float32, the exact map for the nine border classes (vy, vx) = (first /
+ * interior / last row) x (first / interior / last column) - the zero padding of the INTERMEDIATE images only reaches the
+ * outermost low-resolution pixels (srb200/compose.py builds it in float64); output channel (i*r + j)*C + c is sub-pixel
+ * (i, j), channel c.  bias_host: [3][3][r*r*C].  The 16-bit copies hold w * w_scale (a power of two); the kernel multiplies
+ * the accumulators by 1 / w_scale.  cin must be 64, r*r*C <= 48.
+ * srb_upsample_composed: x [B, H, W, 64] fp16 / bf16 NHWC (channel slice of a wider buffer allowed) ->
+ * y [B, H*r, W*r, C] f32 / f16 / bf16 / u8 (u8 = saturate(rint(255 v)) of the [0, 1] image), optionally clipped to [0, 1].
+ * H, W >= 2.  One launch of upsample5_fold_kernel (tcgen05). */
+typedef struct srb_upsampler srb_upsampler;
+int srb_upsampler_create(const float* w_host, const float* bias_host, int cin, int image_channels, int scale, float w_scale,
+                         srb_upsampler** out);
+void srb_upsampler_destroy(srb_upsampler* u);
+int srb_upsample_composed(const srb_upsampler* u, const void* x, int x_dtype, int x_cstride, int x_coffset,
+                          int batch, int height, int width, void* y, int y_dtype, int clip01, srb_stream_t stream);
+
 /* ---- small layout / elementwise helpers used between layers -------------------------------------- */
 int srb_cast(const void* src, int src_dtype, void* dst, int dst_dtype, size_t n, float scale, float shift,
              srb_stream_t stream);                                   /* dst = src * scale + shift */

@@ -308,7 +308,8 @@ class EDSRNet(DeviceModel):
     all conv epilogues; the graph is 2*N+4 (+1 for x4) launches."""
     arch = "EDSR"
 
-    def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16", trunk=None):
+    def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16", trunk=None,
+                 upsampler=None):
         if scale_factor not in (2, 3, 4):
             raise ValueError(f"Scale factor {scale_factor} not supported. Use 2, 3, or 4.")
         head = self._first_conv(weights, "head")
@@ -320,14 +321,39 @@ class EDSRNet(DeviceModel):
                 raise ValueError("trunk must be 'pair8', 'pair', 'fp32' or 'half'")
             self.trunk = trunk
         self.scale_factor, self.num_res_blocks, self.res_scaling = scale_factor, num_res_blocks, float(res_scaling)
+        # the activation-free up-sampling tail (up-convs, depth_to_space, RGB conv: EDSR_model.py:117-123):
+        #   "composed" - ONE 5 x 5 convolution 64 -> r*r*C with the exact composed weights (srb200.compose), a tenth of the
+        #                FLOPs and no full-resolution 64-channel intermediates (16-bit modes, 64 filters; default there)
+        #   "layered"  - layer by layer, as the reference builds it
+        c_img = self.weights["tail/kernel"].shape[3]
+        can_compose = (precision != "fp32" and self.weights["up0/kernel"].shape[2] == 64
+                       and scale_factor * scale_factor * c_img <= 48)
+        if upsampler is None:
+            upsampler = "composed" if can_compose else "layered"
+        if upsampler not in ("composed", "layered"):
+            raise ValueError("upsampler must be 'composed' or 'layered'")
+        if upsampler == "composed" and not can_compose:
+            raise ValueError("the composed up-sampler needs a 16-bit precision mode, 64 filters and scale^2 * channels <= 48")
+        self.upsampler = upsampler
+        self._composed = None
 
     def output_scale(self):
         return self.scale_factor
 
     def _activation_bytes_per_input_pixel(self):
         s = self.scale_factor
+        if self.upsampler == "composed":
+            return 12 * s * s + 6 * 64 * 4
         # widest point: the last up-sampling conv's 64-channel input and output at full resolution + the fp32 RGB result
         return (2 * 64 * 2 + 12) * s * s + 4 * 64 * 4
+
+    def composed_upsampler(self):
+        """The device-resident composed tail (built once: float64 composition on the host, ~1-3 s)."""
+        if self._composed is None:
+            from . import compose
+            w, b = compose.compose_edsr_tail(self.weights, self.scale_factor)
+            self._composed = ops.ComposedUpsampler(w, b, self.scale_factor, compose.weight_scale(w))
+        return self._composed
 
     def forward_device(self, x):
         return self.forward_device_as(x, None)
@@ -368,6 +394,11 @@ class EDSRNet(DeviceModel):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
                 h = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, out_dtype=dt)
             h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
+        if self.upsampler == "composed" and x.shape[1] >= 2 and x.shape[2] >= 2:
+            y = ops.upsample_composed(h, self.composed_upsampler(), clip01=True, out_dtype=out_dtype)
+            if self.event_hook:
+                self.event_hook("tc_end")
+            return y
         if self.scale_factor in (2, 3):
             h = ops.conv2d(h, L["up0"], d2s=self.scale_factor, out_dtype=dt)
         else:

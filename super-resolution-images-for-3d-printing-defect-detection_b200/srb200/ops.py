@@ -255,6 +255,52 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     return out if out2 is None else (out, out2)
 
 
+class ComposedUpsampler:
+    """Device-resident composed EDSR up-sampling tail (``srb200.compose.compose_edsr_tail`` -> ``srb_upsampler_create``):
+    w [3, 3, 5, 5, 64, r*r*C], bias [3, 3, r*r*C]."""
+
+    def __init__(self, w, bias, scale, w_scale=1.0):
+        _torch()
+        w = np.ascontiguousarray(w, dtype=np.float32)
+        b = np.ascontiguousarray(bias, dtype=np.float32)
+        if w.ndim != 6 or w.shape[:4] != (3, 3, 5, 5) or b.shape != (3, 3, w.shape[5]):
+            raise ValueError("composed up-sampler: w must be [3, 3, 5, 5, cin, r*r*C] and bias [3, 3, r*r*C]")
+        self.scale, self.cin, self.cout = int(scale), int(w.shape[4]), int(w.shape[5])
+        if self.cout % (self.scale * self.scale):
+            raise ValueError("composed up-sampler: output channels are not a multiple of scale^2")
+        self.c_img = self.cout // (self.scale * self.scale)
+        handle = C.c_void_p()
+        capi.check(capi.lib().srb_upsampler_create(w.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), self.cin,
+                                                   self.c_img, self.scale, float(w_scale), C.byref(handle)))
+        self._handle = handle
+
+    @property
+    def handle(self):
+        return self._handle
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            try:
+                capi.lib().srb_upsampler_destroy(h)
+            except Exception:
+                pass
+
+
+def upsample_composed(x, up: ComposedUpsampler, clip01=True, out_dtype=None, x_coffset=0):
+    """x [B, H, W, >= 64] fp16 / bf16 -> [B, H*r, W*r, C] (float32 by default): the whole EDSR up-sampling tail
+    (EDSR_model.py:117-123) as one tcgen05 launch."""
+    torch = _torch()
+    _check_nhwc(x, "x")
+    B, H, W, Cx = x.shape
+    out = torch.empty((B, H * up.scale, W * up.scale, up.c_img), dtype=out_dtype or torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        capi.check(capi.lib().srb_upsample_composed(up.handle, capi.ptr(x), capi.dtype_code(x), Cx, int(x_coffset), B, H, W,
+                                                    capi.ptr(out), capi.dtype_code(out), int(bool(clip01)), capi.stream_ptr()))
+    _LAUNCHES[0] += 1
+    return out
+
+
 def conv2d_engine(x, w: ConvWeights, d2s=1):
     """Which engine AUTO dispatch picks for this input/kernel (capi.ENGINE_*)."""
     a = capi.ConvArgs()
