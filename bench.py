@@ -45,6 +45,8 @@ import numpy as np  # noqa: E402
 
 EDSR_FLOP_PER_LR_PX = 2 * 1_983_168          # SURVEY.md section 8 row A5 (x4, 16 blocks, 64 ch)
 EDSR_HEAD_FLOP_PER_LR_PX = 2 * 27 * 64       # the one layer that is not on the tcgen05 kernel
+EDSR_BODY_FLOP_PER_LR_PX = 33 * 2 * 9 * 64 * 64      # 16 x 2 res-block convs + the body-end conv
+EDSR_COMPOSED_TAIL_FLOP_PER_LR_PX = 2 * 25 * 64 * 48  # the up-sampling tail as one 5 x 5 conv 64 -> 4 x 4 x RGB (srb200/compose.py)
 ESPCN_FLOP_PER_LR_PX = 2 * 37_056            # row A14
 SRRESNET_FLOP_PER_LR_PX = 2 * 2_218_176      # row A14
 VGG16_FLOP_PER_INPUT_PX = 2 * 305_856        # row A13
@@ -181,8 +183,18 @@ def layer_group_rooflines(net, x, torch, ops):
                 "res2": None if kw.get("res2") is None else kw["res2"].element_size()}
         records.append((w, xx.shape[0] * xx.shape[1] * xx.shape[2], meta, e0, e1))
         return out
+    orig_up = ops.upsample_composed
+
+    def timed_up(xx, up, **kw):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = orig_up(xx, up, **kw)
+        e1.record()
+        records.append((up, xx.shape[0] * xx.shape[1] * xx.shape[2], {"composed": True, "out_dtype": kw.get("out_dtype")}, e0, e1))
+        return out
     hook, net.event_hook = net.event_hook, None
     ops.conv2d = timed
+    ops.upsample_composed = timed_up
     try:
         per_rep = []
         for _ in range(5):
@@ -192,10 +204,19 @@ def layer_group_rooflines(net, x, torch, ops):
             per_rep.append([(w, npx, kw, e0.elapsed_time(e1)) for (w, npx, kw, e0, e1) in records])
     finally:
         ops.conv2d = orig
+        ops.upsample_composed = orig_up
         net.event_hook = hook
     groups = {}
     for i, (w, npx, kw, _) in enumerate(per_rep[0]):
         ms = statistics.median(rep[i][3] for rep in per_rep)
+        if kw.get("composed"):
+            name = f"up-sampling tail composed: 5x5 64->{w.cout} + depth_to_space({w.scale}) to the image (one launch)"
+            g = groups.setdefault(name, {"layer_group": name, "launches": 0, "ms": 0.0, "flop": 0.0, "bytes": 0.0})
+            g["launches"] += 1
+            g["ms"] += ms
+            g["flop"] += 2.0 * npx * 25 * w.cin * w.cout
+            g["bytes"] += npx * w.cin * 2 + npx * w.cout * (4 if kw.get("out_dtype") in (None, torch.float32) else 2)
+            continue
         in_b = npx * w.cin * (4 if w.cin == 3 else 2)
         out_dt = kw.get("out_dtype")
         out_b = npx * w.cout * (4 if out_dt == torch.float32 else 2)
@@ -299,6 +320,9 @@ def workload_config(args, micro_batch):
             "global_batch": args.batch, "tile": args.tile, "scale": 4, "micro_batch": micro_batch,
             "parallelism": f"dp{args.gpus} (batch-sharded, no data-path collective)",
             "operands": f"{args.dtype} operands, fp32 accumulate, residual trunk = {args.trunk}",
+            "upsampler": ("composed: up-convs + depth_to_space + RGB conv (no activation in between, EDSR_model.py:117-123) folded "
+                          "exactly into one 5x5 conv 64->48 with nine border variants; `layered_upsampler` holds the layer-by-layer run")
+            if getattr(args, "upsampler", "composed") == "composed" else "layered (layer by layer)",
             "l2": "inputs larger than L2 (LR batch + activations stream through HBM every step); no flush needed"}
 
 
@@ -581,8 +605,10 @@ def run_gpu(args):
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic", "config": workload_config(args, mb)}
     ops.reset_launch_count()
-    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype, trunk=args.trunk)
+    net = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype, trunk=args.trunk, upsampler=args.upsampler)
     net.max_device_batch = mb
+    composed = net.upsampler == "composed"
+    launches_per_forward = 34 if composed else 36          # tcgen05 launches between the hooks (every layer but the head)
     x_np = lr_tiles(lo, hi, tile)
     x_host = torch.from_numpy(x_np).pin_memory()
     x_dev = x_host.to(dev)
@@ -616,7 +642,7 @@ def run_gpu(args):
     launches = ops.launch_count() - launches0
     ms = e0.elapsed_time(e1)
     tc_ms = sum(a[1].elapsed_time(b[1]) for a, b in zip(spans[0::2], spans[1::2]))
-    n_tc_launches = args.steps * ((n_local + mb - 1) // mb) * 36 if n_local else 0
+    n_tc_launches = args.steps * ((n_local + mb - 1) // mb) * launches_per_forward if n_local else 0
     net.event_hook = None
 
     # ---- end to end through the reference-facing API with host buffers ----
@@ -654,12 +680,25 @@ def run_gpu(args):
     # per-launch CUDA-event times of one forward (separate, untimed pass on rank 0): which bound each layer group sits at
     layer_groups = layer_group_rooflines(net, x_dev[:mb], torch, ops) if (rank == 0 and n_local and want_headline) else None
 
+    # ---- the same network with the up-sampling tail run layer by layer (three launches, as the reference builds it) ----
+    other_ms = 0.0
+    if want_headline and n_local:
+        net_other = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=args.dtype, trunk=args.trunk,
+                                   upsampler="layered" if composed else "composed")
+
+        def other_step():
+            for i in range(0, n_local, mb):
+                net_other.forward_device(x_dev[i:i + mb])
+        other_ms = cuda_timed(torch, other_step, 2, warm=1)
+        del net_other
+    barrier()
+
     # ---- the bf16 arm (the dtype BASELINE configs[2] names) ----
     alt = None
     net_alt = None
     if want_headline and n_local:
         alt_name = "bf16" if args.dtype != "bf16" else "fp16"
-        net_alt = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=alt_name, trunk=args.trunk)
+        net_alt = engine.EDSRNet(weights.edsr_weights(4), 4, 16, precision=alt_name, trunk=args.trunk, upsampler=args.upsampler)
 
         def alt_step():
             for i in range(0, n_local, mb):
@@ -672,7 +711,7 @@ def run_gpu(args):
     coll = collective_block(torch, D, net, rank, world, tile) if want_headline else None
     barrier()
 
-    vals = [ms, e2e_ms, tc_ms, alt["ms_per_step_this_rank"] if alt else 0.0, link["d2h"], link["h2d"]] + list(variants_ms.values())
+    vals = [ms, e2e_ms, tc_ms, alt["ms_per_step_this_rank"] if alt else 0.0, link["d2h"], link["h2d"], other_ms] + list(variants_ms.values())
     t_max = torch.tensor(vals, dtype=torch.float64, device=dev)
     t_sum = t_max.clone()
     if world > 1:
@@ -680,7 +719,8 @@ def run_gpu(args):
         torch.distributed.all_reduce(t_sum, op=torch.distributed.ReduceOp.SUM)
     ms, e2e_ms, tc_ms_max, alt_ms = (float(v) for v in t_max.tolist()[:4])
     link_sum = [float(v) for v in t_sum.tolist()[4:6]]
-    var_ms = dict(zip(variants_ms, (float(v) for v in t_max.tolist()[6:])))
+    other_ms = float(t_max.tolist()[6])
+    var_ms = dict(zip(variants_ms, (float(v) for v in t_max.tolist()[7:])))
 
     # ---- the other BASELINE configs ----
     configs = None
@@ -708,10 +748,14 @@ def run_gpu(args):
         total_mp = args.batch * out_px / 1e6
         value = total_mp * args.steps / (ms / 1e3)
         e2e = total_mp * args.steps / (e2e_ms / 1e3)
-        tc_flops = (EDSR_FLOP_PER_LR_PX - EDSR_HEAD_FLOP_PER_LR_PX) * tile * tile * n_local * args.steps
+        # FLOPs the tcgen05 launches EXECUTE: with the composed tail that is the 33 body convs + the 5 x 5 conv, not the
+        # reference network's layer-by-layer count (reported next to it as reference_equivalent_tflops)
+        tc_flop_px = (EDSR_BODY_FLOP_PER_LR_PX + EDSR_COMPOSED_TAIL_FLOP_PER_LR_PX) if composed else (EDSR_FLOP_PER_LR_PX - EDSR_HEAD_FLOP_PER_LR_PX)
+        tc_flops = tc_flop_px * tile * tile * n_local * args.steps
         achieved = tc_flops / (tc_ms / 1e3) / 1e12 if tc_ms else 0.0
         h2d_b, d2h_b = args.batch * tile * tile * 3 * 4, args.batch * out_px * 3 * 4
         traffic = measured_traffic()
+        traffic = traffic.get("composed" if composed else "layered") if traffic else None
         line.update({
             "value": value, "ms_per_step": ms / args.steps,
             "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
@@ -725,7 +769,8 @@ def run_gpu(args):
                     "d2h_gbs_achieved": d2h_b / (e2e_ms / args.steps) / 1e6},
             "gpu_launches": launches * world,
             "clocks": clk.result,
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_tc_kernel + conv3x3_fold_kernel (tcgen05 implicit GEMM, all 36 launches of a forward)",
+            "roofline": {"bound": "tensor", "kernel": f"conv3x3_tc_kernel + conv3x3_fold_kernel{' + upsample5_fold_kernel' if composed else ''} "
+                                                      f"(tcgen05 implicit GEMM, all {launches_per_forward} launches of a forward)",
                          "achieved": achieved, "peak": peaks["tflops"],
                          "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "traffic": (traffic["bytes_per_launch_at_32_tiles"] * (mb / 32.0)) if traffic else None,
@@ -734,8 +779,15 @@ def run_gpu(args):
                          "peak_source": f"{peaks['source']} sustained bf16 (MEASURED_PEAKS.json)",
                          "flop_per_launch": tc_flops / max(n_tc_launches, 1),
                          "avg_launch_ms": tc_ms / max(n_tc_launches, 1), "launches": n_tc_launches,
-                         "whole_net_tflops": EDSR_FLOP_PER_LR_PX * tile * tile * args.batch * args.steps / (ms / 1e3) / 1e12},
+                         "flops_counted": "executed by the launches (composed tail = 153,600 FLOP per LR pixel instead of the layered "
+                                          "1,529,856)" if composed else "the reference network's layers",
+                         "reference_equivalent_tflops": EDSR_FLOP_PER_LR_PX * tile * tile * args.batch * args.steps / (ms / 1e3) / 1e12},
         })
+        if other_ms:
+            line["composed_upsampler" if not composed else "layered_upsampler"] = {
+                "value": total_mp / (other_ms / 1e3), "unit": "MP/s", "ms_per_step": other_ms,
+                "note": "same network and trunk, device-resident, 2 steps after 1 warm-up" + (
+                    "; tail as three launches (64->256 + d2s, 64->256 + d2s, 64->3), as the reference builds it" if composed else "")}
         if layer_groups:
             for g in layer_groups:
                 g["tensor_frac"] = g["tflops"] / peaks["tflops"]           # (sustained peak: the pass runs at the power cap)
@@ -813,6 +865,8 @@ def main():
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--trunk", default="pair8", choices=["pair8", "fp32", "pair", "half"],
                     help="residual trunk storage: 16-bit + e5m2 rounding-error pair (default), fp32, compensated 16-bit pair, or plain 16-bit")
+    ap.add_argument("--upsampler", default="composed", choices=["composed", "layered"],
+                    help="EDSR up-sampling tail: one composed 5x5 launch (default) or layer by layer")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
