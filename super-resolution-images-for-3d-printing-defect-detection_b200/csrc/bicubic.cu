@@ -183,7 +183,16 @@ template <> struct Vec4<uint8_t> {
   }
 };
 
-template <typename T, bool FIXED, int KC>    // KC: compile-time channel count (tap offsets become immediates), 0 = run time
+// MAP: which four of its warp's 128 elements a lane owns.  One shared gather of a warp reads 32 source floats spaced
+// ~k / s apart (k = element stride between lanes, s = scale) plus a few floats of per-pixel jitter, and is free of bank
+// conflicts only while that span stays below 32 floats:
+//   1  elements l, 32 + l, 64 + l, 96 + l (k = 1): float32 always (four coalesced 4-byte stores per row); uint8 below x2.3
+//      (four 1-byte stores, 32 contiguous bytes per warp and instruction);
+//   2  pairs (2l, 2l + 1), (64 + 2l, 64 + 2l + 1) (k = 2): uint8 from x2.3 up (two 2-byte stores);
+//   0  four consecutive elements (k = 4, one 4-byte store): uint8 with a channel count the other maps are not built for.
+// With k = 4 the x2 gathers were two- to three-way conflicted and the kernel sat at 85 % of the shared-memory wavefront
+// rate (profiles/r02_ncu_bicubic_u8.txt).
+template <typename T, bool FIXED, int KC, int MAP>    // KC: compile-time channel count (tap offsets become immediates), 0 = run time
 __global__ void __launch_bounds__(kQT)
 bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTap* __restrict__ xtab,
                     const int* __restrict__ xbase, const AxisTap* __restrict__ ytab, const int* __restrict__ ybase,
@@ -288,9 +297,10 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
   // warp covers 32 consecutive output elements (<= 32 consecutive source floats when up-scaling: no bank conflicts) and
   // each of the four 4-byte stores is a fully coalesced 128-byte line.  uint8: thread t owns the four consecutive
   // elements e0 + 4 t + j and packs them into one 4-byte store.
-  constexpr bool kStrided = sizeof(T) == 4;
-  const int ef = kStrided ? e0 + (t >> 5) * (32 * kQE) + (t & 31) : e0 + kQE * t;   // first of this thread's elements
-  constexpr int kStep = kStrided ? 32 : 1;
+  static_assert(sizeof(T) == 1 || MAP == 1, "float32 uses the strided map");
+  const int ef = MAP == 1 ? e0 + (t >> 5) * (32 * kQE) + (t & 31)                   // first of this thread's elements
+               : MAP == 2 ? e0 + (t >> 5) * (32 * kQE) + 2 * (t & 31) : e0 + kQE * t;
+  auto eoff = [](int j) { return MAP == 1 ? 32 * j : MAP == 2 ? (j >> 1) * 64 + (j & 1) : j; };   // offset of the j-th element
   if (ef >= DE) return;
 
   // per-element tap origin (unclamped: the staged tile replicates the borders) and packed horizontal coefficients
@@ -298,7 +308,7 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
   float2 cx[4][kQE / 2];
 #pragma unroll
   for (int j = 0; j < kQE; ++j) {
-    const int e = min(ef + j * kStep, DE - 1);                              // (past the row end: repeat the last element)
+    const int e = min(ef + eoff(j), DE - 1);                                // (past the row end: repeat the last element)
     const int x = e / C, c = e - x * C;
     const float4 k = __ldg(reinterpret_cast<const float4*>(xtab[x].coef));
     ob[j] = __ldg(xbase + x) * C + c - c_lo;
@@ -320,65 +330,91 @@ bicubic_quad_kernel(const T* __restrict__ src, T* __restrict__ dst, const AxisTa
   };
   float2 w0[kQE / 2], w1[kQE / 2], w2[kQE / 2], w3[kQE / 2];
   hrow(0, w0); hrow(1, w1); hrow(2, w2); hrow(3, w3);
-  int u = 0;
-  const bool all4 = ef + (kQE - 1) * kStep < DE;
+  const bool all4 = ef + eoff(kQE - 1) < DE;
   T* out = dst + ((size_t)blockIdx.z * dst_h + y0) * DE + ef;
-  for (int i = 0; i < rows; ++i, out += DE) {
-    const int un = ub[i];                                                   // block-uniform
-    while (u < un) {
-#pragma unroll
-      for (int p = 0; p < kQE / 2; ++p) { w0[p] = w1[p]; w1[p] = w2[p]; w2[p] = w3[p]; }
-      ++u;
-      hrow(u + 3, w3);
-    }
-    const float4 k = cyv[i];
-    float v[kQE];
+
+  // one output row from the window (a, b, c, d) = horizontal results of four consecutive source rows, oldest first
+  auto emit = [&](const float2 (&a)[kQE / 2], const float2 (&b)[kQE / 2], const float2 (&c)[kQE / 2],
+                  const float2 (&d)[kQE / 2], const float4 k) {
+    float2 r[kQE / 2];
 #pragma unroll
     for (int p = 0; p < kQE / 2; ++p) {
-      float2 a;
+      float2 acc;
       if (FIXED) {
         // scalar on purpose: the product and the sum round separately (OpenCV's float32 vertical pass), and ptxas
         // contracts the packed mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 even when written as inline PTX
-        a.x = __fmul_rn(w0[p].x, k.x);                    a.y = __fmul_rn(w0[p].y, k.x);
-        a.x = __fadd_rn(a.x, __fmul_rn(w1[p].x, k.y));    a.y = __fadd_rn(a.y, __fmul_rn(w1[p].y, k.y));
-        a.x = __fadd_rn(a.x, __fmul_rn(w2[p].x, k.z));    a.y = __fadd_rn(a.y, __fmul_rn(w2[p].y, k.z));
-        a.x = __fadd_rn(a.x, __fmul_rn(w3[p].x, k.w));    a.y = __fadd_rn(a.y, __fmul_rn(w3[p].y, k.w));
+        acc.x = __fmul_rn(a[p].x, k.x);                      acc.y = __fmul_rn(a[p].y, k.x);
+        acc.x = __fadd_rn(acc.x, __fmul_rn(b[p].x, k.y));    acc.y = __fadd_rn(acc.y, __fmul_rn(b[p].y, k.y));
+        acc.x = __fadd_rn(acc.x, __fmul_rn(c[p].x, k.z));    acc.y = __fadd_rn(acc.y, __fmul_rn(c[p].y, k.z));
+        acc.x = __fadd_rn(acc.x, __fmul_rn(d[p].x, k.w));    acc.y = __fadd_rn(acc.y, __fmul_rn(d[p].y, k.w));
       } else {
-        a = __fmul2_rn(w0[p], make_float2(k.x, k.x));
-        a = __ffma2_rn(w1[p], make_float2(k.y, k.y), a);
-        a = __ffma2_rn(w2[p], make_float2(k.z, k.z), a);
-        a = __ffma2_rn(w3[p], make_float2(k.w, k.w), a);
+        acc = __fmul2_rn(a[p], make_float2(k.x, k.x));
+        acc = __ffma2_rn(b[p], make_float2(k.y, k.y), acc);
+        acc = __ffma2_rn(c[p], make_float2(k.z, k.z), acc);
+        acc = __ffma2_rn(d[p], make_float2(k.w, k.w), acc);
       }
-      v[2 * p] = a.x; v[2 * p + 1] = a.y;
+      r[p] = acc;
     }
     if (sizeof(T) == 1) {
-      // saturate, then round half to even with the 1.5 * 2^23 trick (== saturate_cast<uchar>(rint(v)) on [0, 255])
-      uint32_t b[kQE];
+      // saturate_cast<uchar>(rint(v)): adding 1.5 * 2^23 rounds half to even and leaves the integer in the low mantissa
+      // bits (two's complement for negative v; |v| < 2^22 here), cvt.pack.sat then saturates two of them into bytes
+      int q[kQE];
 #pragma unroll
-      for (int j = 0; j < kQE; ++j)
-        b[j] = (uint32_t)__float_as_int(__fadd_rn(fminf(fmaxf(v[j], 0.f), 255.f), 12582912.f)) & 0xFFu;
-      if (vec_dst) {
-        *reinterpret_cast<uint32_t*>(out) = b[0] | (b[1] << 8) | (b[2] << 16) | (b[3] << 24);
+      for (int p = 0; p < kQE / 2; ++p) {
+        const float2 m = __fadd2_rn(r[p], make_float2(12582912.f, 12582912.f));
+        q[2 * p] = __float_as_int(m.x) - 0x4B400000;
+        q[2 * p + 1] = __float_as_int(m.y) - 0x4B400000;
+      }
+      uint32_t hi, word;
+      asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q[3]), "r"(q[2]), "r"(0));
+      asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(word) : "r"(q[1]), "r"(q[0]), "r"(hi));
+      if (MAP == 1 && all4) {
+#pragma unroll
+        for (int j = 0; j < kQE; ++j) reinterpret_cast<uint8_t*>(out)[32 * j] = (uint8_t)(word >> (8 * j));
+      } else if (MAP == 2 && vec_dst && all4) {
+        *reinterpret_cast<uint16_t*>(out) = (uint16_t)word;
+        *reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(out) + 64) = (uint16_t)(word >> 16);
+      } else if (MAP == 0 && vec_dst) {
+        *reinterpret_cast<uint32_t*>(out) = word;
       } else {
 #pragma unroll
         for (int j = 0; j < kQE; ++j)
-          if (ef + j < DE) reinterpret_cast<uint8_t*>(out)[j] = (uint8_t)b[j];
+          if (ef + eoff(j) < DE) reinterpret_cast<uint8_t*>(out)[eoff(j)] = (uint8_t)(word >> (8 * j));
       }
     } else {
+      float v[kQE];
+#pragma unroll
+      for (int p = 0; p < kQE / 2; ++p) { v[2 * p] = r[p].x; v[2 * p + 1] = r[p].y; }
       if (clip01) {
 #pragma unroll
         for (int j = 0; j < kQE; ++j) v[j] = fminf(fmaxf(v[j], 0.f), 1.f);
       }
       if (all4) {
 #pragma unroll
-        for (int j = 0; j < kQE; ++j) reinterpret_cast<float*>(out)[j * kStep] = v[j];
+        for (int j = 0; j < kQE; ++j) reinterpret_cast<float*>(out)[eoff(j)] = v[j];
       } else {
 #pragma unroll
         for (int j = 0; j < kQE; ++j)
-          if (ef + j * kStep < DE) reinterpret_cast<float*>(out)[j * kStep] = v[j];
+          if (ef + eoff(j) < DE) reinterpret_cast<float*>(out)[eoff(j)] = v[j];
       }
     }
+    out += DE;
+  };
+  // The window slides by renaming, not by moving registers: the four phases below are the four rotations of
+  // (w0, w1, w2, w3).  A phase emits every output row whose first tap row is the window's, then replaces the oldest row.
+  int i = 0, u = 0;                                                        // next output row / first source row of the window
+#define SRB_QUAD_PHASE(A, B, C, D)                                     \
+  while (i < rows && ub[i] <= u) { emit(A, B, C, D, cyv[i]); ++i; }    \
+  if (i >= rows) break;                                                \
+  ++u;                                                                 \
+  hrow(u + 3, A);
+  for (;;) {
+    SRB_QUAD_PHASE(w0, w1, w2, w3)
+    SRB_QUAD_PHASE(w1, w2, w3, w0)
+    SRB_QUAD_PHASE(w2, w3, w0, w1)
+    SRB_QUAD_PHASE(w3, w0, w1, w2)
   }
+#undef SRB_QUAD_PHASE
 }
 
 // ---- cv2.resize(..., INTER_LANCZOS4) (classic_algorithms.py:19-21, 58-62; the interpolation map of
@@ -649,10 +685,12 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
       const size_t smem = need(tr);
       static size_t configured = 0;                                       // (per template instantiation)
       if (smem > configured) {
-        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        constexpr int kBase = sizeof(T) == 4 ? 1 : 0, kPair = sizeof(T) == 4 ? 1 : 2;   // (float32: every alias is map 1)
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 0, kBase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 1, kBase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 4, kBase>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SRB_CUDA(cudaFuncSetAttribute(bicubic_quad_kernel<T, FIXED, 3, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
       }
       const uintptr_t salign = sizeof(T) == 4 ? 15u : 3u;
@@ -660,8 +698,11 @@ static int run_bicubic(const T* src, int batch, int sh, int sw, int C, T* dst, i
       const int vec_dst = (DE % 4 == 0) && ((reinterpret_cast<uintptr_t>(dst) & salign) == 0);
       dim3 grid((DE + kQT * kQE - 1) / (kQT * kQE), (dh + tr - 1) / tr, batch);
       SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "bicubic: grid too large");
-      auto kern = C == 3 ? bicubic_quad_kernel<T, FIXED, 3> : C == 1 ? bicubic_quad_kernel<T, FIXED, 1>
-                : C == 4 ? bicubic_quad_kernel<T, FIXED, 4> : bicubic_quad_kernel<T, FIXED, 0>;
+      constexpr int kBase = sizeof(T) == 4 ? 1 : 0, kPair = sizeof(T) == 4 ? 1 : 2;
+      const bool pairs = rx <= 1.0 / 2.3;                 // (uint8 RGB only: element stride 2 keeps a gather's span under 32 floats)
+      auto kern = C == 3 ? (pairs ? bicubic_quad_kernel<T, FIXED, 3, kPair> : bicubic_quad_kernel<T, FIXED, 3, 1>)
+                : C == 1 ? bicubic_quad_kernel<T, FIXED, 1, kBase>
+                : C == 4 ? bicubic_quad_kernel<T, FIXED, 4, kBase> : bicubic_quad_kernel<T, FIXED, 0, kBase>;
       kern<<<grid, kQT, smem, stream>>>(src, dst, xtab, xbase, ytab, ybase, sh, sw, C, dh, dw, tr, rows_needed(tr), pitch,
                                         vec_src, vec_dst, clip01);
       rc = launch_check("bicubic_quad_kernel");

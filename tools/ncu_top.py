@@ -15,7 +15,12 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "sm__inst_executed.sum",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__inst_executed.sum", "sm__cycles_active.avg", "launch__grid_size", "launch__shared_mem_per_block_dynamic"]
+        "smsp__inst_executed.sum", "sm__cycles_active.avg", "launch__grid_size", "launch__shared_mem_per_block_dynamic",
+        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "smsp__warps_eligible.avg.per_cycle_active", "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers",
+        "sm__warps_active.avg.per_cycle_active"]
 if "Kernel Name" in hdr:
     i = hdr.index("Kernel Name")
     for k, r in enumerate(rows[2:]):
