@@ -336,6 +336,9 @@ class EDSRNet(DeviceModel):
             raise ValueError("the composed up-sampler needs a 16-bit precision mode, 64 filters and scale^2 * channels <= 48")
         self.upsampler = upsampler
         self._composed = None
+        # res-blocks after the first update the (h, e) trunk pair in place: three live activation tensors instead of five
+        # (smaller working set; 2-4 % faster at micro-batches of 6-12 tiles, equal at 32: tools/graph_probe.py)
+        self.trunk_in_place = True
 
     def output_scale(self):
         return self.scale_factor
@@ -371,8 +374,11 @@ class EDSRNet(DeviceModel):
             h, e = head, head_e
             for i in range(self.num_res_blocks):
                 t = ops.conv2d(h, L[f"rb{i}_c1"], act="relu", out_dtype=dt)
-                h, e = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, res2=e, out_dtype=dt,
-                                  out2_dtype=et, out2_error=True)
+                if i == 0 or not self.trunk_in_place:         # (block 0 leaves the head pair for the global skip)
+                    h, e = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, res2=e, out_dtype=dt,
+                                      out2_dtype=et, out2_error=True)
+                else:                                         # the trunk pair is updated in place: three live tensors
+                    ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, res2=e, out=h, out2=e, out2_error=True)
             h = ops.conv2d(h, L["body"], res1=head, res2=head_e, out_dtype=dt)
         elif self.trunk == "fp32":
             # trunk in fp32 (y), 16-bit copy (y2) as the next conv's tensor-core operand

@@ -208,14 +208,17 @@ class ConvWeights:
 
 def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, beta1=1.0, res2=None, beta2=1.0,
            clip01=False, d2s=1, out_dtype=None, out=None, out_coffset=0, x_coffset=0, engine=capi.ENGINE_AUTO,
-           out2_dtype=None, out2_error=False):
+           out2_dtype=None, out2_error=False, out2=None):
     """y = clip(alpha * act(conv(x, W) + b) + beta1 * res1 + beta2 * res2), optionally depth_to_space'd.
 
     ``x`` may be a wider NHWC buffer of which channels [x_coffset, x_coffset + cin) are read, and
     ``out`` a wider buffer written at ``out_coffset`` (concat-free dense blocks).  With ``out2_dtype`` the
     result is also written in a second dtype and ``(out, out2)`` is returned (fp32 residual trunk next to
     the 16-bit operand of the following layer); with ``out2_error`` the second output is the rounding error
-    ``v - round(out)`` instead, so that ``out + out2`` carries the value to ~22 bits in two 16-bit tensors."""
+    ``v - round(out)`` instead, so that ``out + out2`` carries the value to ~22 bits in two 16-bit tensors.
+    ``out`` / ``out2`` may be the residual tensors themselves (``out is res1``, ``out2 is res2``): every output pixel
+    depends on the residual of the same pixel only, which its own tile reads before it writes - the res-block trunk is
+    updated in place."""
     torch = _torch()
     _check_nhwc(x, "x")
     B, H, W, Cx = x.shape
@@ -228,9 +231,13 @@ def conv2d(x, w: ConvWeights, act=None, act_slope=0.0, alpha=1.0, res1=None, bet
     a = capi.ConvArgs()
     a.x, a.x_dtype, a.x_cstride, a.x_coffset = x.data_ptr(), capi.dtype_code(x), Cx, int(x_coffset)
     a.y, a.y_dtype, a.y_cstride, a.y_coffset = out.data_ptr(), capi.dtype_code(out), out.shape[3], int(out_coffset)
-    out2 = None
-    if out2_dtype is not None:
+    if out2 is not None:
+        _check_nhwc(out2, "out2")
+        if tuple(out2.shape) != (B, H * r, W * r, c_post):
+            raise ValueError(f"out2 shape {tuple(out2.shape)} does not match the output")
+    elif out2_dtype is not None:
         out2 = torch.empty((B, H * r, W * r, c_post), dtype=out2_dtype, device=x.device)
+    if out2 is not None:
         a.y2, a.y2_dtype, a.y2_cstride = out2.data_ptr(), capi.dtype_code(out2), c_post
         a.y2_mode = 1 if out2_error else 0
     a.batch, a.height, a.width = B, H, W
