@@ -24,6 +24,8 @@ Host-side weight preprocessing (like the K-major repacking in ``srb_conv_weights
 """
 from __future__ import annotations
 
+import hashlib
+
 import numpy as np
 
 FOOT = 5          # footprint of the composed kernel in low-resolution pixels
@@ -67,9 +69,32 @@ def layered_tail(weights, x, scale_factor, with_bias=True):
     return _conv_same(x, np.asarray(weights["tail/kernel"], np.float64), None if b is None else np.asarray(b, np.float64))
 
 
+_CACHE = {}          # fingerprint of the tail's layers -> (w, bias); a handful of entries (one per distinct weight set)
+
+
+def _fingerprint(weights, scale_factor):
+    h = hashlib.sha1(str(int(scale_factor)).encode())
+    names, _ = _stages(weights, scale_factor)
+    for name in names + ["tail"]:
+        for part in ("/kernel", "/bias"):
+            a = weights.get(name + part)
+            h.update(b"-" if a is None else np.ascontiguousarray(a, dtype=np.float32).tobytes())
+    return h.hexdigest()
+
+
 def compose_edsr_tail(weights, scale_factor):
     """-> (w [3, 3, 5, 5, cin, r*r*C] float64, bias [3, 3, r*r*C] float64): variant (vy, vx) with vy / vx = 0 for the first
-    row / column of the image, 1 for the interior, 2 for the last; output channel (i*r + j)*C + c."""
+    row / column of the image, 1 for the interior, 2 for the last; output channel (i*r + j)*C + c.  Results are cached by
+    a hash of the layers' values (the float64 probing takes 1-3 s)."""
+    key = _fingerprint(weights, scale_factor)
+    if key not in _CACHE:
+        if len(_CACHE) >= 8:
+            _CACHE.pop(next(iter(_CACHE)))
+        _CACHE[key] = _compose(weights, scale_factor)
+    return _CACHE[key]
+
+
+def _compose(weights, scale_factor):
     r = int(scale_factor)
     cin = int(np.asarray(weights["up0/kernel"]).shape[2])
     c_img = int(np.asarray(weights["tail/kernel"]).shape[3])
