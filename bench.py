@@ -515,11 +515,13 @@ def config_c4(torch, peaks, batch=1024):
 def config_esrgan(torch, peaks):
     """The reference's own GAN generator at its trained configuration (ESRGAN.ipynb cell 6: 4 RRDB, growth 8, x2, 24x24 LR
     patches): the 1,521 patches of one 478x478 image (stride 12), fp16 operands on the tcgen05 engine (dense-block growth convs
-    in 64-channel K chunks), SelfAttention on 576 and 2,304 positions per patch on the CUDA cores."""
+    in 64-channel K chunks, 8-channel slices written by a 16-byte-per-pixel epilogue), SelfAttention on 576 and 2,304 positions
+    per patch as a tcgen05 flash-style kernel (hi / lo split scores, online softmax, fp16 P) in the 16-bit mode."""
     from srb200 import engine, weights
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.rand((1521, 24, 24, 3), device="cuda", generator=g) * 2 - 1
-    out = {"workload": "ESRGAN generator x2 (4 RRDB, growth 8, 2 SelfAttention), 1,521 LR patches 24x24 -> 48x48"}
+    out = {"workload": "ESRGAN generator x2 (4 RRDB, growth 8, 2 SelfAttention), 1,521 LR patches 24x24 -> 48x48; fp16: convolutions and "
+                       "both attention products on tcgen05; fp32: exact CUDA-core engines"}
     for prec in ("fp16", "fp32"):
         net = engine.ESRGANGeneratorNet(weights.esrgan_generator_weights(2, 8, 4), 2, 8, 4, precision=prec)
         ms = cuda_timed(torch, lambda: net.predict_device(x, micro_batch=512), 2, warm=1)

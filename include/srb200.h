@@ -177,6 +177,14 @@ int srb_gap_dense_softmax(const void* x, int dtype, int batch, int hw, int chann
 int srb_self_attention_f32(const float* f, const float* g, const float* h, int batch, int hw, int dk, int dv,
                            float* o, srb_stream_t stream);
 
+/* The same contract on the tensor cores (the 16-bit precision modes): S = g f^T as a tcgen05 product of fp16 (hi, lo)
+ * split operands (float32-grade scores), online softmax in float32, P in fp16 for the second tcgen05 product P h (h in fp16),
+ * float32 accumulation; |o - exact| ~ 1e-3 * max|h|.  dk <= 16, dv in {16, 32, 64}.  workspace: >=
+ * srb_self_attention_tc_workspace(...) bytes, 128-byte aligned (padded 16-bit operands and the transpose of h). */
+size_t srb_self_attention_tc_workspace(int batch, int hw, int dk, int dv);
+int srb_self_attention_tc(const float* f, const float* g, const float* h, int batch, int hw, int dk, int dv,
+                          float* o, void* workspace, size_t workspace_bytes, srb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

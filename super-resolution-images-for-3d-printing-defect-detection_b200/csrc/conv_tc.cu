@@ -44,6 +44,7 @@ struct TcParams {
   uint32_t idesc;
   int epi_mode;          // 0: generic scalar epilogue; 1: staged vector epilogue (smem transpose, coalesced 16-B accesses);
                          // 2: few-channel epilogue (cout <= 4, e.g. an RGB tail with a filter the fold kernel does not take);
+                         // 3: 8 / 16 channels as a 16-bit channel slice (ESRGAN growth convs): 16-byte stores per pixel;
                          // 4: depth_to_space to few channels (ESPCN): r*c_post contiguous floats per output row
   int f_bufs;            // per-warp fp32 staging buffers (0, 1, or 2 when the residual is prefetched)
   int f_dst, h_dst;      // which output is fp32 / 16-bit: 0 none, 1 = y, 2 = y2
@@ -745,6 +746,33 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               sts128(h_buf + my_row_sw * h_rb + ((hc ^ (my_row_sw & h_swz)) << 4), pk);
             }
           }
+        } else if (epi_mode == 3) {
+          // 8 or 16 output channels written as a 16-bit channel slice (the growth convs of the ESRGAN dense blocks,
+          // ESRGAN_model.py:230-246): bias + none / ReLU / leaky, one or two 16-byte stores per pixel
+          if (valid && c0 == 0) {
+            float v[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float b_ = e < 4 ? (&bv[0].x)[e] : e < 8 ? (&bv[1].x)[e - 4] : e < 12 ? (&bv[2].x)[e - 8] : (&bv[3].x)[e - 12];
+              float t = __uint_as_float(rr[e]) + b_;
+              if (p.act == SRB_ACT_RELU) t = fmaxf(t, 0.f);
+              else if (p.act == SRB_ACT_LEAKY) t = fmaf(p.act_slope, fminf(t, 0.f), fmaxf(t, 0.f));
+              v[e] = t;
+            }
+            const int dt_ = p.y_dtype;
+            if (dt_ == SRB_F32) {                       // (the f / g projections of SelfAttention: float32 for the softmax)
+              float4* d = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + my_pix * p.y_cstride + p.y_coffset);
+              d[0] = make_float4(v[0], v[1], v[2], v[3]);
+              d[1] = make_float4(v[4], v[5], v[6], v[7]);
+              if (p.cout > 8) { d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]); }
+            } else {
+              uint16_t* d = reinterpret_cast<uint16_t*>(p.y) + my_pix * p.y_cstride + p.y_coffset;
+              *reinterpret_cast<uint4*>(d) = make_uint4(pack2(v[0], v[1], dt_), pack2(v[2], v[3], dt_), pack2(v[4], v[5], dt_), pack2(v[6], v[7], dt_));
+              if (p.cout > 8)
+                *reinterpret_cast<uint4*>(d + 8) = make_uint4(pack2(v[8], v[9], dt_), pack2(v[10], v[11], dt_), pack2(v[12], v[13], dt_),
+                                                              pack2(v[14], v[15], dt_));
+            }
+          }
         } else if (epi_mode == 2) {
           // few output channels (the RGB tail layers): <= 4 channels per pixel, no residual, no shuffle
           if (valid && c0 == 0) {
@@ -937,6 +965,11 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (p.y2 && !pair && !pair8 && (p.y2_mode != 0 || ((p.y_dtype == SRB_F32) == (p.y2_dtype == SRB_F32)))) vec = false;   // one of each kind
     q.epi_mode = vec ? 1 : 0;
     if (!vec && p.cout <= 4 && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2) q.epi_mode = 2;
+    // 8 / 16 output channels as a 16-bit or float32 channel slice (ESRGAN growth convs at growth 8 / 16, SelfAttention f / g)
+    if (!vec && nt == 16 && (p.cout == 8 || p.cout == 16) && p.d2s == 1 && !p.res1 && !p.res2 && !p.y2 && !p.clip01 && p.alpha == 1.f &&
+        (dt16(p.y_dtype) || p.y_dtype == SRB_F32) && (p.act == SRB_ACT_NONE || p.act == SRB_ACT_RELU || p.act == SRB_ACT_LEAKY) &&
+        p.y_cstride % 8 == 0 && p.y_coffset % 8 == 0 && aligned16(p.y))
+      q.epi_mode = 3;
     // depth_to_space onto a few-channel fp32 image: every warp's column range is whole sub-rows of r*c_post floats
     if (!vec && p.d2s > 1 && p.y_dtype == SRB_F32 && !p.res1 && !p.res2 && !p.y2 && p.act != SRB_ACT_PRELU &&
         p.y_cstride == p.c_post && p.y_coffset == 0 && (p.d2s * p.c_post) % 4 == 0 && aligned16(p.y) &&

@@ -80,6 +80,9 @@ _SIGNATURES = {
     "srb_self_attention_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p]),
     "srb_conv_tc_set_cta_pairs": (C.c_int, [C.c_int]),
+    "srb_self_attention_tc_workspace": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "srb_self_attention_tc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "srb_upsampler_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_void_p)]),
     "srb_upsampler_destroy": (None, [C.c_void_p]),
     "srb_upsample_composed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -545,7 +545,10 @@ class ESRGANGeneratorNet(DeviceModel):
         f = ops.conv2d(x, L[name + "_f"], out_dtype=torch.float32)
         g = ops.conv2d(x, L[name + "_g"], out_dtype=torch.float32)
         h = ops.conv2d(x, L[name + "_h"], out_dtype=torch.float32)
-        o = ops.self_attention_core(f.view(B, H * W, -1), g.view(B, H * W, -1), h.view(B, H * W, -1))
+        tc = x.dtype != torch.float32 and ops.self_attention_tc_eligible(f.shape[3], h.shape[3])
+        o = ops.self_attention_core(f.view(B, H * W, -1), g.view(B, H * W, -1), h.view(B, H * W, -1), tensor_cores=tc)
+        if x.dtype != torch.float32 and o.shape[2] % 8 == 0 and o.shape[2] >= 32:
+            o = ops.cast(o, x.dtype)              # 16-bit operand: the 1x1 output projection runs on the tensor cores
         return ops.conv2d(o.view(B, H, W, -1), L[name + "_v"], res1=x, out_dtype=x.dtype)
 
     def forward_device(self, x):

@@ -294,13 +294,19 @@ class ComposedUpsampler:
                 pass
 
 
-def upsample_composed(x, up: ComposedUpsampler, clip01=True, out_dtype=None, x_coffset=0):
+def upsample_composed(x, up: ComposedUpsampler, clip01=True, out_dtype=None, x_coffset=0, out=None):
     """x [B, H, W, >= 64] fp16 / bf16 -> [B, H*r, W*r, C] (float32 by default): the whole EDSR up-sampling tail
     (EDSR_model.py:117-123) as one tcgen05 launch."""
     torch = _torch()
     _check_nhwc(x, "x")
     B, H, W, Cx = x.shape
-    out = torch.empty((B, H * up.scale, W * up.scale, up.c_img), dtype=out_dtype or torch.float32, device=x.device)
+    shape = (B, H * up.scale, W * up.scale, up.c_img)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype or torch.float32, device=x.device)
+    else:
+        _check_nhwc(out, "out")
+        if tuple(out.shape) != shape:
+            raise ValueError(f"out must have shape {shape}, got {tuple(out.shape)}")
     with torch.cuda.device(x.device):
         capi.check(capi.lib().srb_upsample_composed(up.handle, capi.ptr(x), capi.dtype_code(x), Cx, int(x_coffset), B, H, W,
                                                     capi.ptr(out), capi.dtype_code(out), int(bool(clip01)), capi.stream_ptr()))
@@ -359,12 +365,28 @@ def gap_dense_softmax(x, w1, b1, w2, b2):
     return probs
 
 
-def self_attention_core(f, g, h):
-    """o = softmax(g f^T) h per image.  f, g: [B,HW,dk]; h: [B,HW,dv] float32 (ESRGAN_model.py:58-66)."""
+def self_attention_tc_eligible(dk, dv):
+    return 1 <= dk <= 16 and dv in (16, 32, 64)
+
+
+def self_attention_core(f, g, h, tensor_cores=False):
+    """o = softmax(g f^T) h per image.  f, g: [B,HW,dk]; h: [B,HW,dv] float32 (ESRGAN_model.py:58-66).
+    ``tensor_cores``: both products on tcgen05 (fp16 hi/lo-split scores, fp16 P and h, float32 accumulation) - the 16-bit
+    precision modes; default: exact float32 on the CUDA cores."""
     torch = _torch()
     B, HW, dk = f.shape
     dv = h.shape[2]
     o = torch.empty((B, HW, dv), dtype=torch.float32, device=f.device)
+    if tensor_cores:
+        if not self_attention_tc_eligible(dk, dv):
+            raise NotImplementedError(f"tensor-core attention needs dk <= 16 and dv in (16, 32, 64); got dk={dk}, dv={dv}")
+        ws_bytes = capi.lib().srb_self_attention_tc_workspace(B, HW, dk, dv)
+        ws = torch.empty(max(ws_bytes, 256), dtype=torch.uint8, device=f.device)
+        with torch.cuda.device(f.device):
+            capi.check(capi.lib().srb_self_attention_tc(capi.ptr(f.contiguous()), capi.ptr(g.contiguous()), capi.ptr(h.contiguous()),
+                                                        B, HW, dk, dv, capi.ptr(o), capi.ptr(ws), ws_bytes, capi.stream_ptr()))
+        _LAUNCHES[0] += 2
+        return o
     with torch.cuda.device(f.device):
         capi.check(capi.lib().srb_self_attention_f32(capi.ptr(f.contiguous()), capi.ptr(g.contiguous()),
                                                      capi.ptr(h.contiguous()), B, HW, dk, dv, capi.ptr(o),

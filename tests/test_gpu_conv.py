@@ -230,3 +230,33 @@ def test_self_attention_core_vs_float64(hw, dk, dv, batch):
         want = (p / p.sum(-1, keepdims=True)) @ h.astype(np.float64)
         got = ops.self_attention_core(torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda(), torch.from_numpy(h).cuda()).cpu().numpy()
         assert got.shape == want.shape and np.abs(got - want).max() <= 2e-5 * max(1.0, scale * scale)
+
+
+@pytest.mark.parametrize("hw,dk,dv,batch", [(576, 8, 32, 3), (2304, 8, 32, 2), (130, 8, 32, 2), (61, 4, 16, 2), (200, 16, 64, 1),
+                                            (128, 8, 32, 1), (129, 8, 32, 1)])
+def test_self_attention_tensor_core_vs_float64(hw, dk, dv, batch):
+    """srb_self_attention_tc (both products on tcgen05, online softmax in between) against a float64 evaluation: the sizes of
+    the trained ESRGAN configuration, ragged lengths (last key block masked, last query block clipped), every head size, and
+    large logits - the hi / lo split keeps the SCORES at float32 grade, so the tolerance is the fp16 rounding of P and h."""
+    from srb200 import ops
+    rng = np.random.default_rng(hw + dk)
+    for scale in (1.0, 6.0):
+        f = (rng.standard_normal((batch, hw, dk)) * scale).astype(np.float32)
+        g = (rng.standard_normal((batch, hw, dk)) * scale).astype(np.float32)
+        h = rng.standard_normal((batch, hw, dv)).astype(np.float32)
+        s = np.einsum("bqd,bkd->bqk", g.astype(np.float64), f.astype(np.float64))
+        p = np.exp(s - s.max(-1, keepdims=True))
+        want = (p / p.sum(-1, keepdims=True)) @ h.astype(np.float64)
+        ft, gt, ht = (torch.from_numpy(a).cuda() for a in (f, g, h))
+        got = ops.self_attention_core(ft, gt, ht, tensor_cores=True).cpu().numpy()
+        err = float(np.abs(got - want).max())
+        print(f"attention tc hw={hw} dk={dk} dv={dv} scale={scale}: max-abs {err:.2e} (max|h| {np.abs(h).max():.2f})")
+        assert got.shape == want.shape and np.isfinite(got).all() and err <= 3e-3 * float(np.abs(h).max()), (hw, scale, err)
+
+
+def test_self_attention_tensor_core_argument_checks():
+    from srb200 import ops
+    z = lambda *s: torch.zeros(s, device="cuda")
+    with pytest.raises(NotImplementedError):
+        ops.self_attention_core(z(1, 64, 8), z(1, 64, 8), z(1, 64, 24), tensor_cores=True)
+    assert ops.self_attention_core(z(0, 64, 8), z(0, 64, 8), z(0, 64, 32), tensor_cores=True).shape == (0, 64, 32)

@@ -172,3 +172,49 @@ def test_metrics_and_tiling_kernels_stay_inside_their_tensors():
     torch.cuda.synchronize()
     check()
     assert np.abs(out.cpu().numpy() - ot.reconstruct(want, pos, (ph, pw, 3), (50, 43), 1)).max() <= 1e-6
+
+
+@pytest.mark.parametrize("scale,shape,dout", [(4, (2, 13, 21), "fp32"), (4, (1, 2, 2), "u8"), (4, (1, 31, 57), "fp16"),
+                                               (3, (1, 9, 5), "fp32"), (2, (2, 7, 30), "fp32")])
+def test_composed_upsampler_stays_inside_its_tensors(scale, shape, dout):
+    """upsample5_fold_kernel: nine segments with their own rectangles, per-lane vector stores into the image - every one of
+    them inside the output, and nothing outside the 64-channel input slice reaches a result (NaN surroundings)."""
+    from srb200 import compose, ops, weights
+    dts = {"fp16": torch.float16, "fp32": torch.float32, "u8": torch.uint8}
+    w = weights.edsr_weights(scale, num_res_blocks=1, bias_scale=0.05, seed=scale)
+    wc, bc = compose.compose_edsr_tail(w, scale)
+    up = ops.ComposedUpsampler(wc, bc, scale, compose.weight_scale(wc))
+    B, H, W = shape
+    x = np.random.default_rng(H * W).uniform(-0.3, 0.3, (B, H, W, 64)).astype(np.float32)
+    xd = _nan_in((B, H, W, 64), torch.float16, x)
+    out, check = _guarded((B, H * scale, W * scale, 3), dts[dout])
+    ops.upsample_composed(xd, up, clip01=True, out=out)
+    torch.cuda.synchronize()
+    check()
+    want = np.clip(compose.layered_tail(w, xd.float().cpu().numpy().astype(np.float64), scale), 0, 1)
+    got = out.float().cpu().numpy()
+    if dout == "u8":
+        assert np.abs(got - want * 255).max() <= 0.5 + 255 * 4e-3
+    else:
+        assert np.isfinite(got).all() and np.abs(got - want).max() <= 4e-3 + (1e-3 if dout == "fp16" else 0)
+
+
+def test_in_place_trunk_update_stays_inside_its_tensors():
+    """Res-block second conv with the (h, e) trunk pair updated in place (out is res1, out2 is res2)."""
+    from srb200 import ops
+    rng = np.random.default_rng(5)
+    B, H, W = 2, 19, 13
+    t = rng.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)
+    kern = rng.uniform(-0.1, 0.1, (3, 3, 64, 64)).astype(np.float32)
+    bias = rng.uniform(-0.1, 0.1, (64,)).astype(np.float32)
+    h0 = rng.uniform(-1, 1, (B, H, W, 64)).astype(np.float32)
+    td = _nan_in((B, H, W, 64), torch.float16, t)
+    h, check_h = _guarded((B, H, W, 64), torch.float16, h0)
+    e, check_e = _guarded((B, H, W, 64), torch.float8_e5m2, torch.zeros((B, H, W, 64), device="cuda").to(torch.float8_e5m2))
+    h_before = h.float().cpu().numpy()
+    ops.conv2d(td, ops.ConvWeights(kern, bias), alpha=0.1, res1=h, res2=e, out=h, out2=e, out2_error=True)
+    torch.cuda.synchronize()
+    check_h(); check_e()
+    want = 0.1 * oc.conv2d_same_numpy(td.float().cpu().numpy(), kern, bias) + h_before
+    got = h.float().cpu().numpy() + e.float().cpu().numpy()
+    assert np.abs(got - want).max() <= 2e-3
