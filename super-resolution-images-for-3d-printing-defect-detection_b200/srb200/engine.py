@@ -520,23 +520,32 @@ class ESRGANGeneratorNet(DeviceModel):
     def output_scale(self):
         return self.scale_factor
 
-    def _dense(self, x, name, outer=None):
-        """x + 0.2 * conv5(...) (ESRGAN_model.py:249-252).  With ``outer`` (the RRDB input) the block's
-        own ``outer + 0.2 * (.)`` (ESRGAN_model.py:277-280) is folded into the same epilogue."""
-        torch = _torch()
+    def _dense(self, src, dst, name, outer=None):
+        """Dense block (ESRGAN_model.py:212-254) on WIDE buffers [B, H, W, 64 + 4 g]: channels [0, 64) of ``src`` hold the
+        block input x, the four growth convs append their slices to ``src`` in place (concat-free), and
+        ``x + 0.2 * conv5(.)`` lands in channels [0, 64) of ``dst`` - the next block's input, so nothing is copied between
+        blocks.  With ``outer`` (the wide buffer holding the RRDB input) the RRDB's own ``outer + 0.2 * (.)``
+        (ESRGAN_model.py:277-280) is folded into the same epilogue."""
         L, g = self.layers, self.growth
-        B, H, W, Cc = x.shape
-        # (zeros, not empty: the tcgen05 engine reads the input in 64-channel chunks, so a growth conv also reads the slices
-        #  that later convs of the block will write - against zero weight columns, which only cancel finite values)
-        buf = torch.zeros((B, H, W, 64 + 4 * g), dtype=x.dtype, device=x.device)
-        buf[..., :64].copy_(x)
         for j in range(4):
             # reads channels [0, 64 + j*g) of the wide buffer via cstride; writes slice j
-            ops.conv2d(buf, L[f"{name}_conv{j + 1}"], act="relu", out=buf, out_coffset=64 + j * g)
+            ops.conv2d(src, L[f"{name}_conv{j + 1}"], act="relu", out=src, out_coffset=64 + j * g)
         if outer is None:
-            return ops.conv2d(buf, L[f"{name}_conv5"], alpha=0.2, res1=x, out_dtype=x.dtype)
-        return ops.conv2d(buf, L[f"{name}_conv5"], alpha=0.04, res1=x, beta1=0.2, res2=outer, beta2=1.0,
-                          out_dtype=x.dtype)
+            ops.conv2d(src, L[f"{name}_conv5"], alpha=0.2, res1=src, out=dst, out_coffset=0)
+        else:
+            ops.conv2d(src, L[f"{name}_conv5"], alpha=0.04, res1=src, beta1=0.2, res2=outer, beta2=1.0, out=dst, out_coffset=0)
+
+    def _dense_buffers(self, B, H, W, dtype, device):
+        """Three wide buffers that rotate through the dense blocks of an RRDB (block input / output / the RRDB input kept for
+        its skip).  Allocated ZEROED once per shape: the tcgen05 engine reads the input in 64-channel chunks, so a growth conv
+        also reads the slices later convs of the block will write - against zero weight columns, which only cancel finite
+        values; after the first use those slices hold the previous block's (finite) activations."""
+        torch = _torch()
+        key = (B, H, W, dtype, str(device))
+        if getattr(self, "_dense_key", None) != key:
+            self._dense_bufs = [torch.zeros((B, H, W, 64 + 4 * self.growth), dtype=dtype, device=device) for _ in range(3)]
+            self._dense_key = key
+        return self._dense_bufs
 
     def _attention(self, x, name):
         torch = _torch()
@@ -554,13 +563,18 @@ class ESRGANGeneratorNet(DeviceModel):
     def forward_device(self, x):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        h = ops.conv2d(x, L["initial_conv"], out_dtype=dt)
-        trunk = h
+        trunk = ops.conv2d(x, L["initial_conv"], out_dtype=dt)
+        B, H, W, _ = trunk.shape
+        bufs = self._dense_buffers(B, H, W, dt, trunk.device)
+        cur = 0
+        bufs[cur][..., :64].copy_(trunk)
         for i in range(self.num_rrdb):
-            inp = h
-            for d in (1, 2, 3):
-                h = self._dense(h, f"rrdb_{i}_dense{d}", outer=inp if d == 3 else None)
-        h = ops.conv2d(h, L["trunk_conv"], res1=trunk, out_dtype=dt)
+            a, b, c = cur, (cur + 1) % 3, (cur + 2) % 3       # a keeps the RRDB input until the third block's skip
+            self._dense(bufs[a], bufs[b], f"rrdb_{i}_dense1")
+            self._dense(bufs[b], bufs[c], f"rrdb_{i}_dense2")
+            self._dense(bufs[c], bufs[b], f"rrdb_{i}_dense3", outer=bufs[a])
+            cur = b
+        h = ops.conv2d(bufs[cur], L["trunk_conv"], res1=trunk, out_dtype=dt)
         h = self._attention(h, "self_attention_trunk")
         for i in range(int(math.log2(self.scale_factor))):
             h = ops.conv2d(h, L[f"upsample_{i}_conv"], act="leaky_relu", act_slope=0.2, d2s=2, out_dtype=dt)
