@@ -86,4 +86,6 @@ struct srb_conv_weights {
   __nv_bfloat16* tc_head; // cin == 3, cout == 64 only: im2col GEMM operand [n_kb][64 cout rows][64 k], k = (dy*kw + dx)*3 + c, or nullptr
   __half* tc_head_f16;
   int tc_head_kb;         // 64-wide K blocks
+  __nv_bfloat16* tc_head8;   // cin <= 8, cout == 64, 3x3 / 5x5 only: un-swizzled core-matrix order [dy][8-row group][K chunk = dx][row][8 ch]
+  __half* tc_head8_f16;      //   for the NHWC8 head kernel (conv_head8.cu), or nullptr
 };

@@ -54,6 +54,29 @@ extern "C" int srb_conv_weights_create(const float* hwio, const float* bias, int
       return cuda_fail(e, "conv_weights_create(tc head)");
     }
   }
+  // small-filter RGB heads (cin <= 8, cout == 64, 3x3 / 5x5): B operand of the NHWC8 head kernel in the un-swizzled canonical
+  // order - address(n, chunk) = dy block + (n / 8) * (KC * 128 B) + chunk * 128 B + (n % 8) * 16 B, chunk = dx, 8 channels each
+  if (cin <= 8 && cout == 64 && kh == kw && (kh == 3 || kh == 5)) {
+    const int kc = 2 * ((kw * 8 + 15) / 16);
+    std::vector<__nv_bfloat16> hb((size_t)kh * 64 * kc * 8, __float2bfloat16_rn(0.f));
+    std::vector<__half> hh((size_t)kh * 64 * kc * 8, __float2half_rn(0.f));
+    for (int dy = 0; dy < kh; ++dy)
+      for (int n = 0; n < 64; ++n)
+        for (int dx = 0; dx < kw; ++dx)
+          for (int c = 0; c < cin; ++c) {
+            const float v = hwio[((size_t)(dy * kw + dx) * cin + c) * cout + n];
+            const size_t idx = (((size_t)dy * 8 + n / 8) * kc + dx) * 64 + (size_t)(n % 8) * 8 + c;
+            hb[idx] = __float2bfloat16_rn(v);
+            hh[idx] = __float2half_rn(v);
+          }
+    if ((e = cudaMalloc(&w->tc_head8, hb.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc_head8, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&w->tc_head8_f16, hh.size() * 2)) != cudaSuccess ||
+        (e = cudaMemcpy(w->tc_head8_f16, hh.data(), hh.size() * 2, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      srb_conv_weights_destroy(w);
+      return cuda_fail(e, "conv_weights_create(tc head8)");
+    }
+  }
   // tensor-core copies: [tap][cout_pad16][cin_pad64] K(cin)-major rows in bf16 and fp16.  cin = 64 is the native shape of
   // the tcgen05 engine; wider inputs (VGG16 blocks 2-5: 128 .. 512 channels, the ESRGAN dense blocks' growing concatenation:
   // 64 + j * growth) are walked in 64-channel K chunks with zero columns past cin.
@@ -139,6 +162,8 @@ extern "C" void srb_conv_weights_destroy(srb_conv_weights* w) {
   if (w->tc_fold_f16) cudaFree(w->tc_fold_f16);
   if (w->tc_head) cudaFree(w->tc_head);
   if (w->tc_head_f16) cudaFree(w->tc_head_f16);
+  if (w->tc_head8) cudaFree(w->tc_head8);
+  if (w->tc_head8_f16) cudaFree(w->tc_head8_f16);
   free(w);
 }
 
@@ -175,6 +200,7 @@ static int fill_params(const srb_conv_args* a, ConvParams& p) {
   p.w_tc_cin = w->tc_cin_pad;
   p.w_tc_fold = a->x_dtype == SRB_F16 ? (const void*)w->tc_fold_f16 : (const void*)w->tc_fold;
   p.w_tc_head = a->y_dtype == SRB_F16 ? (const void*)w->tc_head_f16 : (const void*)w->tc_head; p.w_tc_head_kb = w->tc_head_kb;
+  p.w_tc_head8 = a->y_dtype == SRB_F16 ? (const void*)w->tc_head8_f16 : (const void*)w->tc_head8;
   p.bias = w->bias;
   p.act = a->act; p.act_slope = a->act_slope; p.prelu = a->prelu;
   SRB_REQUIRE(a->act >= SRB_ACT_NONE && a->act <= SRB_ACT_TANH, "conv2d: unknown activation %d", a->act);
@@ -191,7 +217,7 @@ extern "C" int srb_conv2d_engine(const srb_conv_args* a) {
   ConvParams p;
   int rc = fill_params(a, p);
   if (rc) return rc;
-  return (conv_tc_eligible(p) || conv_headtc_eligible(p)) ? SRB_ENGINE_TCGEN05 : SRB_ENGINE_DIRECT;
+  return (conv_tc_eligible(p) || conv_head8_eligible(p) || conv_headtc_eligible(p)) ? SRB_ENGINE_TCGEN05 : SRB_ENGINE_DIRECT;
 }
 
 extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
@@ -201,6 +227,10 @@ extern "C" int srb_conv2d_nhwc(const srb_conv_args* a, srb_stream_t stream) {
   if (rc) return rc;
   if (p.B == 0) return SRB_OK;
   const bool tc_ok = conv_tc_eligible(p);
+  if (a->engine != SRB_ENGINE_DIRECT && !tc_ok && conv_head8_eligible(p)) {        // 3x3 / 5x5 RGB heads: NHWC8 rows as the A operand
+    rc = conv_head8_launch(p, (cudaStream_t)stream);
+    if (rc != SRB_E_UNSUPPORTED) return rc;
+  }
   if (a->engine != SRB_ENGINE_DIRECT && !tc_ok && conv_headtc_eligible(p)) {       // RGB head layers: im2col GEMM on the tensor cores
     rc = conv_headtc_launch(p, (cudaStream_t)stream);
     if (rc != SRB_E_UNSUPPORTED || a->engine == SRB_ENGINE_TCGEN05) return rc;

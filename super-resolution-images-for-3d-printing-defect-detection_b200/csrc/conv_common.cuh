@@ -15,6 +15,7 @@ struct ConvParams {
   int w_tc_cin;                             // cin rounded up to a multiple of 64 (the kernel walks it in 64-channel chunks)
   const void* w_tc_fold;                    // dx-folded weights ([dy][16][cin] for cout <= 4, [dy][192][cin] for cout == 64), or nullptr
   const void* w_tc_head; int w_tc_head_kb;  // cin == 3 im2col weights in the 16-bit dtype of y, or nullptr
+  const void* w_tc_head8;                   // cin <= 8, 3x3 / 5x5: core-matrix-ordered weights of the NHWC8 head kernel, or nullptr
   const float* bias;                        // [cout], never null
   int act; float act_slope; const float* prelu;
   float alpha;
@@ -102,6 +103,8 @@ bool conv_head_eligible(const ConvParams& p);
 int conv_tc_launch(const ConvParams& p, cudaStream_t stream);
 int conv_headtc_launch(const ConvParams& p, cudaStream_t stream);
 bool conv_headtc_eligible(const ConvParams& p);
+int conv_head8_launch(const ConvParams& p, cudaStream_t stream);
+bool conv_head8_eligible(const ConvParams& p);
 bool conv_tc_eligible(const ConvParams& p);
 
 }  // namespace srb

