@@ -524,7 +524,7 @@ def config_esrgan(torch, peaks):
                        "both attention products on tcgen05; fp32: exact CUDA-core engines"}
     for prec in ("fp16", "fp32"):
         net = engine.ESRGANGeneratorNet(weights.esrgan_generator_weights(2, 8, 4), 2, 8, 4, precision=prec)
-        ms = cuda_timed(torch, lambda: net.predict_device(x, micro_batch=512), 2, warm=1)
+        ms = cuda_timed(torch, lambda: net.predict_device(x), 2, warm=1)
         out[prec] = {"ms": ms, "out_MPps": 1521 * 48 * 48 / ms / 1e3, "patches_per_s": 1521 / ms * 1e3}
     return out
 

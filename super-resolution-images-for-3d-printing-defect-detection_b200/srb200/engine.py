@@ -121,7 +121,8 @@ class DeviceModel:
         ``budget_bytes`` (the reference predicts 16 patches at a time, EDSR_model.py:274; one launch sequence over the
         whole input would need ~9 GB for the 1,849 patches of a 1024 x 1024 LR image and overflow 32-bit tile counts at 4K)."""
         per_image = max(1, int(h) * int(w) * self._activation_bytes_per_input_pixel())
-        return int(max(1, min(256, budget_bytes // per_image)))
+        cap = max(256, (1 << 21) // max(1, int(h) * int(w)))      # small patches (24 x 24): up to ~2 M pixels per launch sequence
+        return int(max(1, min(cap, budget_bytes // per_image)))
 
     def forward_device_as(self, x, out_dtype=None):
         """forward_device with the result in ``out_dtype`` (None = float32).  uint8 = saturate(rint(255 v)) of the [0, 1]

@@ -21,17 +21,18 @@ def main():
     ap.add_argument("--growth", type=int, default=8)
     ap.add_argument("--patches", type=int, default=1521)
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--micro-batch", type=int, default=512)
     a = ap.parse_args()
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.rand((a.patches, 24, 24, 3), device="cuda", generator=g) * 2 - 1
     for prec in ("fp16", "fp32"):
         net = engine.ESRGANGeneratorNet(weights.esrgan_generator_weights(2, a.growth, a.rrdb), 2, a.growth, a.rrdb, precision=prec)
-        net.predict_device(x, micro_batch=512)
+        net.predict_device(x, micro_batch=a.micro_batch)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(a.reps):
-            net.predict_device(x, micro_batch=512)
+            net.predict_device(x, micro_batch=a.micro_batch)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
