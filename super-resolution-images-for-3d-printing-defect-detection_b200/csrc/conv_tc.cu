@@ -53,7 +53,6 @@ struct TcParams {
   uint32_t epi_warp_bytes;
   int two_cta;           // launched as CTA pairs (cluster of 2, cta_group::2 MMAs)
   int n_kc;              // 64-channel K chunks of the input (cin_pad / 64): one halo load and one set of tap MMAs per chunk
-  int k_last;            // k16 steps of the LAST chunk that hold real input channels (1..4): the zero columns past cin are skipped
   int kh, kw;            // filter size (odd, <= 9); 3x3 is the unrolled fast path
   int halo_rows;         // kTileH + kh - 1
   uint32_t magic_tpi, magic_tx;   // ceil(2^32 / tiles_per_img), ceil(2^32 / tiles_x) for multiply-high division, or 0
@@ -284,7 +283,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
           tc_fence_after();
           const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo);
           const uint64_t b_kc = b_desc0 + (uint64_t)((uint32_t)kc * (w_kc_bytes >> 4));
-          const int ks = kc == n_kc - 1 ? q.k_last : 4;          // (a growth conv's last chunk may hold as few as 8 real channels)
           if (elect_one()) {
             int tap = 0;
             for (int ty_ = 0; ty_ < q.kh; ++ty_)
@@ -292,8 +290,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 const uint64_t ad = a_desc0 + (uint64_t)((uint32_t)ty_ * a_dy + (uint32_t)tx_ * 8u);
                 const uint64_t bd = b_kc + (uint64_t)tap * b_tap_step;
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  if (k < ks) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((kc | tap | k) != 0));
+                for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((kc | tap | k) != 0));
               }
             commit(empty_bar(s));
             if (kc == n_kc - 1) commit(tfull_bar(acc));
@@ -929,7 +926,6 @@ int conv_tc_launch(const ConvParams& p, cudaStream_t stream) {
     if (try_pair && nt < 32) continue;
     q = TcParams{};
     q.n_kc = n_kc;
-    q.k_last = (p.cin - 64 * (n_kc - 1) + 15) / 16;
     q.kh = p.kh; q.kw = p.kw;
     q.halo_rows = kTileH + p.kh - 1;
     q.n_tile = nt;
