@@ -251,30 +251,35 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     const uint64_t b_desc0 = make_desc(w_smem, 1024u);
     const uint32_t b_tap_step = (n_local * 128u) >> 4;                  // descriptor address units (16 B)
     const uint32_t a_dy = (uint32_t)q.pitch * 8u;                       // one halo row, in 16-B units (one pixel = 8 units)
-    const bool unrolled = n_kc == 1 && q.kh == 3 && q.kw == 3;          // the hot case: nine taps from uniform registers
+    const bool unrolled = q.kh == 3 && q.kw == 3;                       // the hot case: nine taps from uniform registers
     for (int tile = first_tile; tile < tile_end; tile += tile_step, ++it) {
       const int acc = it & 1;
       const uint32_t acc_ph = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_ph ^ 1u);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * q.n_tile);
       if (unrolled) {
-        mbar_wait(full_bar(s), ph);
-        tc_fence_after();
-        // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
-        const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo);
-        if (elect_one()) {
+        // 3 x 3: the 36 MMAs of a K chunk fully unrolled (the issuing thread spends ~10 instructions per MMA in the rolled
+        // loop below, which is what bounds the narrow-N wide-input layers); wide inputs repeat the block per 64-channel chunk
+        for (int kc = 0; kc < n_kc; ++kc) {
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          // start-address field arithmetic: tap / k offsets never carry out of the 14-bit field (smem < 256 KB)
+          const uint64_t a_desc0 = make_desc(a_smem + (uint32_t)s * q.stage_bytes, sbo);
+          const uint64_t b_kc = b_desc0 + (uint64_t)((uint32_t)kc * (w_kc_bytes >> 4));
+          if (elect_one()) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * 8u);
-            const uint64_t bd = b_desc0 + (uint64_t)tap * b_tap_step;
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint64_t ad = a_desc0 + (uint64_t)((tap / 3) * a_dy + (tap % 3) * 8u);
+              const uint64_t bd = b_kc + (uint64_t)tap * b_tap_step;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (uint32_t)((tap | k) != 0));
+              for (int k = 0; k < 4; ++k) mma(d_tmem, ad + 2u * k, bd + 2u * k, (tap | k) != 0 ? 1u : (uint32_t)(kc != 0));
+            }
+            commit(empty_bar(s));            // smem stage reusable once these MMAs have read it (both CTAs in k2)
+            if (kc == n_kc - 1) commit(tfull_bar(acc));          // accumulator complete
           }
-          commit(empty_bar(s));            // smem stage reusable once these MMAs have read it (both CTAs in k2)
-          commit(tfull_bar(acc));          // accumulator complete
+          __syncwarp();
+          if (++s == q.stages) { s = 0; ph ^= 1u; }
         }
-        __syncwarp();
-        if (++s == q.stages) { s = 0; ph ^= 1u; }
       } else {
         // general odd filter and / or wide input: the accumulator collects every (K chunk, tap) product; each 64-channel
         // chunk has its own halo stage and its own block of resident weight rows
