@@ -45,6 +45,23 @@ for k in range(len(secs) - 1):
             if r[i].isdigit():
                 agg[c] = agg.get(c, 0) + int(r[i])
     print("   stall totals:", sorted(((v, c[6:]) for c, v in agg.items() if v), reverse=True)[:8])
+    byop = {}
+    for r in data:
+        if not r[isamp].isdigit():
+            continue
+        toks = [t for t in r[ia].split() if not t.startswith("@")]
+        op = toks[0] if toks else "?"
+        d = byop.setdefault(op, {"n": 0, "samples": 0, "ex": 0})
+        d["n"] += 1
+        d["samples"] += int(r[isamp])
+        d["ex"] += int(r[iex]) if r[iex].isdigit() else 0
+        for i, c in stall:
+            if r[i].isdigit() and int(r[i]):
+                d[c[6:]] = d.get(c[6:], 0) + int(r[i])
+    print("   by opcode (static count, executed, samples, top stalls):")
+    for op, d in sorted(byop.items(), key=lambda kv: -kv[1]["samples"])[:14]:
+        st = sorted(((v, k) for k, v in d.items() if k not in ("n", "samples", "ex")), reverse=True)[:4]
+        print(f"     {op:22s} n={d['n']:5d} ex={d['ex']:>11d} samples={d['samples']:6d} ({100 * d['samples'] / max(tot, 1):4.1f}%) {st}")
     for r in sorted(data, key=lambda r: -int(r[isamp]) if r[isamp].isdigit() else 0)[:ntop]:
         st = sorted(((int(r[i]), c[6:]) for i, c in stall if r[i].isdigit() and int(r[i]) > 0), reverse=True)[:3]
         print(f"{int(r[isamp]):6d} {100 * int(r[isamp]) / max(tot, 1):5.1f}% ex={r[iex]:>9s} {r[ia].strip()[:64]:64s} {st}")
