@@ -59,8 +59,11 @@ int srb_psnr_ssim_f32(const float* a, const float* b, int batch, int height, int
  * reference's classical benchmark uses (super_resolucion_clasica.ipynb cell 7: skimage.metrics.peak_signal_noise_ratio
  * and structural_similarity(..., data_range, channel_axis=2) with their defaults - 7 x 7 uniform window, sample
  * covariance N/(N-1), K1 = 0.01, K2 = 0.03, borders cropped by 3): psnr = 10 log10(max_val^2 / mse), ssim = mean over the
- * (H-6) x (W-6) valid windows and channels.  Needs H, W >= 7. */
-enum { SRB_SSIM_TF = 0, SRB_SSIM_SKIMAGE = 1 };
+ * (H-6) x (W-6) valid windows and channels.  Needs H, W >= 7.
+ * SRB_SSIM_TF on wide 1- / 3-channel images runs both filter passes on the tensor path with the Gaussian rounded to an
+ * fp16 window that sums to exactly 1 (|dSSIM| <= ~3e-6 against the float32 Gaussian, data kept to 22 bits);
+ * SRB_SSIM_TF_EXACT keeps the float32 Gaussian on the CUDA cores for every size (also: environment SRB_SSIM_EXACT=1). */
+enum { SRB_SSIM_TF = 0, SRB_SSIM_SKIMAGE = 1, SRB_SSIM_TF_EXACT = 2 };
 int srb_psnr_ssim_window_f32(const float* a, const float* b, int batch, int height, int width, int channels,
                              float max_val, int window, float* psnr /* [B] or NULL */, float* ssim /* [B] or NULL */,
                              float* mse /* [B] or NULL */, double* sums /* [4] or NULL, accumulated */,

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "srb200", "libsrb200.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "metrics.cu", "bicubic.cu", "tiling.cu", "conv.cu", "conv_direct.cu", "conv_head.cu", "conv_tc.cu", "conv_fold.cu", "conv_headtc.cu", "conv_up.cu", "attention_tc.cu", "conv_head8.cu"]
+SOURCES = ["core.cu", "metrics.cu", "metrics_mma.cu", "bicubic.cu", "tiling.cu", "conv.cu", "conv_direct.cu", "conv_head.cu", "conv_tc.cu", "conv_fold.cu", "conv_headtc.cu", "conv_up.cu", "attention_tc.cu", "conv_head8.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

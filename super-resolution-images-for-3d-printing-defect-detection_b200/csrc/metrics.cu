@@ -10,6 +10,7 @@
 // from the same loaded lines over a non-overlapping ownership partition of the image.
 // Per-image double-precision accumulators receive one atomicAdd per block and statistic.
 #include "common.cuh"
+#include "metrics_mma.cuh"
 #include <stdlib.h>
 
 namespace srb {
@@ -401,9 +402,10 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
                          int window, float* psnr, float* ssim, float* mse, double* sums, void* workspace,
                          size_t workspace_bytes, cudaStream_t stream) {
   SRB_REQUIRE(a && b && workspace, "psnr_ssim: null pointer");
-  SRB_REQUIRE(window == SRB_SSIM_TF || window == SRB_SSIM_SKIMAGE, "psnr_ssim: unknown window kind %d", window);
+  SRB_REQUIRE(window == SRB_SSIM_TF || window == SRB_SSIM_SKIMAGE || window == SRB_SSIM_TF_EXACT,
+              "psnr_ssim: unknown window kind %d", window);
   SRB_REQUIRE(batch >= 0 && channels >= 1 && channels <= 4, "psnr_ssim: channels must be 1..4 (got %d)", channels);
-  const int K = window == SRB_SSIM_TF ? 11 : 7;
+  const int K = window == SRB_SSIM_SKIMAGE ? 7 : 11;
   SRB_REQUIRE(workspace_bytes >= srb_psnr_ssim_workspace(batch), "psnr_ssim: workspace too small");
   double* acc = (double*)workspace;
   if (!ssim) {
@@ -434,9 +436,13 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
   SRB_CUDA(cudaMemsetAsync(acc, 0, srb_psnr_ssim_workspace(batch), stream));
   const int OH = height - (K - 1), OW = width - (K - 1), OE = OW * channels;
   const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
-  const float cov_norm = window == SRB_SSIM_TF ? 1.f : (float)(49.0 / 48.0);
+  const float cov_norm = window == SRB_SSIM_SKIMAGE ? (float)(49.0 / 48.0) : 1.f;
   static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
-  if (window == SRB_SSIM_TF && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread, one warp per plane
+  static const bool force_exact = getenv("SRB_SSIM_EXACT") != nullptr;
+  if (window == SRB_SSIM_TF && !force_exact && !force_narrow && psnr_ssim_mma_eligible(a, b, height, width, channels)) {
+    // wide RGB / grey images: both filter passes on the warp-level tensor path (fp16 window summing to 1, hi/lo-split data)
+    rc = run_psnr_ssim_mma(a, b, batch, height, width, channels, c1, c2, acc, stream);
+  } else if (window != SRB_SSIM_SKIMAGE && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread, one warp per plane
     const int px = kPairPx * (channels == 1 ? 4 : channels == 2 ? 2 : 1);   // map pixels per block row
     const int gxp = (OW + px - 1) / px;
     int rows = 256;                                // (10 halo rows per strip: 4 % extra horizontal work at 256)

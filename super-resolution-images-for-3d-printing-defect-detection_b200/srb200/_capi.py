@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libsrb200.so")
 SRB_OK, SRB_E_INVALID, SRB_E_UNSUPPORTED, SRB_E_CUDA, SRB_E_NOMEM = 0, -1, -2, -3, -4
 F32, BF16, U8, F16, F8E5M2 = 0, 1, 2, 3, 4
 INTER_LINEAR, INTER_CUBIC, INTER_AREA, INTER_LANCZOS4 = 1, 2, 3, 4          # OpenCV's interpolation codes
-SSIM_TF, SSIM_SKIMAGE = 0, 1                                             # srb_psnr_ssim_window_f32 window kinds
+SSIM_TF, SSIM_SKIMAGE, SSIM_TF_EXACT = 0, 1, 2                            # srb_psnr_ssim_window_f32 window kinds
 ACT_NONE, ACT_RELU, ACT_PRELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3, 4
 ENGINE_AUTO, ENGINE_DIRECT, ENGINE_TCGEN05 = 0, 1, 2
 ACTIVATIONS = {None: ACT_NONE, "linear": ACT_NONE, "relu": ACT_RELU, "prelu": ACT_PRELU,

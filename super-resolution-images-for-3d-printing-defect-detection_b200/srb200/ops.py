@@ -65,7 +65,9 @@ def psnr(a, b, max_val=1.0, want_mse=False, window=capi.SSIM_TF):
 def psnr_ssim(a, b, max_val=1.0, sums=None, want_mse=False, window=capi.SSIM_TF):
     """a, b: [B,H,W,C] float32 CUDA tensors -> (psnr [B], ssim [B][, mse [B]]) float32.
 
-    ``window``: ``SSIM_TF`` (tf.image definitions, metrics.py:3-7) or ``SSIM_SKIMAGE`` (skimage.metrics definitions
+    ``window``: ``SSIM_TF`` (tf.image definitions, metrics.py:3-7; wide 1- / 3-channel images run on the tensor path with
+    the Gaussian rounded to an fp16 window that sums to 1, |dSSIM| <= ~3e-6), ``SSIM_TF_EXACT`` (the float32 Gaussian on the
+    CUDA cores for every size) or ``SSIM_SKIMAGE`` (skimage.metrics definitions
     with their defaults, as used by super_resolucion_clasica.ipynb cell 7).
 
     ``sums`` (optional float64[4] CUDA tensor) is accumulated with (sum psnr, sum ssim, count,

@@ -39,6 +39,53 @@ def test_against_oracle(shape):
     assert np.abs(s - om.ssim(a, b, dtype=np.float64)).max() <= SSIM_TOL
 
 
+# shapes the tensor-path kernel takes (1 / 3 channels, map at least 96 wide, 16-byte rows): ragged strips (22 columns) and
+# steps (16 rows), a single step, the minimum height, several chunks
+MMA_SHAPES = [(2, 130, 300, 3), (1, 27, 116, 3), (1, 11, 108, 3), (2, 200, 256, 1), (1, 478, 480, 3), (1, 300, 1000, 3),
+              (1, 1100, 128, 3), (3, 26, 106, 1)]
+
+
+@pytest.mark.parametrize("shape", MMA_SHAPES)
+def test_tensor_path_against_oracle(shape):
+    """mma.sync kernel (fp16 window summing to 1, hi/lo-split data) vs the float64 oracle and vs the float32-Gaussian kernel."""
+    from srb200 import metrics
+    a, b = _pair(shape, seed=shape[1] + shape[2])
+    p, s = metrics.psnr_ssim(a, b)
+    pe, se = metrics.psnr_ssim(a, b, exact=True)
+    assert np.abs(p - om.psnr(a, b, dtype=np.float64)).max() <= PSNR_TOL
+    assert np.abs(s - om.ssim(a, b, dtype=np.float64)).max() <= SSIM_TOL
+    assert np.abs(p - pe).max() <= 1e-4            # same squared error, other summation order
+    assert np.abs(s - se).max() <= 2e-5            # window rounding + 22-bit data (measured <= 3e-6)
+
+
+@pytest.mark.parametrize("noise", [0.0, 0.002, 0.3])
+def test_tensor_path_flat_and_identical_images(noise):
+    """Variance cancellation: flat images with tiny / no noise, where E[a^2] - mu^2 is ~1e-6 against c2 = 9e-4."""
+    from srb200 import metrics
+    rng = np.random.default_rng(3)
+    a = np.full((2, 96, 160, 3), 0.5, np.float32)
+    a[1] = 0.9
+    b = np.clip(a + noise * rng.standard_normal(a.shape).astype(np.float32), 0, 1)
+    s = metrics.ssim(a, b)
+    assert np.abs(s - om.ssim(a, b, dtype=np.float64)).max() <= SSIM_TOL
+    if noise == 0.0:
+        assert np.allclose(s, 1.0, atol=1e-6)
+
+
+def test_tensor_path_unaligned_rows_fall_back():
+    """Rows that are not 16-byte multiples (W C % 4 != 0) or unaligned views take the CUDA-core kernel: same answers."""
+    import torch
+    from srb200 import metrics, ops
+    a, b = _pair((1, 64, 134, 3), seed=2)          # 402 floats per row
+    s = metrics.ssim(a, b)
+    assert np.abs(s - om.ssim(a, b, dtype=np.float64)).max() <= SSIM_TOL
+    ta = torch.from_numpy(_pair((2, 64, 136, 3), seed=4)[0]).cuda()
+    tb = (ta * 0.9).contiguous()
+    p0, s0 = ops.psnr_ssim(ta[1:], tb[1:])         # second image: base pointer offset by 64 * 136 * 3 * 4 bytes (aligned)
+    p1, s1 = ops.psnr_ssim(ta, tb)
+    assert torch.allclose(p0, p1[1:], atol=1e-4) and torch.allclose(s0, s1[1:], atol=1e-6)
+
+
 def test_known_answers():
     from srb200 import metrics
     a = np.full((2, 16, 20, 3), 0.3, np.float32)
