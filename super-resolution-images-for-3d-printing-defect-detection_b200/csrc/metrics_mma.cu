@@ -34,7 +34,7 @@ namespace {
 
 constexpr int kMW = 22;       // output columns per strip (32 input columns)
 constexpr int kMH = 16;       // output rows per step
-constexpr int kSlots = 4;     // resident 16-row halves per array
+constexpr int kSlots = 2;     // resident 16-row halves per array (the one being read, the one in flight)
 
 __constant__ float c_h16[11];   // the fp16-exact window (as float)
 
@@ -84,7 +84,7 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
                      int steps_per_chunk, float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
   constexpr int RS = Geom<C>::RS;
   constexpr int kHalf = 16 * RS;                    // words per half
-  extern __shared__ __align__(128) float smem[];    // [a | b][kSlots][16][RS]
+  extern __shared__ __align__(128) float smem[];    // [a | b][kSlots][16][RS] raw rows, then the fragment stash
   float* sa = smem;
   float* sb = smem + kSlots * kHalf;
   __shared__ __align__(8) uint64_t bars[2 * kSlots];   // full[kSlots], empty[kSlots]
@@ -92,6 +92,9 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
   const int OW = W - 10, OH = H - 10;
   const int tid = threadIdx.x, ch = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  // stash[(m, nb)][thread]: the hi / lo B fragments this lane built from the rows of the newest half - they are the k-block 0
+  // operands of the next step (same lane, same registers), so every input row is squared, multiplied and split ONCE
+  uint4* stash = reinterpret_cast<uint4*>(smem + 2 * kSlots * kHalf) + tid;
   const int x0 = blockIdx.x * kMW;
   const int ych = blockIdx.y * steps_per_chunk * kMH;                 // first output row of this chunk
   const int nsteps = min(steps_per_chunk, (OH - ych + kMH - 1) / kMH);
@@ -110,7 +113,7 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   __syncthreads();
 
   // one TMA box per array and half: rows ych + 16 hf ... + 15, 32 C (+ pad) floats from column x0; rows / columns past
-  // the image arrive as zeros.  Half hf lives in slot hf % kSlots; it is read by steps hf - 1 and hf.
+  // the image arrive as zeros.  Half hf lives in slot hf % kSlots; it is read once, by step hf - 1 (half 0: the prologue).
   auto fill = [&](int hf) {
     if (hf <= nsteps) {
       const int slot = hf & (kSlots - 1);
@@ -161,69 +164,85 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const float2 c1_2 = make_float2(c1, c1), c2_2 = make_float2(c2, c2), two2 = make_float2(2.f, 2.f), neg1 = make_float2(-1.f, -1.f);
   const int frag_off = 2 * t * RS + xsh + g * C + ch;   // this lane's element of a half: row 2t, column g of its channel
 
-  for (int s = 0; s < nsteps; ++s) {
-    if (tid == 0) fill(s + 2);
-    const int y0 = ych + kMH * s;
-    const bool edge = last_chunk && s == nsteps - 1;   // the step that also owns the rows below its 16 (squared error)
-    const int rows_left = H - y0 - 2 * t;           // input rows at and below this lane's first one
-
-    float d1[4][4][4];
+  // rows 2 t + 8 i + {0, 1}, columns g + 8 nb of half hf -> registers; their squared error (every half is loaded exactly once
+  // per chunk, the half two chunks share counts for the lower one; zero-filled rows / columns add nothing)
+  auto load_half = [&](int hf, float2 (&va)[4][2], float2 (&vb)[4][2]) {
+    const int slot = hf & (kSlots - 1);
+    mbar_wait(full0 + 8 * slot, (hf / kSlots) & 1);
+    const int so = slot * kHalf + frag_off;
 #pragma unroll
-    for (int kb = 0; kb < 2; ++kb) {
-      const int hf = s + kb, slot = hf & (kSlots - 1);
-      mbar_wait(full0 + 8 * slot, (hf / kSlots) & 1);
-      const int so = slot * kHalf + frag_off;
-      float2 va[4][2], vb[4][2];                    // [nb][i]: rows 16 kb + 2 t + 8 i + {0, 1}, column g + 8 nb
+    for (int nb = 0; nb < 4; ++nb)
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        va[nb][i] = make_float2(sa[so + (8 * i) * RS + 8 * nb * C], sa[so + (8 * i + 1) * RS + 8 * nb * C]);
+        vb[nb][i] = make_float2(sb[so + (8 * i) * RS + 8 * nb * C], sb[so + (8 * i + 1) * RS + 8 * nb * C]);
+      }
+    if (hf < nsteps || last_chunk) {
 #pragma unroll
       for (int nb = 0; nb < 4; ++nb)
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          va[nb][i] = make_float2(sa[so + (8 * i) * RS + 8 * nb * C], sa[so + (8 * i + 1) * RS + 8 * nb * C]);
-          vb[nb][i] = make_float2(sb[so + (8 * i) * RS + 8 * nb * C], sb[so + (8 * i + 1) * RS + 8 * nb * C]);
+          const float2 d = __ffma2_rn(vb[nb][i], neg1, va[nb][i]);
+          sse_nb[nb] = __ffma2_rn(d, d, sse_nb[nb]);
         }
-      // squared error over the owned input pixels: the step's own 16 rows, plus everything below them in the last step
-      if (kb == 0 && !edge) {
+    }
+  };
+  // the four map inputs of one row pair, split into fp16 hi / lo B-fragment registers
+  auto frag = [&](int m, const float2 (&va)[4][2], const float2 (&vb)[4][2], int nb, uint4& f) {
+    uint32_t bh[2], bl[2];
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
+    for (int i = 0; i < 2; ++i) {
+      float2 v;
+      if (m == 0) v = va[nb][i];
+      else if (m == 1) v = vb[nb][i];
+      else if (m == 2) v = __ffma2_rn(va[nb][i], va[nb][i], __fmul2_rn(vb[nb][i], vb[nb][i]));
+      else v = __fmul2_rn(va[nb][i], vb[nb][i]);
+      split2(v, bh[i], bl[i]);
+    }
+    f = make_uint4(bh[0], bh[1], bl[0], bl[1]);
+  };
+  auto release = [&](int hf) {                     // this warp has the half in registers
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty0 + 8 * (hf & (kSlots - 1)));
+  };
+
+  {                                                // prologue: half 0 -> stash
+    float2 va[4][2], vb[4][2];
+    load_half(0, va, vb);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const float2 d = __ffma2_rn(vb[nb][i], neg1, va[nb][i]);
-            sse_nb[nb] = __ffma2_rn(d, d, sse_nb[nb]);
-          }
-      } else if (edge) {
+    for (int m = 0; m < 4; ++m)
 #pragma unroll
-        for (int nb = 0; nb < 4; ++nb)
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            float2 d = __ffma2_rn(vb[nb][i], neg1, va[nb][i]);
-            if (16 * kb + 8 * i >= rows_left) d.x = 0.f;
-            if (16 * kb + 8 * i + 1 >= rows_left) d.y = 0.f;
-            sse_nb[nb] = __ffma2_rn(d, d, sse_nb[nb]);
-          }
+      for (int nb = 0; nb < 4; ++nb) {
+        uint4 f;
+        frag(m, va, vb, nb, f);
+        stash[(m * 4 + nb) * (32 * C)] = f;
       }
+    release(0);
+  }
+
+  for (int s = 0; s < nsteps; ++s) {
+    if (tid == 0) fill(s + 2);
+    const int y0 = ych + kMH * s;
+
+    float d1[4][4][4];
+    {
+      float2 va[4][2], vb[4][2];
+      load_half(s + 1, va, vb);
 #pragma unroll
-      for (int m = 0; m < 4; ++m) {
+      for (int m = 0; m < 4; ++m)
 #pragma unroll
         for (int nb = 0; nb < 4; ++nb) {
-          uint32_t bh[2], bl[2];
-#pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            float2 v;
-            if (m == 0) v = va[nb][i];
-            else if (m == 1) v = vb[nb][i];
-            else if (m == 2) v = __ffma2_rn(va[nb][i], va[nb][i], __fmul2_rn(vb[nb][i], vb[nb][i]));
-            else v = __fmul2_rn(va[nb][i], vb[nb][i]);
-            split2(v, bh[i], bl[i]);
-          }
-          if (kb == 0) mma16816_first(d1[m][nb], tv[kb], bh[0], bh[1]);
-          else mma16816(d1[m][nb], tv[kb], bh[0], bh[1]);
-          mma16816(d1[m][nb], tv[kb], bl[0], bl[1]);
+          uint4* st = stash + (m * 4 + nb) * (32 * C);
+          const uint4 f0 = *st;                    // k-block 0: the rows the last step (or the prologue) split
+          mma16816_first(d1[m][nb], tv[0], f0.x, f0.y);
+          mma16816(d1[m][nb], tv[0], f0.z, f0.w);
+          uint4 f1;
+          frag(m, va, vb, nb, f1);                 // k-block 1: the new half
+          mma16816(d1[m][nb], tv[1], f1.x, f1.y);
+          mma16816(d1[m][nb], tv[1], f1.z, f1.w);
+          *st = f1;
         }
-      }
-      if (kb == 0) {                                // half s is not read again by this warp
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty0 + 8 * slot);
-      }
+      release(s + 1);
     }
 
     // pass 2: the accumulators of n-blocks 2 kb2, 2 kb2 + 1 are the A fragment of k-block kb2
@@ -323,7 +342,7 @@ static int launch_mma(const float* a, const float* b, int batch, int H, int W, f
   while (spc > 2 && (long)strips * ((steps + spc - 1) / spc) * batch < target) spc >>= 1;
   dim3 grid(strips, (steps + spc - 1) / spc, batch);
   SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "psnr_ssim: grid too large");
-  const size_t smem = (size_t)2 * kSlots * 16 * Geom<C>::RS * sizeof(float);
+  const size_t smem = (size_t)2 * kSlots * 16 * Geom<C>::RS * sizeof(float) + (size_t)16 * 32 * C * sizeof(uint4);
   EncodeTiledFn encode = tc_encode_fn();
   SRB_REQUIRE(encode != nullptr, "psnr_ssim: cuTensorMapEncodeTiled is not available from the driver");
   CUtensorMap tma_, tmb_;
