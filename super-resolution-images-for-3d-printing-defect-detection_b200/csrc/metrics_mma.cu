@@ -79,7 +79,7 @@ template <> struct Geom<3> { static constexpr int RS = 100; };
 }  // namespace
 
 template <int C>
-__global__ void __launch_bounds__(32 * C, C == 3 ? 4 : 8)
+__global__ void __launch_bounds__(32 * C, C == 3 ? 4 : 12)
 psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, int H, int W,
                      int steps_per_chunk, float c1, float c2, double* __restrict__ acc /* [B][2] = {sse, ssim_sum} */) {
   constexpr int RS = Geom<C>::RS;
