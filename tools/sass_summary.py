@@ -33,7 +33,8 @@ def main():
                 kernels[cur][k] += 1
     arch = sorted(set(re.findall(r"arch = (sm_\w+)", sass)))
     print(f"# SASS summary of {os.path.relpath(LIB, ROOT)} ({', '.join(arch)}; cuobjdump -sass, instruction counts per kernel)")
-    print("# tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG / UTMASTG, cp.async -> LDGSTS; HMMA would be the legacy mma.sync path")
+    print("# tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM, cp.async.bulk.tensor -> UTMALDG / UTMASTG, cp.async -> LDGSTS; HMMA = warp-level mma.sync:\n"
+          "# none in the convolution / attention kernels; psnr_ssim_mma_kernel uses it on purpose (M = 16 banded-Toeplitz filters, DESIGN 4.5)")
     hdr = f"{'kernel':92s}" + "".join(f"{k:>12s}" for k, _ in PATTERNS)
     print(hdr)
     tot = {k: 0 for k, _ in PATTERNS}
