@@ -554,11 +554,23 @@ def config_c5(torch, peaks, reps=5):
         a = torch.rand((batch, oh, ow, 3), device="cuda", generator=g)
         b = (a + 0.05 * torch.randn(a.shape, device="cuda", generator=g)).clamp_(0, 1)
         alg = batch * oh * ow * 24
-        for name, fn in (("psnr_ssim_f32", lambda: ops.psnr_ssim(a, b)), ("psnr_f32", lambda: ops.psnr(a, b))):
+        from srb200 import _capi as capi
+        for name, fn in (("psnr_ssim_f32", lambda: ops.psnr_ssim(a, b)),
+                         ("psnr_ssim_exact_window_f32", lambda: ops.psnr_ssim(a, b, window=capi.SSIM_TF_EXACT)),
+                         ("psnr_f32", lambda: ops.psnr(a, b))):
             ms = cuda_timed(torch, fn, reps)
             row = {"op": name, "out": f"{ow}x{oh}", "batch": batch, "ms": ms, "GBps": alg / ms / 1e6,
                    "hbm_frac": alg / ms / 1e6 / peaks["hbm_gbs"], "out_MPps": batch * oh * ow / ms / 1e3}
-            if name == "psnr_ssim_f32":                           # ~600 FLOP per RGB pixel: the FP32-pipe roofline
+            if name == "psnr_ssim_f32":
+                # tensor-path kernel (mma.sync m16n8k16): 104 HMMAs of 4,096 FLOP per 352 map elements, against the HMMA issue
+                # rate measured on this pool (tools/probes/hmma_rate.cu: 540 TFLOP/s); the reference-equivalent count is
+                # ~600 FLOP per RGB pixel on the FP32 pipe
+                row["kernel"] = "psnr_ssim_mma_kernel (fp16 window summing to 1, hi/lo-split data)"
+                row["hmma_tflops"] = batch * oh * ow * 3 * (104.0 / 352.0) * 4096 / ms / 1e9
+                row["hmma_frac_of_540"] = row["hmma_tflops"] / 540.0
+                row["fp32_equivalent_tflops"] = batch * oh * ow * 600 / ms / 1e9
+            elif name == "psnr_ssim_exact_window_f32":           # CUDA-core kernel with the float32 Gaussian: the FP32-pipe roofline
+                row["kernel"] = "psnr_ssim_pair_kernel (float32 Gaussian, CUDA cores)"
                 row["fp32_tflops"] = batch * oh * ow * 600 / ms / 1e9
                 row["fp32_frac_of_74"] = row["fp32_tflops"] / 74.4
             rows.append(row)
@@ -571,8 +583,9 @@ def summarize_c5(rows):
         v = [r["hbm_frac"] for r in rows if r["op"].startswith(prefix)]
         return [round(min(v), 3), round(max(v), 3)] if v else None
     return {"bicubic_f32_hbm_frac": span("bicubic_f32"), "bicubic_u8_hbm_frac": span("bicubic_u8"),
-            "psnr_hbm_frac": span("psnr_f32"), "psnr_ssim_hbm_frac": span("psnr_ssim"),
-            "psnr_ssim_GPps": [round(r["out_MPps"] / 1e3, 1) for r in rows if r["op"] == "psnr_ssim_f32"]}
+            "psnr_hbm_frac": span("psnr_f32"), "psnr_ssim_hbm_frac": span("psnr_ssim_f32"),
+            "psnr_ssim_GPps": [round(r["out_MPps"] / 1e3, 1) for r in rows if r["op"] == "psnr_ssim_f32"],
+            "psnr_ssim_exact_window_GPps": [round(r["out_MPps"] / 1e3, 1) for r in rows if r["op"] == "psnr_ssim_exact_window_f32"]}
 
 
 # ------------------------------------------------------------------------------------------------
