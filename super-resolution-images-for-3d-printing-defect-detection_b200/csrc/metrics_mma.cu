@@ -63,6 +63,12 @@ __device__ __forceinline__ void split2(float2 v, uint32_t& hi, uint32_t& lo) {
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP alone (den >= c1 c2 > 0: no range fix-up needed)
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float tap(int d) { return (d >= 0 && d <= 10) ? c_h16[d] : 0.f; }
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
@@ -266,6 +272,7 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     }
 
     // point function: out[.][nb2][0..1] = row g, columns 8 nb2 + 2t + {0, 1}; [2..3] = row g + 8
+    const bool full_rows = y0 + kMH <= OH;          // warp-uniform
     const float rv0 = (y0 + g < OH) ? 1.f : 0.f, rv1 = (y0 + g + 8 < OH) ? 1.f : 0.f;
 #pragma unroll
     for (int nb2 = 0; nb2 < 3; ++nb2)
@@ -283,9 +290,9 @@ psnr_ssim_mma_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         const float2 cdm = __ffma2_rn(den0, neg1, es);               // (es - den0) + c2 in this order: for a == b it is
         const float2 cd = make_float2(cdm.x + c2, cdm.y + c2);        // bit-identical to cn, so SSIM(a, a) = 1 exactly
         const float2 num = __fmul2_rn(ln, cn), den = __fmul2_rn(ld, cd);
-        const float rv = hrow ? rv1 : rv0;
-        const float2 w = make_float2(colv[nb2].x * rv, colv[nb2].y * rv);
-        ssim2 = __ffma2_rn(make_float2(__fdividef(num.x, den.x), __fdividef(num.y, den.y)), w, ssim2);
+        const float rv = hrow ? rv1 : rv0;             // (0 only in the last step of the image)
+        const float2 w = full_rows ? colv[nb2] : make_float2(colv[nb2].x * rv, colv[nb2].y * rv);
+        ssim2 = __ffma2_rn(make_float2(num.x * rcp_approx(den.x), num.y * rcp_approx(den.y)), w, ssim2);
       }
   }
 
