@@ -101,7 +101,10 @@ def test_predict_chunk_schedule():
         assert all(ch[k][0] + ch[k][1] == ch[k + 1][0] for k in range(len(ch) - 1))
         assert max(m for _, m in ch) <= mb
     assert [m for _, m in DeviceModel._chunks(512, 32)][-3:] == [16, 8, 8]
+    assert [m for _, m in DeviceModel._chunks(512, 32)][:4] == [8, 8, 16, 32]      # ramped start: the read-back begins early
     assert DeviceModel._chunks(32, 32) == [(0, 32)]
+    assert [m for _, m in DeviceModel._chunks(64, 32)] == [32, 16, 8, 8]           # (too short a job for a ramp)
+    assert [m for _, m in DeviceModel._chunks(128, 32)][:3] == [8, 8, 16]
 
 
 def test_adopt_maps_keras_auto_names_in_creation_order_and_validates_shapes():
