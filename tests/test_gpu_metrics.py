@@ -72,6 +72,21 @@ def test_tensor_path_flat_and_identical_images(noise):
         assert np.allclose(s, 1.0, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(8, 1024, 1024, 3), (2, 1024, 1024, 3), (3, 700, 2048, 1)])
+def test_tensor_path_long_chunks_vs_exact_window_kernel(shape):
+    """BASELINE config 5 sizes: chunks of 16 / 8 / 4 steps per block (the small parity shapes all run 2-step chunks)."""
+    import torch
+    from srb200 import _capi as capi, ops
+    g = torch.Generator(device="cuda").manual_seed(shape[0])
+    a = torch.rand(shape, device="cuda", generator=g)
+    b = (a + 0.04 * torch.randn(shape, device="cuda", generator=g)).clamp_(0, 1)
+    p, s = ops.psnr_ssim(a, b)
+    pe, se = ops.psnr_ssim(a, b, window=capi.SSIM_TF_EXACT)
+    assert torch.allclose(p, pe, atol=1e-4) and (s - se).abs().max().item() <= 2e-5
+    mse = ((a - b) ** 2).mean(dim=(1, 2, 3))
+    assert torch.allclose(p, -10 * torch.log10(mse), atol=PSNR_TOL)
+
+
 def test_tensor_path_unaligned_rows_fall_back():
     """Rows that are not 16-byte multiples (W C % 4 != 0) or unaligned views take the CUDA-core kernel: same answers."""
     import torch
