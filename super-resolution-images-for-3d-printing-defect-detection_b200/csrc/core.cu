@@ -59,6 +59,35 @@ __global__ void maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, in
   }
 }
 
+// 16-bit activations with C % 8 == 0 (every VGG16 block): one output row per block, eight channels (16 bytes) per thread -
+// four coalesced 16-byte loads, packed max, one 16-byte store.  (The element-per-thread kernel above ran at a third of the
+// HBM rate and was 18 % of the VGG16 classifier's time, profiles/r02_vgg_launches.md.)
+template <typename T2>
+__device__ __forceinline__ uint4 max4x8(uint4 a, uint4 b, uint4 c, uint4 d) {
+  uint4 r;
+  const T2* pa = reinterpret_cast<const T2*>(&a); const T2* pb = reinterpret_cast<const T2*>(&b);
+  const T2* pc = reinterpret_cast<const T2*>(&c); const T2* pd = reinterpret_cast<const T2*>(&d);
+  T2* pr = reinterpret_cast<T2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pr[i] = __hmax2(__hmax2(pa[i], pb[i]), __hmax2(pc[i], pd[i]));
+  return r;
+}
+
+template <typename T2>
+__global__ void __launch_bounds__(256)
+maxpool2x2_vec8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int H, int W, int C8) {
+  const int OH = H / 2, OW = W / 2;
+  const int b = blockIdx.x / OH, oy = blockIdx.x % OH;
+  const uint4* r0 = x + ((size_t)b * H + 2 * oy) * W * C8;
+  const uint4* r1 = r0 + (size_t)W * C8;
+  uint4* yo = y + (size_t)blockIdx.x * OW * C8;
+  for (int j = threadIdx.x; j < OW * C8; j += blockDim.x) {
+    const int ox = j / C8, c8 = j - ox * C8;
+    const int i = 2 * ox * C8 + c8;
+    yo[j] = max4x8<T2>(__ldg(r0 + i), __ldg(r0 + i + C8), __ldg(r1 + i), __ldg(r1 + i + C8));
+  }
+}
+
 // GlobalAveragePooling2D -> Dense(hidden, relu) -> Dense(classes, softmax); one block per image.
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -254,6 +283,15 @@ extern "C" int srb_maxpool2x2_nhwc(const void* x, int dtype, int batch, int heig
   SRB_REQUIRE(batch >= 0 && height >= 2 && width >= 2 && channels > 0, "maxpool: bad geometry");
   const size_t total = (size_t)batch * (height / 2) * (width / 2) * channels;
   if (total == 0) return SRB_OK;
+  if ((dtype == SRB_F16 || dtype == SRB_BF16) && channels % 8 == 0 && (long)batch * (height / 2) < (1L << 31) &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const int rows = batch * (height / 2), threads = min(256, max(32, ((width / 2) * (channels / 8) + 31) / 32 * 32));
+    if (dtype == SRB_F16)
+      maxpool2x2_vec8_kernel<__half2><<<rows, threads, 0, stream>>>((const uint4*)x, (uint4*)y, height, width, channels / 8);
+    else
+      maxpool2x2_vec8_kernel<__nv_bfloat162><<<rows, threads, 0, stream>>>((const uint4*)x, (uint4*)y, height, width, channels / 8);
+    return launch_check("maxpool2x2_vec8_kernel");
+  }
   const int g = grid_for(total, 256);
   if (dtype == SRB_F32) maxpool2x2_kernel<float><<<g, 256, 0, stream>>>((const float*)x, (float*)y, batch, height, width, channels);
   else if (dtype == SRB_BF16) maxpool2x2_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, height, width, channels);

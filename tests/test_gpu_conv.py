@@ -260,3 +260,16 @@ def test_self_attention_tensor_core_argument_checks():
     with pytest.raises(NotImplementedError):
         ops.self_attention_core(z(1, 64, 8), z(1, 64, 8), z(1, 64, 24), tensor_cores=True)
     assert ops.self_attention_core(z(0, 64, 8), z(0, 64, 8), z(0, 64, 32), tensor_cores=True).shape == (0, 64, 32)
+
+
+@pytest.mark.parametrize("shape,dtype", [((3, 16, 16, 64), "float16"), ((2, 9, 7, 128), "float16"), ((5, 8, 8, 512), "bfloat16"),
+                                         ((2, 128, 128, 64), "float16"), ((2, 10, 6, 12), "float16"), ((2, 6, 10, 5), "float32")])
+def test_maxpool2x2_vectorised_and_generic(shape, dtype):
+    """Keras MaxPooling2D(2) (VGG16_model.py:57-83): the 16-byte kernel (16-bit, C % 8 == 0) and the generic one; exact."""
+    import torch
+    from srb200 import ops
+    g = torch.Generator(device="cuda").manual_seed(shape[1])
+    x = torch.randn(shape, device="cuda", generator=g).to(getattr(torch, dtype))
+    want = torch.nn.functional.max_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).to(x.dtype)
+    got = ops.maxpool2x2(x)
+    assert got.shape == want.shape and torch.equal(got, want)
