@@ -19,10 +19,13 @@
 // 104 per 352 map elements.  SRB_SSIM_TF_EXACT selects the CUDA-core kernels with the float32 Gaussian instead.
 //
 // A block is one warp per channel; the warps share the raw interleaved rows of their strip, which arrive by TMA (one
-// {32 C + 4 floats, 16 rows} box per array and half, zero-filled past the image) into a four-slot ring of 16-row halves
-// guarded by full / empty mbarriers: step s reads halves s and s + 1 while half s + 2 is in flight, and no block-wide
-// barrier is left in the loop.  The row stride (100 words for C = 3) makes the fragment loads (rows 2t + {0, 1, 8, 9},
-// columns g + 8 nb) conflict-free.
+// {32 C + 4 floats, 16 rows} box per array and half, zero-filled past the image) into two slots guarded by full / empty
+// mbarriers: step s reads half s + 1 while half s + 2 is in flight, and no block-wide barrier is left in the loop.  The B
+// fragments a lane builds from the newest half are the k-block 0 operands of its next step, so they are parked in a
+// lane-private shared-memory stash: every input row is squared, multiplied and split once.  The row stride (100 words for
+// C = 3) makes the fragment loads (rows 2t + {0, 1, 8, 9}, columns g + 8 nb) conflict-free; the TMA box must start on a
+// 16-byte boundary of global memory (an unaligned inner coordinate traps as "illegal instruction"), so the strip start is
+// rounded down and the fragment offset takes the remainder.
 // The squared error for PSNR is taken from the same fragment registers over a non-overlapping ownership partition.
 #include "common.cuh"
 #include "metrics_mma.cuh"
