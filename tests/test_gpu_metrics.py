@@ -87,6 +87,22 @@ def test_tensor_path_long_chunks_vs_exact_window_kernel(shape):
     assert torch.allclose(p, -10 * torch.log10(mse), atol=PSNR_TOL)
 
 
+def test_tensor_path_random_shapes_vs_exact_window_kernel():
+    """Forty random (batch, height, width, channels): ragged strips / steps / chunks must neither hang nor drift."""
+    import torch
+    from srb200 import _capi as capi, ops
+    rng = np.random.default_rng(11)
+    for k in range(40):
+        c = int(rng.choice([1, 3]))
+        shape = (int(rng.integers(1, 4)), int(rng.integers(11, 300)), int(rng.integers(27, 120)) * 4, c)
+        g = torch.Generator(device="cuda").manual_seed(k)
+        a = torch.rand(shape, device="cuda", generator=g)
+        b = (a + float(rng.choice([0.003, 0.05, 0.3])) * torch.randn(shape, device="cuda", generator=g)).clamp_(0, 1)
+        p, s = ops.psnr_ssim(a, b)
+        pe, se = ops.psnr_ssim(a, b, window=capi.SSIM_TF_EXACT)
+        assert (s - se).abs().max().item() <= 2e-5 and (p - pe).abs().max().item() <= 1e-3, shape
+
+
 def test_tensor_path_unaligned_rows_fall_back():
     """Rows that are not 16-byte multiples (W C % 4 != 0) or unaligned views take the CUDA-core kernel: same answers."""
     import torch
