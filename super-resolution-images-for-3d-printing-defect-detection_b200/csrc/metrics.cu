@@ -439,7 +439,7 @@ static int run_psnr_ssim(const float* a, const float* b, int batch, int height, 
   const float cov_norm = window == SRB_SSIM_SKIMAGE ? (float)(49.0 / 48.0) : 1.f;
   static const bool force_narrow = getenv("SRB_SSIM_NARROW") != nullptr;
   static const bool force_exact = getenv("SRB_SSIM_EXACT") != nullptr;
-  if (window == SRB_SSIM_TF && !force_exact && !force_narrow && psnr_ssim_mma_eligible(a, b, height, width, channels)) {
+  if (window == SRB_SSIM_TF && !force_exact && !force_narrow && psnr_ssim_mma_eligible(a, b, height, width, channels, max_val)) {
     // wide RGB / grey images: both filter passes on the warp-level tensor path (fp16 window summing to 1, hi/lo-split data)
     rc = run_psnr_ssim_mma(a, b, batch, height, width, channels, c1, c2, acc, stream);
   } else if (window != SRB_SSIM_SKIMAGE && OW >= 96 && !force_narrow) {   // wide images: two map pixels per thread, one warp per plane

@@ -337,8 +337,10 @@ static int upload_window16() {
   return SRB_OK;
 }
 
-bool psnr_ssim_mma_eligible(const float* a, const float* b, int height, int width, int channels) {
-  return (channels == 1 || channels == 3) && width - 10 >= 96 && height >= 11 &&
+// (max_val: a^2 + b^2 and its filtered maps go through fp16 operands - images on a [0, 255] scale would overflow 65504;
+//  the reference calls tf.image.ssim with max_val = 1.0 only, metrics.py:6-7)
+bool psnr_ssim_mma_eligible(const float* a, const float* b, int height, int width, int channels, float max_val) {
+  return (channels == 1 || channels == 3) && width - 10 >= 96 && height >= 11 && max_val <= 64.f &&
          (width * channels) % 4 == 0 && aligned16(a) && aligned16(b) && tc_encode_fn() != nullptr;   // TMA: 16-byte rows
 }
 

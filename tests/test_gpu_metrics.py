@@ -103,6 +103,18 @@ def test_tensor_path_random_shapes_vs_exact_window_kernel():
         assert (s - se).abs().max().item() <= 2e-5 and (p - pe).abs().max().item() <= 1e-3, shape
 
 
+def test_large_max_val_takes_the_float32_kernels():
+    """Images on a [0, 255] scale: a^2 + b^2 would overflow the fp16 operands of the tensor path - it must not be taken."""
+    import torch
+    from srb200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.rand((1, 64, 160, 3), device="cuda", generator=g) * 255.0
+    b = (a + 8.0 * torch.randn(a.shape, device="cuda", generator=g)).clamp_(0, 255)
+    p, s = ops.psnr_ssim(a, b, max_val=255.0)
+    p1, s1 = ops.psnr_ssim(a / 255.0, b / 255.0, max_val=1.0)
+    assert torch.isfinite(s).all() and torch.allclose(s, s1, atol=1e-4) and torch.allclose(p, p1, atol=1e-2)
+
+
 def test_tensor_path_unaligned_rows_fall_back():
     """Rows that are not 16-byte multiples (W C % 4 != 0) or unaligned views take the CUDA-core kernel: same answers."""
     import torch
