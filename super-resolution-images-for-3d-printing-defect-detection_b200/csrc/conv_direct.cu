@@ -11,24 +11,31 @@
 
 namespace srb {
 
-constexpr int kDT = 16;      // tile edge (pixels)
-constexpr int kDN = 32;      // output channels per block
-constexpr int kDCK = 8;      // input channels per slab
+// kCG = output-channel groups of four per block: 8 (32 channels, 16 x 16 pixel tile) or 1 (layers with up to four outputs such
+// as SRCNN's 5x5x32 -> 3: all 256 threads are pixel groups of a 32 x 64 tile instead of 7/8 of them multiplying zero filters)
+template <int kCG> struct DirectGeom {
+  static constexpr int kDN = 4 * kCG;                  // output channels per block
+  static constexpr int kTCG = kCG == 8 ? 2 : 8;        // eight-pixel groups per tile row
+  static constexpr int kTR = 256 / kCG / kTCG;         // tile rows
+  static constexpr int kTW = 8 * kTCG;                 // tile columns
+};
 
+template <int kDCK, int kCG>  // kDCK = input channels per slab: 8, or 3 for RGB inputs (a 9x9x3 head spent 5/8 of its FMAs on zero channels)
 __global__ void __launch_bounds__(256)
 conv_direct_kernel(const ConvParams p) {
+  constexpr int kDN = DirectGeom<kCG>::kDN, kTCG = DirectGeom<kCG>::kTCG, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
   extern __shared__ float smem[];
-  const int HH = kDT + p.kh - 1, HW = kDT + p.kw - 1;
+  const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1;
   const int HWp = HW | 1;                               // odd row pitch
   float* halo = smem;                                   // [kDCK][HH][HWp]
   float* wsm = smem + kDCK * HH * HWp;                  // [kw][kDCK][kDN]
 
   const int tid = threadIdx.x;
-  const int cg = tid & 7, pg = tid >> 3;
-  const int py = pg >> 1, x0 = (pg & 1) * 8;
+  const int cg = tid % kCG, pg = tid / kCG;
+  const int py = pg / kTCG, x0 = (pg % kTCG) * 8;
   const int n_chunks = (p.cout + kDN - 1) / kDN;
   const int b = blockIdx.z / n_chunks, cc = blockIdx.z % n_chunks;
-  const int ty0 = blockIdx.y * kDT, tx0 = blockIdx.x * kDT;
+  const int ty0 = blockIdx.y * kTR, tx0 = blockIdx.x * kTW;
   const int ph = p.kh / 2, pw = p.kw / 2;
 
   // packed fp32x2 accumulators (FFMA2, sm_100): output-channel pairs (0,1) and (2,3) of each of the 8 pixels
@@ -94,21 +101,32 @@ conv_direct_kernel(const ConvParams p) {
   }
 }
 
-int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
-  if (conv_head_eligible(p)) return conv_head_launch(p, stream);   // RGB 3x3 head layers: coalesced-store kernel
-  const int HH = kDT + p.kh - 1, HW = kDT + p.kw - 1, HWp = HW | 1;
+template <int kDCK, int kCG>
+static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
+  constexpr int kDN = DirectGeom<kCG>::kDN, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
+  const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1, HWp = HW | 1;
   const size_t smem = ((size_t)kDCK * HH * HWp + (size_t)p.kw * kDCK * kDN) * sizeof(float);
   SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);
   static size_t configured = 0;
   if (smem > configured) {
-    SRB_CUDA(cudaFuncSetAttribute(conv_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA(cudaFuncSetAttribute(conv_direct_kernel<kDCK, kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int n_chunks = (p.cout + kDN - 1) / kDN;
-  dim3 grid((p.W + kDT - 1) / kDT, (p.H + kDT - 1) / kDT, p.B * n_chunks);
+  dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTR - 1) / kTR, p.B * n_chunks);
   SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv(direct): grid too large");
-  conv_direct_kernel<<<grid, 256, smem, stream>>>(p);
+  conv_direct_kernel<kDCK, kCG><<<grid, 256, smem, stream>>>(p);
   return launch_check("conv_direct_kernel");
+}
+
+int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
+  if (conv_head_eligible(p)) return conv_head_launch(p, stream);   // RGB 3x3 head layers: coalesced-store kernel
+  if (p.cout <= 4 && p.kh * p.kw <= 49 && p.W >= 32) {             // few outputs: every thread a pixel group (32 x 64 tiles)
+    if (p.cin == 3) return conv_direct_launch_t<3, 1>(p, stream);
+    return conv_direct_launch_t<8, 1>(p, stream);
+  }
+  if (p.cin == 3) return conv_direct_launch_t<3, 8>(p, stream);
+  return conv_direct_launch_t<8, 8>(p, stream);
 }
 
 }  // namespace srb
