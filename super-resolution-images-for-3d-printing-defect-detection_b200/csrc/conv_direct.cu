@@ -20,7 +20,10 @@ template <int kCG> struct DirectGeom {
   static constexpr int kTW = 8 * kTCG;                 // tile columns
 };
 
-template <int kDCK, int kCG>  // kDCK = input channels per slab: 8, or 3 for RGB inputs (a 9x9x3 head spent 5/8 of its FMAs on zero channels)
+// kDCK = input channels per slab: 8, or 3 for RGB inputs (a 9x9x3 head spent 5/8 of its FMAs on zero channels).
+// kKW = filter width when it is 1 / 3 / 5 / 9 (0: any): a thread then reads the 8 + kKW - 1 inputs of a halo row once into
+// registers and slides over the horizontal taps, instead of eight shared-memory loads per tap (the loop was LSU-bound).
+template <int kDCK, int kCG, int kKW>
 __global__ void __launch_bounds__(256)
 conv_direct_kernel(const ConvParams p) {
   constexpr int kDN = DirectGeom<kCG>::kDN, kTCG = DirectGeom<kCG>::kTCG, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
@@ -69,18 +72,39 @@ conv_direct_kernel(const ConvParams p) {
         wsm[idx] = v;
       }
       __syncthreads();
-      for (int dx = 0; dx < p.kw; ++dx) {
+      if (kKW > 0) {
 #pragma unroll
         for (int c = 0; c < kDCK; ++c) {
-          const float4 w4 = *reinterpret_cast<const float4*>(wsm + (dx * kDCK + c) * kDN + cg * 4);
-          const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
-          const float* hrow = halo + (c * HH + py + dy) * HWp + x0 + dx;
+          const float* hrow = halo + (c * HH + py + dy) * HWp + x0;
+          float win[8 + (kKW > 0 ? kKW : 1) - 1];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float a = hrow[i];
-            const float2 aa = make_float2(a, a);
-            acc01[i] = __ffma2_rn(aa, w01, acc01[i]);
-            acc23[i] = __ffma2_rn(aa, w23, acc23[i]);
+          for (int i = 0; i < 8 + kKW - 1; ++i) win[i] = hrow[i];
+#pragma unroll
+          for (int dx = 0; dx < kKW; ++dx) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wsm + (dx * kDCK + c) * kDN + cg * 4);
+            const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 aa = make_float2(win[i + dx], win[i + dx]);
+              acc01[i] = __ffma2_rn(aa, w01, acc01[i]);
+              acc23[i] = __ffma2_rn(aa, w23, acc23[i]);
+            }
+          }
+        }
+      } else {
+        for (int dx = 0; dx < p.kw; ++dx) {
+#pragma unroll
+          for (int c = 0; c < kDCK; ++c) {
+            const float4 w4 = *reinterpret_cast<const float4*>(wsm + (dx * kDCK + c) * kDN + cg * 4);
+            const float2 w01 = make_float2(w4.x, w4.y), w23 = make_float2(w4.z, w4.w);
+            const float* hrow = halo + (c * HH + py + dy) * HWp + x0 + dx;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float a = hrow[i];
+              const float2 aa = make_float2(a, a);
+              acc01[i] = __ffma2_rn(aa, w01, acc01[i]);
+              acc23[i] = __ffma2_rn(aa, w23, acc23[i]);
+            }
           }
         }
       }
@@ -101,7 +125,7 @@ conv_direct_kernel(const ConvParams p) {
   }
 }
 
-template <int kDCK, int kCG>
+template <int kDCK, int kCG, int kKW>
 static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   constexpr int kDN = DirectGeom<kCG>::kDN, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
   const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1, HWp = HW | 1;
@@ -109,24 +133,35 @@ static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);
   static size_t configured = 0;
   if (smem > configured) {
-    SRB_CUDA(cudaFuncSetAttribute(conv_direct_kernel<kDCK, kCG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SRB_CUDA(cudaFuncSetAttribute(conv_direct_kernel<kDCK, kCG, kKW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const int n_chunks = (p.cout + kDN - 1) / kDN;
   dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTR - 1) / kTR, p.B * n_chunks);
   SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv(direct): grid too large");
-  conv_direct_kernel<kDCK, kCG><<<grid, 256, smem, stream>>>(p);
+  conv_direct_kernel<kDCK, kCG, kKW><<<grid, 256, smem, stream>>>(p);
   return launch_check("conv_direct_kernel");
+}
+
+template <int kDCK, int kCG>
+static int conv_direct_launch_kw(const ConvParams& p, cudaStream_t stream) {
+  switch (p.kw) {
+    case 1: return conv_direct_launch_t<kDCK, kCG, 1>(p, stream);
+    case 3: return conv_direct_launch_t<kDCK, kCG, 3>(p, stream);
+    case 5: return conv_direct_launch_t<kDCK, kCG, 5>(p, stream);
+    case 9: return conv_direct_launch_t<kDCK, kCG, 9>(p, stream);
+    default: return conv_direct_launch_t<kDCK, kCG, 0>(p, stream);
+  }
 }
 
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
   if (conv_head_eligible(p)) return conv_head_launch(p, stream);   // RGB 3x3 head layers: coalesced-store kernel
   if (p.cout <= 4 && p.kh * p.kw <= 49 && p.W >= 32) {             // few outputs: every thread a pixel group (32 x 64 tiles)
-    if (p.cin == 3) return conv_direct_launch_t<3, 1>(p, stream);
-    return conv_direct_launch_t<8, 1>(p, stream);
+    if (p.cin == 3) return conv_direct_launch_kw<3, 1>(p, stream);
+    return conv_direct_launch_kw<8, 1>(p, stream);
   }
-  if (p.cin == 3) return conv_direct_launch_t<3, 8>(p, stream);
-  return conv_direct_launch_t<8, 8>(p, stream);
+  if (p.cin == 3) return conv_direct_launch_kw<3, 8>(p, stream);
+  return conv_direct_launch_kw<8, 8>(p, stream);
 }
 
 }  // namespace srb
