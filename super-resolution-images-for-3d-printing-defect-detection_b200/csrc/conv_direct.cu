@@ -49,15 +49,33 @@ conv_direct_kernel(const ConvParams p) {
   const size_t x_img = (size_t)b * p.H * p.W;
   for (int c0 = 0; c0 < p.cin; c0 += kDCK) {
     __syncthreads();
-    for (int idx = tid; idx < kDCK * HH * HW; idx += 256) {
-      const int c = idx % kDCK;
-      const int hp = idx / kDCK;
-      const int hx = hp % HW, hy = hp / HW;
-      const int gy = ty0 + hy - ph, gx = tx0 + hx - pw;
-      float v = 0.f;
-      if (c0 + c < p.cin && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
-        v = load_elem(p.x, p.x_dtype, (x_img + (size_t)gy * p.W + gx) * p.x_cstride + p.x_coffset + c0 + c);
-      halo[(c * HH + hy) * HWp + hx] = v;
+    if (256 % kDCK == 0) {
+      // a thread keeps its channel and walks the halo positions in steps of 256 / kDCK: no division per element
+      constexpr int kStep = 256 / (256 % kDCK == 0 ? kDCK : 1);
+      const int c = tid % kDCK;
+      int hp = tid / kDCK;
+      int hy = hp / HW, hx = hp - hy * HW;
+      const bool c_ok = c0 + c < p.cin;
+      for (; hp < HH * HW; hp += kStep) {
+        const int gy = ty0 + hy - ph, gx = tx0 + hx - pw;
+        float v = 0.f;
+        if (c_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+          v = load_elem(p.x, p.x_dtype, (x_img + (size_t)gy * p.W + gx) * p.x_cstride + p.x_coffset + c0 + c);
+        halo[(c * HH + hy) * HWp + hx] = v;
+        hx += kStep;
+        while (hx >= HW) { hx -= HW; ++hy; }
+      }
+    } else {
+      for (int idx = tid; idx < kDCK * HH * HW; idx += 256) {
+        const int c = idx % kDCK;
+        const int hp = idx / kDCK;
+        const int hx = hp % HW, hy = hp / HW;
+        const int gy = ty0 + hy - ph, gx = tx0 + hx - pw;
+        float v = 0.f;
+        if (c0 + c < p.cin && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+          v = load_elem(p.x, p.x_dtype, (x_img + (size_t)gy * p.W + gx) * p.x_cstride + p.x_coffset + c0 + c);
+        halo[(c * HH + hy) * HWp + hx] = v;
+      }
     }
     for (int dy = 0; dy < p.kh; ++dy) {
       __syncthreads();
@@ -113,10 +131,24 @@ conv_direct_kernel(const ConvParams p) {
 
   const int oy = ty0 + py;
   if (oy >= p.H) return;
+  // float32 outputs without depth_to_space / second output: the thread's four channels of a pixel leave as one 16-byte store
+  const int co0 = cc * kDN + cg * 4;
+  const bool vec4 = p.d2s == 1 && !p.y2 && p.y_dtype == SRB_F32 && ((p.y_cstride | p.y_coffset) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && co0 + 3 < p.cout;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int ox = tx0 + x0 + i;
     if (ox >= p.W) continue;
+    if (vec4) {
+      const size_t out_pix = ((size_t)b * p.H + oy) * p.W + ox;
+      float4 v;
+      v.x = epilogue_value(p, acc01[i].x, co0, co0, out_pix);
+      v.y = epilogue_value(p, acc01[i].y, co0 + 1, co0 + 1, out_pix);
+      v.z = epilogue_value(p, acc23[i].x, co0 + 2, co0 + 2, out_pix);
+      v.w = epilogue_value(p, acc23[i].y, co0 + 3, co0 + 3, out_pix);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_pix * p.y_cstride + p.y_coffset + co0) = v;
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = cc * kDN + cg * 4 + j;
@@ -161,6 +193,8 @@ int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
     return conv_direct_launch_kw<8, 1>(p, stream);
   }
   if (p.cin == 3) return conv_direct_launch_kw<3, 8>(p, stream);
+  if (p.kh == 1 && p.kw == 1 && p.cin >= 32)                       // 1x1 layers: 32-channel slabs (a slab of 8 is three barriers
+    return conv_direct_launch_t<32, 8, 1>(p, stream);              // and a staging pass per 128 packed FMAs of a thread)
   return conv_direct_launch_kw<8, 8>(p, stream);
 }
 
