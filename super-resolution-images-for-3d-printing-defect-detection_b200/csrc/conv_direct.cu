@@ -135,6 +135,22 @@ conv_direct_kernel(const ConvParams p) {
   const int co0 = cc * kDN + cg * 4;
   const bool vec4 = p.d2s == 1 && !p.y2 && p.y_dtype == SRB_F32 && ((p.y_cstride | p.y_coffset) & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && co0 + 3 < p.cout;
+  // RGB float32 outputs (cout = 3, packed NHWC): the thread's eight pixels are 24 consecutive floats = six 16-byte stores
+  if (kCG == 1 && p.cout == 3 && p.d2s == 1 && !p.y2 && p.y_dtype == SRB_F32 && p.y_cstride == 3 && p.y_coffset == 0 &&
+      (p.W & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && tx0 + x0 + 8 <= p.W) {
+    const size_t pix0 = ((size_t)b * p.H + oy) * p.W + tx0 + x0;
+    float v[24];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[3 * i + 0] = epilogue_value(p, acc01[i].x, 0, 0, pix0 + i);
+      v[3 * i + 1] = epilogue_value(p, acc01[i].y, 1, 1, pix0 + i);
+      v[3 * i + 2] = epilogue_value(p, acc23[i].x, 2, 2, pix0 + i);
+    }
+    float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + pix0 * 3);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int ox = tx0 + x0 + i;
