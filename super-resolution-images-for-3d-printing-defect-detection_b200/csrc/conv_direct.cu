@@ -133,7 +133,8 @@ conv_direct_kernel(const ConvParams p) {
   if (oy >= p.H) return;
   // float32 outputs without depth_to_space / second output: the thread's four channels of a pixel leave as one 16-byte store
   const int co0 = cc * kDN + cg * 4;
-  const bool vec4 = p.d2s == 1 && !p.y2 && p.y_dtype == SRB_F32 && ((p.y_cstride | p.y_coffset) & 3) == 0 &&
+  // (with depth_to_space the four channels stay together when the post-shuffle channel count is a multiple of four)
+  const bool vec4 = (p.d2s == 1 || (p.c_post & 3) == 0) && !p.y2 && p.y_dtype == SRB_F32 && ((p.y_cstride | p.y_coffset) & 3) == 0 &&
                     (reinterpret_cast<uintptr_t>(p.y) & 15) == 0 && co0 + 3 < p.cout;
   // RGB float32 outputs (cout = 3, packed NHWC): the thread's eight pixels are 24 consecutive floats = six 16-byte stores
   if (kCG == 1 && p.cout == 3 && p.d2s == 1 && !p.y2 && p.y_dtype == SRB_F32 && p.y_cstride == 3 && p.y_coffset == 0 &&
@@ -156,13 +157,14 @@ conv_direct_kernel(const ConvParams p) {
     const int ox = tx0 + x0 + i;
     if (ox >= p.W) continue;
     if (vec4) {
-      const size_t out_pix = ((size_t)b * p.H + oy) * p.W + ox;
+      size_t out_pix; int c_out;
+      d2s_map(p, b, oy, ox, co0, out_pix, c_out);
       float4 v;
-      v.x = epilogue_value(p, acc01[i].x, co0, co0, out_pix);
-      v.y = epilogue_value(p, acc01[i].y, co0 + 1, co0 + 1, out_pix);
-      v.z = epilogue_value(p, acc23[i].x, co0 + 2, co0 + 2, out_pix);
-      v.w = epilogue_value(p, acc23[i].y, co0 + 3, co0 + 3, out_pix);
-      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_pix * p.y_cstride + p.y_coffset + co0) = v;
+      v.x = epilogue_value(p, acc01[i].x, co0, c_out, out_pix);
+      v.y = epilogue_value(p, acc01[i].y, co0 + 1, c_out + 1, out_pix);
+      v.z = epilogue_value(p, acc23[i].x, co0 + 2, c_out + 2, out_pix);
+      v.w = epilogue_value(p, acc23[i].y, co0 + 3, c_out + 3, out_pix);
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.y) + out_pix * p.y_cstride + p.y_coffset + c_out) = v;
       continue;
     }
 #pragma unroll
