@@ -13,9 +13,10 @@ namespace srb {
 
 // kCG = output-channel groups of four per block: 8 (32 channels, 16 x 16 pixel tile) or 1 (layers with up to four outputs such
 // as SRCNN's 5x5x32 -> 3: all 256 threads are pixel groups of a 32 x 64 tile instead of 7/8 of them multiplying zero filters)
+// (kCG = 2: up to eight outputs - the growth convs of ESRGAN's dense blocks in the float32 mode - on 32 x 32 tiles)
 template <int kCG> struct DirectGeom {
   static constexpr int kDN = 4 * kCG;                  // output channels per block
-  static constexpr int kTCG = kCG == 8 ? 2 : 8;        // eight-pixel groups per tile row
+  static constexpr int kTCG = kCG == 8 ? 2 : kCG == 2 ? 4 : 8;   // eight-pixel groups per tile row
   static constexpr int kTR = 256 / kCG / kTCG;         // tile rows
   static constexpr int kTW = 8 * kTCG;                 // tile columns
 };
@@ -193,27 +194,30 @@ static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   return launch_check("conv_direct_kernel");
 }
 
-template <int kDCK, int kCG>
-static int conv_direct_launch_kw(const ConvParams& p, cudaStream_t stream) {
-  switch (p.kw) {
-    case 1: return conv_direct_launch_t<kDCK, kCG, 1>(p, stream);
-    case 3: return conv_direct_launch_t<kDCK, kCG, 3>(p, stream);
-    case 5: return conv_direct_launch_t<kDCK, kCG, 5>(p, stream);
-    case 9: return conv_direct_launch_t<kDCK, kCG, 9>(p, stream);
-    default: return conv_direct_launch_t<kDCK, kCG, 0>(p, stream);
-  }
-}
-
+// Instantiated (slab, channel groups, filter width) combinations - the ones the reference's networks reach in the float32 mode;
+// every other filter width runs the any-width form of its geometry.
 int conv_direct_launch(const ConvParams& p, cudaStream_t stream) {
   if (conv_head_eligible(p)) return conv_head_launch(p, stream);   // RGB 3x3 head layers: coalesced-store kernel
-  if (p.cout <= 4 && p.kh * p.kw <= 49 && p.W >= 32) {             // few outputs: every thread a pixel group (32 x 64 tiles)
-    if (p.cin == 3) return conv_direct_launch_kw<3, 1>(p, stream);
-    return conv_direct_launch_kw<8, 1>(p, stream);
+  if (p.cout <= 4 && p.kh * p.kw <= 81 && p.W >= 32) {             // few outputs: every thread a pixel group (32 x 64 tiles)
+    if (p.cin == 3) return conv_direct_launch_t<3, 1, 0>(p, stream);
+    if (p.kw == 3) return conv_direct_launch_t<8, 1, 3>(p, stream);           // EDSR / ESRGAN RGB tails
+    if (p.kw == 5) return conv_direct_launch_t<8, 1, 5>(p, stream);           // SRCNN 5x5x32 -> 3
+    if (p.kw == 9) return conv_direct_launch_t<8, 1, 9>(p, stream);           // SRResNet 9x9x64 -> 3 tail
+    return conv_direct_launch_t<8, 1, 0>(p, stream);
   }
-  if (p.cin == 3) return conv_direct_launch_kw<3, 8>(p, stream);
+  if (p.cout <= 8 && p.cin != 3 && p.kh * p.kw <= 25) {            // up to eight outputs: 32 x 32 tiles, two channel groups
+    if (p.kw == 3) return conv_direct_launch_t<8, 2, 3>(p, stream);           // ESRGAN growth convs
+    return conv_direct_launch_t<8, 2, 0>(p, stream);
+  }
+  if (p.cin == 3) {
+    if (p.kw == 9) return conv_direct_launch_t<3, 8, 9>(p, stream);           // SRCNN / SRResNet 9x9 heads
+    if (p.kw == 5) return conv_direct_launch_t<3, 8, 5>(p, stream);           // ESPCN 5x5 head
+    return conv_direct_launch_t<3, 8, 0>(p, stream);
+  }
   if (p.kh == 1 && p.kw == 1 && p.cin >= 32)                       // 1x1 layers: 32-channel slabs (a slab of 8 is three barriers
     return conv_direct_launch_t<32, 8, 1>(p, stream);              // and a staging pass per 128 packed FMAs of a thread)
-  return conv_direct_launch_kw<8, 8>(p, stream);
+  if (p.kw == 3) return conv_direct_launch_t<8, 8, 3>(p, stream);
+  return conv_direct_launch_t<8, 8, 0>(p, stream);
 }
 
 }  // namespace srb
