@@ -32,7 +32,7 @@ conv_direct_kernel(const ConvParams p) {
   const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1;
   const int HWp = HW | 1;                               // odd row pitch
   float* halo = smem;                                   // [kDCK][HH][HWp]
-  float* wsm = smem + kDCK * HH * HWp;                  // [kw][kDCK][kDN]
+  float* wsm = smem + ((kDCK * HH * HWp + 3) & ~3);     // [kw][kDCK][kDN], 16-byte aligned (the halo of a 3-channel slab need not be)
 
   const int tid = threadIdx.x;
   const int cg = tid % kCG, pg = tid / kCG;
@@ -180,7 +180,7 @@ template <int kDCK, int kCG, int kKW>
 static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   constexpr int kDN = DirectGeom<kCG>::kDN, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
   const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1, HWp = HW | 1;
-  const size_t smem = ((size_t)kDCK * HH * HWp + (size_t)p.kw * kDCK * kDN) * sizeof(float);
+  const size_t smem = ((((size_t)kDCK * HH * HWp + 3) & ~(size_t)3) + (size_t)p.kw * kDCK * kDN) * sizeof(float);
   SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);
   static size_t configured = 0;
   if (smem > configured) {

@@ -59,6 +59,19 @@ LAYER_CASES = [
     (1, 14, 9, 3, 64, 64, dict(alpha=0.04, res1=True, beta1=0.2, res2=True)),   # RRDB tail, two residuals
     (1, 8, 8, 3, 64, 3, dict(act="tanh")),                         # ESRGAN final conv
     (1, 16, 16, 3, 64, 256, dict(act="leaky_relu", slope=0.2, d2s=2)),
+    # geometries of the CUDA-core engine added in round 2 (32 x 64 few-output tiles, 32 x 32 eight-output tiles, 32-channel slabs
+    # for 1x1 layers, 16-byte stores), each with ragged tile edges
+    (2, 37, 70, 5, 32, 3, dict()),                                 # few outputs, width not a multiple of 4 (scalar stores)
+    (2, 37, 72, 5, 32, 3, dict(clip=True)),                        # few outputs, RGB vector stores + ragged last group
+    (1, 40, 64, 9, 64, 3, dict()),                                 # SRResNet 9x9 tail on the few-output geometry
+    (1, 33, 36, 3, 3, 3, dict()),                                  # RGB -> RGB (3-channel slab, few outputs)
+    (2, 24, 24, 3, 88, 8, dict(act="relu")),                       # ESRGAN growth conv, 24 x 24 patch on a 32 x 32 tile
+    (1, 45, 50, 5, 16, 6, dict()),                                 # eight-output geometry, any-width filter form
+    (1, 19, 45, 1, 96, 32, dict(act="relu")),                      # 1x1 layer on 32-channel slabs
+    (1, 21, 23, 1, 40, 32, dict()),                                # 1x1, cin not a multiple of the slab
+    (1, 33, 33, 9, 3, 96, dict(act="relu")),                       # 9x9 RGB head, register window
+    (1, 18, 20, 7, 8, 32, dict()),                                 # any-width filter form (7x7)
+    (1, 26, 18, 3, 64, 256, dict(d2s=2, alpha=0.5)),               # 16-byte stores under depth_to_space
 ]
 
 
