@@ -234,7 +234,7 @@ class DeviceModel:
     def _chunks(n, mb):
         """(start, size) pieces of n images: micro-batches of ``mb``, with the last one cut into a half and two quarters -
         only the final piece's device->host copy cannot hide behind later kernels, so it is kept small - and, when the
-        read-back is the longer leg (four micro-batches or more), the first one cut into two quarters and a half, so that the
+        read-back is the longer leg (two micro-batches or more), the first one cut into two quarters and a half, so that the
         device->host link starts after a quarter of a micro-batch's kernels instead of a whole one."""
         sizes = [mb] * (n // mb) + ([n % mb] if n % mb else [])
         last = sizes.pop()
@@ -243,7 +243,7 @@ class DeviceModel:
             sizes += [h, q, last - h - q]
         else:
             sizes.append(last)
-        if n >= 4 * mb and mb >= 16:
+        if n >= 2 * mb and mb >= 16:
             q = mb // 4
             sizes = [q, q, mb - 2 * q] + sizes[1:]
         out, i = [], 0

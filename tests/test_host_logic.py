@@ -103,7 +103,8 @@ def test_predict_chunk_schedule():
     assert [m for _, m in DeviceModel._chunks(512, 32)][-3:] == [16, 8, 8]
     assert [m for _, m in DeviceModel._chunks(512, 32)][:4] == [8, 8, 16, 32]      # ramped start: the read-back begins early
     assert DeviceModel._chunks(32, 32) == [(0, 32)]
-    assert [m for _, m in DeviceModel._chunks(64, 32)] == [32, 16, 8, 8]           # (too short a job for a ramp)
+    assert [m for _, m in DeviceModel._chunks(64, 32)] == [8, 8, 16, 16, 8, 8]
+    assert [m for _, m in DeviceModel._chunks(48, 32)] == [32, 8, 4, 4]            # (too short a job for a ramp)
     assert [m for _, m in DeviceModel._chunks(128, 32)][:3] == [8, 8, 16]
 
 
