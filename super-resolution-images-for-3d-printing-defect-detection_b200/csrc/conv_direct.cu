@@ -14,6 +14,12 @@ namespace srb {
 // kCG = output-channel groups of four per block: 8 (32 channels, 16 x 16 pixel tile) or 1 (layers with up to four outputs such
 // as SRCNN's 5x5x32 -> 3: all 256 threads are pixel groups of a 32 x 64 tile instead of 7/8 of them multiplying zero filters)
 // (kCG = 2: up to eight outputs - the growth convs of ESRGAN's dense blocks in the float32 mode - on 32 x 32 tiles)
+// the element-wise epilogue, out of line: it is the fallback of the 16-byte stores below, and inlining its 32 copies made the
+// 9x9 kernel 16.8k instructions long (10 % of its stall samples were instruction fetches)
+static __device__ __noinline__ void epilogue_store_elem(const ConvParams& p, int b, int y, int x, int co, float acc) {
+  epilogue_store(p, b, y, x, co, acc);
+}
+
 template <int kCG> struct DirectGeom {
   static constexpr int kDN = 4 * kCG;                  // output channels per block
   static constexpr int kTCG = kCG == 8 ? 2 : kCG == 2 ? 4 : 8;   // eight-pixel groups per tile row
@@ -171,7 +177,7 @@ conv_direct_kernel(const ConvParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int co = cc * kDN + cg * 4 + j;
-      if (co < p.cout) epilogue_store(p, b, oy, ox, co, j == 0 ? acc01[i].x : j == 1 ? acc01[i].y : j == 2 ? acc23[i].x : acc23[i].y);
+      if (co < p.cout) epilogue_store_elem(p, b, oy, ox, co, j == 0 ? acc01[i].x : j == 1 ? acc01[i].y : j == 2 ? acc23[i].x : acc23[i].y);
     }
   }
 }
