@@ -54,9 +54,30 @@ conv_direct_kernel(const ConvParams p) {
   for (int i = 0; i < 8; ++i) acc01[i] = acc23[i] = make_float2(0.f, 0.f);
 
   const size_t x_img = (size_t)b * p.H * p.W;
+  const bool vec_in = p.x_dtype == SRB_F32 && ((p.x_cstride | p.x_coffset | p.cin) & 3) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.x) & 15) == 0;
   for (int c0 = 0; c0 < p.cin; c0 += kDCK) {
     __syncthreads();
-    if (256 % kDCK == 0) {
+    if (kDCK % 4 == 0 && vec_in) {
+      // float32 NHWC inputs with 16-byte channel groups: a thread keeps four channels and walks the halo positions - one
+      // 16-byte load and four plane stores per position (a quarter of the loads, bounds checks and address arithmetic)
+      constexpr int kG = (kDCK % 4 == 0 ? kDCK : 4) / 4, kStepV = 256 / kG;
+      const int g4 = (tid % kG) * 4;
+      int hp = tid / kG;
+      int hy = hp / HW, hx = hp - hy * HW;
+      const bool g_ok = c0 + g4 < p.cin;              // (cin % 4 == 0: a group is valid as a whole)
+      const float* xf = reinterpret_cast<const float*>(p.x);
+      for (; hp < HH * HW; hp += kStepV) {
+        const int gy = ty0 + hy - ph, gx = tx0 + hx - pw;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (g_ok && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W)
+          v = __ldg(reinterpret_cast<const float4*>(xf + (x_img + (size_t)gy * p.W + gx) * p.x_cstride + p.x_coffset + c0 + g4));
+        float* hd = halo + (g4 * HH + hy) * HWp + hx;
+        hd[0] = v.x; hd[HH * HWp] = v.y; hd[2 * HH * HWp] = v.z; hd[3 * HH * HWp] = v.w;
+        hx += kStepV;
+        while (hx >= HW) { hx -= HW; ++hy; }
+      }
+    } else if (256 % kDCK == 0) {
       // a thread keeps its channel and walks the halo positions in steps of 256 / kDCK: no division per element
       constexpr int kStep = 256 / (256 % kDCK == 0 ? kDCK : 1);
       const int c = tid % kDCK;
