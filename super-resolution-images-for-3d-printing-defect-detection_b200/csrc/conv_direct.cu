@@ -32,13 +32,13 @@ template <int kCG> struct DirectGeom {
 // registers and slides over the horizontal taps, instead of eight shared-memory loads per tap (the loop was LSU-bound).
 template <int kDCK, int kCG, int kKW>
 __global__ void __launch_bounds__(256)
-conv_direct_kernel(const ConvParams p) {
+conv_direct_kernel(const ConvParams p, const int all_rows /* every filter row of a slab staged at once */) {
   constexpr int kDN = DirectGeom<kCG>::kDN, kTCG = DirectGeom<kCG>::kTCG, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
   extern __shared__ float smem[];
   const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1;
   const int HWp = HW | 1;                               // odd row pitch
   float* halo = smem;                                   // [kDCK][HH][HWp]
-  float* wsm = smem + ((kDCK * HH * HWp + 3) & ~3);     // [kw][kDCK][kDN], 16-byte aligned (the halo of a 3-channel slab need not be)
+  float* wsm_base = smem + ((kDCK * HH * HWp + 3) & ~3);   // [kh or 1][kw][kDCK][kDN], 16-byte aligned (the halo of a 3-channel slab need not be)
 
   const int tid = threadIdx.x;
   const int cg = tid % kCG, pg = tid / kCG;
@@ -105,19 +105,36 @@ conv_direct_kernel(const ConvParams p) {
         halo[(c * HH + hy) * HWp + hx] = v;
       }
     }
-    for (int dy = 0; dy < p.kh; ++dy) {
-      __syncthreads();
-      for (int idx = tid; idx < p.kw * kDCK * kDN; idx += 256) {
+    const int row_words = p.kw * kDCK * kDN;
+    if (all_rows) {                       // small filters: one staging pass and one barrier per slab instead of one per row
+      for (int idx = tid; idx < p.kh * row_words; idx += 256) {
         const int co = idx % kDN;
         const int c = (idx / kDN) % kDCK;
-        const int dx = idx / (kDN * kDCK);
+        const int tap = idx / (kDN * kDCK);          // dy * kw + dx
         float v = 0.f;
         const int gco = cc * kDN + co;
         if (c0 + c < p.cin && gco < p.w_cout_pad)
-          v = __ldg(p.w_hwio + ((size_t)(dy * p.kw + dx) * p.cin + c0 + c) * p.w_cout_pad + gco);
-        wsm[idx] = v;
+          v = __ldg(p.w_hwio + ((size_t)tap * p.cin + c0 + c) * p.w_cout_pad + gco);
+        wsm_base[idx] = v;
       }
       __syncthreads();
+    }
+    for (int dy = 0; dy < p.kh; ++dy) {
+      const float* wsm = all_rows ? wsm_base + dy * row_words : wsm_base;
+      if (!all_rows) {
+        __syncthreads();
+        for (int idx = tid; idx < row_words; idx += 256) {
+          const int co = idx % kDN;
+          const int c = (idx / kDN) % kDCK;
+          const int dx = idx / (kDN * kDCK);
+          float v = 0.f;
+          const int gco = cc * kDN + co;
+          if (c0 + c < p.cin && gco < p.w_cout_pad)
+            v = __ldg(p.w_hwio + ((size_t)(dy * p.kw + dx) * p.cin + c0 + c) * p.w_cout_pad + gco);
+          wsm_base[idx] = v;
+        }
+        __syncthreads();
+      }
       if (kKW > 0) {
 #pragma unroll
         for (int c = 0; c < kDCK; ++c) {
@@ -207,7 +224,9 @@ template <int kDCK, int kCG, int kKW>
 static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   constexpr int kDN = DirectGeom<kCG>::kDN, kTR = DirectGeom<kCG>::kTR, kTW = DirectGeom<kCG>::kTW;
   const int HH = kTR + p.kh - 1, HW = kTW + p.kw - 1, HWp = HW | 1;
-  const size_t smem = ((((size_t)kDCK * HH * HWp + 3) & ~(size_t)3) + (size_t)p.kw * kDCK * kDN) * sizeof(float);
+  const size_t halo_words = ((size_t)kDCK * HH * HWp + 3) & ~(size_t)3, row_words = (size_t)p.kw * kDCK * kDN;
+  const int all_rows = (halo_words + p.kh * row_words) * sizeof(float) <= 64 * 1024;
+  const size_t smem = (halo_words + (all_rows ? p.kh : 1) * row_words) * sizeof(float);
   SRB_REQUIRE(smem <= 200 * 1024, "conv(direct): kernel %dx%d too large for the shared-memory halo", p.kh, p.kw);
   static size_t configured = 0;
   if (smem > configured) {
@@ -217,7 +236,7 @@ static int conv_direct_launch_t(const ConvParams& p, cudaStream_t stream) {
   const int n_chunks = (p.cout + kDN - 1) / kDN;
   dim3 grid((p.W + kTW - 1) / kTW, (p.H + kTR - 1) / kTR, p.B * n_chunks);
   SRB_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "conv(direct): grid too large");
-  conv_direct_kernel<kDCK, kCG, kKW><<<grid, 256, smem, stream>>>(p);
+  conv_direct_kernel<kDCK, kCG, kKW><<<grid, 256, smem, stream>>>(p, all_rows);
   return launch_check("conv_direct_kernel");
 }
 
