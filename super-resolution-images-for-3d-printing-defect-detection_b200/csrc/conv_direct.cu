@@ -1,26 +1,30 @@
 // CUDA-core convolution engine (Keras Conv2D padding="same", stride 1) - the general path.
 //
 // Covers every shape the tcgen05 engine does not (Cin = 3 head layers, odd channel counts, fp32
-// mode with <= 1e-3 parity) with exact fp32 FMA accumulation.  Register-tiled implicit GEMM:
-// a block owns a 16 x 16 pixel tile x 32 output channels; a thread owns 8 pixels along x times 4
-// output channels.  The input halo is staged per 8-channel slab as [c][y][x] in shared memory, the
-// filter row (kw taps x 8 channels x 32 couts) alongside it.  The epilogue is the same fused
-// bias / activation / scaled-residual / clip / depth_to_space store as the tensor-core engine.
+// mode with <= 1e-3 parity) with exact fp32 FMA accumulation (packed FFMA2).  Register-tiled implicit GEMM: a thread owns
+// 8 pixels along x times 4 output channels; a block of 256 threads owns, depending on the layer's output count,
+//   kCG = 8: 16 x 16 pixels x 32 output channels (the general case),
+//   kCG = 2: 32 x 32 pixels x  8 output channels (growth convs of ESRGAN's dense blocks),
+//   kCG = 1: 32 x 64 pixels x  4 output channels (RGB tails such as SRCNN's 5x5x32 -> 3: every thread a pixel group
+//            instead of 7/8 of them multiplying zero filters).
+// The input halo is staged per slab of kDCK channels (8; 3 for RGB inputs; 32 for 1x1 layers) as [c][y][x] in shared memory
+// - with one 16-byte load per four channels when the input is float32 NHWC - and the filter rows (all of them at once when
+// they fit 64 KB, else one row per pass) alongside it.  For 1 / 3 / 5 / 9-wide filters a thread reads the 8 + kw - 1 inputs of
+// a halo row into registers once and slides over the taps.  The epilogue is the same fused bias / activation / scaled-
+// residual / clip / depth_to_space as the tensor-core engine; float32 outputs leave as 16-byte stores (four channels of a
+// pixel, or eight RGB pixels as six stores), everything else through the element-wise form.
 #include "common.cuh"
 #include "conv_common.cuh"
 
 namespace srb {
 
-// kCG = output-channel groups of four per block: 8 (32 channels, 16 x 16 pixel tile) or 1 (layers with up to four outputs such
-// as SRCNN's 5x5x32 -> 3: all 256 threads are pixel groups of a 32 x 64 tile instead of 7/8 of them multiplying zero filters)
-// (kCG = 2: up to eight outputs - the growth convs of ESRGAN's dense blocks in the float32 mode - on 32 x 32 tiles)
-// the element-wise epilogue, out of line: it is the fallback of the 16-byte stores below, and inlining its 32 copies made the
-// 9x9 kernel 16.8k instructions long (10 % of its stall samples were instruction fetches)
+// the element-wise epilogue, out of line: it is the fallback of the 16-byte stores, and inlining its 32 copies made the 9x9
+// kernel 16.8k instructions long (10 % of its stall samples were instruction fetches)
 static __device__ __noinline__ void epilogue_store_elem(const ConvParams& p, int b, int y, int x, int co, float acc) {
   epilogue_store(p, b, y, x, co, acc);
 }
 
-template <int kCG> struct DirectGeom {
+template <int kCG> struct DirectGeom {                 // kCG = output-channel groups of four per block (see the file header)
   static constexpr int kDN = 4 * kCG;                  // output channels per block
   static constexpr int kTCG = kCG == 8 ? 2 : kCG == 2 ? 4 : 8;   // eight-pixel groups per tile row
   static constexpr int kTR = 256 / kCG / kTCG;         // tile rows
