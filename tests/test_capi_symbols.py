@@ -63,3 +63,14 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+
+
+def test_ssim_window_kinds_match_the_header():
+    """include/srb200.h enum { SRB_SSIM_TF, SRB_SSIM_SKIMAGE, SRB_SSIM_TF_EXACT } <-> srb200._capi constants."""
+    import re
+    from srb200 import _capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "include", "srb200.h")).read()
+    m = re.search(r"enum\s*\{\s*SRB_SSIM_TF\s*=\s*(\d+)\s*,\s*SRB_SSIM_SKIMAGE\s*=\s*(\d+)\s*,\s*SRB_SSIM_TF_EXACT\s*=\s*(\d+)\s*\}", text)
+    assert m, "SSIM window enum not found in include/srb200.h"
+    assert tuple(int(v) for v in m.groups()) == (_capi.SSIM_TF, _capi.SSIM_SKIMAGE, _capi.SSIM_TF_EXACT)
